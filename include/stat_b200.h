@@ -1,0 +1,189 @@
+/*
+ * stat_b200.h -- C ABI of the B200-native spatial-temporal-attention caption
+ * decoder (libstat_b200.so).
+ *
+ * The reference (tuyunbin/Video-Description-with-Spatial-Temporal-Attention) has
+ * no native code and no FFI: its boundary for this path is the set of Theano
+ * callables built in model_attention.py.  Each entry point below names the
+ * reference callable / graph fragment it replaces (file:line into the
+ * reference).  The Python host mirror that keeps the reference's own names
+ * (init_params / build_model / f_log_probs / build_sampler / f_init / f_next /
+ * gen_sample) sits on top of this ABI, see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no C++ or torch types; every pointer is a DEVICE pointer owned
+ *     by the caller (inputs, outputs and workspace); the library never
+ *     allocates, frees or retains device memory;
+ *   - every function enqueues work on the caller's stream and returns without
+ *     synchronising; all entry points may be stream-captured into a CUDA graph;
+ *   - return 0 on success, a negative STAT_E* code otherwise;
+ *     stat_last_error() gives a thread-local message;
+ *   - all tensors fp32 row-major, tokens int64 (model_attention.py:587,798);
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with STAT_ECUDA.
+ */
+#ifndef STAT_B200_H
+#define STAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STAT_ABI_VERSION 1
+
+/* error codes */
+#define STAT_OK       0
+#define STAT_EINVAL  -1   /* bad argument / unsupported shape            */
+#define STAT_ECUDA   -2   /* CUDA runtime or driver error                */
+#define STAT_EALIGN  -3   /* pointer or leading dimension not 16B aligned */
+
+/* option flags (config.py:17-49; global_proj is decision D1, the layer the
+ * reference left commented out at model_attention.py:553-554,661-662) */
+#define STAT_SELECTOR     1
+#define STAT_PREV2OUT     2
+#define STAT_CTX2OUT      4
+#define STAT_GLOBAL_PROJ  8
+
+typedef struct StatDims {
+  int32_t B;      /* clips in the batch                                        */
+  int32_t T;      /* frames per clip                                           */
+  int32_t R;      /* regions per frame (<= 16)                                 */
+  int32_t Dg;     /* ctxg_dim  (multiple of 4)                                 */
+  int32_t Dm;     /* ctxm_dim  (multiple of 4)                                 */
+  int32_t Dr;     /* ctxl_dim  (multiple of 4)                                 */
+  int32_t H;      /* dim       (multiple of 4)                                 */
+  int32_t E;      /* dim_word  (multiple of 4)                                 */
+  int32_t V;      /* n_words                                                   */
+  int32_t flags;  /* STAT_* option flags                                       */
+} StatDims;
+
+/* The reference's parameter dict (init_params, model_attention.py:518-581;
+ * SURVEY App. B order).  Optional tensors may be NULL when their flag is off. */
+typedef struct StatParams {
+  const float *Wemb;                            /* (V,E)            :522     */
+  const float *ff_state_W, *ff_state_b;         /* (Dg,H),(H)       :549     */
+  const float *ff_memory_W, *ff_memory_b;       /* (Dg,H),(H)       :551     */
+  const float *ff_global_W, *ff_global_b;       /* (Dg,H),(H)  D1   :553     */
+  const float *ff_local_W, *ff_local_b;         /* (Dr,H),(H)       :556     */
+  const float *ff_motion_W, *ff_motion_b;       /* (Dm,H),(H)       :558     */
+  const float *decoder_W, *decoder_U, *decoder_b, *decoder_Wc;  /* :189-207  */
+  const float *decoder_Wcg_att, *decoder_Wcm_att, *decoder_Wclt_att; /* :210 */
+  const float *decoder_Wdg_att, *decoder_Wdm_att, *decoder_Wdlt_att; /* :222 */
+  const float *decoder_bg_att, *decoder_bm_att, *decoder_blt_att;    /* :232 */
+  const float *decoder_Wcl_att, *decoder_Wdl_att, *decoder_bl_att;   /* :243 */
+  const float *decoder_Ug_att, *decoder_cg_att;                      /* :255 */
+  const float *decoder_Um_att, *decoder_cm_att;
+  const float *decoder_Ult_att, *decoder_clt_att;
+  const float *decoder_Ul_att, *decoder_cl_att;
+  const float *decoder_W_sel, *decoder_b_sel;   /* (H,1),()  selector :276   */
+  const float *ff_logit_lstm_W, *ff_logit_lstm_b;      /* (H,E),(E)   :566   */
+  const float *ff_logit_ctxglm_W, *ff_logit_ctxglm_b;  /* (H,E),(E)   :569   */
+  const float *ff_logit_W, *ff_logit_b;                /* (E,V),(V)   :578   */
+} StatParams;
+
+int         stat_version(void);
+const char *stat_last_error(void);
+
+/* 0 = tcgen05 3xTF32 tensor-core GEMM (default), 1 = plain fp32 SIMT GEMM (a
+ * device-side cross-check used by the GPU tests; never a CPU path). */
+int stat_set_gemm_impl(int impl);
+
+/* ---- parameter preparation (once per parameter set) ----------------------
+ * Packs the reference tensors into the K-major concatenations the kernels
+ * read and builds the token->gate-input table EW = Wemb.decoder_W + decoder_b
+ * (model_attention.py:334-335 hoisted out of the step: row x of EW is the
+ * `state_below` row of token x; row V is the bias alone = "no previous word",
+ * :803-804).  `prepared` must hold stat_prepared_bytes() bytes. */
+size_t stat_prepared_bytes(const StatDims *d);
+int    stat_prepare_params(const StatDims *d, const StatParams *p, void *prepared,
+                           void *stream);
+
+/* ---- workspace -----------------------------------------------------------
+ * `rows` = decode rows (= B for greedy / teacher forcing, = B*k for beams). */
+size_t stat_workspace_bytes(const StatDims *d, int rows);
+/* byte offset/size of a named workspace region (tests read intermediates):
+ * "ctxg0","pctxg","ctxm0","pctxm","ctxl0","pctxl","qctxl","h0","c0","h","c",
+ * "hp","ctx","logits","att_scores","alpha_l". Returns STAT_EINVAL if unknown. */
+int    stat_workspace_region(const StatDims *d, int rows, const char *name,
+                             size_t *offset, size_t *bytes);
+
+/* ---- K0: per-batch prologue ----------------------------------------------
+ * Replaces build_model's prologue (model_attention.py:618,649 mean-pool,
+ * :657-660 init state, :664-667 ff_local/ff_motion) and lstm_cond_layer's
+ * context projections (:322-326), plus Q = ctxl0.Wclt_att (the :416 GEMM made
+ * step-invariant by linearity).  Results stay in `ws`. */
+int stat_precompute(const StatDims *d, const void *prepared,
+                    const float *ctxg, const float *mask_ctxg,
+                    const float *ctxl, const float *ctxm,
+                    void *ws, void *stream);
+
+/* ---- f_init (model_attention.py:791-795; graph :739-777) -------------------
+ * Initial LSTM state of the B clips: mean over all T frames of ctxg divided by
+ * the number of non-zero frames (:618,:649), then tanh(ff_state) / tanh(ff_memory)
+ * (:657-660).  out_h0 / out_c0 (B,H).  Uses the gbar / h0 regions of `ws`. */
+int stat_init_state(const StatDims *d, const void *prepared, const float *ctxg,
+                    const float *mask_ctxg, void *ws, float *out_h0, float *out_c0,
+                    void *stream);
+
+/* ---- f_log_probs (model_attention.py:1126; graph :583-717) ----------------
+ * Teacher-forced forward over L steps for the B clips already precomputed in
+ * `ws`.  x (L,B) int64, mask (L,B).  dp_gates (L,B,3H) / dp_h (L,B,H) / dp_z
+ * (L,B,E) are the dropout factors; NULL = eval mode constants 0.5
+ * (use_noise=0, common.py:94-99, model_attention.py:469-477).
+ * out_logprob (B) = sum_t mask*log(p[x]+1e-8).  Optional outputs (may be NULL):
+ * out_alpha_l (L,B,T,R), out_alpha_g/m/lt (L,B,T), out_h (L,B,H). */
+int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws,
+                         int L, const int64_t *x, const float *mask,
+                         const float *dp_gates, const float *dp_h, const float *dp_z,
+                         float *out_logprob,
+                         float *out_alpha_l, float *out_alpha_g,
+                         float *out_alpha_m, float *out_alpha_lt, float *out_h,
+                         void *stream);
+
+/* ---- greedy decode = gen_sample(k=1) for B clips at once -------------------
+ * (model_attention.py:852-994 with k=1, stochastic=False).  out_tokens
+ * (B,maxlen) int64, -1 after the eos; out_lengths (B) int32 incl. the eos;
+ * out_scores (B) = cumulative -log p (un-normalised, :921). */
+int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws,
+                       int maxlen, int64_t *out_tokens, int32_t *out_lengths,
+                       float *out_scores, void *stream);
+
+/* ---- f_next (model_attention.py:845-848): one step for `rows` hypotheses ---
+ * row_clip (rows) int32 maps a hypothesis to its clip in `ws` (NULL = row i
+ * uses clip i).  x (rows) int64, -1 = no previous word.  h_in/c_in (rows,H).
+ * out_probs (rows,V), out_h/out_c (rows,H). */
+int stat_step(const StatDims *d, const void *prepared, void *ws, int rows,
+              const int32_t *row_clip, const int64_t *x,
+              const float *h_in, const float *c_in,
+              float *out_probs, float *out_h, float *out_c, void *stream);
+
+/* ---- the dense primitive, exposed for the parity tests ---------------------
+ * C[m][n] = post * act(alpha * sum_k A[m][k]*Bt[n][k] + bias[n]),  A (M,K) and
+ * Bt (N,K) row-major (both "K-major"); act: 0 none, 1 tanh.  swap != 0 runs
+ * the same problem with the operands exchanged on the tensor core (Bt rows on
+ * the 128-lane axis), the form used for skinny activations. */
+int stat_gemm(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc,
+              int M, int N, int K, const float *bias, float alpha, float post,
+              int act, int swap, void *stream);
+
+/* ---- measurement hooks (no reference counterpart) ---------------------------
+ * stat_launch_count: kernels launched by this library so far in this process
+ * (launches recorded into a CUDA graph count once, at capture).
+ * stat_profile_*: when enabled, every launch group of stat_precompute / the
+ * decode step is bracketed by CUDA events on the caller's stream;
+ * stat_profile_collect synchronises on them and returns the summed milliseconds
+ * and number of occurrences per phase (stat_profile_phase_name).  Do not enable
+ * while capturing a graph. */
+unsigned long long stat_launch_count(void);
+int         stat_profile_enable(int on);
+int         stat_profile_phases(void);
+const char *stat_profile_phase_name(int phase);
+int         stat_profile_collect(float *ms_by_phase, int *count_by_phase, int nphase);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAT_B200_H */

@@ -1,0 +1,286 @@
+"""GPU parity: the CUDA path, called through the C ABI (via the reference-shaped host
+mirror), against (i) the committed fixtures produced by the reference's own source
+and (ii) the CPU oracle on seeded synthetic batches of BASELINE width.
+
+Tolerances (BASELINE.json north_star): 1e-4 absolute on log-probs and
+cumulative caption scores, 1e-5 on attention weights / states, identical token ids."""
+import numpy as np
+import pytest
+
+import video_description_with_spatial_temporal_attention_b200 as stat
+from video_description_with_spatial_temporal_attention_b200 import model_attention as ma, synthetic
+from oracle import stat_oracle as so
+from tests.golden_util import NAMES, Golden
+
+pytestmark = pytest.mark.gpu
+
+TOL_LP = 1e-4
+TOL_A = 1e-5
+
+
+@pytest.fixture(scope='module')
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _build(options, params):
+    model = ma.Attention()
+    tp = model.init_tparams(params)
+    r = model.build_model(tp, options)
+    trng, use_noise = r[0], r[1]
+    inps, alphas, cost = list(r[2:10]), list(r[10:14]), r[14]
+    f_log_probs = ma.function(inps, -cost)
+    f_alphas = ma.function(inps, alphas)
+    f_init, f_next = model.build_sampler(tp, options, use_noise, trng)
+    return model, tp, f_log_probs, f_alphas, f_init, f_next
+
+
+# ---------------------------------------------------------------------------
+# the dense primitive
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('M,N,K,swap', [(64, 4097, 512, True), (300, 512, 4096, False), (1, 50, 24, True),
+                                        (128, 128, 32, False), (13, 100, 40, True), (257, 96, 36, False),
+                                        (64, 12594, 512, True), (1664, 512, 512, False)])
+def test_gemm_matches_fp64(torch_cuda, impl, M, N, K, swap):
+    torch = torch_cuda
+    from video_description_with_spatial_temporal_attention_b200 import _lib
+    from video_description_with_spatial_temporal_attention_b200.engine import Engine
+    eng = Engine(stat.default_options())
+    g = torch.Generator(device='cpu').manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g)
+    Bt = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    want = torch.tanh(0.5 * (A.double() @ Bt.double().t()) + bias.double()) * 0.5
+    _lib.check(eng.lib.stat_set_gemm_impl(impl))
+    try:
+        got = eng.gemm(A.cuda(), Bt.cuda(), bias.cuda(), alpha=0.5, post=0.5, act=1, swap=swap).cpu()
+        got_lin = eng.gemm(A.cuda(), Bt.cuda(), None, swap=swap).cpu()
+    finally:
+        _lib.check(eng.lib.stat_set_gemm_impl(0))
+    np.testing.assert_allclose(got.numpy(), want.float().numpy(), atol=3e-6, rtol=0)
+    want_lin = (A.double() @ Bt.double().t()).float().numpy()
+    np.testing.assert_allclose(got_lin.numpy(), want_lin, atol=2e-5, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------
+# fixtures produced by the reference's own source
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('name', NAMES)
+def test_golden_f_log_probs_and_alphas(torch_cuda, name):
+    g = Golden(name)
+    _, _, f_log_probs, f_alphas, _, _ = _build(g.options, g.params)
+    lp = f_log_probs(*g.batch)
+    assert lp.shape == g.out('f_log_probs').shape and lp.dtype == np.float32
+    np.testing.assert_allclose(lp, g.out('f_log_probs'), atol=TOL_LP, rtol=0)
+    al, ag, am, alt = f_alphas(*g.batch)
+    np.testing.assert_allclose(al, g.out('alphals'), atol=TOL_A)
+    np.testing.assert_allclose(ag, g.out('alphags'), atol=TOL_A)
+    np.testing.assert_allclose(am, g.out('alphams'), atol=TOL_A)
+    np.testing.assert_allclose(alt, g.out('alphalts'), atol=TOL_A)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_golden_sampler_functions(torch_cuda, name):
+    g = Golden(name)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = g.batch
+    _, _, _, _, f_init, f_next = _build(g.options, g.params)
+    r = f_init(ctxg[0], mg[0])
+    np.testing.assert_allclose(r[1], g.out('f_init_h0'), atol=TOL_A)
+    np.testing.assert_allclose(r[2], g.out('f_init_c0'), atol=TOL_A)
+    r1 = f_next(-np.ones((1,), 'int64'), ctxg[0], mg[0], ctxl[0], ml[0], ctxm[0], mm[0], r[1][None], r[2][None])
+    np.testing.assert_allclose(r1[0], g.out('f_next0_probs'), atol=TOL_A)
+    np.testing.assert_allclose(r1[2], g.out('f_next0_h'), atol=TOL_A)
+    np.testing.assert_allclose(r1[3], g.out('f_next0_c'), atol=TOL_A)
+    r2 = f_next(g.inp('f_next1_x'), ctxg[0], mg[0], ctxl[0], ml[0], ctxm[0], mm[0], g.inp('f_next1_h'),
+                g.inp('f_next1_c'))
+    np.testing.assert_allclose(r2[0], g.out('f_next1_probs'), atol=TOL_A)
+    np.testing.assert_allclose(r2[2], g.out('f_next1_h'), atol=TOL_A)
+    np.testing.assert_allclose(r2[3], g.out('f_next1_c'), atol=TOL_A)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_golden_gen_sample(torch_cuda, name):
+    g = Golden(name)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = g.batch
+    model, tp, _, _, f_init, f_next = _build(g.options, g.params)
+    for k in g.ks:
+        for b in range(ctxg.shape[0]):
+            want, want_sc = g.hyps(k, b)
+            got, got_sc, _, _ = model.gen_sample(tp, f_init, f_next, ctxg[b], mg[b], ctxl[b], ml[b], ctxm[b], mm[b],
+                                                 g.options, None, k, g.maxlen, False)
+            assert got == want, (name, k, b)
+            np.testing.assert_allclose(np.asarray(got_sc), want_sc, atol=TOL_LP)
+
+
+@pytest.mark.parametrize('name', NAMES)
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_golden_greedy_batch(torch_cuda, name, use_graph):
+    g = Golden(name)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = g.batch
+    model, tp, _, _, _, _ = _build(g.options, g.params)
+    toks, lens, scores = model.greedy_batch(tp, g.options, ctxg, mg, ctxl, ctxm, maxlen=g.maxlen,
+                                            use_graph=use_graph)
+    for b in range(ctxg.shape[0]):
+        want, want_sc = g.hyps(1, b)
+        assert [int(t) for t in toks[b, :lens[b]]] == want[0]
+        assert (toks[b, lens[b]:] == -1).all()
+        np.testing.assert_allclose(scores[b], want_sc[0], atol=TOL_LP)
+
+
+# ---------------------------------------------------------------------------
+# BASELINE width against the oracle, both Dg == H (faithful) and Dg = 2048 (D1)
+# ---------------------------------------------------------------------------
+def _case(kind, B, T=26, R=8, L=20, seed=5, **kw):
+    if kind == 'faithful':
+        o = stat.default_options(**kw)
+    else:
+        o = stat.baseline_options()
+        o.update(kw)
+    params = so.trained_like_params(o, seed=seed)
+    batch = synthetic.make_batch(o, B=B, T=T, R=R, L=L, seed=seed, zero_tail=True)
+    return o, params, batch
+
+
+@pytest.mark.parametrize('kind', ['faithful', 'baseline'])
+def test_full_width_f_log_probs_vs_oracle(torch_cuda, kind):
+    o, params, batch = _case(kind, B=5, L=12)
+    _, _, f_log_probs, f_alphas, _, _ = _build(o, params)
+    lp = f_log_probs(*batch)
+    want64, allv = so.forward_teacher(params, o, *batch, dtype=np.float64, return_all=True)
+    np.testing.assert_allclose(lp, want64, atol=TOL_LP, rtol=0)
+    al, ag, am, alt = f_alphas(*batch)
+    st = allv['steps']
+    np.testing.assert_allclose(al, np.stack([s['alphaL'] for s in st]), atol=TOL_A)
+    np.testing.assert_allclose(ag, np.stack([s['alphaG'] for s in st]), atol=TOL_A)
+    np.testing.assert_allclose(am, np.stack([s['alphaM'] for s in st]), atol=TOL_A)
+    np.testing.assert_allclose(alt, np.stack([s['alphaLT'] for s in st]), atol=TOL_A)
+    # attention rows are distributions
+    for a in (al, ag, am, alt):
+        np.testing.assert_allclose(a.sum(-1), 1.0, atol=1e-5)
+
+
+def test_config1_single_clip_len20(torch_cuda):
+    """BASELINE config 1: one clip, one caption of 20 tokens."""
+    o, params, batch = _case('baseline', B=1, L=20, seed=1234)
+    x, m = synthetic.make_captions(1, o['n_words'], 20, seed=1234, ragged=False)
+    batch = (x, m) + tuple(batch[2:])
+    _, _, f_log_probs, _, _, _ = _build(o, params)
+    lp = f_log_probs(*batch)
+    want = so.forward_teacher(params, o, *batch, dtype=np.float64)
+    assert m.sum() == 20
+    np.testing.assert_allclose(lp, want, atol=TOL_LP, rtol=0)
+
+
+@pytest.mark.parametrize('kind', ['faithful', 'baseline'])
+def test_full_width_greedy_vs_oracle(torch_cuda, kind):
+    o, params, batch = _case(kind, B=6, seed=9)
+    params['ff_logit_b'] = params['ff_logit_b'].copy()
+    params['ff_logit_b'][0] += 2.0          # let some captions end before maxlen
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+    model, tp, _, _, _, _ = _build(o, params)
+    maxlen = 12
+    toks, lens, scores = model.greedy_batch(tp, o, ctxg, mg, ctxl, ctxm, maxlen=maxlen)
+    wt, wl, ws, margins = so.greedy_decode_batch(params, o, ctxg, mg, ctxl, ctxm, maxlen, dtype=np.float64,
+                                                 return_all=True)
+    for b in range(ctxg.shape[0]):
+        # an fp32 path may legitimately flip an argmax whose top-2 logit margin is at
+        # rounding level; compare up to the first such step (none expected)
+        n = int(wl[b])
+        tight = np.where(margins[b, :n] < 1e-4)[0]
+        upto = int(tight[0]) if len(tight) else n
+        assert [int(t) for t in toks[b, :upto]] == [int(t) for t in wt[b, :upto]], b
+        if upto == n:
+            assert lens[b] == n
+            np.testing.assert_allclose(scores[b], ws[b], atol=TOL_LP)
+
+
+# ---------------------------------------------------------------------------
+# size-independent properties at BASELINE size (B=64)
+# ---------------------------------------------------------------------------
+def test_baseline_size_properties(torch_cuda):
+    torch = torch_cuda
+    o, params, batch = _case('baseline', B=64, seed=21)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+    model, tp, f_log_probs, _, f_init, f_next = _build(o, params)
+    lp = f_log_probs(*batch)
+    assert lp.shape == (64,) and np.isfinite(lp).all() and (lp < 0).all()
+    # (1) permutation equivariance over the batch
+    perm = np.random.RandomState(0).permutation(64)
+    pb = (x[:, perm], m[:, perm], ctxg[perm], mg[perm], ctxl[perm], ml[perm], ctxm[perm], mm[perm])
+    np.testing.assert_allclose(f_log_probs(*pb), lp[perm], atol=2e-5)
+    # (2) a clip's log-prob does not depend on its batch mates
+    sub = [3, 17]
+    sb = (x[:, sub], m[:, sub], ctxg[sub], mg[sub], ctxl[sub], ml[sub], ctxm[sub], mm[sub])
+    np.testing.assert_allclose(f_log_probs(*sb), lp[sub], atol=2e-5)
+    # (3) f_next chained over the caption == teacher-forced forward (:806-814 vs :669-676)
+    b = 17
+    r = f_init(ctxg[b], mg[b])
+    h, c = r[1][None], r[2][None]
+    prev = -np.ones((1,), 'int64')
+    acc = 0.0
+    for t in range(x.shape[0]):
+        p, _, h2, c2 = f_next(prev, ctxg[b], mg[b], ctxl[b], ml[b], ctxm[b], mm[b], h, c)
+        np.testing.assert_allclose(p.sum(), 1.0, atol=1e-5)
+        if m[t, b] > 0:
+            acc += np.log(p[0, x[t, b]] + 1e-8)
+            h, c = h2, c2
+        prev = x[t:t + 1, b]
+    np.testing.assert_allclose(acc, lp[b], atol=TOL_LP)
+    # (4) greedy: graph replay == direct launches, bit for bit; k=1 gen_sample == batch row
+    t1 = model.greedy_batch(tp, o, ctxg, mg, ctxl, ctxm, maxlen=20, use_graph=False)
+    t2 = model.greedy_batch(tp, o, ctxg, mg, ctxl, ctxm, maxlen=20, use_graph=True)
+    t3 = model.greedy_batch(tp, o, ctxg, mg, ctxl, ctxm, maxlen=20, use_graph=True)
+    for a, bb in zip(t1, t2):
+        np.testing.assert_array_equal(a, bb)
+    for a, bb in zip(t2, t3):
+        np.testing.assert_array_equal(a, bb)
+    hyp, sc, _, _ = model.gen_sample(tp, f_init, f_next, ctxg[5], mg[5], ctxl[5], ml[5], ctxm[5], mm[5], o, None,
+                                     1, 20, False)
+    toks, lens, scores = t1
+    assert hyp[0] == [int(v) for v in toks[5, :lens[5]]]
+    np.testing.assert_allclose(sc[0], scores[5], atol=TOL_LP)
+
+
+def test_dropout_masks_path(torch_cuda):
+    """use_noise=1 (D2): explicit masks through the C ABI == oracle with the same masks."""
+    torch = torch_cuda
+    from video_description_with_spatial_temporal_attention_b200.engine import Engine
+    o, params, batch = _case('faithful', B=3, L=6, seed=3, dim=128, dim_word=64, ctxg_dim=128, ctxl_dim=256,
+                             ctxm_dim=192, n_words=500)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+    L, B = x.shape
+    H, E = o['dim'], o['dim_word']
+    r = np.random.RandomState(4)
+    dpg = (r.rand(L, B, 3 * H) < 0.5).astype('float32')
+    dph = (r.rand(L, B, H) < 0.5).astype('float32')
+    dpz = (r.rand(L, B, E) < 0.5).astype('float32')
+    want = so.forward_teacher(params, o, *batch, dtype=np.float64, dp_gates=dpg, dp_h=dph, dp_z=dpz)
+    eng = Engine(o)
+    eng.set_params(params)
+    f32 = torch.float32
+    ws, d = eng.precompute(eng.to_device(ctxg, f32), eng.to_device(mg, f32), eng.to_device(ctxl, f32),
+                           eng.to_device(ctxm, f32))
+    lp, _, _ = eng.forward_teacher(ws, d, eng.to_device(x, torch.int64), eng.to_device(m, f32),
+                                   eng.to_device(dpg, f32), eng.to_device(dph, f32), eng.to_device(dpz, f32))
+    np.testing.assert_allclose(lp.cpu().numpy(), want, atol=TOL_LP)
+
+
+def test_edge_cases(torch_cuda):
+    """R=1, T=1, a single clip, a caption that is only the eos, all-but-one frame zero."""
+    o = stat.default_options(dim=64, dim_word=32, ctxg_dim=64, ctxl_dim=48, ctxm_dim=40, n_words=37)
+    params = so.trained_like_params(o, seed=2)
+    for (B, T, R, L) in [(1, 1, 1, 1), (2, 3, 1, 4), (1, 26, 16, 3), (130, 2, 2, 3)]:
+        batch = list(synthetic.make_batch(o, B=B, T=T, R=R, L=L, seed=B + T))
+        batch[0][:, 0] = 0                       # clip 0: caption is just the eos
+        batch[1][:, 0] = 0
+        batch[1][0, 0] = 1
+        if T > 1:
+            batch[2][0, 1:] = 0                  # clip 0: only the first frame is non-zero
+            batch[3][0, 1:] = 0
+        _, _, f_log_probs, _, _, _ = _build(o, params)
+        lp = f_log_probs(*batch)
+        want = so.forward_teacher(params, o, *batch, dtype=np.float64)
+        np.testing.assert_allclose(lp, want, atol=TOL_LP, err_msg=str((B, T, R, L)))

@@ -1,0 +1,86 @@
+// Launch-argument structs and launchers of the non-GEMM kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace stat {
+
+// ---- att_step.cu -------------------------------------------------------------
+struct AttArgs {
+  const float *pctxl, *ctxl0, *qctxl;            // (clips,T,R,H)
+  const float *pctxg, *ctxg0, *pctxm, *ctxm0;    // (clips,T,H)
+  const float *hp;                               // (rows,ldhp) hidden-state projections
+  int ldhp;
+  int off_sl, off_sg, off_sm, off_slt, off_sel;  // column offsets inside a hp row
+  const float *Ul, *Ug, *Um, *Ult;               // (H) score vectors
+  const float *cl, *cg, *cm, *clt;               // (1) score biases
+  const int32_t *row_clip;                       // (rows) or null = identity
+  int rows, T, R, H;
+  int S, Tc;                                     // segments per row, frames per segment
+  int selector;
+  float *ctx;                                    // (rows,H) out: fused, gated context
+  float *rec_vec;                                // (rows,S,3,H) partial weighted sums
+  float *rec_ms;                                 // (rows,S,3,2) partial (max,sum)
+  unsigned int *counters;                        // (rows) tickets, zero between launches
+  float *att_scores;                             // (3,rows,T) raw temporal scores or null
+  float *alpha_l;                                // (rows,T,R) spatial weights or null
+};
+int att_step_launch(const AttArgs &a, cudaStream_t stream);
+
+// ---- recurrent.cu --------------------------------------------------------------
+// LSTM gates + state update (model_attention.py:437-457) and the emb / bias part of
+// the readout pre-activation (:689-693).
+struct GateArgs {
+  int rows, H, E, V;
+  const float *pre_c;      // (rows,ldpc): [0,4H) ctx.Wc ; [zc_off, zc_off+E) ctx.Wctx (zc_off < 0: absent)
+  int ldpc, zc_off;
+  const float *hp;         // (rows,ldhp): h_.U at off_u
+  int ldhp, off_u;
+  const float *EW;         // (V+1,4H) token -> emb.W + b
+  const float *Wemb;       // (V,E)
+  const int64_t *tok_prev; // (rows) or null = no previous word
+  const float *mask;       // (rows) or null = 1
+  const float *dp_gates;   // (rows,3H) or null = 0.5
+  const float *dp_h;       // (rows,H) or null
+  const float *h_in, *c_in;
+  float *h_out, *c_out;    // may alias the inputs
+  float *hd_out;           // (rows,H) h * dp_h when dp_h != null
+  const float *bz;         // (E) readout bias: ff_logit_lstm_b (+ ff_logit_ctxglm_b)
+  float *zadd;             // (rows,E) out: bz + ctx.Wctx (ctx2out) + Wemb[tok] (prev2out)
+  int prev2out;
+  float *h_all;            // (rows,H) copy of h_out or null
+};
+int gates_launch(const GateArgs &a, cudaStream_t stream);
+
+// vocabulary reduction of one step: log-softmax statistics, argmax, bookkeeping
+struct PickArgs {
+  int rows, V, ldl;
+  const float *logits;       // (rows,ldl)
+  // greedy bookkeeping (all null in the other modes)
+  int64_t *tokens;           // (rows,maxlen)
+  int maxlen, t;
+  int32_t *lengths;          // (rows)
+  float *scores;             // (rows)
+  int32_t *alive;            // (rows)
+  int64_t *tok_prev;         // (rows)
+  // teacher forcing
+  const int64_t *x_t;        // (rows) target tokens of this step or null
+  const float *mask_t;       // (rows)
+  float *logprob;            // (rows) accumulated
+  // f_next
+  float *probs;              // (rows,V) or null
+};
+int pick_launch(const PickArgs &a, cudaStream_t stream);
+
+int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, int T, int D,
+                    cudaStream_t stream);
+// dst (rows_out, ld_dst) [r0 + n][k] = src (K, N) [k][n]   (weights -> K-major)
+int transpose_launch(const float *src, int K, int N, float *dst, int ld_dst, int r0, cudaStream_t stream);
+int softmax_rows_launch(const float *scores, float *out, int nrows, int n, cudaStream_t stream);
+int scale_launch(float *x, const float *f, size_t n, cudaStream_t stream);
+int init_rows_launch(int rows, int64_t *tok_prev, int32_t *alive, int32_t *lengths, float *scores,
+                     int64_t *tokens, int maxlen, cudaStream_t stream);
+int add_vec_launch(float *dst, const float *a, const float *b, int n, cudaStream_t stream);
+
+}  // namespace stat

@@ -1,0 +1,260 @@
+// Small per-step kernels around the attention and the GEMMs: LSTM gate update,
+// vocabulary reduction (log-softmax statistics / argmax / target gather), and the
+// one-off helpers of the prologue (mean pool, weight transposes).
+#include "stat_common.cuh"
+#include "kernels.cuh"
+
+namespace stat {
+namespace {
+
+// ---------------------------------------------------------------------------
+// gates: S10-S13 of SURVEY App. A  (model_attention.py:437-457)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gates_kernel(const GateArgs a) {
+  const int row = blockIdx.y;
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const long long tok = a.tok_prev ? a.tok_prev[row] : -1;
+  const int H = a.H;
+  if (j < H) {
+    const float *pc = a.pre_c + static_cast<size_t>(row) * a.ldpc;
+    const float *u = a.hp + static_cast<size_t>(row) * a.ldhp + a.off_u;
+    const float *ew = a.EW + static_cast<size_t>(tok >= 0 ? tok : a.V) * 4 * H;
+    float di = 0.5f, df = 0.5f, dO = 0.5f;
+    if (a.dp_gates) {
+      const float *dp = a.dp_gates + static_cast<size_t>(row) * 3 * H;
+      di = dp[j];
+      df = dp[H + j];
+      dO = dp[2 * H + j];
+    }
+    const float pi = (u[j] + __ldg(ew + j)) + pc[j];
+    const float pf = (u[H + j] + __ldg(ew + H + j)) + pc[H + j];
+    const float po = (u[2 * H + j] + __ldg(ew + 2 * H + j)) + pc[2 * H + j];
+    const float pg = (u[3 * H + j] + __ldg(ew + 3 * H + j)) + pc[3 * H + j];
+    const float ig = sigmoid_acc(pi * di);
+    const float fg = sigmoid_acc(pf * df);
+    const float og = sigmoid_acc(po * dO);
+    const float gg = tanhf(pg);
+    const size_t idx = static_cast<size_t>(row) * H + j;
+    const float c_ = a.c_in[idx], h_ = a.h_in[idx];
+    const float m = a.mask ? a.mask[row] : 1.0f;
+    float c = fg * c_ + ig * gg;
+    c = m * c + (1.0f - m) * c_;
+    float h = og * tanhf(c);
+    h = m * h + (1.0f - m) * h_;
+    a.c_out[idx] = c;
+    a.h_out[idx] = h;
+    if (a.h_all) a.h_all[idx] = h;
+    if (a.dp_h) a.hd_out[idx] = h * a.dp_h[idx];
+  }
+  if (j < a.E) {
+    // everything of the readout pre-activation that does not depend on the new h (:689-693)
+    float z = a.bz[j];
+    if (a.zc_off >= 0) z += a.pre_c[static_cast<size_t>(row) * a.ldpc + a.zc_off + j];
+    if (a.prev2out && tok >= 0) z += __ldg(a.Wemb + static_cast<size_t>(tok) * a.E + j);
+    a.zadd[static_cast<size_t>(row) * a.E + j] = z;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// vocabulary reduction
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pick_kernel(const PickArgs a) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ float s_sum[8];
+  __shared__ float s_bm;
+  __shared__ int s_bi;
+  __shared__ float s_bs;
+  const int row = blockIdx.x;
+  const float *l = a.logits + static_cast<size_t>(row) * a.ldl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < a.V; v += 256) {
+    const float x = l[v];
+    if (x > best) { best = x; bi = v; }      // strided ascending: first hit wins ties
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = s_val[0];
+    int i = s_idx[0];
+    for (int w = 1; w < 8; ++w)
+      if (s_val[w] > b || (s_val[w] == b && s_idx[w] < i)) { b = s_val[w]; i = s_idx[w]; }
+    s_bm = b;
+    s_bi = i;
+  }
+  __syncthreads();
+  const float m = s_bm;
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < a.V; v += 256) sum += expf(l[v] - m);
+  sum = warp_sum(sum);
+  if (lane == 0) s_sum[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += s_sum[w];
+    s_bs = s;
+    const int tok = s_bi;
+    if (a.tokens) {
+      const bool live = a.alive[row] != 0;
+      a.tokens[static_cast<size_t>(row) * a.maxlen + a.t] = live ? tok : -1;
+      if (live) {
+        a.scores[row] += logf(s);              // -log p(argmax) = log sum exp(l - max)
+        a.lengths[row] = a.t + 1;
+        a.alive[row] = tok != 0;
+        a.tok_prev[row] = tok;
+      }
+    }
+    if (a.x_t) {
+      const float p = expf(l[a.x_t[row]] - m) / s;
+      a.logprob[row] += a.mask_t[row] * logf(p + 1e-8f);   // model_attention.py:712-715
+    }
+  }
+  if (a.probs) {
+    __syncthreads();
+    const float inv = 1.0f / s_bs;
+    float *p = a.probs + static_cast<size_t>(row) * a.V;
+    for (int v = threadIdx.x; v < a.V; v += 256) p[v] = expf(l[v] - m) * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// prologue helpers
+// ---------------------------------------------------------------------------
+__global__ void meanpool_kernel(const float *__restrict__ ctxg, const float *__restrict__ mask,
+                                float *__restrict__ gbar, int T, int D) {
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float cnt = 0.f;
+  for (int t = 0; t < T; ++t) cnt += mask[b * T + t];
+  float s = 0.f;
+  const float *p = ctxg + static_cast<size_t>(b) * T * D + d;
+  for (int t = 0; t < T; ++t) s += p[static_cast<size_t>(t) * D];
+  gbar[static_cast<size_t>(b) * D + d] = s / cnt;        // :618, :649
+}
+
+__global__ void transpose_kernel(const float *__restrict__ src, int K, int N, float *__restrict__ dst,
+                                 int ld_dst, int r0) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? src[static_cast<size_t>(k) * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N && k < K) dst[static_cast<size_t>(r0 + n) * ld_dst + k] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void softmax_rows_kernel(const float *__restrict__ sc, float *__restrict__ out, int nrows, int n) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const float *p = sc + static_cast<size_t>(row) * n;
+  float m = -INFINITY;
+  for (int i = lane; i < n; i += 32) m = fmaxf(m, p[i]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) s += expf(p[i] - m);
+  s = warp_sum(s);
+  for (int i = lane; i < n; i += 32) out[static_cast<size_t>(row) * n + i] = expf(p[i] - m) / s;
+}
+
+__global__ void scale_kernel(float *__restrict__ x, const float *__restrict__ f, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= f[i];
+}
+
+__global__ void init_rows_kernel(int rows, int64_t *tok_prev, int32_t *alive, int32_t *lengths, float *scores,
+                                 int64_t *tokens, int maxlen) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) {
+    tok_prev[i] = -1;
+    alive[i] = 1;
+    if (lengths) lengths[i] = 0;
+    if (scores) scores[i] = 0.f;
+  }
+  if (tokens && i < rows * maxlen) tokens[i] = -1;
+}
+
+__global__ void add_vec_kernel(float *dst, const float *a, const float *b, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+}  // namespace
+
+int gates_launch(const GateArgs &a, cudaStream_t stream) {
+  const int w = a.H > a.E ? a.H : a.E;
+  dim3 grid((w + 127) / 128, a.rows);
+  gates_kernel<<<grid, 128, 0, stream>>>(a);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int pick_launch(const PickArgs &a, cudaStream_t stream) {
+  pick_kernel<<<a.rows, 256, 0, stream>>>(a);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, int T, int D,
+                    cudaStream_t stream) {
+  dim3 grid((D + 255) / 256, B);
+  meanpool_kernel<<<grid, 256, 0, stream>>>(ctxg, mask, gbar, T, D);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int transpose_launch(const float *src, int K, int N, float *dst, int ld_dst, int r0, cudaStream_t stream) {
+  dim3 grid((N + 31) / 32, (K + 31) / 32);
+  transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, K, N, dst, ld_dst, r0);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int softmax_rows_launch(const float *scores, float *out, int nrows, int n, cudaStream_t stream) {
+  softmax_rows_kernel<<<(nrows + 3) / 4, 128, 0, stream>>>(scores, out, nrows, n);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int scale_launch(float *x, const float *f, size_t n, cudaStream_t stream) {
+  scale_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(x, f, n);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int init_rows_launch(int rows, int64_t *tok_prev, int32_t *alive, int32_t *lengths, float *scores,
+                     int64_t *tokens, int maxlen, cudaStream_t stream) {
+  const int n = tokens ? rows * maxlen : rows;
+  init_rows_kernel<<<(n + 255) / 256, 256, 0, stream>>>(rows, tok_prev, alive, lengths, scores, tokens, maxlen);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int add_vec_launch(float *dst, const float *a, const float *b, int n, cudaStream_t stream) {
+  add_vec_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dst, a, b, n);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+}  // namespace stat

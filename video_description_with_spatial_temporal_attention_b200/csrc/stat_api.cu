@@ -1,0 +1,729 @@
+// C ABI of libstat_b200.so (include/stat_b200.h): parameter packing, workspace
+// layout and the per-step launch sequences built from the kernels in
+// gemm_tf32x3.cu / att_step.cu / recurrent.cu.  Everything is enqueued on the
+// caller's stream; nothing here allocates, synchronises or touches the host side
+// of a tensor.
+#include <string.h>
+
+#include "kernels.cuh"
+#include "stat_common.cuh"
+
+#include <vector>
+
+namespace stat {
+const char *get_error();
+unsigned long long launch_count();
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// optional in-situ phase timing (stat_profile_*): CUDA events recorded on the
+// caller's stream around each launch group.  Off by default; never used while a
+// stream is being captured.
+// ---------------------------------------------------------------------------
+enum Phase { PH_INIT = 0, PH_K0_GLOBAL, PH_K0_MOTION, PH_K0_LOCAL, PH_K0_PROJ, PH_HPROJ, PH_ATT, PH_CTXPROJ,
+             PH_GATES, PH_READOUT, PH_LOGITS, PH_PICK, PH_COUNT };
+const char *const kPhaseNames[PH_COUNT] = {"init_state", "k0_ff_global", "k0_ff_motion", "k0_ff_local",
+                                           "k0_ctx_proj", "step_h_proj", "step_attention", "step_ctx_proj",
+                                           "step_gates", "step_readout", "step_logits", "step_pick"};
+struct ProfRec { int phase; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfRec r;
+  ProfScope(int phase, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (!on) return;
+    r.phase = phase;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, st);
+    g_prof.push_back(r);
+  }
+};
+
+inline size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------
+// prepared parameters: K-major ("transposed") concatenations, float offsets
+// ---------------------------------------------------------------------------
+struct Prep {
+  // weights, each (features, K) row-major
+  size_t WhT;    // (8H+1, H): Wdl | Wdg | Wdm | Wdlt | U (4H) | W_sel      K = H
+  size_t bh;     // (8H+1)   : 0 | 0 | 0 | blt | 0 | b_sel
+  size_t WcT;    // (4H+E, H): Wc (4H) | ff_logit_ctxglm_W (E)               K = H
+  size_t WlT;    // (E, H)   : ff_logit_lstm_W                               K = H
+  size_t bz;     // (E)      : ff_logit_lstm_b (+ ff_logit_ctxglm_b)
+  size_t WvT;    // (V, E)   : ff_logit_W                                    K = E
+  size_t bv;     // (V)
+  size_t WstT;   // (2H, Dg) : ff_state_W | ff_memory_W                      K = Dg
+  size_t bst;    // (2H)
+  size_t WgT;    // (H, Dg)  : ff_global_W (global_proj)                     K = Dg
+  size_t bg0;    // (H)
+  size_t WlocT;  // (H, Dr)                                                  K = Dr
+  size_t bloc;   // (H)
+  size_t WmotT;  // (H, Dm)                                                  K = Dm
+  size_t bmot;   // (H)
+  size_t WcgT;   // (H, H)   : Wcg_att
+  size_t bcg;    // (H)
+  size_t WcmT;   // (H, H)   : Wcm_att
+  size_t bcm;    // (H)
+  size_t WclT;   // (2H, H)  : Wcl_att | Wclt_att
+  size_t bcl;    // (2H)     : bl_att | 0
+  size_t WdT;    // (4H, E)  : decoder_W                                     K = E
+  size_t U4;     // Ul | Ug | Um | Ult (4 x H) then cl, cg, cm, clt (4 scalars)
+  size_t EW;     // (V+1, 4H): token -> emb.W + b ; row V = b
+  size_t Wemb;   // (V, E) copy (prev2out add)
+  size_t total;  // floats
+  int NH, NC;
+};
+
+Prep prep_layout(const StatDims &d) {
+  Prep p;
+  const size_t H = d.H, E = d.E, V = d.V, Dg = d.Dg, Dr = d.Dr, Dm = d.Dm;
+  size_t o = 0;
+  auto take = [&](size_t n) {
+    size_t at = o;
+    o = up(o + n, 64);  // 256-byte aligned regions
+    return at;
+  };
+  p.NH = static_cast<int>(8 * H + 1);
+  p.NC = static_cast<int>(4 * H + ((d.flags & STAT_CTX2OUT) ? E : 0));
+  p.WhT = take((8 * H + 1) * H);
+  p.bh = take(8 * H + 1);
+  p.WcT = take((4 * H + E) * H);
+  p.WlT = take(E * H);
+  p.bz = take(E);
+  p.WvT = take(V * E);
+  p.bv = take(V);
+  p.WstT = take(2 * H * Dg);
+  p.bst = take(2 * H);
+  p.WgT = take(H * Dg);
+  p.bg0 = take(H);
+  p.WlocT = take(H * Dr);
+  p.bloc = take(H);
+  p.WmotT = take(H * Dm);
+  p.bmot = take(H);
+  p.WcgT = take(H * H);
+  p.bcg = take(H);
+  p.WcmT = take(H * H);
+  p.bcm = take(H);
+  p.WclT = take(2 * H * H);
+  p.bcl = take(2 * H);
+  p.WdT = take(4 * H * E);
+  p.U4 = take(4 * H + 4);
+  p.EW = take((V + 1) * 4 * H);
+  p.Wemb = take(V * E);
+  p.total = o;
+  return p;
+}
+
+// ---------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------
+struct Ws {
+  size_t ctxg0, pctxg, ctxm0, pctxm, ctxl0, pctxl, qctxl;
+  size_t gbar, h0c0;
+  size_t h, c, hp, ctx, pre_c, zadd, hd, z, logits;
+  size_t rec_vec, rec_ms, att_scores, alpha_l;
+  size_t counters, tok_prev, alive;  // byte-typed regions (still float offsets)
+  size_t total;                      // floats
+  int ldhp, ldpc, ldl, S, Tc;
+};
+
+void pick_segments(const StatDims &d, int rows, int *S, int *Tc) {
+  // enough CTAs to cover the 148 SMs twice, frames split as evenly as possible
+  int s = (2 * 148 + rows - 1) / rows;
+  if (s < 1) s = 1;
+  if (s > d.T) s = d.T;
+  int tc = (d.T + s - 1) / s;
+  const int tc_max = static_cast<int>((160 * 1024) / (static_cast<size_t>(d.H) * 4));
+  if (tc > tc_max) tc = tc_max;
+  if (tc < 1) tc = 1;
+  s = (d.T + tc - 1) / tc;
+  *S = s;
+  *Tc = tc;
+}
+
+Ws ws_layout(const StatDims &d, int rows) {
+  Ws w;
+  const size_t B = d.B, T = d.T, R = d.R, H = d.H, E = d.E, V = d.V;
+  const size_t n = rows;
+  size_t o = 0;
+  auto take = [&](size_t k) {
+    size_t at = o;
+    o = up(o + k, 64);
+    return at;
+  };
+  pick_segments(d, rows, &w.S, &w.Tc);
+  w.ldhp = static_cast<int>(up(8 * H + 1, 4));
+  w.ldpc = static_cast<int>(4 * H + E);
+  w.ldl = static_cast<int>(up(V, 4));
+  w.ctxg0 = take(B * T * H);
+  w.pctxg = take(B * T * H);
+  w.ctxm0 = take(B * T * H);
+  w.pctxm = take(B * T * H);
+  w.ctxl0 = take(B * T * R * H);
+  w.pctxl = take(B * T * R * H);
+  w.qctxl = take(B * T * R * H);
+  w.gbar = take(B * d.Dg);
+  w.h0c0 = take(B * 2 * H);
+  w.h = take(n * H);
+  w.c = take(n * H);
+  w.hp = take(n * w.ldhp);
+  w.ctx = take(n * H);
+  w.pre_c = take(n * w.ldpc);
+  w.zadd = take(n * E);
+  w.hd = take(n * H);
+  w.z = take(n * E);
+  w.logits = take(n * w.ldl);
+  w.rec_vec = take(n * w.S * 3 * H);
+  w.rec_ms = take(n * w.S * 6);
+  w.att_scores = take(3 * n * T);
+  w.alpha_l = take(n * T * R);
+  w.counters = take(n);
+  w.tok_prev = take(2 * n);
+  w.alive = take(n);
+  w.total = o;
+  return w;
+}
+
+int check_dims(const StatDims *d) {
+  STAT_REQUIRE(d != nullptr, STAT_EINVAL, "dims is NULL");
+  STAT_REQUIRE(d->B >= 1 && d->T >= 1 && d->R >= 1 && d->R <= 16, STAT_EINVAL,
+               "dims: need B>=1, T>=1, 1<=R<=16 (B=%d T=%d R=%d)", d->B, d->T, d->R);
+  STAT_REQUIRE(d->H >= 1 && d->H <= 1024 && d->E >= 1 && d->V >= 2, STAT_EINVAL,
+               "dims: need 1<=H<=1024, E>=1, V>=2 (H=%d E=%d V=%d)", d->H, d->E, d->V);
+  STAT_REQUIRE(d->Dg >= 1 && d->Dm >= 1 && d->Dr >= 1, STAT_EINVAL, "dims: feature widths must be >= 1");
+  STAT_REQUIRE((d->flags & STAT_GLOBAL_PROJ) || d->Dg == d->H, STAT_EINVAL,
+               "dims: the reference graph needs ctxg_dim == dim (Dg=%d H=%d) unless STAT_GLOBAL_PROJ is set",
+               d->Dg, d->H);
+  return STAT_OK;
+}
+
+int check_device() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no CUDA device: %s (libstat_b200 has no CPU path)", cudaGetErrorString(e));
+    return STAT_ECUDA;
+  }
+  return STAT_OK;
+}
+
+// out (rows, ldc)[r][f] = post*act(alpha * x[r,:].Wt[f,:] + bias[f] + addend[r][f]); skinny activations
+// ride the tensor-core column axis ("swap"), wide ones the 128-lane axis.
+int dense(const float *x, int ldx, int rows, const float *Wt, int K, int nfeat, const float *bias, float *out,
+          int ldc, int act, float alpha, float post, const float *addend, int ld_add, cudaStream_t st) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.K = K;
+  g.nseg = 1;
+  g.seg[0] = GemmSeg{out, ldc, bias, addend, ld_add, alpha, post, act, 0, nfeat};
+  if (rows <= 128) {
+    g.P = Wt; g.ldp = K; g.NP = nfeat;
+    g.Q = x; g.ldq = ldx; g.NQ = rows;
+    g.feat_on_p = 1;
+  } else {
+    g.P = x; g.ldp = ldx; g.NP = rows;
+    g.Q = Wt; g.ldq = K; g.NQ = nfeat;
+    g.feat_on_p = 0;
+  }
+  return gemm_launch(g, st);
+}
+
+// P2, P3: mean-pooled global feature -> h0 | c0   (:618,649,657-660)
+int init_state(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const float *ctxg,
+               const float *mask_ctxg, cudaStream_t st) {
+  ProfScope ps(PH_INIT, st);
+  STAT_TRY(meanpool_launch(ctxg, mask_ctxg, W + w.gbar, d.B, d.T, d.Dg, st));
+  return dense(W + w.gbar, d.Dg, d.B, P + p.WstT, d.Dg, 2 * d.H, P + p.bst, W + w.h0c0, 2 * d.H, 1, 1.f, 1.f,
+               nullptr, 0, st);
+}
+
+struct StepIO {
+  int rows;
+  const int32_t *row_clip;
+  const int64_t *tok_prev;  // (rows) or null
+  const float *mask;        // (rows) or null
+  const float *dp_gates, *dp_h, *dp_z;
+  const float *h_in, *c_in;
+  float *h_out, *c_out;
+  float *h_all;
+  float *alpha_l;     // (rows,T,R) or null
+  float *att_scores;  // (3,rows,T) or null
+};
+
+// one decode step up to the logits (S1-S13 + R1-R3 without the softmax)
+int step_core(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io,
+              cudaStream_t st) {
+  const int H = d.H, E = d.E, V = d.V, rows = io.rows;
+  const bool ctx2out = (d.flags & STAT_CTX2OUT) != 0;
+  // hidden-state projections: 4 attention queries, h.U, selector logit (:371,389,402,415,433,437)
+  {
+    ProfScope ps(PH_HPROJ, st);
+    STAT_TRY(dense(io.h_in, H, rows, P + p.WhT, H, (d.flags & STAT_SELECTOR) ? 8 * H + 1 : 8 * H, P + p.bh,
+                   W + w.hp, w.ldhp, 0, 1.f, 1.f, nullptr, 0, st));
+  }
+  AttArgs a;
+  memset(&a, 0, sizeof(a));
+  a.pctxl = W + w.pctxl; a.ctxl0 = W + w.ctxl0; a.qctxl = W + w.qctxl;
+  a.pctxg = W + w.pctxg; a.ctxg0 = W + w.ctxg0; a.pctxm = W + w.pctxm; a.ctxm0 = W + w.ctxm0;
+  a.hp = W + w.hp; a.ldhp = w.ldhp;
+  a.off_sl = 0; a.off_sg = H; a.off_sm = 2 * H; a.off_slt = 3 * H; a.off_sel = 8 * H;
+  a.Ul = P + p.U4; a.Ug = P + p.U4 + H; a.Um = P + p.U4 + 2 * H; a.Ult = P + p.U4 + 3 * H;
+  a.cl = P + p.U4 + 4 * H; a.cg = a.cl + 1; a.cm = a.cl + 2; a.clt = a.cl + 3;
+  a.row_clip = io.row_clip;
+  a.rows = rows; a.T = d.T; a.R = d.R; a.H = H;
+  a.S = w.S; a.Tc = w.Tc;
+  a.selector = (d.flags & STAT_SELECTOR) ? 1 : 0;
+  a.ctx = W + w.ctx;
+  a.rec_vec = W + w.rec_vec; a.rec_ms = W + w.rec_ms;
+  a.counters = reinterpret_cast<unsigned int *>(W + w.counters);
+  a.att_scores = io.att_scores;
+  a.alpha_l = io.alpha_l;
+  {
+    ProfScope ps(PH_ATT, st);
+    STAT_TRY(att_step_launch(a, st));
+  }
+  // ctx.Wc (gates, :439) and ctx.ff_logit_ctxglm_W (:691-693) in one pass
+  {
+    ProfScope ps(PH_CTXPROJ, st);
+    STAT_TRY(dense(W + w.ctx, H, rows, P + p.WcT, H, p.NC, nullptr, W + w.pre_c, w.ldpc, 0, 1.f, 1.f, nullptr, 0,
+                   st));
+  }
+  GateArgs g;
+  memset(&g, 0, sizeof(g));
+  g.rows = rows; g.H = H; g.E = E; g.V = V;
+  g.pre_c = W + w.pre_c; g.ldpc = w.ldpc; g.zc_off = ctx2out ? 4 * H : -1;
+  g.hp = W + w.hp; g.ldhp = w.ldhp; g.off_u = 4 * H;
+  g.EW = P + p.EW; g.Wemb = P + p.Wemb;
+  g.tok_prev = io.tok_prev; g.mask = io.mask;
+  g.dp_gates = io.dp_gates; g.dp_h = io.dp_h;
+  g.h_in = io.h_in; g.c_in = io.c_in; g.h_out = io.h_out; g.c_out = io.c_out;
+  g.hd_out = W + w.hd;
+  g.bz = P + p.bz; g.zadd = W + w.zadd;
+  g.prev2out = (d.flags & STAT_PREV2OUT) ? 1 : 0;
+  g.h_all = io.h_all;
+  {
+    ProfScope ps(PH_GATES, st);
+    STAT_TRY(gates_launch(g, st));
+  }
+  // z = tanh(dp_h*h . Wl + b + emb + ctx.Wctx) * dp_z   (:684-696)
+  {
+    ProfScope ps(PH_READOUT, st);
+    if (io.dp_h) {
+      STAT_TRY(dense(W + w.hd, H, rows, P + p.WlT, H, E, nullptr, W + w.z, E, 1, 1.f, io.dp_z ? 1.f : 0.5f,
+                     W + w.zadd, E, st));
+    } else {
+      STAT_TRY(dense(io.h_out, H, rows, P + p.WlT, H, E, nullptr, W + w.z, E, 1, 0.5f, io.dp_z ? 1.f : 0.5f,
+                     W + w.zadd, E, st));
+    }
+    if (io.dp_z) STAT_TRY(scale_launch(W + w.z, io.dp_z, static_cast<size_t>(rows) * E, st));
+  }
+  // logits = z . ff_logit_W + b  (:704-705)
+  ProfScope pl(PH_LOGITS, st);
+  STAT_TRY(dense(W + w.z, E, rows, P + p.WvT, E, V, P + p.bv, W + w.logits, w.ldl, 0, 1.f, 1.f, nullptr, 0, st));
+  return STAT_OK;
+}
+
+}  // namespace
+}  // namespace stat
+
+using namespace stat;
+
+extern "C" {
+
+int stat_version(void) { return STAT_ABI_VERSION; }
+
+const char *stat_last_error(void) { return stat::get_error(); }
+
+unsigned long long stat_launch_count(void) { return stat::launch_count(); }
+
+int stat_profile_enable(int on) {
+  for (auto &r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return STAT_OK;
+}
+
+int stat_profile_phases(void) { return PH_COUNT; }
+
+const char *stat_profile_phase_name(int phase) {
+  return (phase >= 0 && phase < PH_COUNT) ? kPhaseNames[phase] : nullptr;
+}
+
+int stat_profile_collect(float *ms_by_phase, int *count_by_phase, int nphase) {
+  STAT_REQUIRE(ms_by_phase && count_by_phase && nphase >= PH_COUNT, STAT_EINVAL,
+               "profile_collect: need arrays of %d entries", PH_COUNT);
+  for (int i = 0; i < nphase; ++i) {
+    ms_by_phase[i] = 0.f;
+    count_by_phase[i] = 0;
+  }
+  for (auto &r : g_prof) {
+    STAT_CUDA_CHECK(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    STAT_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_phase[r.phase] += ms;
+    count_by_phase[r.phase] += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return STAT_OK;
+}
+
+int stat_set_gemm_impl(int impl) {
+  STAT_REQUIRE(impl == 0 || impl == 1, STAT_EINVAL, "gemm impl must be 0 (tcgen05 3xTF32) or 1 (fp32 SIMT)");
+  gemm_set_impl(impl);
+  return STAT_OK;
+}
+
+size_t stat_prepared_bytes(const StatDims *d) {
+  if (check_dims(d) != STAT_OK) return 0;
+  return prep_layout(*d).total * sizeof(float);
+}
+
+int stat_prepare_params(const StatDims *d, const StatParams *sp, void *prepared, void *stream) {
+  STAT_TRY(check_dims(d));
+  STAT_TRY(check_device());
+  STAT_REQUIRE(sp != nullptr && prepared != nullptr, STAT_EINVAL, "prepare: NULL argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Prep p = prep_layout(*d);
+  float *P = static_cast<float *>(prepared);
+  const int H = d->H, E = d->E, V = d->V;
+  const bool sel = d->flags & STAT_SELECTOR, c2o = d->flags & STAT_CTX2OUT, gp = d->flags & STAT_GLOBAL_PROJ;
+#define NEED(f) STAT_REQUIRE(sp->f != nullptr, STAT_EINVAL, "prepare: parameter %s is NULL", #f)
+  NEED(Wemb); NEED(ff_state_W); NEED(ff_state_b); NEED(ff_memory_W); NEED(ff_memory_b);
+  NEED(ff_local_W); NEED(ff_local_b); NEED(ff_motion_W); NEED(ff_motion_b);
+  NEED(decoder_W); NEED(decoder_U); NEED(decoder_b); NEED(decoder_Wc);
+  NEED(decoder_Wcg_att); NEED(decoder_Wcm_att); NEED(decoder_Wclt_att);
+  NEED(decoder_Wdg_att); NEED(decoder_Wdm_att); NEED(decoder_Wdlt_att);
+  NEED(decoder_bg_att); NEED(decoder_bm_att); NEED(decoder_blt_att);
+  NEED(decoder_Wcl_att); NEED(decoder_Wdl_att); NEED(decoder_bl_att);
+  NEED(decoder_Ug_att); NEED(decoder_cg_att); NEED(decoder_Um_att); NEED(decoder_cm_att);
+  NEED(decoder_Ult_att); NEED(decoder_clt_att); NEED(decoder_Ul_att); NEED(decoder_cl_att);
+  NEED(ff_logit_lstm_W); NEED(ff_logit_lstm_b); NEED(ff_logit_W); NEED(ff_logit_b);
+  if (sel) { NEED(decoder_W_sel); NEED(decoder_b_sel); }
+  if (c2o) { NEED(ff_logit_ctxglm_W); NEED(ff_logit_ctxglm_b); }
+  if (gp) { NEED(ff_global_W); NEED(ff_global_b); }
+#undef NEED
+  STAT_CUDA_CHECK(cudaMemsetAsync(P, 0, p.total * sizeof(float), st));
+  auto cp = [&](size_t dst, const float *src, size_t n) {
+    return cudaMemcpyAsync(P + dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  };
+  // hidden-state projections
+  STAT_TRY(transpose_launch(sp->decoder_Wdl_att, H, H, P + p.WhT, H, 0, st));
+  STAT_TRY(transpose_launch(sp->decoder_Wdg_att, H, H, P + p.WhT, H, H, st));
+  STAT_TRY(transpose_launch(sp->decoder_Wdm_att, H, H, P + p.WhT, H, 2 * H, st));
+  STAT_TRY(transpose_launch(sp->decoder_Wdlt_att, H, H, P + p.WhT, H, 3 * H, st));
+  STAT_TRY(transpose_launch(sp->decoder_U, H, 4 * H, P + p.WhT, H, 4 * H, st));
+  STAT_CUDA_CHECK(cp(p.bh + 3 * H, sp->decoder_blt_att, H));
+  if (sel) {
+    STAT_CUDA_CHECK(cp(p.WhT + static_cast<size_t>(8) * H * H, sp->decoder_W_sel, H));
+    STAT_CUDA_CHECK(cp(p.bh + 8 * H, sp->decoder_b_sel, 1));
+  }
+  // context -> gates / readout
+  STAT_TRY(transpose_launch(sp->decoder_Wc, H, 4 * H, P + p.WcT, H, 0, st));
+  if (c2o) STAT_TRY(transpose_launch(sp->ff_logit_ctxglm_W, H, E, P + p.WcT, H, 4 * H, st));
+  STAT_TRY(transpose_launch(sp->ff_logit_lstm_W, H, E, P + p.WlT, H, 0, st));
+  STAT_TRY(add_vec_launch(P + p.bz, sp->ff_logit_lstm_b, c2o ? sp->ff_logit_ctxglm_b : nullptr, E, st));
+  STAT_TRY(transpose_launch(sp->ff_logit_W, E, V, P + p.WvT, E, 0, st));
+  STAT_CUDA_CHECK(cp(p.bv, sp->ff_logit_b, V));
+  // prologue
+  STAT_TRY(transpose_launch(sp->ff_state_W, d->Dg, H, P + p.WstT, d->Dg, 0, st));
+  STAT_TRY(transpose_launch(sp->ff_memory_W, d->Dg, H, P + p.WstT, d->Dg, H, st));
+  STAT_CUDA_CHECK(cp(p.bst, sp->ff_state_b, H));
+  STAT_CUDA_CHECK(cp(p.bst + H, sp->ff_memory_b, H));
+  if (gp) {
+    STAT_TRY(transpose_launch(sp->ff_global_W, d->Dg, H, P + p.WgT, d->Dg, 0, st));
+    STAT_CUDA_CHECK(cp(p.bg0, sp->ff_global_b, H));
+  }
+  STAT_TRY(transpose_launch(sp->ff_local_W, d->Dr, H, P + p.WlocT, d->Dr, 0, st));
+  STAT_CUDA_CHECK(cp(p.bloc, sp->ff_local_b, H));
+  STAT_TRY(transpose_launch(sp->ff_motion_W, d->Dm, H, P + p.WmotT, d->Dm, 0, st));
+  STAT_CUDA_CHECK(cp(p.bmot, sp->ff_motion_b, H));
+  STAT_TRY(transpose_launch(sp->decoder_Wcg_att, H, H, P + p.WcgT, H, 0, st));
+  STAT_CUDA_CHECK(cp(p.bcg, sp->decoder_bg_att, H));
+  STAT_TRY(transpose_launch(sp->decoder_Wcm_att, H, H, P + p.WcmT, H, 0, st));
+  STAT_CUDA_CHECK(cp(p.bcm, sp->decoder_bm_att, H));
+  STAT_TRY(transpose_launch(sp->decoder_Wcl_att, H, H, P + p.WclT, H, 0, st));
+  STAT_TRY(transpose_launch(sp->decoder_Wclt_att, H, H, P + p.WclT, H, H, st));
+  STAT_CUDA_CHECK(cp(p.bcl, sp->decoder_bl_att, H));
+  // score vectors and their scalar biases
+  STAT_CUDA_CHECK(cp(p.U4, sp->decoder_Ul_att, H));
+  STAT_CUDA_CHECK(cp(p.U4 + H, sp->decoder_Ug_att, H));
+  STAT_CUDA_CHECK(cp(p.U4 + 2 * H, sp->decoder_Um_att, H));
+  STAT_CUDA_CHECK(cp(p.U4 + 3 * H, sp->decoder_Ult_att, H));
+  STAT_CUDA_CHECK(cp(p.U4 + 4 * H, sp->decoder_cl_att, 1));
+  STAT_CUDA_CHECK(cp(p.U4 + 4 * H + 1, sp->decoder_cg_att, 1));
+  STAT_CUDA_CHECK(cp(p.U4 + 4 * H + 2, sp->decoder_cm_att, 1));
+  STAT_CUDA_CHECK(cp(p.U4 + 4 * H + 3, sp->decoder_clt_att, 1));
+  // token -> gate input table: EW[x] = Wemb[x].W + b ; EW[V] = b (no previous word)
+  STAT_CUDA_CHECK(cp(p.Wemb, sp->Wemb, static_cast<size_t>(V) * E));
+  STAT_TRY(transpose_launch(sp->decoder_W, E, 4 * H, P + p.WdT, E, 0, st));
+  STAT_TRY(dense(P + p.Wemb, E, V, P + p.WdT, E, 4 * H, sp->decoder_b, P + p.EW, 4 * H, 0, 1.f, 1.f, nullptr, 0,
+                 st));
+  STAT_CUDA_CHECK(cp(p.EW + static_cast<size_t>(V) * 4 * H, sp->decoder_b, 4 * H));
+  return STAT_OK;
+}
+
+size_t stat_workspace_bytes(const StatDims *d, int rows) {
+  if (check_dims(d) != STAT_OK || rows < 1) return 0;
+  return ws_layout(*d, rows).total * sizeof(float);
+}
+
+int stat_workspace_region(const StatDims *d, int rows, const char *name, size_t *offset, size_t *bytes) {
+  STAT_TRY(check_dims(d));
+  STAT_REQUIRE(rows >= 1 && name && offset && bytes, STAT_EINVAL, "workspace_region: bad argument");
+  const Ws w = ws_layout(*d, rows);
+  const size_t B = d->B, T = d->T, R = d->R, H = d->H, n = rows;
+  struct { const char *nm; size_t off, cnt; } tab[] = {
+      {"ctxg0", w.ctxg0, B * T * H}, {"pctxg", w.pctxg, B * T * H}, {"ctxm0", w.ctxm0, B * T * H},
+      {"pctxm", w.pctxm, B * T * H}, {"ctxl0", w.ctxl0, B * T * R * H}, {"pctxl", w.pctxl, B * T * R * H},
+      {"qctxl", w.qctxl, B * T * R * H}, {"h0", w.h0c0, B * 2 * H}, {"c0", w.h0c0 + H, B * 2 * H - H},
+      {"h", w.h, n * H}, {"c", w.c, n * H}, {"hp", w.hp, n * w.ldhp}, {"ctx", w.ctx, n * H},
+      {"logits", w.logits, n * w.ldl}, {"att_scores", w.att_scores, 3 * n * T},
+      {"alpha_l", w.alpha_l, n * T * R}, {"z", w.z, n * static_cast<size_t>(d->E)},
+  };
+  for (const auto &e : tab) {
+    if (strcmp(e.nm, name) == 0) {
+      *offset = e.off * sizeof(float);
+      *bytes = e.cnt * sizeof(float);
+      return STAT_OK;
+    }
+  }
+  set_error("workspace_region: unknown region '%s'", name);
+  return STAT_EINVAL;
+}
+
+int stat_precompute(const StatDims *d, const void *prepared, const float *ctxg, const float *mask_ctxg,
+                    const float *ctxl, const float *ctxm, void *ws, void *stream) {
+  STAT_TRY(check_dims(d));
+  STAT_TRY(check_device());
+  STAT_REQUIRE(prepared && ctxg && mask_ctxg && ctxl && ctxm && ws, STAT_EINVAL, "precompute: NULL argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Prep p = prep_layout(*d);
+  const Ws w = ws_layout(*d, d->B);  // context blocks sit first; their offsets do not depend on rows
+  const float *P = static_cast<const float *>(prepared);
+  float *W = static_cast<float *>(ws);
+  const int B = d->B, T = d->T, R = d->R, H = d->H;
+  STAT_TRY(init_state(*d, p, P, w, W, ctxg, mask_ctxg, st));
+  // P4: context blocks
+  {
+    ProfScope ps(PH_K0_GLOBAL, st);
+    if (d->flags & STAT_GLOBAL_PROJ) {
+      STAT_TRY(dense(ctxg, d->Dg, B * T, P + p.WgT, d->Dg, H, P + p.bg0, W + w.ctxg0, H, 1, 1.f, 1.f, nullptr, 0,
+                     st));
+    } else {
+      STAT_CUDA_CHECK(cudaMemcpyAsync(W + w.ctxg0, ctxg, sizeof(float) * B * T * H, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  {
+    ProfScope ps(PH_K0_MOTION, st);
+    STAT_TRY(dense(ctxm, d->Dm, B * T, P + p.WmotT, d->Dm, H, P + p.bmot, W + w.ctxm0, H, 1, 1.f, 1.f, nullptr, 0,
+                   st));
+  }
+  {
+    ProfScope ps(PH_K0_LOCAL, st);
+    STAT_TRY(dense(ctxl, d->Dr, B * T * R, P + p.WlocT, d->Dr, H, P + p.bloc, W + w.ctxl0, H, 1, 1.f, 1.f, nullptr,
+                   0, st));
+  }
+  // P5: projected blocks, and Q = ctxl0.Wclt_att (the :416 product made step-invariant)
+  ProfScope ps5(PH_K0_PROJ, st);
+  STAT_TRY(dense(W + w.ctxg0, H, B * T, P + p.WcgT, H, H, P + p.bcg, W + w.pctxg, H, 0, 1.f, 1.f, nullptr, 0, st));
+  STAT_TRY(dense(W + w.ctxm0, H, B * T, P + p.WcmT, H, H, P + p.bcm, W + w.pctxm, H, 0, 1.f, 1.f, nullptr, 0, st));
+  const int nlr = B * T * R;
+  if (H % 128 == 0 && nlr > 128) {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.P = W + w.ctxl0; g.ldp = H; g.NP = nlr;
+    g.Q = P + p.WclT; g.ldq = H; g.NQ = 2 * H;
+    g.K = H; g.feat_on_p = 0; g.nseg = 2;
+    g.seg[0] = GemmSeg{W + w.pctxl, H, P + p.bcl, nullptr, 0, 1.f, 1.f, 0, 0, H};
+    g.seg[1] = GemmSeg{W + w.qctxl, H, nullptr, nullptr, 0, 1.f, 1.f, 0, H, 2 * H};
+    STAT_TRY(gemm_launch(g, st));
+  } else {
+    STAT_TRY(dense(W + w.ctxl0, H, nlr, P + p.WclT, H, H, P + p.bcl, W + w.pctxl, H, 0, 1.f, 1.f, nullptr, 0, st));
+    STAT_TRY(dense(W + w.ctxl0, H, nlr, P + p.WclT + static_cast<size_t>(H) * H, H, H, nullptr, W + w.qctxl, H, 0,
+                   1.f, 1.f, nullptr, 0, st));
+  }
+  return STAT_OK;
+}
+
+int stat_init_state(const StatDims *d, const void *prepared, const float *ctxg, const float *mask_ctxg, void *ws,
+                    float *out_h0, float *out_c0, void *stream) {
+  STAT_TRY(check_dims(d));
+  STAT_TRY(check_device());
+  STAT_REQUIRE(prepared && ctxg && mask_ctxg && ws && out_h0 && out_c0, STAT_EINVAL, "init_state: NULL argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Prep p = prep_layout(*d);
+  const Ws w = ws_layout(*d, d->B);
+  const float *P = static_cast<const float *>(prepared);
+  float *W = static_cast<float *>(ws);
+  const int H = d->H;
+  STAT_TRY(init_state(*d, p, P, w, W, ctxg, mask_ctxg, st));
+  STAT_CUDA_CHECK(cudaMemcpy2DAsync(out_h0, sizeof(float) * H, W + w.h0c0, sizeof(float) * 2 * H,
+                                    sizeof(float) * H, d->B, cudaMemcpyDeviceToDevice, st));
+  STAT_CUDA_CHECK(cudaMemcpy2DAsync(out_c0, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
+                                    sizeof(float) * H, d->B, cudaMemcpyDeviceToDevice, st));
+  return STAT_OK;
+}
+
+int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int L, const int64_t *x,
+                         const float *mask, const float *dp_gates, const float *dp_h, const float *dp_z,
+                         float *out_logprob, float *out_alpha_l, float *out_alpha_g, float *out_alpha_m,
+                         float *out_alpha_lt, float *out_h, void *stream) {
+  STAT_TRY(check_dims(d));
+  STAT_TRY(check_device());
+  STAT_REQUIRE(prepared && ws && x && mask && out_logprob && L >= 1, STAT_EINVAL, "forward_teacher: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Prep p = prep_layout(*d);
+  const Ws w = ws_layout(*d, d->B);
+  const float *P = static_cast<const float *>(prepared);
+  float *W = static_cast<float *>(ws);
+  const int B = d->B, T = d->T, R = d->R, H = d->H, E = d->E;
+  const bool want_t = out_alpha_g || out_alpha_m || out_alpha_lt;
+  STAT_CUDA_CHECK(cudaMemsetAsync(out_logprob, 0, sizeof(float) * B, st));
+  STAT_CUDA_CHECK(cudaMemsetAsync(W + w.counters, 0, sizeof(float) * B, st));
+  STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.h, sizeof(float) * H, W + w.h0c0, sizeof(float) * 2 * H,
+                                    sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+  STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
+                                    sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+  for (int t = 0; t < L; ++t) {
+    StepIO io;
+    memset(&io, 0, sizeof(io));
+    io.rows = B;
+    io.tok_prev = t > 0 ? x + static_cast<size_t>(t - 1) * B : nullptr;   // emb shifted by one step (:613-617)
+    io.mask = mask + static_cast<size_t>(t) * B;
+    io.dp_gates = dp_gates ? dp_gates + static_cast<size_t>(t) * B * 3 * H : nullptr;
+    io.dp_h = dp_h ? dp_h + static_cast<size_t>(t) * B * H : nullptr;
+    io.dp_z = dp_z ? dp_z + static_cast<size_t>(t) * B * E : nullptr;
+    io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.h; io.c_out = W + w.c;
+    io.h_all = out_h ? out_h + static_cast<size_t>(t) * B * H : nullptr;
+    io.alpha_l = out_alpha_l ? out_alpha_l + static_cast<size_t>(t) * B * T * R : nullptr;
+    io.att_scores = want_t ? W + w.att_scores : nullptr;
+    STAT_TRY(step_core(*d, p, P, w, W, io, st));
+    if (want_t) {
+      const size_t n = static_cast<size_t>(B) * T;
+      if (out_alpha_g) STAT_TRY(softmax_rows_launch(W + w.att_scores, out_alpha_g + t * n, B, T, st));
+      if (out_alpha_m) STAT_TRY(softmax_rows_launch(W + w.att_scores + n, out_alpha_m + t * n, B, T, st));
+      if (out_alpha_lt) STAT_TRY(softmax_rows_launch(W + w.att_scores + 2 * n, out_alpha_lt + t * n, B, T, st));
+    }
+    PickArgs k;
+    memset(&k, 0, sizeof(k));
+    k.rows = B; k.V = d->V; k.ldl = w.ldl; k.logits = W + w.logits;
+    k.x_t = x + static_cast<size_t>(t) * B;
+    k.mask_t = mask + static_cast<size_t>(t) * B;
+    k.logprob = out_logprob;
+    {
+      ProfScope ps(PH_PICK, st);
+      STAT_TRY(pick_launch(k, st));
+    }
+  }
+  return STAT_OK;
+}
+
+int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws, int maxlen, int64_t *out_tokens,
+                       int32_t *out_lengths, float *out_scores, void *stream) {
+  STAT_TRY(check_dims(d));
+  STAT_TRY(check_device());
+  STAT_REQUIRE(prepared && ws && out_tokens && out_lengths && out_scores && maxlen >= 1, STAT_EINVAL,
+               "decode_greedy: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Prep p = prep_layout(*d);
+  const Ws w = ws_layout(*d, d->B);
+  const float *P = static_cast<const float *>(prepared);
+  float *W = static_cast<float *>(ws);
+  const int B = d->B, H = d->H;
+  int64_t *tok_prev = reinterpret_cast<int64_t *>(W + w.tok_prev);
+  int32_t *alive = reinterpret_cast<int32_t *>(W + w.alive);
+  STAT_CUDA_CHECK(cudaMemsetAsync(W + w.counters, 0, sizeof(float) * B, st));
+  STAT_TRY(init_rows_launch(B, tok_prev, alive, out_lengths, out_scores, out_tokens, maxlen, st));
+  STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.h, sizeof(float) * H, W + w.h0c0, sizeof(float) * 2 * H,
+                                    sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+  STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
+                                    sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+  for (int t = 0; t < maxlen; ++t) {
+    StepIO io;
+    memset(&io, 0, sizeof(io));
+    io.rows = B;
+    io.tok_prev = tok_prev;   // -1 on the first step: no previous word (:893, :803-804)
+    io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.h; io.c_out = W + w.c;
+    STAT_TRY(step_core(*d, p, P, w, W, io, st));
+    PickArgs k;
+    memset(&k, 0, sizeof(k));
+    k.rows = B; k.V = d->V; k.ldl = w.ldl; k.logits = W + w.logits;
+    k.tokens = out_tokens; k.maxlen = maxlen; k.t = t;
+    k.lengths = out_lengths; k.scores = out_scores; k.alive = alive; k.tok_prev = tok_prev;
+    {
+      ProfScope ps(PH_PICK, st);
+      STAT_TRY(pick_launch(k, st));
+    }
+  }
+  return STAT_OK;
+}
+
+int stat_step(const StatDims *d, const void *prepared, void *ws, int rows, const int32_t *row_clip,
+              const int64_t *x, const float *h_in, const float *c_in, float *out_probs, float *out_h,
+              float *out_c, void *stream) {
+  STAT_TRY(check_dims(d));
+  STAT_TRY(check_device());
+  STAT_REQUIRE(prepared && ws && x && h_in && c_in && out_probs && out_h && out_c && rows >= 1, STAT_EINVAL,
+               "step: bad argument");
+  STAT_REQUIRE(row_clip != nullptr || rows <= d->B, STAT_EINVAL, "step: rows=%d > B=%d needs row_clip", rows, d->B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Prep p = prep_layout(*d);
+  const Ws w = ws_layout(*d, rows);
+  const float *P = static_cast<const float *>(prepared);
+  float *W = static_cast<float *>(ws);
+  STAT_CUDA_CHECK(cudaMemsetAsync(W + w.counters, 0, sizeof(float) * rows, st));
+  StepIO io;
+  memset(&io, 0, sizeof(io));
+  io.rows = rows;
+  io.row_clip = row_clip;
+  io.tok_prev = x;
+  io.h_in = h_in; io.c_in = c_in; io.h_out = out_h; io.c_out = out_c;
+  STAT_TRY(step_core(*d, p, P, w, W, io, st));
+  PickArgs k;
+  memset(&k, 0, sizeof(k));
+  k.rows = rows; k.V = d->V; k.ldl = w.ldl; k.logits = W + w.logits;
+  k.probs = out_probs;
+  {
+    ProfScope ps(PH_PICK, st);
+    STAT_TRY(pick_launch(k, st));
+  }
+  return STAT_OK;
+}
+
+int stat_gemm(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K,
+              const float *bias, float alpha, float post, int act, int swap, void *stream) {
+  STAT_TRY(check_device());
+  STAT_REQUIRE(A && Bt && C, STAT_EINVAL, "gemm: NULL operand");
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.K = K;
+  g.nseg = 1;
+  g.seg[0] = GemmSeg{C, ldc, bias, nullptr, 0, alpha, post, act, 0, N};
+  if (swap) {
+    g.P = Bt; g.ldp = ldb; g.NP = N;
+    g.Q = A; g.ldq = lda; g.NQ = M;
+    g.feat_on_p = 1;
+  } else {
+    g.P = A; g.ldp = lda; g.NP = M;
+    g.Q = Bt; g.ldq = ldb; g.NQ = N;
+    g.feat_on_p = 0;
+  }
+  return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

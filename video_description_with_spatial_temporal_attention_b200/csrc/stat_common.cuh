@@ -1,0 +1,119 @@
+// Shared device helpers for the STAT decoder kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/stat_b200.h"
+
+namespace stat {
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+// every kernel launch of the library passes through here (stat_launch_count)
+void note_launch();
+
+#define STAT_CUDA_CHECK(expr)                                                      \
+  do {                                                                             \
+    cudaError_t e__ = (expr);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      stat::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,                 \
+                      cudaGetErrorString(e__));                                    \
+      return STAT_ECUDA;                                                           \
+    }                                                                              \
+  } while (0)
+
+#define STAT_REQUIRE(cond, code, ...)                                              \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      stat::set_error(__VA_ARGS__);                                                \
+      return (code);                                                               \
+    }                                                                              \
+  } while (0)
+
+#define STAT_TRY(expr)                                                             \
+  do {                                                                             \
+    int r__ = (expr);                                                              \
+    if (r__ != STAT_OK) return r__;                                                \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// math.  The attention loop evaluates ~9.4 M tanh per decode step, so the hot
+// variant is two MUFU ops (ex2, rcp) plus three FMA-pipe ops; its absolute
+// error is ~1.5e-7, far inside the 1e-5 tolerance on attention weights.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// tanh(x) = 1 - 2/(1+e^{2x});  e^{2x} = 2^{x * 2*log2(e)}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float t = ex2_approx(x * 2.885390081777927f);
+  return fmaf(-2.0f, rcp_approx(t + 1.0f), 1.0f);
+}
+
+// accurate variants for the few elementwise sites outside the attention loop
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// dense primitive (gemm_tf32x3.cu)
+// ---------------------------------------------------------------------------
+// out[i][j] = post * act(alpha * dot(P[i,:], Q[j,:]) + bias + addend)
+// P (NP,K) and Q (NQ,K) are row-major (K-major operands).  P rides the 128-lane
+// axis of the tensor core tile, Q the column axis.
+//   feat_on_p == 0 ("normal"):  C[i*ldc + j], bias[j], features = Q index
+//   feat_on_p == 1 ("swap")  :  C[j*ldc + i], bias[i], features = P index
+// Up to two feature segments (boundaries multiples of 128) may route to
+// different outputs with different epilogues.
+struct GemmSeg {
+  float *C;
+  int ldc;
+  const float *bias;     // per feature, indexed from the segment start; or null
+  const float *addend;   // same indexing as C; or null
+  int ld_add;
+  float alpha;
+  float post;
+  int act;               // 0 none, 1 tanh
+  int f0, f1;            // feature range [f0,f1) of this segment
+};
+
+struct GemmArgs {
+  const float *P;
+  int ldp;
+  int NP;
+  const float *Q;
+  int ldq;
+  int NQ;
+  int K;
+  int feat_on_p;
+  int nseg;
+  GemmSeg seg[2];
+};
+
+int gemm_launch(const GemmArgs &a, cudaStream_t stream);
+void gemm_set_impl(int impl);
+int gemm_get_impl();
+
+}  // namespace stat

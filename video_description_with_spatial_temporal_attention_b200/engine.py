@@ -1,0 +1,262 @@
+"""Device engine: owns the packed parameters and the per-batch workspace (torch
+tensors as the container for device memory) and drives ``libstat_b200.so``.
+
+This is plumbing between the reference-shaped host API (``model_attention.py``
+in this package) and the C ABI; all arithmetic happens in the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import StatDims, StatParams, check
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine(object):
+    """One parameter set on one GPU."""
+
+    def __init__(self, options, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.StatError('no CUDA device: the STAT decoder has no CPU path')
+        self.lib = _lib.load()
+        self.options = dict(options)
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        o = self.options
+        if not o.get('global_proj') and o['ctxg_dim'] != o['dim']:
+            raise ValueError('the reference graph needs ctxg_dim == dim; set global_proj=True otherwise')
+        self.flags = _lib.flags_of(o)
+        self.prepared = None
+        self._dev_params = None
+        self._ws = {}
+        self._pinned = {}
+        self._graphs = {}
+
+    # ---- dims / buffers --------------------------------------------------
+    def dims(self, B, T, R):
+        o = self.options
+        return StatDims(B=B, T=T, R=R, Dg=o['ctxg_dim'], Dm=o['ctxm_dim'], Dr=o['ctxl_dim'], H=o['dim'],
+                        E=o['dim_word'], V=o['n_words'], flags=self.flags)
+
+    def workspace(self, B, T, R, rows=None):
+        rows = B if rows is None else rows
+        key = (B, T, R, rows)
+        ws = self._ws.get(key)
+        if ws is None:
+            d = self.dims(B, T, R)
+            # a workspace made for `rows` decode rows also serves any smaller row count
+            n = max(self.lib.stat_workspace_bytes(C.byref(d), r)
+                    for r in (range(1, rows + 1) if rows != B else (rows,)))
+            if n == 0:
+                check(-1)
+            ws = torch.zeros((n + 3) // 4, dtype=torch.float32, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def region(self, ws, B, T, R, name, rows=None):
+        d = self.dims(B, T, R)
+        off, nb = C.c_size_t(), C.c_size_t()
+        check(self.lib.stat_workspace_region(C.byref(d), B if rows is None else rows, name.encode(),
+                                             C.byref(off), C.byref(nb)))
+        return ws[off.value // 4:(off.value + nb.value) // 4]
+
+    def to_device(self, a, dtype, name=None):
+        """numpy / torch (host or device) -> contiguous device tensor.  Host arrays go
+        through a cached pinned staging buffer so the copy is a real async H2D."""
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        a = np.ascontiguousarray(a)
+        t = torch.from_numpy(a)
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        key = (name, tuple(t.shape), dtype)
+        if name is not None:
+            pin = self._pinned.get(key)
+            if pin is None:
+                pin = torch.empty(t.shape, dtype=dtype).pin_memory()
+                self._pinned[key] = pin
+            pin.copy_(t)
+            t = pin
+        return t.to(self.device, non_blocking=True)
+
+    # ---- parameters --------------------------------------------------------
+    def set_params(self, params):
+        """params: mapping name -> numpy / torch array in the reference's layout
+        (init_params, model_attention.py:518-581)."""
+        o = self.options
+        dev = {}
+        for k, v in params.items():
+            t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(v, 'float32')))
+            dev[k] = t.to(device=self.device, dtype=torch.float32).contiguous().reshape(-1)
+        sp = StatParams()
+        for f in _lib.PARAM_FIELDS:
+            if f in dev:
+                setattr(sp, f, dev[f].data_ptr())
+        d = self.dims(1, 1, 1)
+        n = self.lib.stat_prepared_bytes(C.byref(d))
+        if n == 0:
+            check(-1)
+        if self.prepared is None or self.prepared.numel() * 4 < n:
+            self.prepared = torch.empty((n + 3) // 4, dtype=torch.float32, device=self.device)
+        check(self.lib.stat_prepare_params(C.byref(d), C.byref(sp), _ptr(self.prepared), _stream()))
+        self._dev_params = dev      # keep alive until the packing kernels have run
+        self._graphs.clear()
+
+    def _need_params(self):
+        if self.prepared is None:
+            raise _lib.StatError('set_params() has not been called')
+
+    # ---- K0 ----------------------------------------------------------------
+    def precompute(self, ctxg, mask_ctxg, ctxl, ctxm, rows=None):
+        """ctxg (B,T,Dg) mask (B,T) ctxl (B,T,R,Dr) ctxm (B,T,Dm), device fp32 tensors."""
+        self._need_params()
+        B, T = ctxg.shape[0], ctxg.shape[1]
+        R = ctxl.shape[2]
+        ws = self.workspace(B, T, R, rows)
+        d = self.dims(B, T, R)
+        check(self.lib.stat_precompute(C.byref(d), _ptr(self.prepared), _ptr(ctxg), _ptr(mask_ctxg), _ptr(ctxl),
+                                       _ptr(ctxm), _ptr(ws), _stream()))
+        return ws, d
+
+    # ---- f_init ----------------------------------------------------------------
+    def init_state(self, ctxg, mask_ctxg):
+        self._need_params()
+        B, T = ctxg.shape[0], ctxg.shape[1]
+        ws = self.workspace(B, T, 1)
+        d = self.dims(B, T, 1)
+        h0 = torch.empty((B, d.H), dtype=torch.float32, device=self.device)
+        c0 = torch.empty_like(h0)
+        check(self.lib.stat_init_state(C.byref(d), _ptr(self.prepared), _ptr(ctxg), _ptr(mask_ctxg), _ptr(ws),
+                                       _ptr(h0), _ptr(c0), _stream()))
+        return h0, c0
+
+    # ---- f_log_probs ---------------------------------------------------------
+    def forward_teacher(self, ws, d, x, mask, dp_gates=None, dp_h=None, dp_z=None, want_alphas=False,
+                        want_h=False):
+        L, B = x.shape
+        T, R, H = d.T, d.R, d.H
+        out = torch.empty(B, dtype=torch.float32, device=self.device)
+        al = ag = am = alt = hh = None
+        if want_alphas:
+            al = torch.empty((L, B, T, R), dtype=torch.float32, device=self.device)
+            ag = torch.empty((L, B, T), dtype=torch.float32, device=self.device)
+            am = torch.empty_like(ag)
+            alt = torch.empty_like(ag)
+        if want_h:
+            hh = torch.empty((L, B, H), dtype=torch.float32, device=self.device)
+        check(self.lib.stat_forward_teacher(C.byref(d), _ptr(self.prepared), _ptr(ws), L, _ptr(x), _ptr(mask),
+                                            _ptr(dp_gates), _ptr(dp_h), _ptr(dp_z), _ptr(out), _ptr(al), _ptr(ag),
+                                            _ptr(am), _ptr(alt), _ptr(hh), _stream()))
+        return out, (al, ag, am, alt), hh
+
+    # ---- greedy ----------------------------------------------------------------
+    def decode_greedy(self, ws, d, maxlen, out=None):
+        B = d.B
+        if out is None:
+            out = (torch.empty((B, maxlen), dtype=torch.int64, device=self.device),
+                   torch.empty(B, dtype=torch.int32, device=self.device),
+                   torch.empty(B, dtype=torch.float32, device=self.device))
+        tokens, lengths, scores = out
+        check(self.lib.stat_decode_greedy(C.byref(d), _ptr(self.prepared), _ptr(ws), maxlen, _ptr(tokens),
+                                          _ptr(lengths), _ptr(scores), _stream()))
+        return tokens, lengths, scores
+
+    # ---- f_next ----------------------------------------------------------------
+    def step(self, ws, d, x, h, c, row_clip=None):
+        rows = x.shape[0]
+        if self.lib.stat_workspace_bytes(C.byref(d), rows) > ws.numel() * 4:
+            raise _lib.StatError('workspace too small for %d decode rows' % rows)
+        probs = torch.empty((rows, d.V), dtype=torch.float32, device=self.device)
+        h2 = torch.empty((rows, d.H), dtype=torch.float32, device=self.device)
+        c2 = torch.empty_like(h2)
+        check(self.lib.stat_step(C.byref(d), _ptr(self.prepared), _ptr(ws), rows, _ptr(row_clip), _ptr(x), _ptr(h),
+                                 _ptr(c), _ptr(probs), _ptr(h2), _ptr(c2), _stream()))
+        return probs, h2, c2
+
+    # ---- whole-batch greedy captioning, optionally replayed from a CUDA graph ------
+    def greedy_captions(self, ctxg, mask_ctxg, ctxl, ctxm, maxlen, use_graph=True):
+        """Features already on the device -> (tokens (B,maxlen) i64, lengths (B,) i32,
+        scores (B,) f32), all device tensors.  Runs K0 + the maxlen-step decode; with
+        use_graph the launch sequence is captured once per shape and replayed."""
+        self._need_params()
+        B, T = ctxg.shape[0], ctxg.shape[1]
+        R = ctxl.shape[2]
+        if not use_graph:
+            ws, d = self.precompute(ctxg, mask_ctxg, ctxl, ctxm)
+            return self.decode_greedy(ws, d, maxlen)
+        key = ('greedy', B, T, R, maxlen)
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(ctxg=torch.empty_like(ctxg), mask=torch.empty_like(mask_ctxg), ctxl=torch.empty_like(ctxl),
+                      ctxm=torch.empty_like(ctxm))
+            for k, v in (('ctxg', ctxg), ('mask', mask_ctxg), ('ctxl', ctxl), ('ctxm', ctxm)):
+                st[k].copy_(v)
+            out = (torch.empty((B, maxlen), dtype=torch.int64, device=self.device),
+                   torch.empty(B, dtype=torch.int32, device=self.device),
+                   torch.empty(B, dtype=torch.float32, device=self.device))
+
+            def run():
+                ws, d = self.precompute(st['ctxg'], st['mask'], st['ctxl'], st['ctxm'])
+                self.decode_greedy(ws, d, maxlen, out)
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                run()                       # warm-up: function attributes, workspace allocation
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run()
+            g = (graph, st, out)
+            self._graphs[key] = g
+        graph, st, out = g
+        if ctxg.data_ptr() != st['ctxg'].data_ptr():
+            st['ctxg'].copy_(ctxg, non_blocking=True)
+            st['mask'].copy_(mask_ctxg, non_blocking=True)
+            st['ctxl'].copy_(ctxl, non_blocking=True)
+            st['ctxm'].copy_(ctxm, non_blocking=True)
+        graph.replay()
+        return out
+
+    def graph_inputs(self, B, T, R, maxlen):
+        """The static input tensors of the captured greedy graph (fill these in place to
+        avoid the device-to-device staging copy)."""
+        g = self._graphs.get(('greedy', B, T, R, maxlen))
+        return None if g is None else g[1]
+
+    # ---- in-situ phase timing ------------------------------------------------------
+    def profile(self, fn):
+        """Run fn() with the library's per-phase CUDA-event timing on; returns
+        {phase: (total_ms, launches_groups)}.  Not for use under graph capture."""
+        check(self.lib.stat_profile_enable(1))
+        try:
+            fn()
+            n = self.lib.stat_profile_phases()
+            ms = (C.c_float * n)()
+            cnt = (C.c_int * n)()
+            check(self.lib.stat_profile_collect(ms, cnt, n))
+        finally:
+            self.lib.stat_profile_enable(0)
+        return {self.lib.stat_profile_phase_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def launch_count(self):
+        return int(self.lib.stat_launch_count())
+
+    # ---- the dense primitive (tests) ---------------------------------------------
+    def gemm(self, A, Bt, bias=None, alpha=1.0, post=1.0, act=0, swap=False):
+        M, K = A.shape
+        N = Bt.shape[0]
+        Cc = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        check(self.lib.stat_gemm(_ptr(A), A.stride(0), _ptr(Bt), Bt.stride(0), _ptr(Cc), N, M, N, K, _ptr(bias),
+                                 alpha, post, act, 1 if swap else 0, _stream()))
+        return Cc

@@ -60,3 +60,38 @@ def make_batch(options, B, T, R, L, seed=1234, ragged=True, nonneg=False,
         B, T, R, o['ctxg_dim'], o['ctxl_dim'], o['ctxm_dim'], seed, nonneg, zero_tail)
     x, m = make_captions(B, o['n_words'], L, seed, ragged)
     return x, m, ctxg, mg, ctxl, ml, ctxm, mm
+
+
+def trained_like_params(options, seed=7):
+    """The reference's parameter dict (init_params key order and shapes) filled with
+    magnitudes resembling a trained model, so attention and vocabulary softmaxes are
+    far from uniform.  Random-init stand-in for the checkpoints that are not shipped
+    (bench / smoke input only)."""
+    from collections import OrderedDict
+    from . import common
+    from .model_attention import Attention
+    state = common.rng_numpy.get_state()
+    common.rng_numpy.seed(1234)
+    try:
+        p = Attention().init_params(options)
+    finally:
+        common.rng_numpy.set_state(state)
+    r = np.random.RandomState(seed)
+    H = options['dim']
+    out = OrderedDict()
+    for k, v in p.items():
+        v = np.asarray(v, 'float32')
+        if v.ndim == 2 and v.shape[1] == 1:
+            out[k] = (r.randn(*v.shape) * (2.0 / np.sqrt(H))).astype('float32')
+        elif v.ndim == 2:
+            if k == 'Wemb':
+                out[k] = (r.randn(*v.shape) * 0.5).astype('float32')
+                continue
+            gain = 3.0 if k == 'ff_logit_W' else (2.0 if k.split('_')[1] in ('local', 'motion', 'global', 'state',
+                                                                             'memory') and k.startswith('ff_') else 1.0)
+            out[k] = (r.randn(*v.shape) * (gain / np.sqrt(v.shape[0]))).astype('float32')
+        elif v.ndim == 1:
+            out[k] = (r.randn(*v.shape) * 0.1).astype('float32')
+        else:
+            out[k] = np.float32(r.randn() * 0.1)
+    return out
