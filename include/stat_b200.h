@@ -160,6 +160,14 @@ int stat_step(const StatDims *d, const void *prepared, void *ws, int rows,
               const float *h_in, const float *c_in,
               float *out_probs, float *out_h, float *out_c, void *stream);
 
+/* ---- the attention fragment of one step alone (model_attention.py:370-435) ---
+ * S1-S9 for `rows` decode rows whose hidden-state projections (h.Wd*_att, selector
+ * logit) already sit in the "hp" region of `ws` (left there by the previous
+ * stat_step / decode step); writes the fused, gated context to the "ctx" region.
+ * Exposed so that the HBM-bound kernel of the path can be timed in isolation. */
+int stat_attention(const StatDims *d, const void *prepared, void *ws, int rows,
+                   const int32_t *row_clip, void *stream);
+
 /* ---- the dense primitive, exposed for the parity tests ---------------------
  * C[m][n] = post * act(alpha * sum_k A[m][k]*Bt[n][k] + bias[n]),  A (M,K) and
  * Bt (N,K) row-major (both "K-major"); act: 0 none, 1 tanh.  swap != 0 runs

@@ -65,6 +65,7 @@ def _declare(lib):
     lib.stat_forward_teacher.argtypes = [dp, vp, vp, i32] + [vp] * 12
     lib.stat_decode_greedy.argtypes = [dp, vp, vp, i32, vp, vp, vp, vp]
     lib.stat_step.argtypes = [dp, vp, vp, i32] + [vp] * 8
+    lib.stat_attention.argtypes = [dp, vp, vp, i32, vp, vp]
     lib.stat_gemm.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, C.c_float, C.c_float, i32, i32, vp]
     lib.stat_launch_count.restype = C.c_ulonglong
     lib.stat_profile_enable.argtypes = [i32]
@@ -72,7 +73,7 @@ def _declare(lib):
     lib.stat_profile_phase_name.restype = C.c_char_p
     lib.stat_profile_phase_name.argtypes = [i32]
     lib.stat_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int), i32]
-    for n in ('stat_profile_enable', 'stat_profile_collect', 'stat_set_gemm_impl', 'stat_prepare_params', 'stat_init_state', 'stat_workspace_region', 'stat_precompute',
+    for n in ('stat_attention', 'stat_profile_enable', 'stat_profile_collect', 'stat_set_gemm_impl', 'stat_prepare_params', 'stat_init_state', 'stat_workspace_region', 'stat_precompute',
               'stat_forward_teacher', 'stat_decode_greedy', 'stat_step', 'stat_gemm'):
         getattr(lib, n).restype = i32
 

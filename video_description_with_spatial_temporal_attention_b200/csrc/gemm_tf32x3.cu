@@ -163,14 +163,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r & 0xFFFFE000u);   // the 13 bits the tensor core ignores, cleared explicitly
+}
+
 // hi/lo split of one 16-byte chunk, in place + sibling buffer
 __device__ __forceinline__ void split4(float4 *hi_ptr, float4 *lo_ptr) {
   float4 x = *hi_ptr;
   float4 h, l;
-  h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-  h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-  h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-  h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+  // hi = x rounded to nearest TF32 (|x - hi| <= 2^-12 |x|), so the dropped lo.lo term is <= 2^-24 relative
+  h.x = rna_tf32(x.x);
+  h.y = rna_tf32(x.y);
+  h.z = rna_tf32(x.z);
+  h.w = rna_tf32(x.w);
   uint32_t a, b, c, d;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(x.x - h.x));
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x.y - h.y));

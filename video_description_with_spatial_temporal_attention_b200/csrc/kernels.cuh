@@ -27,6 +27,10 @@ struct AttArgs {
   float *alpha_l;                                // (rows,T,R) spatial weights or null
 };
 int att_step_launch(const AttArgs &a, cudaStream_t stream);
+// att_stream.cu: persistent TMA-fed variant (H % 4 == 0, two ring slots fit in shared memory).
+// a.S = capacity (parts per row) of rec_vec / rec_ms; a.Tc unused.
+bool att_stream_plan(int rows, int T, int R, int H, int *nchunks, int *max_parts, int *nstages);
+int att_stream_launch(const AttArgs &a, cudaStream_t stream);
 
 // ---- recurrent.cu --------------------------------------------------------------
 // LSTM gates + state update (model_attention.py:437-457) and the emb / bias part of

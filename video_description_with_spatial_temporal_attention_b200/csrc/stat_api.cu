@@ -29,6 +29,18 @@ const char *const kPhaseNames[PH_COUNT] = {"init_state", "k0_ff_global", "k0_ff_
 struct ProfRec { int phase; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;   // recycled, so the hot path never creates events
+
+cudaEvent_t prof_event() {
+  if (g_event_pool.empty()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  cudaEvent_t e = g_event_pool.back();
+  g_event_pool.pop_back();
+  return e;
+}
 
 struct ProfScope {
   cudaStream_t st;
@@ -37,8 +49,8 @@ struct ProfScope {
   ProfScope(int phase, cudaStream_t s) : st(s), on(g_prof_on) {
     if (!on) return;
     r.phase = phase;
-    cudaEventCreate(&r.a);
-    cudaEventCreate(&r.b);
+    r.a = prof_event();
+    r.b = prof_event();
     cudaEventRecord(r.a, st);
   }
   ~ProfScope() {
@@ -135,6 +147,7 @@ struct Ws {
   size_t counters, tok_prev, alive;  // byte-typed regions (still float offsets)
   size_t total;                      // floats
   int ldhp, ldpc, ldl, S, Tc;
+  bool stream_att;   // att_stream_kernel (TMA ring) vs the generic att_step_kernel
 };
 
 void pick_segments(const StatDims &d, int rows, int *S, int *Tc) {
@@ -161,7 +174,14 @@ Ws ws_layout(const StatDims &d, int rows) {
     o = up(o + k, 64);
     return at;
   };
-  pick_segments(d, rows, &w.S, &w.Tc);
+  int nchunks = 0, nparts = 0, nstages = 0;
+  w.stream_att = att_stream_plan(rows, d.T, d.R, d.H, &nchunks, &nparts, &nstages);
+  if (w.stream_att) {
+    w.S = nparts;
+    w.Tc = 0;
+  } else {
+    pick_segments(d, rows, &w.S, &w.Tc);
+  }
   w.ldhp = static_cast<int>(up(8 * H + 1, 4));
   w.ldpc = static_cast<int>(4 * H + E);
   w.ldl = static_cast<int>(up(V, 4));
@@ -247,6 +267,29 @@ int init_state(const StatDims &d, const Prep &p, const float *P, const Ws &w, fl
                nullptr, 0, st);
 }
 
+AttArgs att_args(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, int rows,
+                 const int32_t *row_clip, float *att_scores, float *alpha_l) {
+  const int H = d.H;
+  AttArgs a;
+  memset(&a, 0, sizeof(a));
+  a.pctxl = W + w.pctxl; a.ctxl0 = W + w.ctxl0; a.qctxl = W + w.qctxl;
+  a.pctxg = W + w.pctxg; a.ctxg0 = W + w.ctxg0; a.pctxm = W + w.pctxm; a.ctxm0 = W + w.ctxm0;
+  a.hp = W + w.hp; a.ldhp = w.ldhp;
+  a.off_sl = 0; a.off_sg = H; a.off_sm = 2 * H; a.off_slt = 3 * H; a.off_sel = 8 * H;
+  a.Ul = P + p.U4; a.Ug = P + p.U4 + H; a.Um = P + p.U4 + 2 * H; a.Ult = P + p.U4 + 3 * H;
+  a.cl = P + p.U4 + 4 * H; a.cg = a.cl + 1; a.cm = a.cl + 2; a.clt = a.cl + 3;
+  a.row_clip = row_clip;
+  a.rows = rows; a.T = d.T; a.R = d.R; a.H = H;
+  a.S = w.S; a.Tc = w.Tc;
+  a.selector = (d.flags & STAT_SELECTOR) ? 1 : 0;
+  a.ctx = W + w.ctx;
+  a.rec_vec = W + w.rec_vec; a.rec_ms = W + w.rec_ms;
+  a.counters = reinterpret_cast<unsigned int *>(W + w.counters);
+  a.att_scores = att_scores;
+  a.alpha_l = alpha_l;
+  return a;
+}
+
 struct StepIO {
   int rows;
   const int32_t *row_clip;
@@ -271,26 +314,10 @@ int step_core(const StatDims &d, const Prep &p, const float *P, const Ws &w, flo
     STAT_TRY(dense(io.h_in, H, rows, P + p.WhT, H, (d.flags & STAT_SELECTOR) ? 8 * H + 1 : 8 * H, P + p.bh,
                    W + w.hp, w.ldhp, 0, 1.f, 1.f, nullptr, 0, st));
   }
-  AttArgs a;
-  memset(&a, 0, sizeof(a));
-  a.pctxl = W + w.pctxl; a.ctxl0 = W + w.ctxl0; a.qctxl = W + w.qctxl;
-  a.pctxg = W + w.pctxg; a.ctxg0 = W + w.ctxg0; a.pctxm = W + w.pctxm; a.ctxm0 = W + w.ctxm0;
-  a.hp = W + w.hp; a.ldhp = w.ldhp;
-  a.off_sl = 0; a.off_sg = H; a.off_sm = 2 * H; a.off_slt = 3 * H; a.off_sel = 8 * H;
-  a.Ul = P + p.U4; a.Ug = P + p.U4 + H; a.Um = P + p.U4 + 2 * H; a.Ult = P + p.U4 + 3 * H;
-  a.cl = P + p.U4 + 4 * H; a.cg = a.cl + 1; a.cm = a.cl + 2; a.clt = a.cl + 3;
-  a.row_clip = io.row_clip;
-  a.rows = rows; a.T = d.T; a.R = d.R; a.H = H;
-  a.S = w.S; a.Tc = w.Tc;
-  a.selector = (d.flags & STAT_SELECTOR) ? 1 : 0;
-  a.ctx = W + w.ctx;
-  a.rec_vec = W + w.rec_vec; a.rec_ms = W + w.rec_ms;
-  a.counters = reinterpret_cast<unsigned int *>(W + w.counters);
-  a.att_scores = io.att_scores;
-  a.alpha_l = io.alpha_l;
+  AttArgs a = att_args(d, p, P, w, W, rows, io.row_clip, io.att_scores, io.alpha_l);
   {
     ProfScope ps(PH_ATT, st);
-    STAT_TRY(att_step_launch(a, st));
+    STAT_TRY(w.stream_att ? att_stream_launch(a, st) : att_step_launch(a, st));
   }
   // ctx.Wc (gates, :439) and ctx.ff_logit_ctxglm_W (:691-693) in one pass
   {
@@ -348,10 +375,17 @@ unsigned long long stat_launch_count(void) { return stat::launch_count(); }
 
 int stat_profile_enable(int on) {
   for (auto &r : g_prof) {
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
+    g_event_pool.push_back(r.a);
+    g_event_pool.push_back(r.b);
   }
   g_prof.clear();
+  if (on) {
+    while (g_event_pool.size() < 1024) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      g_event_pool.push_back(e);
+    }
+  }
   g_prof_on = on != 0;
   return STAT_OK;
 }
@@ -375,8 +409,8 @@ int stat_profile_collect(float *ms_by_phase, int *count_by_phase, int nphase) {
     STAT_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
     ms_by_phase[r.phase] += ms;
     count_by_phase[r.phase] += 1;
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
+    g_event_pool.push_back(r.a);
+    g_event_pool.push_back(r.b);
   }
   g_prof.clear();
   return STAT_OK;
@@ -703,6 +737,22 @@ int stat_step(const StatDims *d, const void *prepared, void *ws, int rows, const
     STAT_TRY(pick_launch(k, st));
   }
   return STAT_OK;
+}
+
+int stat_attention(const StatDims *d, const void *prepared, void *ws, int rows, const int32_t *row_clip,
+                   void *stream) {
+  STAT_TRY(check_dims(d));
+  STAT_TRY(check_device());
+  STAT_REQUIRE(prepared && ws && rows >= 1, STAT_EINVAL, "attention: bad argument");
+  STAT_REQUIRE(row_clip != nullptr || rows <= d->B, STAT_EINVAL, "attention: rows=%d > B=%d needs row_clip", rows,
+               d->B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Prep p = prep_layout(*d);
+  const Ws w = ws_layout(*d, rows);
+  AttArgs a = att_args(*d, p, static_cast<const float *>(prepared), w, static_cast<float *>(ws), rows, row_clip,
+                       nullptr, nullptr);
+  ProfScope ps(PH_ATT, st);
+  return w.stream_att ? att_stream_launch(a, st) : att_step_launch(a, st);
 }
 
 int stat_gemm(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K,

@@ -234,6 +234,11 @@ class Engine(object):
         g = self._graphs.get(('greedy', B, T, R, maxlen))
         return None if g is None else g[1]
 
+    # ---- the attention fragment alone (timing) ------------------------------------
+    def attention(self, ws, d, rows=None, row_clip=None):
+        check(self.lib.stat_attention(C.byref(d), _ptr(self.prepared), _ptr(ws), d.B if rows is None else rows,
+                                      _ptr(row_clip), _stream()))
+
     # ---- in-situ phase timing ------------------------------------------------------
     def profile(self, fn):
         """Run fn() with the library's per-phase CUDA-event timing on; returns
