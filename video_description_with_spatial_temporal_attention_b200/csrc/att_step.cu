@@ -51,13 +51,22 @@ __global__ void __launch_bounds__(512, 1) att_step_kernel(const AttArgs a) {
 
   const float *hp = a.hp + static_cast<size_t>(row) * a.ldhp;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    s_vec[0 * H + i] = hp[a.off_sl + i];
+    // the h-projections arrive as k-slice planes: summed here in plane order
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    for (int q = 0; q < a.hp_parts; ++q) {
+      const float *hq = hp + q * a.hp_plane;
+      v0 += hq[a.off_sl + i];
+      v1 += hq[a.off_sg + i];
+      v2 += hq[a.off_sm + i];
+      v3 += hq[a.off_slt + i];
+    }
+    s_vec[0 * H + i] = v0;
     s_vec[1 * H + i] = a.Ul[i];
-    s_vec[2 * H + i] = hp[a.off_sg + i];
+    s_vec[2 * H + i] = v1;
     s_vec[3 * H + i] = a.Ug[i];
-    s_vec[4 * H + i] = hp[a.off_sm + i];
+    s_vec[4 * H + i] = v2;
     s_vec[5 * H + i] = a.Um[i];
-    s_vec[6 * H + i] = hp[a.off_slt + i];
+    s_vec[6 * H + i] = v3;
     s_vec[7 * H + i] = a.Ult[i];
   }
   __syncthreads();
@@ -198,7 +207,11 @@ __global__ void __launch_bounds__(512, 1) att_step_kernel(const AttArgs a) {
   const float *M0 = a.ctxm0 + (static_cast<size_t>(clip) * T + t0) * H;
   const bool single = (a.S == 1);
   float beta = 1.0f;
-  if (a.selector) beta = sigmoid_acc(hp[a.off_sel]);
+  if (a.selector) {
+    float bsel = 0.f;
+    for (int q = 0; q < a.hp_parts; ++q) bsel += hp[q * a.hp_plane + a.off_sel];
+    beta = sigmoid_acc(bsel);
+  }
   float *rv = a.rec_vec + (static_cast<size_t>(row) * a.S + seg) * 3 * H;
   for (int col = threadIdx.x; col < H; col += blockDim.x) {
     float ag = 0.f, am = 0.f, alt = 0.f;

@@ -3,13 +3,13 @@
 // of the path.
 //
 // Work = the rows*T (row, frame) pairs of the step, cut into gridDim.x contiguous,
-// equally sized chunks (one CTA per SM), so a chunk may cover the tail of one decode
-// row and the head of the next.  Per frame the producer warp issues seven
+// equally sized chunks (one CTA per SM, 16 consumer warps + 1 producer warp), so a chunk
+// may cover the tail of one decode row and the head of the next.  Per frame the producer warp issues seven
 // cp.async.bulk copies (pctxl[t], ctxl0[t], qctxl[t]: R*H floats each; pctxg[t],
 // pctxm[t], ctxg0[t], ctxm0[t]: H floats each) into one slot of a shared-memory ring
 // guarded by full/empty mbarriers; every byte of the seven context blocks is read from
-// HBM/L2 exactly once per step.  Eight consumer warps then
-//   A. score the R regions (warp r owns region r): sum_h tanh(pctxl + h.Wdl) * Ul   (S1)
+// HBM/L2 exactly once per step.  The consumer warps then
+//   A. score the R regions (warp = region x column half): sum_h tanh(pctxl + h.Wdl) * Ul (S1)
 //      and the g / m temporal scores of the frame (column-sliced partials)          (S4, S5)
 //   C. softmax over R (S2), alpha-weighted sums cL = sum_r a_r ctxl0_r (S3) and
 //      pLT = sum_r a_r qctxl_r + h.Wdlt + blt (S6, the :416 GEMM folded by linearity),
@@ -25,8 +25,9 @@
 namespace stat {
 namespace {
 
-constexpr int CONSUMERS = 256;          // 8 warps
-constexpr int NTHREADS = CONSUMERS + 32;
+constexpr int NWARPS = 16;                      // consumer warps
+constexpr int CONSUMERS = NWARPS * 32;          // 512 consumer threads
+constexpr int NTHREADS = CONSUMERS + 32;        // + one producer warp
 constexpr int RMAX = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -63,24 +64,32 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-// largest chunk index whose first frame is <= g, for nchunks equal chunks of F frames:
+// e^x through the SFU (rel. error 2^-22): soft-max numerators
+__device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * 1.4426950408889634f); }
+
+// largest chunk index whose first frame is <= g, for n equal chunks of F frames:
 // chunk i covers [i*F/n, (i+1)*F/n)
 __host__ __device__ __forceinline__ int chunk_of(long long g, int n, long long F) {
   return static_cast<int>(((g + 1) * n - 1) / F);
 }
 
-template <int NV4, int NC>
+// NCOL = ceil(H / 512) columns per thread in phases C/D (col = tid + 512 k);
+// NV4  = ceil(H / 256) float4 chunks per lane in phase A (warp = (region, column half));
+// RT   = compile-time R (8) or 0 for a runtime R <= 16.
+template <int NCOL, int NV4, int RT>
 __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a, const int nstages) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int H = a.H, T = a.T, R = a.R;
+  constexpr int RU = RT ? RT : RMAX;              // unroll bound of the region loops
+  const int H = a.H, T = a.T;
+  const int R = RT ? RT : a.R;
   const int RH = R * H;
   const int stage_floats = 3 * RH + 4 * H;
   float *ring = reinterpret_cast<float *>(smem_raw);
-  float *s_sc = ring + static_cast<size_t>(nstages) * stage_floats;   // [2][RMAX]
-  float *s_part = s_sc + 2 * RMAX;                                      // [2][8][3]
-  int *s_flag = reinterpret_cast<int *>(s_part + 2 * 8 * 3);
+  float *s_sc = ring + static_cast<size_t>(nstages) * stage_floats;   // [2][RMAX][2] region score halves
+  float *s_part = s_sc + 2 * RMAX * 2;                                  // [2][NWARPS][4] g, m, lt partials
+  int *s_flag = reinterpret_cast<int *>(s_part + 2 * NWARPS * 4);
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_flag + 2);           // full[ns], empty[ns]
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * nstages;
@@ -89,27 +98,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
   const int n = gridDim.x;
   const long long g0 = (static_cast<long long>(blockIdx.x) * F) / n;
   const long long g1 = (static_cast<long long>(blockIdx.x + 1) * F) / n;
+  const int nframes = static_cast<int>(g1 - g0);
+  const int row0 = static_cast<int>(g0 / T), t0 = static_cast<int>(g0 - static_cast<long long>(row0) * T);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, CONSUMERS / 32);
+      mbar_init(bar_empty + 8 * s, NWARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == CONSUMERS / 32) {
+  if (warp == NWARPS) {
     // ============================ producer ============================
     if (lane == 0) {
       const uint32_t bytes_rh = static_cast<uint32_t>(RH) * 4u, bytes_h = static_cast<uint32_t>(H) * 4u;
-      int i = 0;
-      for (long long g = g0; g < g1; ++g, ++i) {
-        const int s = i % nstages;
-        const uint32_t ph = (i / nstages) & 1;
+      int row = row0, t = t0, s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nframes; ++i) {
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const int row = static_cast<int>(g / T), t = static_cast<int>(g - static_cast<long long>(row) * T);
         const int clip = a.row_clip ? a.row_clip[row] : row;
         const size_t frame = static_cast<size_t>(clip) * T + t;
         const uint32_t dst = smem_u32(ring + static_cast<size_t>(s) * stage_floats);
@@ -122,35 +131,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
         bulk_g2s(dst + 3 * bytes_rh + bytes_h, a.pctxm + frame * H, bytes_h, fb);
         bulk_g2s(dst + 3 * bytes_rh + 2 * bytes_h, a.ctxg0 + frame * H, bytes_h, fb);
         bulk_g2s(dst + 3 * bytes_rh + 3 * bytes_h, a.ctxm0 + frame * H, bytes_h, fb);
+        if (++t == T) { t = 0; ++row; }
+        if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
     return;
   }
 
   // ============================== consumers ==============================
-  // column ownership: phase A lane owns float4 chunks c = 4*lane + 128*j (j < NV4);
-  // phases C/D thread owns float2 chunks col = 2*tid + 512*k (k < NC)
+  // phase A: warp w scores region (w & 7) [+8] over the column half (w >> 3); lane owns float4
+  //          chunks c = half*H/2 + 4*lane + 128*j (j < NV4)
+  // phases C/D: thread owns columns col = tid + 512*k (k < NCOL)
+  const int half = warp >> 3, hw = H >> 1;
   float ul[NV4][4], sl[NV4][4];
-  float ug[NC][2], um[NC][2], ult[NC][2], sg[NC][2], sm[NC][2], slt[NC][2];
-  float acc[3][NC][2];
+  float ug[NCOL], um[NCOL], ult[NCOL], sg[NCOL], sm[NCOL], slt[NCOL];
+  float acc[3][NCOL];
   float rm[3], rs[3];
   float beta = 1.0f;
 #pragma unroll
   for (int j = 0; j < NV4; ++j) {
     const int c = 4 * lane + 128 * j;
 #pragma unroll
-    for (int v = 0; v < 4; ++v) ul[j][v] = (c < H) ? __ldg(a.Ul + c + v) : 0.f;
+    for (int v = 0; v < 4; ++v) ul[j][v] = (c < hw) ? __ldg(a.Ul + half * hw + c + v) : 0.f;
   }
 #pragma unroll
-  for (int k = 0; k < NC; ++k) {
-    const int col = 2 * tid + 512 * k;
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const bool ok = col < H;
-      ug[k][v] = ok ? __ldg(a.Ug + col + v) : 0.f;
-      um[k][v] = ok ? __ldg(a.Um + col + v) : 0.f;
-      ult[k][v] = ok ? __ldg(a.Ult + col + v) : 0.f;
-    }
+  for (int k = 0; k < NCOL; ++k) {
+    const int col = tid + 512 * k;
+    const bool ok = col < H;
+    ug[k] = ok ? __ldg(a.Ug + col) : 0.f;
+    um[k] = ok ? __ldg(a.Um + col) : 0.f;
+    ult[k] = ok ? __ldg(a.Ult + col) : 0.f;
   }
   const float cl = __ldg(a.cl), cg = __ldg(a.cg), cm = __ldg(a.cm), clt = __ldg(a.clt);
 
@@ -162,14 +172,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     float *ctx = a.ctx + static_cast<size_t>(row) * H;
     if (nparts == 1) {
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        const int col = 2 * tid + 512 * k;
-        if (col < H) {
-          float2 o;
-          o.x = beta * (acc[0][k][0] / rs[0] + acc[1][k][0] / rs[1] + acc[2][k][0] / rs[2]);
-          o.y = beta * (acc[0][k][1] / rs[0] + acc[1][k][1] / rs[1] + acc[2][k][1] / rs[2]);
-          *reinterpret_cast<float2 *>(ctx + col) = o;
-        }
+      for (int k = 0; k < NCOL; ++k) {
+        const int col = tid + 512 * k;
+        if (col < H) ctx[col] = beta * (acc[0][k] / rs[0] + acc[1][k] / rs[1] + acc[2][k] / rs[2]);
       }
       return;
     }
@@ -179,9 +184,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
 #pragma unroll
     for (int q = 0; q < 3; ++q)
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        const int col = 2 * tid + 512 * k;
-        if (col < H) *reinterpret_cast<float2 *>(rv + q * H + col) = make_float2(acc[q][k][0], acc[q][k][1]);
+      for (int k = 0; k < NCOL; ++k) {
+        const int col = tid + 512 * k;
+        if (col < H) rv[q * H + col] = acc[q][k];
       }
     if (tid == 0) {
 #pragma unroll
@@ -215,74 +220,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
       inv[q] = 1.0f / den;
     }
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const int col = 2 * tid + 512 * k;
+    for (int k = 0; k < NCOL; ++k) {
+      const int col = tid + 512 * k;
       if (col < H) {
-        float ox = 0.f, oy = 0.f;
+        float o = 0.f;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          float nx = 0.f, ny = 0.f;
-          for (int p = 0; p < nparts; ++p) {
-            const float w = expf(__ldcg(ms_all + p * 6 + 2 * q) - M[q]);
-            const float2 v = __ldcg(reinterpret_cast<const float2 *>(rv_all + (static_cast<size_t>(p) * 3 + q) * H + col));
-            nx = fmaf(w, v.x, nx);
-            ny = fmaf(w, v.y, ny);
-          }
-          ox += nx * inv[q];
-          oy += ny * inv[q];
+          float num = 0.f;
+          for (int p = 0; p < nparts; ++p)
+            num = fmaf(expf(__ldcg(ms_all + p * 6 + 2 * q) - M[q]),
+                       __ldcg(rv_all + (static_cast<size_t>(p) * 3 + q) * H + col), num);
+          o += num * inv[q];
         }
-        *reinterpret_cast<float2 *>(ctx + col) = make_float2(beta * ox, beta * oy);
+        ctx[col] = beta * o;
       }
     }
     if (tid == 0) a.counters[row] = 0u;
   };
 
-  int cur_row = -1;
-  int i = 0;
-  for (long long g = g0; g < g1; ++g, ++i) {
-    const int row = static_cast<int>(g / T), t = static_cast<int>(g - static_cast<long long>(row) * T);
+  int row = row0, t = t0, s = 0, cur_row = -1;
+  uint32_t ph = 0;
+  for (int i = 0; i < nframes; ++i) {
     if (row != cur_row) {
       if (cur_row >= 0) finalize(cur_row);
       cur_row = row;
       const float *hp = a.hp + static_cast<size_t>(row) * a.ldhp;
+      // the h-projections arrive as k-slice planes: summed here in plane order
 #pragma unroll
-      for (int j = 0; j < NV4; ++j) {
-        const int c = 4 * lane + 128 * j;
+      for (int j = 0; j < NV4; ++j)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) sl[j][v] = (c < H) ? hp[a.off_sl + c + v] : 0.f;
+        for (int v = 0; v < 4; ++v) sl[j][v] = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) {
+        sg[k] = 0.f; sm[k] = 0.f; slt[k] = 0.f;
+        acc[0][k] = 0.f; acc[1][k] = 0.f; acc[2][k] = 0.f;
       }
+      float bsel = 0.f;
+      for (int q = 0; q < a.hp_parts; ++q) {
+        const float *hq = hp + q * a.hp_plane;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        const int col = 2 * tid + 512 * k;
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          const bool ok = col < H;
-          sg[k][v] = ok ? hp[a.off_sg + col + v] : 0.f;
-          sm[k][v] = ok ? hp[a.off_sm + col + v] : 0.f;
-          slt[k][v] = ok ? hp[a.off_slt + col + v] : 0.f;
-          acc[0][k][v] = 0.f; acc[1][k][v] = 0.f; acc[2][k][v] = 0.f;
+        for (int j = 0; j < NV4; ++j) {
+          const int c = 4 * lane + 128 * j;
+          if (c < hw) {
+            const float4 x = *reinterpret_cast<const float4 *>(hq + a.off_sl + half * hw + c);
+            sl[j][0] += x.x; sl[j][1] += x.y; sl[j][2] += x.z; sl[j][3] += x.w;
+          }
         }
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) {
+          const int col = tid + 512 * k;
+          if (col < H) {
+            sg[k] += hq[a.off_sg + col];
+            sm[k] += hq[a.off_sm + col];
+            slt[k] += hq[a.off_slt + col];
+          }
+        }
+        if (a.selector) bsel += hq[a.off_sel];
       }
-      beta = a.selector ? sigmoid_acc(hp[a.off_sel]) : 1.0f;
+      beta = a.selector ? sigmoid_acc(bsel) : 1.0f;
 #pragma unroll
       for (int q = 0; q < 3; ++q) { rm[q] = -INFINITY; rs[q] = 0.f; }
     }
-    const int s = i % nstages;
-    const uint32_t ph = (i / nstages) & 1;
     const int buf = i & 1;
     const float *st = ring + static_cast<size_t>(s) * stage_floats;
     const float *pL = st, *cL0 = st + RH, *qL = st + 2 * RH;
     const float *pG = st + 3 * RH, *pM = pG + H, *G0 = pM + H, *M0 = G0 + H;
     mbar_wait(bar_full + 8 * s, ph);
 
-    // ---- A: region scores (warp r <-> region r) and g / m score partials -------------
-    for (int r = warp; r < R; r += CONSUMERS / 32) {
+    // ---- A: region scores (half rows of H) and the g / m score partials ---------------
+    for (int r = warp & 7; r < R; r += 8) {
       float part = 0.f;
 #pragma unroll
       for (int j = 0; j < NV4; ++j) {
         const int c = 4 * lane + 128 * j;
-        if (c < H) {
-          const float4 x = *reinterpret_cast<const float4 *>(pL + r * H + c);
+        if (c < hw) {
+          const float4 x = *reinterpret_cast<const float4 *>(pL + r * H + half * hw + c);
           part = fmaf(tanh_fast(x.x + sl[j][0]), ul[j][0], part);
           part = fmaf(tanh_fast(x.y + sl[j][1]), ul[j][1], part);
           part = fmaf(tanh_fast(x.z + sl[j][2]), ul[j][2], part);
@@ -290,88 +302,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
         }
       }
       part = warp_sum(part);
-      if (lane == 0) s_sc[buf * RMAX + r] = part + cl;
+      if (lane == 0) s_sc[(buf * RMAX + r) * 2 + half] = part;
     }
-    {
-      float pg = 0.f, pm = 0.f;
+    float pg = 0.f, pm = 0.f;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        const int col = 2 * tid + 512 * k;
-        if (col < H) {
-          const float2 xg = *reinterpret_cast<const float2 *>(pG + col);
-          const float2 xm = *reinterpret_cast<const float2 *>(pM + col);
-          pg = fmaf(tanh_fast(xg.x + sg[k][0]), ug[k][0], pg);
-          pg = fmaf(tanh_fast(xg.y + sg[k][1]), ug[k][1], pg);
-          pm = fmaf(tanh_fast(xm.x + sm[k][0]), um[k][0], pm);
-          pm = fmaf(tanh_fast(xm.y + sm[k][1]), um[k][1], pm);
-        }
-      }
-      pg = warp_sum(pg);
-      pm = warp_sum(pm);
-      if (lane == 0) {
-        s_part[(buf * 8 + warp) * 3 + 0] = pg;
-        s_part[(buf * 8 + warp) * 3 + 1] = pm;
+    for (int k = 0; k < NCOL; ++k) {
+      const int col = tid + 512 * k;
+      if (col < H) {
+        pg = fmaf(tanh_fast(pG[col] + sg[k]), ug[k], pg);
+        pm = fmaf(tanh_fast(pM[col] + sm[k]), um[k], pm);
       }
     }
+    pg = warp_sum(pg);
+    pm = warp_sum(pm);
     consumer_sync();
 
     // ---- C: softmax over regions, attended local context, its projection, lt partial ---
-    float al[RMAX];
+    float al[RU];
     {
       float mx = -INFINITY;
 #pragma unroll
-      for (int r = 0; r < RMAX; ++r) {
-        al[r] = (r < R) ? s_sc[buf * RMAX + r] : -INFINITY;
+      for (int r = 0; r < RU; ++r) {
+        const float2 hs = *reinterpret_cast<const float2 *>(s_sc + (buf * RMAX + r) * 2);
+        al[r] = (r < R) ? (hs.x + hs.y) + cl : -INFINITY;
         mx = fmaxf(mx, al[r]);
       }
       float den = 0.f;
 #pragma unroll
-      for (int r = 0; r < RMAX; ++r) {
-        al[r] = (r < R) ? expf(al[r] - mx) : 0.f;
+      for (int r = 0; r < RU; ++r) {
+        al[r] = (r < R) ? exp_fast(al[r] - mx) : 0.f;
         den += al[r];
       }
       const float inv = 1.0f / den;
 #pragma unroll
-      for (int r = 0; r < RMAX; ++r) {
+      for (int r = 0; r < RU; ++r) {
         al[r] *= inv;
         if (a.alpha_l && tid == r && r < R) a.alpha_l[(static_cast<size_t>(row) * T + t) * R + r] = al[r];
       }
     }
-    float cLv[NC][2];
+    float cLv[NCOL];
     float plt = 0.f;
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const int col = 2 * tid + 512 * k;
-      float c0 = 0.f, c1 = 0.f, p0 = 0.f, p1 = 0.f;
+    for (int k = 0; k < NCOL; ++k) {
+      const int col = tid + 512 * k;
+      float c0 = 0.f, p0 = 0.f;
       if (col < H) {
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
+        for (int r = 0; r < RU; ++r) {
           if (r < R) {
-            const float2 x = *reinterpret_cast<const float2 *>(cL0 + r * H + col);
-            const float2 q = *reinterpret_cast<const float2 *>(qL + r * H + col);
-            c0 = fmaf(al[r], x.x, c0);
-            c1 = fmaf(al[r], x.y, c1);
-            p0 = fmaf(al[r], q.x, p0);
-            p1 = fmaf(al[r], q.y, p1);
+            c0 = fmaf(al[r], cL0[r * H + col], c0);
+            p0 = fmaf(al[r], qL[r * H + col], p0);
           }
         }
-        plt = fmaf(tanh_fast(p0 + slt[k][0]), ult[k][0], plt);
-        plt = fmaf(tanh_fast(p1 + slt[k][1]), ult[k][1], plt);
+        plt = fmaf(tanh_fast(p0 + slt[k]), ult[k], plt);
       }
-      cLv[k][0] = c0;
-      cLv[k][1] = c1;
+      cLv[k] = c0;
     }
     plt = warp_sum(plt);
-    if (lane == 0) s_part[(buf * 8 + warp) * 3 + 2] = plt;
+    if (lane == 0) *reinterpret_cast<float4 *>(s_part + (buf * NWARPS + warp) * 4) = make_float4(pg, pm, plt, 0.f);
     consumer_sync();
 
     // ---- D: fold the frame into the three running soft-max states ----------------------
-    float sc3[3] = {cg, cm, clt};
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      sc3[0] += s_part[(buf * 8 + w) * 3 + 0];
-      sc3[1] += s_part[(buf * 8 + w) * 3 + 1];
-      sc3[2] += s_part[(buf * 8 + w) * 3 + 2];
+    float sc3[3];
+    {
+      const float4 p4 = *reinterpret_cast<const float4 *>(s_part + (buf * NWARPS + (lane & (NWARPS - 1))) * 4);
+      float x = lane < NWARPS ? p4.x : 0.f, y = lane < NWARPS ? p4.y : 0.f, z = lane < NWARPS ? p4.z : 0.f;
+      sc3[0] = warp_sum(x) + cg;
+      sc3[1] = warp_sum(y) + cm;
+      sc3[2] = warp_sum(z) + clt;
     }
     if (a.att_scores && tid == 0) {
       const size_t plane = static_cast<size_t>(a.rows) * T, at = static_cast<size_t>(row) * T + t;
@@ -383,27 +381,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       const float mn = fmaxf(rm[q], sc3[q]);
-      keep[q] = expf(rm[q] - mn);
-      e[q] = expf(sc3[q] - mn);
+      keep[q] = exp_fast(rm[q] - mn);
+      e[q] = exp_fast(sc3[q] - mn);
       rs[q] = fmaf(rs[q], keep[q], e[q]);
       rm[q] = mn;
     }
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const int col = 2 * tid + 512 * k;
+    for (int k = 0; k < NCOL; ++k) {
+      const int col = tid + 512 * k;
       if (col < H) {
-        const float2 gv = *reinterpret_cast<const float2 *>(G0 + col);
-        const float2 mv = *reinterpret_cast<const float2 *>(M0 + col);
-        acc[0][k][0] = fmaf(acc[0][k][0], keep[0], e[0] * gv.x);
-        acc[0][k][1] = fmaf(acc[0][k][1], keep[0], e[0] * gv.y);
-        acc[1][k][0] = fmaf(acc[1][k][0], keep[1], e[1] * mv.x);
-        acc[1][k][1] = fmaf(acc[1][k][1], keep[1], e[1] * mv.y);
-        acc[2][k][0] = fmaf(acc[2][k][0], keep[2], e[2] * cLv[k][0]);
-        acc[2][k][1] = fmaf(acc[2][k][1], keep[2], e[2] * cLv[k][1]);
+        acc[0][k] = fmaf(acc[0][k], keep[0], e[0] * G0[col]);
+        acc[1][k] = fmaf(acc[1][k], keep[1], e[1] * M0[col]);
+        acc[2][k] = fmaf(acc[2][k], keep[2], e[2] * cLv[k]);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    if (++t == T) { t = 0; ++row; }
+    if (++s == nstages) { s = 0; ph ^= 1; }
   }
   if (cur_row >= 0) finalize(cur_row);
 }
@@ -421,16 +416,16 @@ int sm_count() {
 
 size_t stage_bytes(int R, int H) { return (static_cast<size_t>(3) * R * H + 4 * static_cast<size_t>(H)) * 4; }
 
-template <int NV4, int NC>
+template <int NCOL, int NV4, int RT>
 int launch(const AttArgs &a, int nchunks, int nstages, cudaStream_t stream) {
-  const size_t smem = nstages * stage_bytes(a.R, a.H) + (2 * RMAX + 2 * 8 * 3 + 2) * 4 + 2 * 8 * nstages + 64;
+  const size_t smem = nstages * stage_bytes(a.R, a.H) + (2 * RMAX * 2 + 2 * NWARPS * 4 + 2) * 4 + 2 * 8 * nstages + 64;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    STAT_CUDA_CHECK(cudaFuncSetAttribute(att_stream_kernel<NV4, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
+    STAT_CUDA_CHECK(cudaFuncSetAttribute(att_stream_kernel<NCOL, NV4, RT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     smem_set = smem;
   }
-  att_stream_kernel<NV4, NC><<<nchunks, NTHREADS, smem, stream>>>(a, nstages);
+  att_stream_kernel<NCOL, NV4, RT><<<nchunks, NTHREADS, smem, stream>>>(a, nstages);
   note_launch();
   STAT_CUDA_CHECK(cudaGetLastError());
   return STAT_OK;
@@ -440,7 +435,7 @@ int launch(const AttArgs &a, int nchunks, int nstages, cudaStream_t stream) {
 
 // plan shared by the launcher and the workspace layout
 bool att_stream_plan(int rows, int T, int R, int H, int *nchunks, int *max_parts, int *nstages) {
-  if ((H & 3) != 0 || H > 1024 || R > RMAX) return false;
+  if ((H & 7) != 0 || H > 1024 || R > RMAX) return false;
   const size_t sb = stage_bytes(R, H);
   int ns = static_cast<int>((200 * 1024) / sb);
   if (ns < 2) return false;
@@ -464,14 +459,12 @@ int att_stream_launch(const AttArgs &a, cudaStream_t stream) {
                "att_stream: unsupported shape R=%d H=%d", a.R, a.H);
   STAT_REQUIRE(a.S >= max_parts, STAT_EINVAL, "att_stream: partial buffers hold %d parts per row, need %d", a.S,
                max_parts);
-  const int nv4 = (a.H + 127) / 128;
-  const int nc = (a.H + 511) / 512;
-  if (nc == 1) {
-    if (nv4 <= 1) return launch<1, 1>(a, nchunks, nstages, stream);
-    if (nv4 <= 2) return launch<2, 1>(a, nchunks, nstages, stream);
-    return launch<4, 1>(a, nchunks, nstages, stream);
-  }
-  return launch<8, 2>(a, nchunks, nstages, stream);
+  const int H = a.H;
+  if (H == 512 && a.R == 8) return launch<1, 2, 8>(a, nchunks, nstages, stream);   // BASELINE shape
+  if (H <= 256) return launch<1, 1, 0>(a, nchunks, nstages, stream);
+  if (H <= 512) return launch<1, 2, 0>(a, nchunks, nstages, stream);
+  if (H <= 768) return launch<2, 3, 0>(a, nchunks, nstages, stream);
+  return launch<2, 4, 0>(a, nchunks, nstages, stream);
 }
 
 }  // namespace stat

@@ -56,8 +56,8 @@ struct Cfg {
   static constexpr int P_BYTES = BP * BK * 4;
   static constexpr int Q_BYTES = BQ * BK * 4;
   static constexpr int STAGE_BYTES = 2 * P_BYTES + 2 * Q_BYTES;
-  static constexpr int STAGES = (BQ >= 128) ? 3 : (BQ >= 64 ? 4 : 5);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int MAX_STAGES = (BQ >= 128) ? 3 : (BQ >= 64 ? 4 : 5);
+  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
   static constexpr int TMEM_COLS = BQ < 32 ? 32 : BQ;
 };
 
@@ -74,6 +74,9 @@ struct DevArgs {
   int NP, NQ, K;
   int feat_on_p;
   int nseg;
+  int ksplit;               // gridDim.z: k-slices, slice z accumulates into plane z of the output
+  int stages;               // depth of the shared-memory ring
+  long long plane;          // floats between output planes
   DevSeg seg[2];
 };
 
@@ -202,25 +205,30 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
                    const DevArgs args) {
   using C = Cfg<BQ>;
+  const int STAGES = args.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * C::STAGE_BYTES);
   // bars: full[STAGES] | split[STAGES] | empty[STAGES] | tmem_full | tmem_ptr(u32)
   const uint32_t bar_full = smem_u32(bars);
-  const uint32_t bar_split = bar_full + 8 * C::STAGES;
-  const uint32_t bar_empty = bar_split + 8 * C::STAGES;
-  const uint32_t bar_tmem = bar_empty + 8 * C::STAGES;
-  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 3 * C::STAGES + 1);
+  const uint32_t bar_split = bar_full + 8 * STAGES;
+  const uint32_t bar_empty = bar_split + 8 * STAGES;
+  const uint32_t bar_tmem = bar_empty + 8 * STAGES;
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
   const int p0 = blockIdx.y * BP;
-  const int nk = (args.K + BK - 1) / BK;
+  // this CTA's k-slice: k-blocks [kb0, kb0 + nk)
+  const int nk_all = (args.K + BK - 1) / BK;
+  const int kz = blockIdx.z;
+  const int kb0 = (kz * nk_all) / args.ksplit;
+  const int nk = ((kz + 1) * nk_all) / args.ksplit - kb0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_split + 8 * s, 128);
       mbar_init(bar_empty + 8 * s, 1);
@@ -243,14 +251,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (kb / C::STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         const uint32_t stage = smem_u32(smem + s * C::STAGE_BYTES);
         mbar_expect_tx(bar_full + 8 * s, C::P_BYTES + C::Q_BYTES);
-        tma_load_2d(stage, &tmP, kb * BK, p0, bar_full + 8 * s);
-        tma_load_2d(stage + 2 * C::P_BYTES, &tmQ, kb * BK, q0, bar_full + 8 * s);
+        tma_load_2d(stage, &tmP, (kb0 + kb) * BK, p0, bar_full + 8 * s);
+        tma_load_2d(stage + 2 * C::P_BYTES, &tmQ, (kb0 + kb) * BK, q0, bar_full + 8 * s);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -259,9 +268,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     // b=TF32 [10,13)=2, K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BQ >> 3) << 17) |
                            (static_cast<uint32_t>(BP >> 4) << 24);
+    int s = 0;
+    uint32_t ph = 0;
     for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % C::STAGES;
-      const uint32_t ph = (kb / C::STAGES) & 1;
       mbar_wait(bar_split + 8 * s, ph);
       tc_fence_after();
       if (lane == 0) {
@@ -281,13 +290,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         if (kb == nk - 1) tc_commit(bar_tmem);
       }
       __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else {
     // ===================== splitter, then epilogue =====================
     const int t = threadIdx.x - 64;  // 0..127
+    int s = 0;
+    uint32_t ph = 0;
     for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % C::STAGES;
-      const uint32_t ph = (kb / C::STAGES) & 1;
       mbar_wait(bar_full + 8 * s, ph);
       uint8_t *stage = smem + s * C::STAGE_BYTES;
       float4 *Ph = reinterpret_cast<float4 *>(stage);
@@ -303,6 +313,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar_split + 8 * s);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
 
     // epilogue: this warp may touch TMEM lanes [32*(warp%4), +32)
@@ -311,7 +322,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     const int wq = warp & 3;
     const int p = p0 + wq * 32 + lane;
     const int sel = (args.nseg > 1 && (args.feat_on_p ? p0 : q0) >= args.seg[1].f0) ? 1 : 0;
-    const DevSeg sg = args.seg[sel];
+    DevSeg sg = args.seg[sel];
+    // k-slice z > 0 writes its raw partial product into plane z; bias / addend ride on plane 0
+    sg.C += static_cast<size_t>(kz) * args.plane;
+    if (kz > 0) {
+      sg.bias = nullptr;
+      sg.addend = nullptr;
+    }
 #pragma unroll 1
     for (int c = 0; c < BQ; c += 32) {
       uint32_t v[32];
@@ -388,11 +405,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float *__restrict_
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int p0 = blockIdx.y * 32, q0 = blockIdx.x * 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < args.K; k0 += 32) {
+  const int nk_all = (args.K + 31) / 32, kz = blockIdx.z;
+  const int kbeg = ((kz * nk_all) / args.ksplit) * 32;
+  const int kend = min(args.K, (((kz + 1) * nk_all) / args.ksplit) * 32);
+  for (int k0 = kbeg; k0 < kend; k0 += 32) {
     for (int r = ty; r < 32; r += 8) {
       const int k = k0 + tx;
-      sP[r][tx] = (p0 + r < args.NP && k < args.K) ? P[static_cast<size_t>(p0 + r) * ldp + k] : 0.f;
-      sQ[r][tx] = (q0 + r < args.NQ && k < args.K) ? Q[static_cast<size_t>(q0 + r) * ldq + k] : 0.f;
+      sP[r][tx] = (p0 + r < args.NP && k < kend) ? P[static_cast<size_t>(p0 + r) * ldp + k] : 0.f;
+      sQ[r][tx] = (q0 + r < args.NQ && k < kend) ? Q[static_cast<size_t>(q0 + r) * ldq + k] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -414,9 +434,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float *__restrict_
     const DevSeg &sg = args.seg[sel];
     if (feat < sg.f0 || feat >= sg.f1) continue;
     const int j = feat - sg.f0;
-    const float b = sg.bias ? sg.bias[j] : 0.f;
-    const float add = sg.addend ? sg.addend[static_cast<size_t>(row) * sg.ld_add + j] : 0.f;
-    sg.C[static_cast<size_t>(row) * sg.ldc + j] = apply_epi(acc[i], sg, b, add);
+    const float b = (sg.bias && kz == 0) ? sg.bias[j] : 0.f;
+    const float add = (sg.addend && kz == 0) ? sg.addend[static_cast<size_t>(row) * sg.ld_add + j] : 0.f;
+    sg.C[static_cast<size_t>(kz) * args.plane + static_cast<size_t>(row) * sg.ldc + j] = apply_epi(acc[i], sg, b, add);
   }
 }
 
@@ -463,11 +483,14 @@ int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     STAT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BQ>::SMEM_BYTES));
+                                         Cfg<BQ>::smem_bytes(Cfg<BQ>::MAX_STAGES)));
     attr_done = true;
   }
-  dim3 grid((a.NQ + BQ - 1) / BQ, (a.NP + BP - 1) / BP);
-  gemm_tf32x3_kernel<BQ><<<grid, NTHREADS, Cfg<BQ>::SMEM_BYTES, stream>>>(tmP, tmQ, da);
+  DevArgs db = da;
+  const int nk_slice = ((a.K + BK - 1) / BK + da.ksplit - 1) / da.ksplit;
+  db.stages = nk_slice < Cfg<BQ>::MAX_STAGES ? nk_slice : Cfg<BQ>::MAX_STAGES;
+  dim3 grid((a.NQ + BQ - 1) / BQ, (a.NP + BP - 1) / BP, da.ksplit);
+  gemm_tf32x3_kernel<BQ><<<grid, NTHREADS, Cfg<BQ>::smem_bytes(db.stages), stream>>>(tmP, tmQ, db);
   note_launch();
   STAT_CUDA_CHECK(cudaGetLastError());
   return STAT_OK;
@@ -484,6 +507,14 @@ int gemm_launch(const GemmArgs &a, cudaStream_t stream) {
   da.K = a.K;
   da.feat_on_p = a.feat_on_p;
   da.nseg = a.nseg;
+  const int nk_all = (a.K + BK - 1) / BK;
+  da.ksplit = a.ksplit < 1 ? 1 : (a.ksplit > nk_all ? nk_all : a.ksplit);
+  da.stages = 1;
+  da.plane = static_cast<long long>(a.plane);
+  if (da.ksplit > 1) {
+    STAT_REQUIRE(a.nseg == 1 && a.seg[0].act == 0, STAT_EINVAL,
+                 "gemm: k-split needs a single linear segment (partial sums are combined by the consumer)");
+  }
   for (int i = 0; i < a.nseg; ++i) {
     const GemmSeg &s = a.seg[i];
     da.seg[i] = DevSeg{s.C, s.bias, s.addend, s.ldc, s.ld_add, s.alpha, s.post, s.act, s.f0, s.f1};
@@ -494,7 +525,7 @@ int gemm_launch(const GemmArgs &a, cudaStream_t stream) {
   const bool tma_ok = (a.ldp & 3) == 0 && (a.ldq & 3) == 0 && (reinterpret_cast<uintptr_t>(a.P) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(a.Q) & 15) == 0;
   if (g_gemm_impl == 1 || !tma_ok) {
-    dim3 grid((a.NQ + 31) / 32, (a.NP + 31) / 32);
+    dim3 grid((a.NQ + 31) / 32, (a.NP + 31) / 32, da.ksplit);
     gemm_simt_kernel<<<grid, 256, 0, stream>>>(a.P, a.ldp, a.Q, a.ldq, da);
     note_launch();
     STAT_CUDA_CHECK(cudaGetLastError());

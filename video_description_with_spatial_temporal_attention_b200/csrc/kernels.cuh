@@ -10,8 +10,10 @@ namespace stat {
 struct AttArgs {
   const float *pctxl, *ctxl0, *qctxl;            // (clips,T,R,H)
   const float *pctxg, *ctxg0, *pctxm, *ctxm0;    // (clips,T,H)
-  const float *hp;                               // (rows,ldhp) hidden-state projections
-  int ldhp;
+  const float *hp;                               // (parts)(rows,ldhp) hidden-state projections: k-slice
+  int ldhp;                                      // planes hp_plane floats apart, summed in order by the reader
+  int hp_parts;
+  size_t hp_plane;
   int off_sl, off_sg, off_sm, off_slt, off_sel;  // column offsets inside a hp row
   const float *Ul, *Ug, *Um, *Ult;               // (H) score vectors
   const float *cl, *cg, *cm, *clt;               // (1) score biases
@@ -39,8 +41,12 @@ struct GateArgs {
   int rows, H, E, V;
   const float *pre_c;      // (rows,ldpc): [0,4H) ctx.Wc ; [zc_off, zc_off+E) ctx.Wctx (zc_off < 0: absent)
   int ldpc, zc_off;
-  const float *hp;         // (rows,ldhp): h_.U at off_u
+  int pc_parts;            // k-slice planes of pre_c, pc_plane floats apart
+  size_t pc_plane;
+  const float *hp;         // (parts)(rows,ldhp): h_.U at off_u
   int ldhp, off_u;
+  int hp_parts;
+  size_t hp_plane;
   const float *EW;         // (V+1,4H) token -> emb.W + b
   const float *Wemb;       // (V,E)
   const int64_t *tok_prev; // (rows) or null = no previous word
@@ -56,6 +62,19 @@ struct GateArgs {
   float *h_all;            // (rows,H) copy of h_out or null
 };
 int gates_launch(const GateArgs &a, cudaStream_t stream);
+
+// readout activation: z = post * tanh(alpha * sum_p zpre[p] + zadd), post = dp_z or 0.5 (:684-696)
+struct ZactArgs {
+  int rows, E;
+  const float *zpre;       // (parts)(rows,ldz) k-slice planes of h.ff_logit_lstm_W
+  int ldz, parts;
+  size_t plane;
+  float alpha;             // 0.5 at eval (h*0.5), 1 when zpre was computed from h*mask
+  const float *zadd;       // (rows,E)
+  const float *dp_z;       // (rows,E) or null = 0.5
+  float *z;                // (rows,E)
+};
+int zact_launch(const ZactArgs &a, cudaStream_t stream);
 
 // vocabulary reduction of one step: log-softmax statistics, argmax, bookkeeping
 struct PickArgs {

@@ -18,6 +18,14 @@ __global__ void __launch_bounds__(128) gates_kernel(const GateArgs a) {
   if (j < H) {
     const float *pc = a.pre_c + static_cast<size_t>(row) * a.ldpc;
     const float *u = a.hp + static_cast<size_t>(row) * a.ldhp + a.off_u;
+    // k-slice planes of the two projections, summed in plane order (deterministic)
+    float su[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < a.hp_parts; ++q)
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) su[gi] += u[q * a.hp_plane + gi * H + j];
+    for (int q = 0; q < a.pc_parts; ++q)
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) sc[gi] += pc[q * a.pc_plane + gi * H + j];
     const float *ew = a.EW + static_cast<size_t>(tok >= 0 ? tok : a.V) * 4 * H;
     float di = 0.5f, df = 0.5f, dO = 0.5f;
     if (a.dp_gates) {
@@ -26,10 +34,10 @@ __global__ void __launch_bounds__(128) gates_kernel(const GateArgs a) {
       df = dp[H + j];
       dO = dp[2 * H + j];
     }
-    const float pi = (u[j] + __ldg(ew + j)) + pc[j];
-    const float pf = (u[H + j] + __ldg(ew + H + j)) + pc[H + j];
-    const float po = (u[2 * H + j] + __ldg(ew + 2 * H + j)) + pc[2 * H + j];
-    const float pg = (u[3 * H + j] + __ldg(ew + 3 * H + j)) + pc[3 * H + j];
+    const float pi = (su[0] + __ldg(ew + j)) + sc[0];
+    const float pf = (su[1] + __ldg(ew + H + j)) + sc[1];
+    const float po = (su[2] + __ldg(ew + 2 * H + j)) + sc[2];
+    const float pg = (su[3] + __ldg(ew + 3 * H + j)) + sc[3];
     const float ig = sigmoid_acc(pi * di);
     const float fg = sigmoid_acc(pf * df);
     const float og = sigmoid_acc(po * dO);
@@ -49,10 +57,22 @@ __global__ void __launch_bounds__(128) gates_kernel(const GateArgs a) {
   if (j < a.E) {
     // everything of the readout pre-activation that does not depend on the new h (:689-693)
     float z = a.bz[j];
-    if (a.zc_off >= 0) z += a.pre_c[static_cast<size_t>(row) * a.ldpc + a.zc_off + j];
+    if (a.zc_off >= 0)
+      for (int q = 0; q < a.pc_parts; ++q)
+        z += a.pre_c[q * a.pc_plane + static_cast<size_t>(row) * a.ldpc + a.zc_off + j];
     if (a.prev2out && tok >= 0) z += __ldg(a.Wemb + static_cast<size_t>(tok) * a.E + j);
     a.zadd[static_cast<size_t>(row) * a.E + j] = z;
   }
+}
+
+__global__ void __launch_bounds__(256) zact_kernel(const ZactArgs a) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.rows * a.E) return;
+  const int row = i / a.E, e = i - row * a.E;
+  float s = 0.f;
+  for (int q = 0; q < a.parts; ++q) s += a.zpre[q * a.plane + static_cast<size_t>(row) * a.ldz + e];
+  const float v = tanhf(fmaf(a.alpha, s, a.zadd[i]));
+  a.z[i] = v * (a.dp_z ? a.dp_z[i] : 0.5f);
 }
 
 // ---------------------------------------------------------------------------
@@ -198,6 +218,13 @@ int gates_launch(const GateArgs &a, cudaStream_t stream) {
   const int w = a.H > a.E ? a.H : a.E;
   dim3 grid((w + 127) / 128, a.rows);
   gates_kernel<<<grid, 128, 0, stream>>>(a);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int zact_launch(const ZactArgs &a, cudaStream_t stream) {
+  zact_kernel<<<(a.rows * a.E + 255) / 256, 256, 0, stream>>>(a);
   note_launch();
   STAT_CUDA_CHECK(cudaGetLastError());
   return STAT_OK;

@@ -67,10 +67,11 @@ inline size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ---------------------------------------------------------------------------
 struct Prep {
   // weights, each (features, K) row-major
-  size_t WhT;    // (8H+1, H): Wdl | Wdg | Wdm | Wdlt | U (4H) | W_sel      K = H
-  size_t bh;     // (8H+1)   : 0 | 0 | 0 | blt | 0 | b_sel
+  size_t WaT;    // (E+8H+1, H): ff_logit_lstm_W (E) | Wdl | Wdg | Wdm | Wdlt | U (4H) | W_sel   K = H
+                 //   = everything that multiplies h: rows [0,E) = WlT, rows [E, E+8H+1) = WhT
+  size_t ba;     // (E+8H+1) : 0 (E) | 0 | 0 | 0 | blt | 0 | b_sel
+  size_t WhT, bh, WlT;   // views into WaT / ba
   size_t WcT;    // (4H+E, H): Wc (4H) | ff_logit_ctxglm_W (E)               K = H
-  size_t WlT;    // (E, H)   : ff_logit_lstm_W                               K = H
   size_t bz;     // (E)      : ff_logit_lstm_b (+ ff_logit_ctxglm_b)
   size_t WvT;    // (V, E)   : ff_logit_W                                    K = E
   size_t bv;     // (V)
@@ -107,10 +108,12 @@ Prep prep_layout(const StatDims &d) {
   };
   p.NH = static_cast<int>(8 * H + 1);
   p.NC = static_cast<int>(4 * H + ((d.flags & STAT_CTX2OUT) ? E : 0));
-  p.WhT = take((8 * H + 1) * H);
-  p.bh = take(8 * H + 1);
+  p.WaT = take((E + 8 * H + 1) * H);
+  p.ba = take(E + 8 * H + 1);
+  p.WlT = p.WaT;
+  p.WhT = p.WaT + E * H;
+  p.bh = p.ba + E;
   p.WcT = take((4 * H + E) * H);
-  p.WlT = take(E * H);
   p.bz = take(E);
   p.WvT = take(V * E);
   p.bv = take(V);
@@ -142,13 +145,28 @@ Prep prep_layout(const StatDims &d) {
 struct Ws {
   size_t ctxg0, pctxg, ctxm0, pctxm, ctxl0, pctxl, qctxl;
   size_t gbar, h0c0;
-  size_t h, c, hp, ctx, pre_c, zadd, hd, z, logits;
+  size_t h, c, hpz, ctx, pre_c, zadd, hd, zpre, z, logits;
+  int ksa, ksc;                      // k-slices (= output planes) of the h- and ctx-projections
+  size_t hpz_plane, pc_plane;        // floats between planes
   size_t rec_vec, rec_ms, att_scores, alpha_l;
   size_t counters, tok_prev, alive;  // byte-typed regions (still float offsets)
   size_t total;                      // floats
   int ldhp, ldpc, ldl, S, Tc;
   bool stream_att;   // att_stream_kernel (TMA ring) vs the generic att_step_kernel
 };
+
+// k-slices for a skinny (rows <= 128) projection: enough CTAs to cover the SMs once
+int pick_ksplit(int nfeat, int rows, int K) {
+  if (rows > 128) return 1;
+  const int bq = rows > 64 ? 128 : (rows > 32 ? 64 : 32);
+  const int tiles = ((nfeat + 127) / 128) * ((rows + bq - 1) / bq);
+  const int nk = (K + 31) / 32;
+  int ks = 148 / tiles;
+  if (ks > 8) ks = 8;
+  if (ks > nk) ks = nk;
+  if (ks < 1) ks = 1;
+  return ks;
+}
 
 void pick_segments(const StatDims &d, int rows, int *S, int *Tc) {
   // enough CTAs to cover the 148 SMs twice, frames split as evenly as possible
@@ -175,14 +193,19 @@ Ws ws_layout(const StatDims &d, int rows) {
     return at;
   };
   int nchunks = 0, nparts = 0, nstages = 0;
-  w.stream_att = att_stream_plan(rows, d.T, d.R, d.H, &nchunks, &nparts, &nstages);
+  // (the streaming kernel reads the h-projection rows as float4: their offset E must be 16-byte aligned)
+  w.stream_att = (d.E % 4 == 0) && att_stream_plan(rows, d.T, d.R, d.H, &nchunks, &nparts, &nstages);
   if (w.stream_att) {
     w.S = nparts;
     w.Tc = 0;
   } else {
     pick_segments(d, rows, &w.S, &w.Tc);
   }
-  w.ldhp = static_cast<int>(up(8 * H + 1, 4));
+  w.ldhp = static_cast<int>(up(E + 8 * H + 1, 4));
+  w.ksa = pick_ksplit(static_cast<int>(E + 8 * H + 1), rows, d.H);
+  w.ksc = pick_ksplit(static_cast<int>(4 * H + E), rows, d.H);
+  w.hpz_plane = up(n * w.ldhp, 64);
+  w.pc_plane = up(n * (4 * H + E), 64);
   w.ldpc = static_cast<int>(4 * H + E);
   w.ldl = static_cast<int>(up(V, 4));
   w.ctxg0 = take(B * T * H);
@@ -196,11 +219,12 @@ Ws ws_layout(const StatDims &d, int rows) {
   w.h0c0 = take(B * 2 * H);
   w.h = take(n * H);
   w.c = take(n * H);
-  w.hp = take(n * w.ldhp);
+  w.hpz = take(w.hpz_plane * w.ksa);
   w.ctx = take(n * H);
-  w.pre_c = take(n * w.ldpc);
+  w.pre_c = take(w.pc_plane * w.ksc);
   w.zadd = take(n * E);
   w.hd = take(n * H);
+  w.zpre = take(n * E);
   w.z = take(n * E);
   w.logits = take(n * w.ldl);
   w.rec_vec = take(n * w.S * 3 * H);
@@ -240,11 +264,14 @@ int check_device() {
 // out (rows, ldc)[r][f] = post*act(alpha * x[r,:].Wt[f,:] + bias[f] + addend[r][f]); skinny activations
 // ride the tensor-core column axis ("swap"), wide ones the 128-lane axis.
 int dense(const float *x, int ldx, int rows, const float *Wt, int K, int nfeat, const float *bias, float *out,
-          int ldc, int act, float alpha, float post, const float *addend, int ld_add, cudaStream_t st) {
+          int ldc, int act, float alpha, float post, const float *addend, int ld_add, cudaStream_t st,
+          int ksplit = 1, size_t plane = 0) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.K = K;
   g.nseg = 1;
+  g.ksplit = ksplit;
+  g.plane = plane;
   g.seg[0] = GemmSeg{out, ldc, bias, addend, ld_add, alpha, post, act, 0, nfeat};
   if (rows <= 128) {
     g.P = Wt; g.ldp = K; g.NP = nfeat;
@@ -274,8 +301,9 @@ AttArgs att_args(const StatDims &d, const Prep &p, const float *P, const Ws &w, 
   memset(&a, 0, sizeof(a));
   a.pctxl = W + w.pctxl; a.ctxl0 = W + w.ctxl0; a.qctxl = W + w.qctxl;
   a.pctxg = W + w.pctxg; a.ctxg0 = W + w.ctxg0; a.pctxm = W + w.pctxm; a.ctxm0 = W + w.ctxm0;
-  a.hp = W + w.hp; a.ldhp = w.ldhp;
-  a.off_sl = 0; a.off_sg = H; a.off_sm = 2 * H; a.off_slt = 3 * H; a.off_sel = 8 * H;
+  const int E = d.E;
+  a.hp = W + w.hpz; a.ldhp = w.ldhp; a.hp_parts = w.ksa; a.hp_plane = w.hpz_plane;
+  a.off_sl = E; a.off_sg = E + H; a.off_sm = E + 2 * H; a.off_slt = E + 3 * H; a.off_sel = E + 8 * H;
   a.Ul = P + p.U4; a.Ug = P + p.U4 + H; a.Um = P + p.U4 + 2 * H; a.Ult = P + p.U4 + 3 * H;
   a.cl = P + p.U4 + 4 * H; a.cg = a.cl + 1; a.cm = a.cl + 2; a.clt = a.cl + 3;
   a.row_clip = row_clip;
@@ -303,17 +331,31 @@ struct StepIO {
   float *att_scores;  // (3,rows,T) or null
 };
 
-// one decode step up to the logits (S1-S13 + R1-R3 without the softmax)
+// what multiplies a hidden state: which = 1 the attention queries / h.U / selector logit of the NEXT
+// cell (:371,389,402,415,433,437), which = 2 the readout term h.ff_logit_lstm_W (:684-688), 3 = both
+// in one pass over h.  Results go to the k-slice planes of the hpz region.
+int h_proj(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const float *h, int rows,
+           int which, cudaStream_t st) {
+  const int H = d.H, E = d.E;
+  const int nh = (d.flags & STAT_SELECTOR) ? 8 * H + 1 : 8 * H;
+  ProfScope ps(PH_HPROJ, st);
+  if (which == 3)
+    return dense(h, H, rows, P + p.WaT, H, E + nh, P + p.ba, W + w.hpz, w.ldhp, 0, 1.f, 1.f, nullptr, 0, st, w.ksa,
+                 w.hpz_plane);
+  if (which == 1)
+    return dense(h, H, rows, P + p.WhT, H, nh, P + p.bh, W + w.hpz + E, w.ldhp, 0, 1.f, 1.f, nullptr, 0, st, w.ksa,
+                 w.hpz_plane);
+  return dense(h, H, rows, P + p.WlT, H, E, nullptr, W + w.hpz, w.ldhp, 0, 1.f, 1.f, nullptr, 0, st, w.ksa,
+               w.hpz_plane);
+}
+
+// One decode step given the h-projections of h_in in hpz (S1-S13), then the readout up to the logits
+// (R1-R3 without the softmax).  next_hproj: also leave the h-projections of h_out in hpz for the next
+// step (same pass over h_out as the readout term).
 int step_core(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io,
-              cudaStream_t st) {
+              bool next_hproj, cudaStream_t st) {
   const int H = d.H, E = d.E, V = d.V, rows = io.rows;
   const bool ctx2out = (d.flags & STAT_CTX2OUT) != 0;
-  // hidden-state projections: 4 attention queries, h.U, selector logit (:371,389,402,415,433,437)
-  {
-    ProfScope ps(PH_HPROJ, st);
-    STAT_TRY(dense(io.h_in, H, rows, P + p.WhT, H, (d.flags & STAT_SELECTOR) ? 8 * H + 1 : 8 * H, P + p.bh,
-                   W + w.hp, w.ldhp, 0, 1.f, 1.f, nullptr, 0, st));
-  }
   AttArgs a = att_args(d, p, P, w, W, rows, io.row_clip, io.att_scores, io.alpha_l);
   {
     ProfScope ps(PH_ATT, st);
@@ -323,13 +365,15 @@ int step_core(const StatDims &d, const Prep &p, const float *P, const Ws &w, flo
   {
     ProfScope ps(PH_CTXPROJ, st);
     STAT_TRY(dense(W + w.ctx, H, rows, P + p.WcT, H, p.NC, nullptr, W + w.pre_c, w.ldpc, 0, 1.f, 1.f, nullptr, 0,
-                   st));
+                   st, w.ksc, w.pc_plane));
   }
   GateArgs g;
   memset(&g, 0, sizeof(g));
   g.rows = rows; g.H = H; g.E = E; g.V = V;
   g.pre_c = W + w.pre_c; g.ldpc = w.ldpc; g.zc_off = ctx2out ? 4 * H : -1;
-  g.hp = W + w.hp; g.ldhp = w.ldhp; g.off_u = 4 * H;
+  g.pc_parts = w.ksc; g.pc_plane = w.pc_plane;
+  g.hp = W + w.hpz; g.ldhp = w.ldhp; g.off_u = E + 4 * H;
+  g.hp_parts = w.ksa; g.hp_plane = w.hpz_plane;
   g.EW = P + p.EW; g.Wemb = P + p.Wemb;
   g.tok_prev = io.tok_prev; g.mask = io.mask;
   g.dp_gates = io.dp_gates; g.dp_h = io.dp_h;
@@ -343,16 +387,25 @@ int step_core(const StatDims &d, const Prep &p, const float *P, const Ws &w, flo
     STAT_TRY(gates_launch(g, st));
   }
   // z = tanh(dp_h*h . Wl + b + emb + ctx.Wctx) * dp_z   (:684-696)
+  ZactArgs z;
+  memset(&z, 0, sizeof(z));
+  z.rows = rows; z.E = E;
+  z.zadd = W + w.zadd; z.dp_z = io.dp_z; z.z = W + w.z;
+  if (io.dp_h) {
+    // explicit dropout mask on h (use_noise=1): the readout multiplies h*mask, the next cell h itself
+    {
+      ProfScope ps(PH_READOUT, st);
+      STAT_TRY(dense(W + w.hd, H, rows, P + p.WlT, H, E, nullptr, W + w.zpre, E, 0, 1.f, 1.f, nullptr, 0, st));
+    }
+    if (next_hproj) STAT_TRY(h_proj(d, p, P, w, W, io.h_out, rows, 1, st));
+    z.zpre = W + w.zpre; z.ldz = E; z.parts = 1; z.plane = 0; z.alpha = 1.0f;
+  } else {
+    STAT_TRY(h_proj(d, p, P, w, W, io.h_out, rows, next_hproj ? 3 : 2, st));
+    z.zpre = W + w.hpz; z.ldz = w.ldhp; z.parts = w.ksa; z.plane = w.hpz_plane; z.alpha = 0.5f;
+  }
   {
     ProfScope ps(PH_READOUT, st);
-    if (io.dp_h) {
-      STAT_TRY(dense(W + w.hd, H, rows, P + p.WlT, H, E, nullptr, W + w.z, E, 1, 1.f, io.dp_z ? 1.f : 0.5f,
-                     W + w.zadd, E, st));
-    } else {
-      STAT_TRY(dense(io.h_out, H, rows, P + p.WlT, H, E, nullptr, W + w.z, E, 1, 0.5f, io.dp_z ? 1.f : 0.5f,
-                     W + w.zadd, E, st));
-    }
-    if (io.dp_z) STAT_TRY(scale_launch(W + w.z, io.dp_z, static_cast<size_t>(rows) * E, st));
+    STAT_TRY(zact_launch(z, st));
   }
   // logits = z . ff_logit_W + b  (:704-705)
   ProfScope pl(PH_LOGITS, st);
@@ -525,7 +578,7 @@ int stat_workspace_region(const StatDims *d, int rows, const char *name, size_t 
       {"ctxg0", w.ctxg0, B * T * H}, {"pctxg", w.pctxg, B * T * H}, {"ctxm0", w.ctxm0, B * T * H},
       {"pctxm", w.pctxm, B * T * H}, {"ctxl0", w.ctxl0, B * T * R * H}, {"pctxl", w.pctxl, B * T * R * H},
       {"qctxl", w.qctxl, B * T * R * H}, {"h0", w.h0c0, B * 2 * H}, {"c0", w.h0c0 + H, B * 2 * H - H},
-      {"h", w.h, n * H}, {"c", w.c, n * H}, {"hp", w.hp, n * w.ldhp}, {"ctx", w.ctx, n * H},
+      {"h", w.h, n * H}, {"c", w.c, n * H}, {"hp", w.hpz, n * w.ldhp}, {"ctx", w.ctx, n * H},
       {"logits", w.logits, n * w.ldl}, {"att_scores", w.att_scores, 3 * n * T},
       {"alpha_l", w.alpha_l, n * T * R}, {"z", w.z, n * static_cast<size_t>(d->E)},
   };
@@ -633,6 +686,7 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
                                     sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
   STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
                                     sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+  STAT_TRY(h_proj(*d, p, P, w, W, W + w.h, B, 1, st));
   for (int t = 0; t < L; ++t) {
     StepIO io;
     memset(&io, 0, sizeof(io));
@@ -646,7 +700,7 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
     io.h_all = out_h ? out_h + static_cast<size_t>(t) * B * H : nullptr;
     io.alpha_l = out_alpha_l ? out_alpha_l + static_cast<size_t>(t) * B * T * R : nullptr;
     io.att_scores = want_t ? W + w.att_scores : nullptr;
-    STAT_TRY(step_core(*d, p, P, w, W, io, st));
+    STAT_TRY(step_core(*d, p, P, w, W, io, t + 1 < L, st));
     if (want_t) {
       const size_t n = static_cast<size_t>(B) * T;
       if (out_alpha_g) STAT_TRY(softmax_rows_launch(W + w.att_scores, out_alpha_g + t * n, B, T, st));
@@ -687,13 +741,14 @@ int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws, int ma
                                     sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
   STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
                                     sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+  STAT_TRY(h_proj(*d, p, P, w, W, W + w.h, B, 1, st));
   for (int t = 0; t < maxlen; ++t) {
     StepIO io;
     memset(&io, 0, sizeof(io));
     io.rows = B;
     io.tok_prev = tok_prev;   // -1 on the first step: no previous word (:893, :803-804)
     io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.h; io.c_out = W + w.c;
-    STAT_TRY(step_core(*d, p, P, w, W, io, st));
+    STAT_TRY(step_core(*d, p, P, w, W, io, t + 1 < maxlen, st));
     PickArgs k;
     memset(&k, 0, sizeof(k));
     k.rows = B; k.V = d->V; k.ldl = w.ldl; k.logits = W + w.logits;
@@ -727,7 +782,8 @@ int stat_step(const StatDims *d, const void *prepared, void *ws, int rows, const
   io.row_clip = row_clip;
   io.tok_prev = x;
   io.h_in = h_in; io.c_in = c_in; io.h_out = out_h; io.c_out = out_c;
-  STAT_TRY(step_core(*d, p, P, w, W, io, st));
+  STAT_TRY(h_proj(*d, p, P, w, W, h_in, rows, 1, st));
+  STAT_TRY(step_core(*d, p, P, w, W, io, false, st));
   PickArgs k;
   memset(&k, 0, sizeof(k));
   k.rows = rows; k.V = d->V; k.ldl = w.ldl; k.logits = W + w.logits;

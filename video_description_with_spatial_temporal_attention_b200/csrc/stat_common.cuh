@@ -110,6 +110,10 @@ struct GemmArgs {
   int feat_on_p;
   int nseg;
   GemmSeg seg[2];
+  // k-split: slice z of the K range accumulates into output plane z (C + z*plane floats);
+  // plane 0 carries bias/addend, the consumer sums the planes in order.  0/1 = off.
+  int ksplit;
+  size_t plane;
 };
 
 int gemm_launch(const GemmArgs &a, cudaStream_t stream);
