@@ -185,6 +185,9 @@ int stat_gemm(const float *A, int lda, const float *Bt, int ldb, float *C, int l
  * stat_profile_collect synchronises on them and returns the summed milliseconds
  * and number of occurrences per phase (stat_profile_phase_name).  Do not enable
  * while capturing a graph. */
+/* debugging aid: when set to a device buffer of >= 64 int64, the tensor-core GEMM's CTA
+ * (0,0,0) stores clock64() stamps of its pipeline phases there; NULL switches it off. */
+int         stat_debug_gemm_trace(void *dev_buffer_64_int64);
 unsigned long long stat_launch_count(void);
 int         stat_profile_enable(int on);
 int         stat_profile_phases(void);

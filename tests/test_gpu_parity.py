@@ -16,6 +16,12 @@ pytestmark = pytest.mark.gpu
 
 TOL_LP = 1e-4
 TOL_A = 1e-5
+# Attention weights at BASELINE width: the feature projections are K=4096 / K=512 3xTF32
+# tensor-core products whose fp32 accumulator rounds once per MMA (1536 / 192 additions per
+# output); the measured worst-case alpha error is 1.9e-5 (1e-5 with the fp32 SIMT GEMM,
+# STAT_GEMM_IMPL=1).  The contract of the path (north_star) is 1e-4 on log-probs and
+# identical tokens, which holds with margin.
+TOL_A_WIDE = 4e-5
 
 
 @pytest.fixture(scope='module')
@@ -60,7 +66,9 @@ def test_gemm_matches_fp64(torch_cuda, impl, M, N, K, swap):
         got_lin = eng.gemm(A.cuda(), Bt.cuda(), None, swap=swap).cpu()
     finally:
         _lib.check(eng.lib.stat_set_gemm_impl(0))
-    np.testing.assert_allclose(got.numpy(), want.float().numpy(), atol=3e-6, rtol=0)
+    # fp32 SIMT: 3e-6; tensor core: one fp32 rounding per MMA, 3*K/8 MMAs per output
+    np.testing.assert_allclose(got.numpy(), want.float().numpy(), atol=3e-6 if (impl == 1 or K < 512) else 1e-5,
+                               rtol=0)
     want_lin = (A.double() @ Bt.double().t()).float().numpy()
     np.testing.assert_allclose(got_lin.numpy(), want_lin, atol=2e-5, rtol=1e-5)
 
@@ -153,10 +161,10 @@ def test_full_width_f_log_probs_vs_oracle(torch_cuda, kind):
     np.testing.assert_allclose(lp, want64, atol=TOL_LP, rtol=0)
     al, ag, am, alt = f_alphas(*batch)
     st = allv['steps']
-    np.testing.assert_allclose(al, np.stack([s['alphaL'] for s in st]), atol=TOL_A)
-    np.testing.assert_allclose(ag, np.stack([s['alphaG'] for s in st]), atol=TOL_A)
-    np.testing.assert_allclose(am, np.stack([s['alphaM'] for s in st]), atol=TOL_A)
-    np.testing.assert_allclose(alt, np.stack([s['alphaLT'] for s in st]), atol=TOL_A)
+    np.testing.assert_allclose(al, np.stack([s['alphaL'] for s in st]), atol=TOL_A_WIDE)
+    np.testing.assert_allclose(ag, np.stack([s['alphaG'] for s in st]), atol=TOL_A_WIDE)
+    np.testing.assert_allclose(am, np.stack([s['alphaM'] for s in st]), atol=TOL_A_WIDE)
+    np.testing.assert_allclose(alt, np.stack([s['alphaLT'] for s in st]), atol=TOL_A_WIDE)
     # attention rows are distributions
     for a in (al, ag, am, alt):
         np.testing.assert_allclose(a.sum(-1), 1.0, atol=1e-5)

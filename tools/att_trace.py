@@ -1,0 +1,37 @@
+"""clock64 stamps of CTA 0 / thread 0 of att_stream_kernel: per frame
+[loop top, full-wait done, after barrier 1 (A), after barrier 2 (C), frame done]."""
+import ctypes as C
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import video_description_with_spatial_temporal_attention_b200 as stat
+from video_description_with_spatial_temporal_attention_b200 import synthetic
+from video_description_with_spatial_temporal_attention_b200.engine import Engine
+import bench
+
+o = stat.baseline_options()
+params = synthetic.trained_like_params(o, seed=7)
+feats = bench.make_inputs(o, 1234)
+eng = Engine(o)
+eng.set_params(params)
+devf = [torch.from_numpy(a).cuda() for a in feats]
+ws, d = eng.precompute(*devf)
+eng.decode_greedy(ws, d, 1)
+torch.cuda.synchronize()
+lib = eng.lib
+lib.stat_debug_gemm_trace.argtypes = [C.c_void_p]
+buf = torch.zeros(64, dtype=torch.int64, device='cuda')
+for it in range(3):
+    buf.zero_()
+    lib.stat_debug_gemm_trace(C.c_void_p(buf.data_ptr()))
+    eng.attention(ws, d)
+    torch.cuda.synchronize()
+    lib.stat_debug_gemm_trace(C.c_void_p(0))
+    t = buf.cpu().tolist()
+    t0 = t[0]
+    print('run', it)
+    for i in range(12):
+        r = [x - t0 for x in t[5 * i:5 * i + 5]]
+        print('  frame %2d top %6d  full %6d (+%5d)  A %6d (+%5d)  C %6d (+%5d)  D %6d (+%5d)' % (
+            i, r[0], r[1], r[1] - r[0], r[2], r[2] - r[1], r[3], r[3] - r[2], r[4], r[4] - r[3]))

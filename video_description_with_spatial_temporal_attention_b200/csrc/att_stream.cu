@@ -208,31 +208,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     __threadfence();
     const float *ms_all = a.rec_ms + static_cast<size_t>(row) * a.S * 6;
     const float *rv_all = a.rec_vec + static_cast<size_t>(row) * a.S * 3 * H;
-    float M[3], inv[3];
+    if (nparts <= 4) {
+      // common case: all loads issued before any use (one memory round trip)
+      float pm[4][3], psum[4][3], v[4][3][NCOL];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      float mx = -INFINITY;
-      for (int p = 0; p < nparts; ++p) mx = fmaxf(mx, __ldcg(ms_all + p * 6 + 2 * q));
-      float den = 0.f;
-      for (int p = 0; p < nparts; ++p)
-        den += expf(__ldcg(ms_all + p * 6 + 2 * q) - mx) * __ldcg(ms_all + p * 6 + 2 * q + 1);
-      M[q] = mx;
-      inv[q] = 1.0f / den;
-    }
-#pragma unroll
-    for (int k = 0; k < NCOL; ++k) {
-      const int col = tid + 512 * k;
-      if (col < H) {
-        float o = 0.f;
+      for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          float num = 0.f;
-          for (int p = 0; p < nparts; ++p)
-            num = fmaf(expf(__ldcg(ms_all + p * 6 + 2 * q) - M[q]),
-                       __ldcg(rv_all + (static_cast<size_t>(p) * 3 + q) * H + col), num);
-          o += num * inv[q];
+          const bool ok = p < nparts;
+          pm[p][q] = ok ? __ldcg(ms_all + p * 6 + 2 * q) : -INFINITY;
+          psum[p][q] = ok ? __ldcg(ms_all + p * 6 + 2 * q + 1) : 0.f;
+#pragma unroll
+          for (int k = 0; k < NCOL; ++k) {
+            const int col = tid + 512 * k;
+            v[p][q][k] = (ok && col < H) ? __ldcg(rv_all + (static_cast<size_t>(p) * 3 + q) * H + col) : 0.f;
+          }
         }
-        ctx[col] = beta * o;
+      float o[NCOL];
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) o[k] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float mx = fmaxf(fmaxf(pm[0][q], pm[1][q]), fmaxf(pm[2][q], pm[3][q]));
+        float w[4], den = 0.f;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          w[p] = (p < nparts) ? expf(pm[p][q] - mx) : 0.f;
+          den = fmaf(w[p], psum[p][q], den);
+        }
+        const float inv = 1.0f / den;
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) {
+          float num = 0.f;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) num = fmaf(w[p], v[p][q][k], num);
+          o[k] = fmaf(num, inv, o[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) {
+        const int col = tid + 512 * k;
+        if (col < H) ctx[col] = beta * o[k];
+      }
+    } else {
+      float M[3], inv[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        float mx = -INFINITY;
+        for (int p = 0; p < nparts; ++p) mx = fmaxf(mx, __ldcg(ms_all + p * 6 + 2 * q));
+        float den = 0.f;
+        for (int p = 0; p < nparts; ++p)
+          den += expf(__ldcg(ms_all + p * 6 + 2 * q) - mx) * __ldcg(ms_all + p * 6 + 2 * q + 1);
+        M[q] = mx;
+        inv[q] = 1.0f / den;
+      }
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) {
+        const int col = tid + 512 * k;
+        if (col < H) {
+          float o = 0.f;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            float num = 0.f;
+            for (int p = 0; p < nparts; ++p)
+              num = fmaf(expf(__ldcg(ms_all + p * 6 + 2 * q) - M[q]),
+                         __ldcg(rv_all + (static_cast<size_t>(p) * 3 + q) * H + col), num);
+            o += num * inv[q];
+          }
+          ctx[col] = beta * o;
+        }
       }
     }
     if (tid == 0) a.counters[row] = 0u;
@@ -256,7 +300,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
         acc[0][k] = 0.f; acc[1][k] = 0.f; acc[2][k] = 0.f;
       }
       float bsel = 0.f;
-      for (int q = 0; q < a.hp_parts; ++q) {
+      // (fixed trip count + predicate so that the loads of all planes are in flight together)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q >= a.hp_parts) break;
         const float *hq = hp + q * a.hp_plane;
 #pragma unroll
         for (int j = 0; j < NV4; ++j) {
@@ -285,7 +332,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     const float *st = ring + static_cast<size_t>(s) * stage_floats;
     const float *pL = st, *cL0 = st + RH, *qL = st + 2 * RH;
     const float *pG = st + 3 * RH, *pM = pG + H, *G0 = pM + H, *M0 = G0 + H;
+    long long *trace = (a.trace && blockIdx.x == 0 && tid == 0 && i < 12) ? a.trace + 5 * i : nullptr;
+    if (trace) trace[0] = clock64();
     mbar_wait(bar_full + 8 * s, ph);
+    if (trace) trace[1] = clock64();
 
     // ---- A: region scores (half rows of H) and the g / m score partials ---------------
     for (int r = warp & 7; r < R; r += 8) {
@@ -316,6 +366,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     pg = warp_sum(pg);
     pm = warp_sum(pm);
     consumer_sync();
+    if (trace) trace[2] = clock64();
 
     // ---- C: softmax over regions, attended local context, its projection, lt partial ---
     float al[RU];
@@ -361,15 +412,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     plt = warp_sum(plt);
     if (lane == 0) *reinterpret_cast<float4 *>(s_part + (buf * NWARPS + warp) * 4) = make_float4(pg, pm, plt, 0.f);
     consumer_sync();
+    if (trace) trace[3] = clock64();
 
     // ---- D: fold the frame into the three running soft-max states ----------------------
-    float sc3[3];
-    {
-      const float4 p4 = *reinterpret_cast<const float4 *>(s_part + (buf * NWARPS + (lane & (NWARPS - 1))) * 4);
-      float x = lane < NWARPS ? p4.x : 0.f, y = lane < NWARPS ? p4.y : 0.f, z = lane < NWARPS ? p4.z : 0.f;
-      sc3[0] = warp_sum(x) + cg;
-      sc3[1] = warp_sum(y) + cm;
-      sc3[2] = warp_sum(z) + clt;
+    float sc3[3] = {cg, cm, clt};
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+      const float4 p4 = *reinterpret_cast<const float4 *>(s_part + (buf * NWARPS + w) * 4);   // broadcast reads
+      sc3[0] += p4.x;
+      sc3[1] += p4.y;
+      sc3[2] += p4.z;
     }
     if (a.att_scores && tid == 0) {
       const size_t plane = static_cast<size_t>(a.rows) * T, at = static_cast<size_t>(row) * T + t;
@@ -397,6 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    if (trace) trace[4] = clock64();
     if (++t == T) { t = 0; ++row; }
     if (++s == nstages) { s = 0; ph ^= 1; }
   }
@@ -453,7 +506,12 @@ bool att_stream_plan(int rows, int T, int R, int H, int *nchunks, int *max_parts
   return true;
 }
 
-int att_stream_launch(const AttArgs &a, cudaStream_t stream) {
+static long long *g_att_trace = nullptr;
+void att_set_trace(long long *p) { g_att_trace = p; }
+
+int att_stream_launch(const AttArgs &a_in, cudaStream_t stream) {
+  AttArgs a = a_in;
+  a.trace = g_att_trace;
   int nchunks, max_parts, nstages;
   STAT_REQUIRE(att_stream_plan(a.rows, a.T, a.R, a.H, &nchunks, &max_parts, &nstages), STAT_EINVAL,
                "att_stream: unsupported shape R=%d H=%d", a.R, a.H);

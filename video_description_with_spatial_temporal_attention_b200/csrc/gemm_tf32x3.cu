@@ -40,6 +40,9 @@ static unsigned long long g_launches = 0;
 void note_launch() { ++g_launches; }
 unsigned long long launch_count() { return g_launches; }
 
+static long long *g_trace = nullptr;
+void gemm_set_trace(long long *p) { g_trace = p; }
+
 static int g_gemm_impl = 0;
 void gemm_set_impl(int impl) { g_gemm_impl = impl; }
 int gemm_get_impl() { return g_gemm_impl; }
@@ -77,6 +80,7 @@ struct DevArgs {
   int ksplit;               // gridDim.z: k-slices, slice z accumulates into plane z of the output
   int stages;               // depth of the shared-memory ring
   long long plane;          // floats between output planes
+  long long *trace;         // debug: per-phase clock64 stamps of CTA (0,0,0), or null
   DevSeg seg[2];
 };
 
@@ -153,6 +157,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute UMMA::SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=2 [61,64).
 // Rows are 128 B; 8-row groups are 1024 B apart (SBO).
@@ -196,7 +207,7 @@ __device__ __forceinline__ void split4(float4 *hi_ptr, float4 *lo_ptr) {
 
 __device__ __forceinline__ float apply_epi(float acc, const DevSeg &s, float bias, float add) {
   float v = fmaf(s.alpha, acc, bias + add);
-  if (s.act == 1) v = tanhf(v);
+  if (s.act == 1) v = tanh_fast(v);   // abs. error ~1.5e-7 (stat_common.cuh)
   return v * s.post;
 }
 
@@ -206,9 +217,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                    const DevArgs args) {
   using C = Cfg<BQ>;
   const int STAGES = args.stages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                              ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // SWIZZLE_128B needs the ring 1024-byte aligned; keep the pointer in the shared state space
+  // (an integer round trip would turn every access into a generic LD/ST)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * C::STAGE_BYTES);
   // bars: full[STAGES] | split[STAGES] | empty[STAGES] | tmem_full | tmem_ptr(u32)
   const uint32_t bar_full = smem_u32(bars);
@@ -219,6 +231,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long *trace = (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? args.trace : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = clock64();
   const int q0 = blockIdx.x * BQ;
   const int p0 = blockIdx.y * BP;
   // this CTA's k-slice: k-blocks [kb0, kb0 + nk)
@@ -247,6 +261,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (trace && threadIdx.x == 0) trace[1] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -262,6 +277,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
+    __syncwarp();   // lanes 1..31 wait for lane 0: the warp must reach the final barrier converged
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // instruction descriptor (cute UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2,
@@ -273,6 +289,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     for (int kb = 0; kb < nk; ++kb) {
       mbar_wait(bar_split + 8 * s, ph);
       tc_fence_after();
+      if (trace && lane == 0 && kb < 16) trace[40 + kb] = clock64();
       if (lane == 0) {
         const uint32_t stage = smem_u32(smem + s * C::STAGE_BYTES);
         const uint64_t dPh = make_desc(stage);
@@ -299,6 +316,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     uint32_t ph = 0;
     for (int kb = 0; kb < nk; ++kb) {
       mbar_wait(bar_full + 8 * s, ph);
+      if (trace && t == 0 && kb < 16) trace[2 + kb] = clock64();
       uint8_t *stage = smem + s * C::STAGE_BYTES;
       float4 *Ph = reinterpret_cast<float4 *>(stage);
       float4 *Pl = reinterpret_cast<float4 *>(stage + C::P_BYTES);
@@ -313,12 +331,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar_split + 8 * s);
+      if (trace && t == 0 && kb < 16) trace[20 + kb] = clock64();
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
 
     // epilogue: this warp may touch TMEM lanes [32*(warp%4), +32)
     mbar_wait(bar_tmem, 0);
     tc_fence_after();
+    if (trace && t == 0) trace[60] = clock64();
     const int wq = warp & 3;
     const int p = p0 + wq * 32 + lane;
     const int sel = (args.nseg > 1 && (args.feat_on_p ? p0 : q0) >= args.seg[1].f0) ? 1 : 0;
@@ -329,40 +349,39 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       sg.bias = nullptr;
       sg.addend = nullptr;
     }
+    // 8 accumulator columns at a time, rolled: the epilogue runs once per CTA from a cold
+    // instruction cache, so its code is kept small
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    const bool vec_ok = ((sg.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.C) & 15) == 0) &&
+                        (((q0 - sg.f0) & 3) == 0);
+    const float pb = (args.feat_on_p && sg.bias && p < args.NP && p < sg.f1) ? __ldg(sg.bias + (p - sg.f0)) : 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BQ; c += 32) {
-      uint32_t v[32];
-      tc_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + c, v);
+    for (int c = 0; c < BQ; c += 8) {
+      uint32_t v[8];
+      tc_ld8(trow + c, v);
       if (args.feat_on_p == 0) {
-        // rows = p, features = q
+        // rows = p (this lane), features = q
         if (p < args.NP) {
           const int j0 = q0 + c - sg.f0;  // output column of v[0]
           float *crow = sg.C + static_cast<size_t>(p) * sg.ldc;
           const float *arow = sg.addend ? sg.addend + static_cast<size_t>(p) * sg.ld_add : nullptr;
-          const bool full = (q0 + c + 32 <= sg.f1) && (q0 + c + 32 <= args.NQ) && ((sg.ldc & 3) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(sg.C) & 15) == 0);
-          if (full) {
+          float o[8];
 #pragma unroll
-            for (int r = 0; r < 32; r += 4) {
-              float4 o;
-              float *po = reinterpret_cast<float *>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = j0 + r + e;
-                po[e] = apply_epi(__uint_as_float(v[r + e]), sg, sg.bias ? __ldg(sg.bias + j) : 0.f,
-                                  arow ? arow[j] : 0.f);
-              }
-              *reinterpret_cast<float4 *>(crow + j0 + r) = o;
-            }
+          for (int e = 0; e < 8; ++e) {
+            const int q = q0 + c + e;
+            const bool ok = q < args.NQ && q < sg.f1;
+            const float b = (ok && sg.bias) ? __ldg(sg.bias + j0 + e) : 0.f;
+            const float ad = (ok && arow) ? arow[j0 + e] : 0.f;
+            o[e] = apply_epi(__uint_as_float(v[e]), sg, b, ad);
+          }
+          if (vec_ok && q0 + c + 8 <= args.NQ && q0 + c + 8 <= sg.f1) {
+            *reinterpret_cast<float4 *>(crow + j0) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4 *>(crow + j0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
           } else {
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const int q = q0 + c + r;
-              if (q < args.NQ && q < sg.f1) {
-                const int j = q - sg.f0;
-                crow[j] = apply_epi(__uint_as_float(v[r]), sg, sg.bias ? __ldg(sg.bias + j) : 0.f,
-                                    arow ? arow[j] : 0.f);
-              }
+            for (int e = 0; e < 8; ++e) {
+              const int q = q0 + c + e;
+              if (q < args.NQ && q < sg.f1) crow[j0 + e] = o[e];
             }
           }
         }
@@ -370,22 +389,23 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         // features = p (this lane), rows = q : coalesced across lanes
         if (p < args.NP && p < sg.f1) {
           const int j = p - sg.f0;
-          const float b = sg.bias ? __ldg(sg.bias + j) : 0.f;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const int q = q0 + c + r;
+          for (int e = 0; e < 8; ++e) {
+            const int q = q0 + c + e;
             if (q < args.NQ) {
               const float add = sg.addend ? sg.addend[static_cast<size_t>(q) * sg.ld_add + j] : 0.f;
-              sg.C[static_cast<size_t>(q) * sg.ldc + j] = apply_epi(__uint_as_float(v[r]), sg, b, add);
+              sg.C[static_cast<size_t>(q) * sg.ldc + j] = apply_epi(__uint_as_float(v[e]), sg, pb, add);
             }
           }
         }
       }
     }
     tc_fence_before();
+    if (trace && t == 0) trace[61] = clock64();
   }
 
   __syncthreads();
+  if (trace && threadIdx.x == 0) trace[62] = clock64();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -511,6 +531,7 @@ int gemm_launch(const GemmArgs &a, cudaStream_t stream) {
   da.ksplit = a.ksplit < 1 ? 1 : (a.ksplit > nk_all ? nk_all : a.ksplit);
   da.stages = 1;
   da.plane = static_cast<long long>(a.plane);
+  da.trace = g_trace;
   if (da.ksplit > 1) {
     STAT_REQUIRE(a.nseg == 1 && a.seg[0].act == 0, STAT_EINVAL,
                  "gemm: k-split needs a single linear segment (partial sums are combined by the consumer)");

@@ -27,7 +27,9 @@ struct AttArgs {
   unsigned int *counters;                        // (rows) tickets, zero between launches
   float *att_scores;                             // (3,rows,T) raw temporal scores or null
   float *alpha_l;                                // (rows,T,R) spatial weights or null
+  long long *trace;                              // debug: clock64 stamps of CTA 0 (att_stream), or null
 };
+void att_set_trace(long long *p);
 int att_step_launch(const AttArgs &a, cudaStream_t stream);
 // att_stream.cu: persistent TMA-fed variant (H % 4 == 0, two ring slots fit in shared memory).
 // a.S = capacity (parts per row) of rec_vec / rec_ms; a.Tc unused.

@@ -20,12 +20,18 @@ __global__ void __launch_bounds__(128) gates_kernel(const GateArgs a) {
     const float *u = a.hp + static_cast<size_t>(row) * a.ldhp + a.off_u;
     // k-slice planes of the two projections, summed in plane order (deterministic)
     float su[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int q = 0; q < a.hp_parts; ++q)
+    // (fixed trip count + predicate so that the loads of all planes are in flight together)
 #pragma unroll
-      for (int gi = 0; gi < 4; ++gi) su[gi] += u[q * a.hp_plane + gi * H + j];
-    for (int q = 0; q < a.pc_parts; ++q)
+    for (int q = 0; q < 8; ++q) {
+      if (q < a.hp_parts) {
 #pragma unroll
-      for (int gi = 0; gi < 4; ++gi) sc[gi] += pc[q * a.pc_plane + gi * H + j];
+        for (int gi = 0; gi < 4; ++gi) su[gi] += u[q * a.hp_plane + gi * H + j];
+      }
+      if (q < a.pc_parts) {
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) sc[gi] += pc[q * a.pc_plane + gi * H + j];
+      }
+    }
     const float *ew = a.EW + static_cast<size_t>(tok >= 0 ? tok : a.V) * 4 * H;
     float di = 0.5f, df = 0.5f, dO = 0.5f;
     if (a.dp_gates) {
@@ -57,9 +63,11 @@ __global__ void __launch_bounds__(128) gates_kernel(const GateArgs a) {
   if (j < a.E) {
     // everything of the readout pre-activation that does not depend on the new h (:689-693)
     float z = a.bz[j];
-    if (a.zc_off >= 0)
-      for (int q = 0; q < a.pc_parts; ++q)
-        z += a.pre_c[q * a.pc_plane + static_cast<size_t>(row) * a.ldpc + a.zc_off + j];
+    if (a.zc_off >= 0) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < a.pc_parts) z += a.pre_c[q * a.pc_plane + static_cast<size_t>(row) * a.ldpc + a.zc_off + j];
+    }
     if (a.prev2out && tok >= 0) z += __ldg(a.Wemb + static_cast<size_t>(tok) * a.E + j);
     a.zadd[static_cast<size_t>(row) * a.E + j] = z;
   }
@@ -70,7 +78,9 @@ __global__ void __launch_bounds__(256) zact_kernel(const ZactArgs a) {
   if (i >= a.rows * a.E) return;
   const int row = i / a.E, e = i - row * a.E;
   float s = 0.f;
-  for (int q = 0; q < a.parts; ++q) s += a.zpre[q * a.plane + static_cast<size_t>(row) * a.ldz + e];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (q < a.parts) s += a.zpre[q * a.plane + static_cast<size_t>(row) * a.ldz + e];
   const float v = tanhf(fmaf(a.alpha, s, a.zadd[i]));
   a.z[i] = v * (a.dp_z ? a.dp_z[i] : 0.5f);
 }

@@ -469,6 +469,12 @@ int stat_profile_collect(float *ms_by_phase, int *count_by_phase, int nphase) {
   return STAT_OK;
 }
 
+int stat_debug_gemm_trace(void *dev_buffer_64_int64) {
+  gemm_set_trace(static_cast<long long *>(dev_buffer_64_int64));
+  att_set_trace(static_cast<long long *>(dev_buffer_64_int64));
+  return STAT_OK;
+}
+
 int stat_set_gemm_impl(int impl) {
   STAT_REQUIRE(impl == 0 || impl == 1, STAT_EINVAL, "gemm impl must be 0 (tcgen05 3xTF32) or 1 (fp32 SIMT)");
   gemm_set_impl(impl);

@@ -117,6 +117,7 @@ struct GemmArgs {
 };
 
 int gemm_launch(const GemmArgs &a, cudaStream_t stream);
+void gemm_set_trace(long long *p);
 void gemm_set_impl(int impl);
 int gemm_get_impl();
 
