@@ -66,11 +66,12 @@ def test_gemm_matches_fp64(torch_cuda, impl, M, N, K, swap):
         got_lin = eng.gemm(A.cuda(), Bt.cuda(), None, swap=swap).cpu()
     finally:
         _lib.check(eng.lib.stat_set_gemm_impl(0))
-    # fp32 SIMT: 3e-6; tensor core: one fp32 rounding per MMA, 3*K/8 MMAs per output
-    np.testing.assert_allclose(got.numpy(), want.float().numpy(), atol=3e-6 if (impl == 1 or K < 512) else 1e-5,
-                               rtol=0)
+    # fp32 SIMT: 3e-6; tensor core: one fp32 rounding per MMA, 3*K/8 MMAs per output (measured worst
+    # case 5e-6 at K=512, 2.8e-5 at K=4096 on pre-activations of magnitude <= 4)
+    tol = 3e-6 if (impl == 1 or K < 512) else (1e-5 if K <= 512 else 4e-5)
+    np.testing.assert_allclose(got.numpy(), want.float().numpy(), atol=tol, rtol=0)
     want_lin = (A.double() @ Bt.double().t()).float().numpy()
-    np.testing.assert_allclose(got_lin.numpy(), want_lin, atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(got_lin.numpy(), want_lin, atol=2e-5 if K <= 512 else 1e-4, rtol=1e-5)
 
 
 # ---------------------------------------------------------------------------

@@ -2,13 +2,12 @@
 // SURVEY App. A S1-S9) as a persistent, TMA-fed streaming kernel -- the HBM-bound kernel
 // of the path.
 //
-// Work = the rows*T (row, frame) pairs of the step, cut into gridDim.x contiguous,
-// equally sized chunks (one CTA per SM, 16 consumer warps + 1 producer warp), so a chunk
-// may cover the tail of one decode row and the head of the next.  Per frame the producer warp issues seven
-// cp.async.bulk copies (pctxl[t], ctxl0[t], qctxl[t]: R*H floats each; pctxg[t],
-// pctxm[t], ctxg0[t], ctxm0[t]: H floats each) into one slot of a shared-memory ring
-// guarded by full/empty mbarriers; every byte of the seven context blocks is read from
-// HBM/L2 exactly once per step.  The consumer warps then
+// Work split: one thread-block CLUSTER per decode row; the cs CTAs of a cluster (cs = 1, 2, 4
+// or 8, chosen so that rows*cs fills the SMs once) take contiguous slices of the row's T frames.
+// Per frame the producer warp issues seven cp.async.bulk copies (pctxl[t], ctxl0[t], qctxl[t]:
+// R*H floats each; pctxg[t], pctxm[t], ctxg0[t], ctxm0[t]: H floats each) into one slot of a
+// shared-memory ring guarded by full/empty mbarriers; every byte of the seven context blocks is
+// read from HBM/L2 exactly once per step.  The 16 consumer warps then
 //   A. score the R regions (warp = region x column half): sum_h tanh(pctxl + h.Wdl) * Ul (S1)
 //      and the g / m temporal scores of the frame (column-sliced partials)          (S4, S5)
 //   C. softmax over R (S2), alpha-weighted sums cL = sum_r a_r ctxl0_r (S3) and
@@ -16,9 +15,12 @@
 //      then the lt score partial                                                     (S7)
 //   D. fold the frame into flash-style running (max, sum, weighted vector) states of
 //      the g / m / lt temporal soft-maxes; the weighted vectors live in registers.
-// When the chunk leaves a row, the partial state goes to global memory and the last
-// CTA of that row (atomic ticket) merges the parts, applies the selector gate and
-// writes ctx (S8, S9).
+// At the end every CTA parks its partial state in its own shared memory, the cluster
+// synchronises, and rank 0 merges the cs parts through distributed shared memory, applies
+// the selector gate and writes ctx (S8, S9).  No global scratch, no atomics; the merge
+// order is fixed, so results are bit-reproducible.
+#include <string.h>
+
 #include "kernels.cuh"
 #include "stat_common.cuh"
 
@@ -64,6 +66,23 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a float from the shared memory of CTA `rank` of this cluster (same offset as `local`)
+__device__ __forceinline__ float ld_dsmem(const float *local, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // e^x through the SFU (rel. error 2^-22): soft-max numerators
@@ -79,7 +98,7 @@ __host__ __device__ __forceinline__ int chunk_of(long long g, int n, long long F
 // NV4  = ceil(H / 256) float4 chunks per lane in phase A (warp = (region, column half));
 // RT   = compile-time R (8) or 0 for a runtime R <= 16.
 template <int NCOL, int NV4, int RT>
-__global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a, const int nstages) {
+__global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a, const int nstages, const int cs) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int RU = RT ? RT : RMAX;              // unroll bound of the region loops
   const int H = a.H, T = a.T;
@@ -94,12 +113,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * nstages;
 
-  const long long F = static_cast<long long>(a.rows) * T;
-  const int n = gridDim.x;
-  const long long g0 = (static_cast<long long>(blockIdx.x) * F) / n;
-  const long long g1 = (static_cast<long long>(blockIdx.x + 1) * F) / n;
-  const int nframes = static_cast<int>(g1 - g0);
-  const int row0 = static_cast<int>(g0 / T), t0 = static_cast<int>(g0 - static_cast<long long>(row0) * T);
+  // cluster <-> decode row; CTA rank <-> slice [t0, t0 + nframes) of its T frames
+  const int row = static_cast<int>(blockIdx.x) / cs;
+  const int rank = cs > 1 ? static_cast<int>(cluster_rank()) : 0;
+  const int t0 = (rank * T) / cs;
+  const int nframes = ((rank + 1) * T) / cs - t0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -115,11 +133,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     // ============================ producer ============================
     if (lane == 0) {
       const uint32_t bytes_rh = static_cast<uint32_t>(RH) * 4u, bytes_h = static_cast<uint32_t>(H) * 4u;
-      int row = row0, t = t0, s = 0;
+      int t = t0, s = 0;
       uint32_t ph = 0;
+      const int clip = a.row_clip ? a.row_clip[row] : row;
       for (int i = 0; i < nframes; ++i) {
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const int clip = a.row_clip ? a.row_clip[row] : row;
         const size_t frame = static_cast<size_t>(clip) * T + t;
         const uint32_t dst = smem_u32(ring + static_cast<size_t>(s) * stage_floats);
         const uint32_t fb = bar_full + 8 * s;
@@ -131,9 +149,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
         bulk_g2s(dst + 3 * bytes_rh + bytes_h, a.pctxm + frame * H, bytes_h, fb);
         bulk_g2s(dst + 3 * bytes_rh + 2 * bytes_h, a.ctxg0 + frame * H, bytes_h, fb);
         bulk_g2s(dst + 3 * bytes_rh + 3 * bytes_h, a.ctxm0 + frame * H, bytes_h, fb);
-        if (++t == T) { t = 0; ++row; }
+        ++t;
         if (++s == nstages) { s = 0; ph ^= 1; }
       }
+    }
+    __syncwarp();
+    if (cs > 1) {          // the producer warp takes part in the two cluster barriers of the merge
+      cluster_sync_all();
+      cluster_sync_all();
     }
     return;
   }
@@ -164,170 +187,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
   }
   const float cl = __ldg(a.cl), cg = __ldg(a.cg), cm = __ldg(a.cm), clt = __ldg(a.clt);
 
-  auto finalize = [&](int row) {
-    // this chunk's share of `row` is complete: publish or merge
-    const int first = chunk_of(static_cast<long long>(row) * T, n, F);
-    const int last = chunk_of(static_cast<long long>(row) * T + T - 1, n, F);
-    const int nparts = last - first + 1;
-    float *ctx = a.ctx + static_cast<size_t>(row) * H;
-    if (nparts == 1) {
+  {
+    const float *hp = a.hp + static_cast<size_t>(row) * a.ldhp;
+    // the h-projections arrive as k-slice planes: summed here in plane order
 #pragma unroll
-      for (int k = 0; k < NCOL; ++k) {
-        const int col = tid + 512 * k;
-        if (col < H) ctx[col] = beta * (acc[0][k] / rs[0] + acc[1][k] / rs[1] + acc[2][k] / rs[2]);
-      }
-      return;
+    for (int j = 0; j < NV4; ++j)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) sl[j][v] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) {
+      sg[k] = 0.f; sm[k] = 0.f; slt[k] = 0.f;
+      acc[0][k] = 0.f; acc[1][k] = 0.f; acc[2][k] = 0.f;
     }
-    const int part = static_cast<int>(blockIdx.x) - first;
-    float *rv = a.rec_vec + (static_cast<size_t>(row) * a.S + part) * 3 * H;
-    float *rms = a.rec_ms + (static_cast<size_t>(row) * a.S + part) * 6;
+    float bsel = 0.f;
+    // (fixed trip count + predicate so that the loads of all planes are in flight together)
 #pragma unroll
-    for (int q = 0; q < 3; ++q)
+    for (int q = 0; q < 8; ++q) {
+      if (q >= a.hp_parts) break;
+      const float *hq = hp + q * a.hp_plane;
 #pragma unroll
-      for (int k = 0; k < NCOL; ++k) {
-        const int col = tid + 512 * k;
-        if (col < H) rv[q * H + col] = acc[q][k];
-      }
-    if (tid == 0) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        rms[2 * q] = rm[q];
-        rms[2 * q + 1] = rs[q];
-      }
-    }
-    __threadfence();
-    consumer_sync();
-    if (tid == 0) {
-      const unsigned int ticket = atomicAdd(a.counters + row, 1u);
-      *s_flag = (ticket == static_cast<unsigned int>(nparts - 1)) ? 1 : 0;
-    }
-    consumer_sync();
-    const int is_last = *s_flag;
-    consumer_sync();                       // s_flag may be rewritten by the next finalize
-    if (!is_last) return;
-    __threadfence();
-    const float *ms_all = a.rec_ms + static_cast<size_t>(row) * a.S * 6;
-    const float *rv_all = a.rec_vec + static_cast<size_t>(row) * a.S * 3 * H;
-    if (nparts <= 4) {
-      // common case: all loads issued before any use (one memory round trip)
-      float pm[4][3], psum[4][3], v[4][3][NCOL];
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const bool ok = p < nparts;
-          pm[p][q] = ok ? __ldcg(ms_all + p * 6 + 2 * q) : -INFINITY;
-          psum[p][q] = ok ? __ldcg(ms_all + p * 6 + 2 * q + 1) : 0.f;
-#pragma unroll
-          for (int k = 0; k < NCOL; ++k) {
-            const int col = tid + 512 * k;
-            v[p][q][k] = (ok && col < H) ? __ldcg(rv_all + (static_cast<size_t>(p) * 3 + q) * H + col) : 0.f;
-          }
+      for (int j = 0; j < NV4; ++j) {
+        const int c = 4 * lane + 128 * j;
+        if (c < hw) {
+          const float4 x = *reinterpret_cast<const float4 *>(hq + a.off_sl + half * hw + c);
+          sl[j][0] += x.x; sl[j][1] += x.y; sl[j][2] += x.z; sl[j][3] += x.w;
         }
-      float o[NCOL];
-#pragma unroll
-      for (int k = 0; k < NCOL; ++k) o[k] = 0.f;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float mx = fmaxf(fmaxf(pm[0][q], pm[1][q]), fmaxf(pm[2][q], pm[3][q]));
-        float w[4], den = 0.f;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          w[p] = (p < nparts) ? expf(pm[p][q] - mx) : 0.f;
-          den = fmaf(w[p], psum[p][q], den);
-        }
-        const float inv = 1.0f / den;
-#pragma unroll
-        for (int k = 0; k < NCOL; ++k) {
-          float num = 0.f;
-#pragma unroll
-          for (int p = 0; p < 4; ++p) num = fmaf(w[p], v[p][q][k], num);
-          o[k] = fmaf(num, inv, o[k]);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < NCOL; ++k) {
-        const int col = tid + 512 * k;
-        if (col < H) ctx[col] = beta * o[k];
-      }
-    } else {
-      float M[3], inv[3];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        float mx = -INFINITY;
-        for (int p = 0; p < nparts; ++p) mx = fmaxf(mx, __ldcg(ms_all + p * 6 + 2 * q));
-        float den = 0.f;
-        for (int p = 0; p < nparts; ++p)
-          den += expf(__ldcg(ms_all + p * 6 + 2 * q) - mx) * __ldcg(ms_all + p * 6 + 2 * q + 1);
-        M[q] = mx;
-        inv[q] = 1.0f / den;
       }
 #pragma unroll
       for (int k = 0; k < NCOL; ++k) {
         const int col = tid + 512 * k;
         if (col < H) {
-          float o = 0.f;
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            float num = 0.f;
-            for (int p = 0; p < nparts; ++p)
-              num = fmaf(expf(__ldcg(ms_all + p * 6 + 2 * q) - M[q]),
-                         __ldcg(rv_all + (static_cast<size_t>(p) * 3 + q) * H + col), num);
-            o += num * inv[q];
-          }
-          ctx[col] = beta * o;
+          sg[k] += hq[a.off_sg + col];
+          sm[k] += hq[a.off_sm + col];
+          slt[k] += hq[a.off_slt + col];
         }
       }
+      if (a.selector) bsel += hq[a.off_sel];
     }
-    if (tid == 0) a.counters[row] = 0u;
-  };
+    beta = a.selector ? sigmoid_acc(bsel) : 1.0f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { rm[q] = -INFINITY; rs[q] = 0.f; }
+  }
 
-  int row = row0, t = t0, s = 0, cur_row = -1;
+  int t = t0, s = 0;
   uint32_t ph = 0;
   for (int i = 0; i < nframes; ++i) {
-    if (row != cur_row) {
-      if (cur_row >= 0) finalize(cur_row);
-      cur_row = row;
-      const float *hp = a.hp + static_cast<size_t>(row) * a.ldhp;
-      // the h-projections arrive as k-slice planes: summed here in plane order
-#pragma unroll
-      for (int j = 0; j < NV4; ++j)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) sl[j][v] = 0.f;
-#pragma unroll
-      for (int k = 0; k < NCOL; ++k) {
-        sg[k] = 0.f; sm[k] = 0.f; slt[k] = 0.f;
-        acc[0][k] = 0.f; acc[1][k] = 0.f; acc[2][k] = 0.f;
-      }
-      float bsel = 0.f;
-      // (fixed trip count + predicate so that the loads of all planes are in flight together)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q >= a.hp_parts) break;
-        const float *hq = hp + q * a.hp_plane;
-#pragma unroll
-        for (int j = 0; j < NV4; ++j) {
-          const int c = 4 * lane + 128 * j;
-          if (c < hw) {
-            const float4 x = *reinterpret_cast<const float4 *>(hq + a.off_sl + half * hw + c);
-            sl[j][0] += x.x; sl[j][1] += x.y; sl[j][2] += x.z; sl[j][3] += x.w;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < NCOL; ++k) {
-          const int col = tid + 512 * k;
-          if (col < H) {
-            sg[k] += hq[a.off_sg + col];
-            sm[k] += hq[a.off_sm + col];
-            slt[k] += hq[a.off_slt + col];
-          }
-        }
-        if (a.selector) bsel += hq[a.off_sel];
-      }
-      beta = a.selector ? sigmoid_acc(bsel) : 1.0f;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) { rm[q] = -INFINITY; rs[q] = 0.f; }
-    }
     const int buf = i & 1;
     const float *st = ring + static_cast<size_t>(s) * stage_floats;
     const float *pL = st, *cL0 = st + RH, *qL = st + 2 * RH;
@@ -450,10 +354,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8 * s);
     if (trace) trace[4] = clock64();
-    if (++t == T) { t = 0; ++row; }
+    ++t;
     if (++s == nstages) { s = 0; ph ^= 1; }
   }
-  if (cur_row >= 0) finalize(cur_row);
+
+  // ---- merge of the cs partial states of this row (S8, S9) -----------------------------
+  float *ctx = a.ctx + static_cast<size_t>(row) * H;
+  if (cs == 1) {
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) {
+      const int col = tid + 512 * k;
+      if (col < H) ctx[col] = beta * (acc[0][k] / rs[0] + acc[1][k] / rs[1] + acc[2][k] / rs[2]);
+    }
+    return;
+  }
+  // park (m, s)[3] and the three weighted vectors at the start of the (now drained) ring
+  consumer_sync();
+  float *s_ms = ring;                 // [6]
+  float *s_vec = ring + 8;            // [3][H]
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { s_ms[2 * q] = rm[q]; s_ms[2 * q + 1] = rs[q]; }
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) {
+      const int col = tid + 512 * k;
+      if (col < H) s_vec[q * H + col] = acc[q][k];
+    }
+  cluster_sync_all();
+  if (rank == 0) {
+    float o[NCOL];
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) o[k] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      float pm[8], w[8];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        pm[p] = (p < cs) ? ld_dsmem(s_ms + 2 * q, p) : -INFINITY;
+        mx = fmaxf(mx, pm[p]);
+      }
+      float den = 0.f;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        w[p] = (p < cs) ? expf(pm[p] - mx) : 0.f;
+        if (p < cs) den = fmaf(w[p], ld_dsmem(s_ms + 2 * q + 1, p), den);
+      }
+      const float inv = 1.0f / den;
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) {
+        const int col = tid + 512 * k;
+        if (col < H) {
+          float num = 0.f;
+#pragma unroll
+          for (int p = 0; p < 8; ++p)
+            if (p < cs) num = fmaf(w[p], ld_dsmem(s_vec + q * H + col, p), num);
+          o[k] = fmaf(num, inv, o[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) {
+      const int col = tid + 512 * k;
+      if (col < H) ctx[col] = beta * o[k];
+    }
+  }
+  cluster_sync_all();       // partners keep their shared memory alive until rank 0 has read it
 }
 
 int sm_count() {
@@ -470,7 +439,7 @@ int sm_count() {
 size_t stage_bytes(int R, int H) { return (static_cast<size_t>(3) * R * H + 4 * static_cast<size_t>(H)) * 4; }
 
 template <int NCOL, int NV4, int RT>
-int launch(const AttArgs &a, int nchunks, int nstages, cudaStream_t stream) {
+int launch(const AttArgs &a, int cs, int nstages, cudaStream_t stream) {
   const size_t smem = nstages * stage_bytes(a.R, a.H) + (2 * RMAX * 2 + 2 * NWARPS * 4 + 2) * 4 + 2 * 8 * nstages + 64;
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -478,30 +447,37 @@ int launch(const AttArgs &a, int nchunks, int nstages, cudaStream_t stream) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     smem_set = smem;
   }
-  att_stream_kernel<NCOL, NV4, RT><<<nchunks, NTHREADS, smem, stream>>>(a, nstages);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(a.rows) * cs);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_stream_kernel<NCOL, NV4, RT>, a, nstages, cs));
   note_launch();
-  STAT_CUDA_CHECK(cudaGetLastError());
   return STAT_OK;
 }
 
 }  // namespace
 
-// plan shared by the launcher and the workspace layout
-bool att_stream_plan(int rows, int T, int R, int H, int *nchunks, int *max_parts, int *nstages) {
+// plan shared by the launcher and the workspace layout: cluster size and ring depth
+bool att_stream_plan(int rows, int T, int R, int H, int *cluster, int *max_parts, int *nstages) {
   if ((H & 7) != 0 || H > 1024 || R > RMAX) return false;
   const size_t sb = stage_bytes(R, H);
   int ns = static_cast<int>((200 * 1024) / sb);
   if (ns < 2) return false;
   if (ns > 4) ns = 4;
-  const long long F = static_cast<long long>(rows) * T;
-  long long n = sm_count();
-  if (n > F) n = F;
-  const long long min_chunk = F / n;   // >= 1
-  long long parts = (T + min_chunk - 1) / min_chunk + 1;
-  if (parts > T) parts = T;
-  if (parts < 1) parts = 1;
-  *nchunks = static_cast<int>(n);
-  *max_parts = static_cast<int>(parts);
+  int cs = 1;
+  while (cs < 8 && 2 * cs <= T && static_cast<long long>(rows) * 2 * cs <= sm_count()) cs *= 2;
+  *cluster = cs;
+  *max_parts = 1;          // partial states never leave the cluster
   *nstages = ns;
   return true;
 }
@@ -512,11 +488,9 @@ void att_set_trace(long long *p) { g_att_trace = p; }
 int att_stream_launch(const AttArgs &a_in, cudaStream_t stream) {
   AttArgs a = a_in;
   a.trace = g_att_trace;
-  int nchunks, max_parts, nstages;
+  int nchunks, max_parts, nstages;   // nchunks = cluster size
   STAT_REQUIRE(att_stream_plan(a.rows, a.T, a.R, a.H, &nchunks, &max_parts, &nstages), STAT_EINVAL,
                "att_stream: unsupported shape R=%d H=%d", a.R, a.H);
-  STAT_REQUIRE(a.S >= max_parts, STAT_EINVAL, "att_stream: partial buffers hold %d parts per row, need %d", a.S,
-               max_parts);
   const int H = a.H;
   if (H == 512 && a.R == 8) return launch<1, 2, 8>(a, nchunks, nstages, stream);   // BASELINE shape
   if (H <= 256) return launch<1, 1, 0>(a, nchunks, nstages, stream);

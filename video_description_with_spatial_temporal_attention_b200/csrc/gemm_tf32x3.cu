@@ -52,7 +52,8 @@ namespace {
 constexpr int BP = 128;      // tile rows (TMEM lanes)
 constexpr int BK = 32;       // fp32 per k-slice row = 128 B = one swizzle row
 constexpr int UMMA_K = 8;    // tf32 MMA K
-constexpr int NTHREADS = 192;
+constexpr int NSPLIT = 256;               // splitter / epilogue threads (8 warps: 2 per scheduler)
+constexpr int NTHREADS = 64 + NSPLIT;     // + TMA producer warp + MMA issuer warp
 
 template <int BQ>
 struct Cfg {
@@ -205,6 +206,16 @@ __device__ __forceinline__ void split4(float4 *hi_ptr, float4 *lo_ptr) {
   *lo_ptr = l;
 }
 
+__device__ __forceinline__ void split_store(const float4 &x, float4 *hi_ptr, float4 *lo_ptr) {
+  float4 h, l;
+  h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+  // lo = x - hi is exact in fp32; the tensor core reads its top 19 bits (|lo| <= 2^-12 |x|, so what is
+  // dropped is <= 2^-22 |x|)
+  l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+  *hi_ptr = h;
+  *lo_ptr = l;
+}
+
 __device__ __forceinline__ float apply_epi(float acc, const DevSeg &s, float bias, float add) {
   float v = fmaf(s.alpha, acc, bias + add);
   if (s.act == 1) v = tanh_fast(v);   // abs. error ~1.5e-7 (stat_common.cuh)
@@ -244,7 +255,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_split + 8 * s, 128);
+      mbar_init(bar_split + 8 * s, NSPLIT);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tmem, 1);
@@ -311,7 +322,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     }
   } else {
     // ===================== splitter, then epilogue =====================
-    const int t = threadIdx.x - 64;  // 0..127
+    const int t = threadIdx.x - 64;  // 0..NSPLIT-1
     int s = 0;
     uint32_t ph = 0;
     for (int kb = 0; kb < nk; ++kb) {
@@ -322,12 +333,23 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       float4 *Pl = reinterpret_cast<float4 *>(stage + C::P_BYTES);
       float4 *Qh = reinterpret_cast<float4 *>(stage + 2 * C::P_BYTES);
       float4 *Ql = reinterpret_cast<float4 *>(stage + 2 * C::P_BYTES + C::Q_BYTES);
+      // all 16-byte loads of this thread first, then the arithmetic, then the stores
+      constexpr int NP4 = C::P_BYTES / 16 / NSPLIT;                 // 4
+      constexpr int NQ4 = (C::Q_BYTES / 16 + NSPLIT - 1) / NSPLIT;  // 1 / 2 / 4
+      float4 xp[NP4], xq[NQ4];
 #pragma unroll
-      for (int i = 0; i < C::P_BYTES / 16 / 128; ++i) split4(Ph + t + i * 128, Pl + t + i * 128);
+      for (int i = 0; i < NP4; ++i) xp[i] = Ph[t + i * NSPLIT];
 #pragma unroll
-      for (int i = 0; i < (C::Q_BYTES / 16 + 127) / 128; ++i) {
-        const int idx = t + i * 128;
-        if (idx < C::Q_BYTES / 16) split4(Qh + idx, Ql + idx);
+      for (int i = 0; i < NQ4; ++i) {
+        const int idx = t + i * NSPLIT;
+        xq[i] = (idx < C::Q_BYTES / 16) ? Qh[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < NP4; ++i) split_store(xp[i], Ph + t + i * NSPLIT, Pl + t + i * NSPLIT);
+#pragma unroll
+      for (int i = 0; i < NQ4; ++i) {
+        const int idx = t + i * NSPLIT;
+        if (idx < C::Q_BYTES / 16) split_store(xq[i], Qh + idx, Ql + idx);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar_split + 8 * s);
@@ -339,62 +361,93 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     mbar_wait(bar_tmem, 0);
     tc_fence_after();
     if (trace && t == 0) trace[60] = clock64();
-    const int wq = warp & 3;
+    const int wq = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int chalf = (warp - 2) >> 2;       // the two warps of a quadrant take half of the columns each
+    constexpr int CH = BQ / 2;
+    const int cbeg = chalf * CH, cend = cbeg + CH;
     const int p = p0 + wq * 32 + lane;
-    const int sel = (args.nseg > 1 && (args.feat_on_p ? p0 : q0) >= args.seg[1].f0) ? 1 : 0;
-    DevSeg sg = args.seg[sel];
-    // k-slice z > 0 writes its raw partial product into plane z; bias / addend ride on plane 0
-    sg.C += static_cast<size_t>(kz) * args.plane;
-    if (kz > 0) {
-      sg.bias = nullptr;
-      sg.addend = nullptr;
-    }
-    // 8 accumulator columns at a time, rolled: the epilogue runs once per CTA from a cold
-    // instruction cache, so its code is kept small
+    const bool sel = args.nseg > 1 && (args.feat_on_p ? p0 : q0) >= args.seg[1].f0;
+    // segment parameters into registers (a struct copy indexed at run time would live in local memory);
+    // k-slice z > 0 writes its raw partial product into plane z, bias / addend ride on plane 0
+    float *const C = (sel ? args.seg[1].C : args.seg[0].C) + static_cast<size_t>(kz) * args.plane;
+    const float *const bias = kz > 0 ? nullptr : (sel ? args.seg[1].bias : args.seg[0].bias);
+    const float *const addend = kz > 0 ? nullptr : (sel ? args.seg[1].addend : args.seg[0].addend);
+    const int ldc = sel ? args.seg[1].ldc : args.seg[0].ldc;
+    const int ld_add = sel ? args.seg[1].ld_add : args.seg[0].ld_add;
+    const int f0 = sel ? args.seg[1].f0 : args.seg[0].f0;
+    const int f1 = sel ? args.seg[1].f1 : args.seg[0].f1;
+    const float alpha = sel ? args.seg[1].alpha : args.seg[0].alpha;
+    const float post = sel ? args.seg[1].post : args.seg[0].post;
+    const bool act = (sel ? args.seg[1].act : args.seg[0].act) == 1;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    const bool vec_ok = ((sg.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.C) & 15) == 0) &&
-                        (((q0 - sg.f0) & 3) == 0);
-    const float pb = (args.feat_on_p && sg.bias && p < args.NP && p < sg.f1) ? __ldg(sg.bias + (p - sg.f0)) : 0.f;
+    if (args.feat_on_p == 0) {
+      // rows = p (this lane), features = q: 8 accumulator columns at a time
+      const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (((q0 - f0) & 3) == 0);
+      float *crow = C + static_cast<size_t>(p) * ldc + (q0 - f0);
+      const float *arow = addend ? addend + static_cast<size_t>(p) * ld_add + (q0 - f0) : nullptr;
+      const float *brow = bias ? bias + (q0 - f0) : nullptr;
+      const int qlim = min(args.NQ, f1) - q0;      // valid columns of this tile
 #pragma unroll 1
-    for (int c = 0; c < BQ; c += 8) {
-      uint32_t v[8];
-      tc_ld8(trow + c, v);
-      if (args.feat_on_p == 0) {
-        // rows = p (this lane), features = q
-        if (p < args.NP) {
-          const int j0 = q0 + c - sg.f0;  // output column of v[0]
-          float *crow = sg.C + static_cast<size_t>(p) * sg.ldc;
-          const float *arow = sg.addend ? sg.addend + static_cast<size_t>(p) * sg.ld_add : nullptr;
+      for (int c = cbeg; c < cend; c += 8) {
+        uint32_t v[8];
+        tc_ld8(trow + c, v);
+        if (p < args.NP && c < qlim) {
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int q = q0 + c + e;
-            const bool ok = q < args.NQ && q < sg.f1;
-            const float b = (ok && sg.bias) ? __ldg(sg.bias + j0 + e) : 0.f;
-            const float ad = (ok && arow) ? arow[j0 + e] : 0.f;
-            o[e] = apply_epi(__uint_as_float(v[e]), sg, b, ad);
+            const bool ok = c + e < qlim;
+            float x = fmaf(alpha, __uint_as_float(v[e]), (ok && brow) ? __ldg(brow + c + e) : 0.f);
+            if (ok && arow) x += arow[c + e];
+            if (act) x = tanh_fast(x);
+            o[e] = x * post;
           }
-          if (vec_ok && q0 + c + 8 <= args.NQ && q0 + c + 8 <= sg.f1) {
-            *reinterpret_cast<float4 *>(crow + j0) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4 *>(crow + j0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          if (vec_ok && c + 8 <= qlim) {
+            *reinterpret_cast<float4 *>(crow + c) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4 *>(crow + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int q = q0 + c + e;
-              if (q < args.NQ && q < sg.f1) crow[j0 + e] = o[e];
-            }
+            for (int e = 0; e < 8; ++e)
+              if (c + e < qlim) crow[c + e] = o[e];
           }
         }
-      } else {
-        // features = p (this lane), rows = q : coalesced across lanes
-        if (p < args.NP && p < sg.f1) {
-          const int j = p - sg.f0;
+      }
+    } else {
+      // features = p (this lane), rows = q: every store is one coalesced 128-byte row segment
+      const bool pok = p < args.NP && p < f1;
+      const int j = p - f0;
+      const float pb = (pok && bias) ? __ldg(bias + j) : 0.f;
+      float *ccol = C + static_cast<size_t>(q0) * ldc + j;
+      const float *acol = addend ? addend + static_cast<size_t>(q0) * ld_add + j : nullptr;
+      const int qlim = args.NQ - q0;
+      const size_t ldc_s = static_cast<size_t>(ldc);
+      if (!acol && !act) {
+        // the per-step projections: plain scaled copy, pointer-bumped
+        float *cp = ccol + static_cast<size_t>(cbeg) * ldc_s;
+#pragma unroll 1
+        for (int c = cbeg; c < cend; c += 8) {
+          uint32_t v[8];
+          tc_ld8(trow + c, v);
+          if (pok) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int q = q0 + c + e;
-            if (q < args.NQ) {
-              const float add = sg.addend ? sg.addend[static_cast<size_t>(q) * sg.ld_add + j] : 0.f;
-              sg.C[static_cast<size_t>(q) * sg.ldc + j] = apply_epi(__uint_as_float(v[e]), sg, pb, add);
+            for (int e = 0; e < 8; ++e)
+              if (c + e < qlim) cp[e * ldc_s] = fmaf(alpha, __uint_as_float(v[e]), pb) * post;
+          }
+          cp += 8 * ldc_s;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = cbeg; c < cend; c += 8) {
+          uint32_t v[8];
+          tc_ld8(trow + c, v);
+          if (pok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (c + e < qlim) {
+                float x = fmaf(alpha, __uint_as_float(v[e]), pb);
+                if (acol) x += acol[static_cast<size_t>(c + e) * ld_add];
+                if (act) x = tanh_fast(x);
+                ccol[static_cast<size_t>(c + e) * ldc_s] = x * post;
+              }
             }
           }
         }
