@@ -21,7 +21,7 @@ eng.decode_greedy(ws, d, 1)
 torch.cuda.synchronize()
 lib = eng.lib
 lib.stat_debug_gemm_trace.argtypes = [C.c_void_p]
-buf = torch.zeros(64, dtype=torch.int64, device='cuda')
+buf = torch.zeros(128, dtype=torch.int64, device='cuda')
 for it in range(3):
     buf.zero_()
     lib.stat_debug_gemm_trace(C.c_void_p(buf.data_ptr()))
@@ -30,8 +30,15 @@ for it in range(3):
     lib.stat_debug_gemm_trace(C.c_void_p(0))
     t = buf.cpu().tolist()
     t0 = t[0]
-    print('run', it)
+    print('run', it, 'kernel stamps: start 0, state loaded %d, loop end %d, cluster sync %d, merged %d, exit %d' % tuple(t[64 + k] - t[64] for k in range(1, 6)), 'first frame top', t[0] - t[64])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        eng.attention(ws, d)
+    e1.record()
+    torch.cuda.synchronize()
+    print('  10 back-to-back launches: %.1f us each' % (e0.elapsed_time(e1) * 100))
     for i in range(12):
         r = [x - t0 for x in t[5 * i:5 * i + 5]]
-        print('  frame %2d top %6d  full %6d (+%5d)  A %6d (+%5d)  C %6d (+%5d)  D %6d (+%5d)' % (
+        print('  frame %2d top %6d  C+bar %6d (+%5d)  full(i+1) %6d (+%5d)  A(i+1) %6d (+%5d)  D+bar %6d (+%5d)' % (
             i, r[0], r[1], r[1] - r[0], r[2], r[2] - r[1], r[3], r[3] - r[2], r[4], r[4] - r[3]))

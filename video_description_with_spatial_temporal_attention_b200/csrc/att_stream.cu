@@ -79,8 +79,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ float ld_dsmem(const float *local, uint32_t rank) {
   uint32_t ra;
   float v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
   return v;
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -98,7 +98,7 @@ __host__ __device__ __forceinline__ int chunk_of(long long g, int n, long long F
 // NV4  = ceil(H / 256) float4 chunks per lane in phase A (warp = (region, column half));
 // RT   = compile-time R (8) or 0 for a runtime R <= 16.
 template <int NCOL, int NV4, int RT>
-__global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a, const int nstages, const int cs) {
+__global__ void __maxnreg__(120) att_stream_kernel(const AttArgs a, const int nstages, const int cs) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int RU = RT ? RT : RMAX;              // unroll bound of the region loops
   const int H = a.H, T = a.T;
@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
   const int t0 = (rank * T) / cs;
   const int nframes = ((rank + 1) * T) / cs - t0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long *ktrace = (a.trace && blockIdx.x == 0 && tid == 0) ? a.trace + 64 : nullptr;
+  if (ktrace) ktrace[0] = clock64();
 
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) {
@@ -188,8 +190,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
   const float cl = __ldg(a.cl), cg = __ldg(a.cg), cm = __ldg(a.cm), clt = __ldg(a.clt);
 
   {
+    // The h-projections arrive as k-slice planes (<= 8), summed here in plane order.  The loads of
+    // four planes are issued together before their values are used (one memory round trip).
     const float *hp = a.hp + static_cast<size_t>(row) * a.ldhp;
-    // the h-projections arrive as k-slice planes: summed here in plane order
 #pragma unroll
     for (int j = 0; j < NV4; ++j)
 #pragma unroll
@@ -200,48 +203,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
       acc[0][k] = 0.f; acc[1][k] = 0.f; acc[2][k] = 0.f;
     }
     float bsel = 0.f;
-    // (fixed trip count + predicate so that the loads of all planes are in flight together)
+    for (int q0 = 0; q0 < a.hp_parts; q0 += 4) {
+      float4 xs[4][NV4];
+      float xg[4][NCOL], xm[4][NCOL], xt[4][NCOL], xb[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (q >= a.hp_parts) break;
-      const float *hq = hp + q * a.hp_plane;
+      for (int qq = 0; qq < 4; ++qq) {
+        const bool okq = q0 + qq < a.hp_parts;
+        const float *hq = hp + static_cast<size_t>(okq ? q0 + qq : q0) * a.hp_plane;
 #pragma unroll
-      for (int j = 0; j < NV4; ++j) {
-        const int c = 4 * lane + 128 * j;
-        if (c < hw) {
-          const float4 x = *reinterpret_cast<const float4 *>(hq + a.off_sl + half * hw + c);
-          sl[j][0] += x.x; sl[j][1] += x.y; sl[j][2] += x.z; sl[j][3] += x.w;
+        for (int j = 0; j < NV4; ++j) {
+          const int c = 4 * lane + 128 * j;
+          xs[qq][j] = (okq && c < hw) ? *reinterpret_cast<const float4 *>(hq + a.off_sl + half * hw + c)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) {
+          const int col = tid + 512 * k;
+          const bool ok = okq && col < H;
+          xg[qq][k] = ok ? hq[a.off_sg + col] : 0.f;
+          xm[qq][k] = ok ? hq[a.off_sm + col] : 0.f;
+          xt[qq][k] = ok ? hq[a.off_slt + col] : 0.f;
+        }
+        xb[qq] = (okq && a.selector) ? hq[a.off_sel] : 0.f;
       }
 #pragma unroll
-      for (int k = 0; k < NCOL; ++k) {
-        const int col = tid + 512 * k;
-        if (col < H) {
-          sg[k] += hq[a.off_sg + col];
-          sm[k] += hq[a.off_sm + col];
-          slt[k] += hq[a.off_slt + col];
+      for (int qq = 0; qq < 4; ++qq) {
+#pragma unroll
+        for (int j = 0; j < NV4; ++j) {
+          sl[j][0] += xs[qq][j].x; sl[j][1] += xs[qq][j].y; sl[j][2] += xs[qq][j].z; sl[j][3] += xs[qq][j].w;
         }
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) { sg[k] += xg[qq][k]; sm[k] += xm[qq][k]; slt[k] += xt[qq][k]; }
+        bsel += xb[qq];
       }
-      if (a.selector) bsel += hq[a.off_sel];
     }
     beta = a.selector ? sigmoid_acc(bsel) : 1.0f;
 #pragma unroll
     for (int q = 0; q < 3; ++q) { rm[q] = -INFINITY; rs[q] = 0.f; }
   }
+  if (ktrace) ktrace[1] = clock64();
 
-  int t = t0, s = 0;
-  uint32_t ph = 0;
-  for (int i = 0; i < nframes; ++i) {
-    const int buf = i & 1;
-    const float *st = ring + static_cast<size_t>(s) * stage_floats;
-    const float *pL = st, *cL0 = st + RH, *qL = st + 2 * RH;
-    const float *pG = st + 3 * RH, *pM = pG + H, *G0 = pM + H, *M0 = G0 + H;
-    long long *trace = (a.trace && blockIdx.x == 0 && tid == 0 && i < 12) ? a.trace + 5 * i : nullptr;
-    if (trace) trace[0] = clock64();
-    mbar_wait(bar_full + 8 * s, ph);
-    if (trace) trace[1] = clock64();
-
-    // ---- A: region scores (half rows of H) and the g / m score partials ---------------
+  // phase A of frame i (ring slot sA, score buffers bufA): region scores and g / m partials
+  auto phase_a = [&](const float *st, int bufA) {
+    const float *pL = st, *pG = st + 3 * RH, *pM = pG + H;
     for (int r = warp & 7; r < R; r += 8) {
       float part = 0.f;
 #pragma unroll
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
         }
       }
       part = warp_sum(part);
-      if (lane == 0) s_sc[(buf * RMAX + r) * 2 + half] = part;
+      if (lane == 0) s_sc[(bufA * RMAX + r) * 2 + half] = part;
     }
     float pg = 0.f, pm = 0.f;
 #pragma unroll
@@ -269,26 +273,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     }
     pg = warp_sum(pg);
     pm = warp_sum(pm);
-    consumer_sync();
-    if (trace) trace[2] = clock64();
+    if (lane == 0) *reinterpret_cast<float2 *>(s_part + (bufA * NWARPS + warp) * 4) = make_float2(pg, pm);
+  };
+
+  // Software pipeline over the frames of this CTA (two block barriers per frame):
+  //   prologue  A(0)                                   | bar
+  //   frame i   C(i)                                   | bar
+  //             D(i) and A(i+1), independent, overlap  | bar
+  int t = t0, s = 0;
+  uint32_t ph = 0;
+  if (nframes > 0) {
+    mbar_wait(bar_full, 0);
+    phase_a(ring, 0);
+  }
+  consumer_sync();
+  for (int i = 0; i < nframes; ++i) {
+    const int buf = i & 1;
+    const float *st = ring + static_cast<size_t>(s) * stage_floats;
+    const float *cL0 = st + RH, *qL = st + 2 * RH;
+    const float *G0 = st + 3 * RH + 2 * H, *M0 = G0 + H;
+    long long *trace = (a.trace && blockIdx.x == 0 && tid == 0 && i < 12) ? a.trace + 5 * i : nullptr;
+    if (trace) trace[0] = clock64();
 
     // ---- C: softmax over regions, attended local context, its projection, lt partial ---
     float al[RU];
     {
+      float sc[RU];
       float mx = -INFINITY;
 #pragma unroll
       for (int r = 0; r < RU; ++r) {
         const float2 hs = *reinterpret_cast<const float2 *>(s_sc + (buf * RMAX + r) * 2);
-        al[r] = (r < R) ? (hs.x + hs.y) + cl : -INFINITY;
-        mx = fmaxf(mx, al[r]);
+        sc[r] = (r < R) ? (hs.x + hs.y) + cl : -INFINITY;
+        mx = fmaxf(mx, sc[r]);
       }
+      // lane r evaluates e_r once for the warp; the numerators are then broadcast
+      float mine = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < RU; ++r) mine = (lane == r) ? sc[r] : mine;
+      const float e_mine = (lane < R) ? exp_fast(mine - mx) : 0.f;
       float den = 0.f;
 #pragma unroll
       for (int r = 0; r < RU; ++r) {
-        al[r] = (r < R) ? exp_fast(al[r] - mx) : 0.f;
+        al[r] = __shfl_sync(0xffffffffu, e_mine, r);
         den += al[r];
       }
-      const float inv = 1.0f / den;
+      const float inv = rcp_approx(den);
 #pragma unroll
       for (int r = 0; r < RU; ++r) {
         al[r] *= inv;
@@ -314,18 +343,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
       cLv[k] = c0;
     }
     plt = warp_sum(plt);
-    if (lane == 0) *reinterpret_cast<float4 *>(s_part + (buf * NWARPS + warp) * 4) = make_float4(pg, pm, plt, 0.f);
+    if (lane == 0) s_part[(buf * NWARPS + warp) * 4 + 2] = plt;
     consumer_sync();
+    if (trace) trace[1] = clock64();
+
+    // ---- A(i+1): next frame's scores, independent of D(i) below ------------------------
+    if (i + 1 < nframes) {
+      int s1 = s + 1;
+      uint32_t ph1 = ph;
+      if (s1 == nstages) { s1 = 0; ph1 ^= 1; }
+      mbar_wait(bar_full + 8 * s1, ph1);
+      if (trace) trace[2] = clock64();
+      phase_a(ring + static_cast<size_t>(s1) * stage_floats, buf ^ 1);
+    }
     if (trace) trace[3] = clock64();
 
-    // ---- D: fold the frame into the three running soft-max states ----------------------
-    float sc3[3] = {cg, cm, clt};
+    // ---- D(i): fold the frame into the three running soft-max states --------------------
+    float sc3[3];
+    {
+      // lane l holds the partials of warp (l & 15); xor-shuffles over 8,4,2,1 sum the 16 warps
+      const float4 p4 = *reinterpret_cast<const float4 *>(s_part + (buf * NWARPS + (lane & (NWARPS - 1))) * 4);
+      float x = p4.x, y = p4.y, z = p4.z;
 #pragma unroll
-    for (int w = 0; w < NWARPS; ++w) {
-      const float4 p4 = *reinterpret_cast<const float4 *>(s_part + (buf * NWARPS + w) * 4);   // broadcast reads
-      sc3[0] += p4.x;
-      sc3[1] += p4.y;
-      sc3[2] += p4.z;
+      for (int o = 8; o > 0; o >>= 1) {
+        x += __shfl_xor_sync(0xffffffffu, x, o);
+        y += __shfl_xor_sync(0xffffffffu, y, o);
+        z += __shfl_xor_sync(0xffffffffu, z, o);
+      }
+      sc3[0] = x + cg;
+      sc3[1] = y + cm;
+      sc3[2] = z + clt;
     }
     if (a.att_scores && tid == 0) {
       const size_t plane = static_cast<size_t>(a.rows) * T, at = static_cast<size_t>(row) * T + t;
@@ -334,13 +381,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
       a.att_scores[2 * plane + at] = sc3[2];
     }
     float e[3], keep[3];
+    {
+      // lanes 0..2 evaluate the three rescale factors, lanes 3..5 the three new numerators
+      float mn[3];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const float mn = fmaxf(rm[q], sc3[q]);
-      keep[q] = exp_fast(rm[q] - mn);
-      e[q] = exp_fast(sc3[q] - mn);
-      rs[q] = fmaf(rs[q], keep[q], e[q]);
-      rm[q] = mn;
+      for (int q = 0; q < 3; ++q) mn[q] = fmaxf(rm[q], sc3[q]);
+      const int q = lane % 3;
+      const float from = (lane < 3) ? (q == 0 ? rm[0] : (q == 1 ? rm[1] : rm[2]))
+                                    : (q == 0 ? sc3[0] : (q == 1 ? sc3[1] : sc3[2]));
+      const float to = q == 0 ? mn[0] : (q == 1 ? mn[1] : mn[2]);
+      const float ex = (lane < 6) ? exp_fast(from - to) : 0.f;
+#pragma unroll
+      for (int qq = 0; qq < 3; ++qq) {
+        keep[qq] = __shfl_sync(0xffffffffu, ex, qq);
+        e[qq] = __shfl_sync(0xffffffffu, ex, 3 + qq);
+        rs[qq] = fmaf(rs[qq], keep[qq], e[qq]);
+        rm[qq] = mn[qq];
+      }
     }
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) {
@@ -353,12 +410,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    consumer_sync();
     if (trace) trace[4] = clock64();
     ++t;
     if (++s == nstages) { s = 0; ph ^= 1; }
   }
 
   // ---- merge of the cs partial states of this row (S8, S9) -----------------------------
+  if (ktrace) ktrace[2] = clock64();
   float *ctx = a.ctx + static_cast<size_t>(row) * H;
   if (cs == 1) {
 #pragma unroll
@@ -384,36 +443,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
       if (col < H) s_vec[q * H + col] = acc[q][k];
     }
   cluster_sync_all();
+  if (ktrace) ktrace[3] = clock64();
   if (rank == 0) {
+    // all remote values first (independent DSMEM loads), then the arithmetic
+    float pm[3][8], psum[3][8], v[3][8][NCOL];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const bool okp = p < cs;
+        pm[q][p] = okp ? ld_dsmem(s_ms + 2 * q, p) : -INFINITY;
+        psum[q][p] = okp ? ld_dsmem(s_ms + 2 * q + 1, p) : 0.f;
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) {
+          const int col = tid + 512 * k;
+          v[q][p][k] = (okp && col < H) ? ld_dsmem(s_vec + q * H + col, p) : 0.f;
+        }
+      }
     float o[NCOL];
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) o[k] = 0.f;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      float pm[8], w[8];
       float mx = -INFINITY;
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        pm[p] = (p < cs) ? ld_dsmem(s_ms + 2 * q, p) : -INFINITY;
-        mx = fmaxf(mx, pm[p]);
-      }
-      float den = 0.f;
+      for (int p = 0; p < 8; ++p) mx = fmaxf(mx, pm[q][p]);
+      float w[8], den = 0.f;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
-        w[p] = (p < cs) ? expf(pm[p] - mx) : 0.f;
-        if (p < cs) den = fmaf(w[p], ld_dsmem(s_ms + 2 * q + 1, p), den);
+        w[p] = (p < cs) ? expf(pm[q][p] - mx) : 0.f;
+        den = fmaf(w[p], psum[q][p], den);
       }
       const float inv = 1.0f / den;
 #pragma unroll
       for (int k = 0; k < NCOL; ++k) {
-        const int col = tid + 512 * k;
-        if (col < H) {
-          float num = 0.f;
+        float num = 0.f;
 #pragma unroll
-          for (int p = 0; p < 8; ++p)
-            if (p < cs) num = fmaf(w[p], ld_dsmem(s_vec + q * H + col, p), num);
-          o[k] = fmaf(num, inv, o[k]);
-        }
+        for (int p = 0; p < 8; ++p) num = fmaf(w[p], v[q][p][k], num);
+        o[k] = fmaf(num, inv, o[k]);
       }
     }
 #pragma unroll
@@ -422,7 +489,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
       if (col < H) ctx[col] = beta * o[k];
     }
   }
+  if (ktrace) ktrace[4] = clock64();
   cluster_sync_all();       // partners keep their shared memory alive until rank 0 has read it
+  if (ktrace) ktrace[5] = clock64();
 }
 
 int sm_count() {

@@ -85,9 +85,106 @@ __global__ void __launch_bounds__(256) zact_kernel(const ZactArgs a) {
   a.z[i] = v * (a.dp_z ? a.dp_z[i] : 0.5f);
 }
 
+// gates for even H: two adjacent units per thread, every load of the thread (<= 4 + 4 k-slice
+// planes x 4 gates, the token's table row, the old state) issued before the first use
+__global__ void __launch_bounds__(128) gates2_kernel(const GateArgs a) {
+  const int row = blockIdx.y;
+  const int j = (blockIdx.x * 128 + threadIdx.x) * 2;
+  const long long tok = a.tok_prev ? a.tok_prev[row] : -1;
+  const int H = a.H;
+  if (j < H) {
+    const float *pc = a.pre_c + static_cast<size_t>(row) * a.ldpc + j;
+    const float *u = a.hp + static_cast<size_t>(row) * a.ldhp + a.off_u + j;
+    const float *ew = a.EW + static_cast<size_t>(tok >= 0 ? tok : a.V) * 4 * H + j;
+    float2 xu[4][4], xc[4][4], xe[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) {
+        xu[q][gi] = (q < a.hp_parts) ? *reinterpret_cast<const float2 *>(u + q * a.hp_plane + gi * H)
+                                     : make_float2(0.f, 0.f);
+        xc[q][gi] = (q < a.pc_parts) ? *reinterpret_cast<const float2 *>(pc + q * a.pc_plane + gi * H)
+                                     : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) xe[gi] = __ldg(reinterpret_cast<const float2 *>(ew + gi * H));
+    const size_t idx = static_cast<size_t>(row) * H + j;
+    const float2 c_ = *reinterpret_cast<const float2 *>(a.c_in + idx);
+    const float2 h_ = *reinterpret_cast<const float2 *>(a.h_in + idx);
+    const float m = a.mask ? a.mask[row] : 1.0f;
+    float2 dp[3] = {make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f)};
+    if (a.dp_gates) {
+      const float *d = a.dp_gates + static_cast<size_t>(row) * 3 * H + j;
+#pragma unroll
+      for (int gi = 0; gi < 3; ++gi) dp[gi] = *reinterpret_cast<const float2 *>(d + gi * H);
+    }
+    float2 pre[4];
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+      float sux = 0.f, suy = 0.f, scx = 0.f, scy = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {          // plane order: deterministic
+        sux += xu[q][gi].x; suy += xu[q][gi].y;
+        scx += xc[q][gi].x; scy += xc[q][gi].y;
+      }
+      pre[gi].x = (sux + xe[gi].x) + scx;
+      pre[gi].y = (suy + xe[gi].y) + scy;
+    }
+    float2 c, h;
+    {
+      const float ig = sigmoid_acc(pre[0].x * dp[0].x), fg = sigmoid_acc(pre[1].x * dp[1].x);
+      const float og = sigmoid_acc(pre[2].x * dp[2].x), gg = tanhf(pre[3].x);
+      c.x = fg * c_.x + ig * gg;
+      c.x = m * c.x + (1.0f - m) * c_.x;
+      h.x = og * tanhf(c.x);
+      h.x = m * h.x + (1.0f - m) * h_.x;
+    }
+    {
+      const float ig = sigmoid_acc(pre[0].y * dp[0].y), fg = sigmoid_acc(pre[1].y * dp[1].y);
+      const float og = sigmoid_acc(pre[2].y * dp[2].y), gg = tanhf(pre[3].y);
+      c.y = fg * c_.y + ig * gg;
+      c.y = m * c.y + (1.0f - m) * c_.y;
+      h.y = og * tanhf(c.y);
+      h.y = m * h.y + (1.0f - m) * h_.y;
+    }
+    *reinterpret_cast<float2 *>(a.c_out + idx) = c;
+    *reinterpret_cast<float2 *>(a.h_out + idx) = h;
+    if (a.h_all) *reinterpret_cast<float2 *>(a.h_all + idx) = h;
+    if (a.dp_h) {
+      const float2 dh = *reinterpret_cast<const float2 *>(a.dp_h + idx);
+      *reinterpret_cast<float2 *>(a.hd_out + idx) = make_float2(h.x * dh.x, h.y * dh.y);
+    }
+  }
+  // everything of the readout pre-activation that does not depend on the new h (:689-693)
+  for (int e = j; e < min(j + 2, a.E); ++e) {
+    float z = a.bz[e];
+    if (a.zc_off >= 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < a.pc_parts) z += a.pre_c[q * a.pc_plane + static_cast<size_t>(row) * a.ldpc + a.zc_off + e];
+    }
+    if (a.prev2out && tok >= 0) z += __ldg(a.Wemb + static_cast<size_t>(tok) * a.E + e);
+    a.zadd[static_cast<size_t>(row) * a.E + e] = z;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // vocabulary reduction
 // ---------------------------------------------------------------------------
+// One CTA per row, one pass over the V logits: every thread issues all of its 16-byte loads up
+// front (V <= 256*4*PICK_MAX4), keeps a running (max, arg-max, sum exp) and the CTA merges them.
+constexpr int PICK_MAX4 = 16;     // float4 loads per thread held in registers: V <= 16384
+
+__device__ __forceinline__ void pick_fold(float x, int v, float &m, int &bi, float &s) {
+  if (x > m) {                     // ascending v per thread: the first maximum wins ties
+    s = s * expf(m - x) + 1.0f;
+    m = x;
+    bi = v;
+  } else {
+    s += expf(x - m);
+  }
+}
+
 __global__ void __launch_bounds__(256) pick_kernel(const PickArgs a) {
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
@@ -98,60 +195,75 @@ __global__ void __launch_bounds__(256) pick_kernel(const PickArgs a) {
   const int row = blockIdx.x;
   const float *l = a.logits + static_cast<size_t>(row) * a.ldl;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float best = -INFINITY;
+  float m = -INFINITY, s = 0.f;
   int bi = 0x7fffffff;
-  for (int v = threadIdx.x; v < a.V; v += 256) {
-    const float x = l[v];
-    if (x > best) { best = x; bi = v; }      // strided ascending: first hit wins ties
+  const int n4 = a.V >> 2;
+  if ((a.ldl & 3) == 0 && n4 <= 256 * PICK_MAX4) {
+    float4 x[PICK_MAX4];
+#pragma unroll
+    for (int i = 0; i < PICK_MAX4; ++i) {
+      const int k = threadIdx.x + 256 * i;
+      x[i] = (k < n4) ? *reinterpret_cast<const float4 *>(l + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < PICK_MAX4; ++i) {
+      const int k = threadIdx.x + 256 * i;
+      if (k < n4) {
+        pick_fold(x[i].x, 4 * k, m, bi, s);
+        pick_fold(x[i].y, 4 * k + 1, m, bi, s);
+        pick_fold(x[i].z, 4 * k + 2, m, bi, s);
+        pick_fold(x[i].w, 4 * k + 3, m, bi, s);
+      }
+    }
+    const int v = 4 * n4 + threadIdx.x;            // the V % 4 tail
+    if (v < a.V) pick_fold(l[v], v, m, bi, s);
+  } else {
+    for (int v = threadIdx.x; v < a.V; v += 256) pick_fold(l[v], v, m, bi, s);
   }
+  // merge (max, arg-max, sum) over the warp, then over the 8 warps: larger value, then lower index
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    const float os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, om);
+    s = s * expf(m - mn) + os * expf(om - mn);     // exp(-inf) = 0 for idle threads
+    if (om > m || (om == m && oi < bi)) bi = oi;
+    m = mn;
   }
-  if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+  if (lane == 0) { s_val[warp] = m; s_idx[warp] = bi; s_sum[warp] = s; }
   __syncthreads();
   if (threadIdx.x == 0) {
     float b = s_val[0];
     int i = s_idx[0];
     for (int w = 1; w < 8; ++w)
       if (s_val[w] > b || (s_val[w] == b && s_idx[w] < i)) { b = s_val[w]; i = s_idx[w]; }
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += s_sum[w] * expf(s_val[w] - b);
     s_bm = b;
     s_bi = i;
-  }
-  __syncthreads();
-  const float m = s_bm;
-  float sum = 0.f;
-  for (int v = threadIdx.x; v < a.V; v += 256) sum += expf(l[v] - m);
-  sum = warp_sum(sum);
-  if (lane == 0) s_sum[warp] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += s_sum[w];
-    s_bs = s;
-    const int tok = s_bi;
+    s_bs = tot;
+    const int tok = i;
     if (a.tokens) {
       const bool live = a.alive[row] != 0;
       a.tokens[static_cast<size_t>(row) * a.maxlen + a.t] = live ? tok : -1;
       if (live) {
-        a.scores[row] += logf(s);              // -log p(argmax) = log sum exp(l - max)
+        a.scores[row] += logf(tot);              // -log p(argmax) = log sum exp(l - max)
         a.lengths[row] = a.t + 1;
         a.alive[row] = tok != 0;
         a.tok_prev[row] = tok;
       }
     }
     if (a.x_t) {
-      const float p = expf(l[a.x_t[row]] - m) / s;
+      const float p = expf(l[a.x_t[row]] - b) / tot;
       a.logprob[row] += a.mask_t[row] * logf(p + 1e-8f);   // model_attention.py:712-715
     }
   }
   if (a.probs) {
     __syncthreads();
-    const float inv = 1.0f / s_bs;
+    const float mm = s_bm, inv = 1.0f / s_bs;
     float *p = a.probs + static_cast<size_t>(row) * a.V;
-    for (int v = threadIdx.x; v < a.V; v += 256) p[v] = expf(l[v] - m) * inv;
+    for (int v = threadIdx.x; v < a.V; v += 256) p[v] = expf(l[v] - mm) * inv;
   }
 }
 
@@ -226,6 +338,15 @@ __global__ void add_vec_kernel(float *dst, const float *a, const float *b, int n
 
 int gates_launch(const GateArgs &a, cudaStream_t stream) {
   const int w = a.H > a.E ? a.H : a.E;
+  const bool vec2 = (a.H % 2 == 0) && (a.ldhp % 2 == 0) && (a.ldpc % 2 == 0) && (a.off_u % 2 == 0) &&
+                    a.hp_parts <= 4 && a.pc_parts <= 4 && (a.hp_plane % 2 == 0) && (a.pc_plane % 2 == 0);
+  if (vec2) {
+    dim3 grid((w / 2 + 127) / 128 + ((w % 2) ? 1 : 0), a.rows);
+    gates2_kernel<<<grid, 128, 0, stream>>>(a);
+    note_launch();
+    STAT_CUDA_CHECK(cudaGetLastError());
+    return STAT_OK;
+  }
   dim3 grid((w + 127) / 128, a.rows);
   gates_kernel<<<grid, 128, 0, stream>>>(a);
   note_launch();

@@ -162,7 +162,7 @@ int pick_ksplit(int nfeat, int rows, int K) {
   const int tiles = ((nfeat + 127) / 128) * ((rows + bq - 1) / bq);
   const int nk = (K + 31) / 32;
   int ks = 148 / tiles;
-  if (ks > 8) ks = 8;
+  if (ks > 4) ks = 4;      // the consumers sum at most 4 planes in one batch of loads
   if (ks > nk) ks = nk;
   if (ks < 1) ks = 1;
   return ks;
