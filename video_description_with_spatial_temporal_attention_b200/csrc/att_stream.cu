@@ -98,7 +98,7 @@ __host__ __device__ __forceinline__ int chunk_of(long long g, int n, long long F
 // NV4  = ceil(H / 256) float4 chunks per lane in phase A (warp = (region, column half));
 // RT   = compile-time R (8) or 0 for a runtime R <= 16.
 template <int NCOL, int NV4, int RT>
-__global__ void __maxnreg__(112) att_stream_kernel(const AttArgs a, const int nstages, const int cs) {
+__global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a, const int nstages, const int cs) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int RU = RT ? RT : RMAX;              // unroll bound of the region loops
   const int H = a.H, T = a.T;
