@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(256) pick_kernel(const PickArgs a) {
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     const float os = __shfl_xor_sync(0xffffffffu, s, o);
     const float mn = fmaxf(m, om);
-    s = s * expf(m - mn) + os * expf(om - mn);     // exp(-inf) = 0 for idle threads
+    // idle threads carry (-inf, 0): -inf - -inf would be NaN, so their weight is forced to 0
+    const float w1 = (m == -INFINITY) ? 0.f : expf(m - mn);
+    const float w2 = (om == -INFINITY) ? 0.f : expf(om - mn);
+    s = s * w1 + os * w2;
     if (om > m || (om == m && oi < bi)) bi = oi;
     m = mn;
   }
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(256) pick_kernel(const PickArgs a) {
     for (int w = 1; w < 8; ++w)
       if (s_val[w] > b || (s_val[w] == b && s_idx[w] < i)) { b = s_val[w]; i = s_idx[w]; }
     float tot = 0.f;
-    for (int w = 0; w < 8; ++w) tot += s_sum[w] * expf(s_val[w] - b);
+    for (int w = 0; w < 8; ++w) tot += (s_val[w] == -INFINITY) ? 0.f : s_sum[w] * expf(s_val[w] - b);
     s_bm = b;
     s_bi = i;
     s_bs = tot;
