@@ -87,8 +87,9 @@ typedef struct StatParams {
 int         stat_version(void);
 const char *stat_last_error(void);
 
-/* 0 = tcgen05 3xTF32 tensor-core GEMM (default), 1 = plain fp32 SIMT GEMM (a
- * device-side cross-check used by the GPU tests; never a CPU path). */
+/* 0 = tcgen05 3xTF32 tensor-core GEMM with the 128-lane operand in tensor memory
+ * (default), 2 = the same with both operands in shared memory, 1 = plain fp32 SIMT
+ * GEMM (device-side cross-checks used by the GPU tests; never a CPU path). */
 int stat_set_gemm_impl(int impl);
 
 /* ---- parameter preparation (once per parameter set) ----------------------

@@ -46,7 +46,7 @@ def _build(options, params):
 # ---------------------------------------------------------------------------
 # the dense primitive
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('impl', [0, 1, 2])
 @pytest.mark.parametrize('M,N,K,swap', [(64, 4097, 512, True), (300, 512, 4096, False), (1, 50, 24, True),
                                         (128, 128, 32, False), (13, 100, 40, True), (257, 96, 36, False),
                                         (64, 12594, 512, True), (1664, 512, 512, False)])

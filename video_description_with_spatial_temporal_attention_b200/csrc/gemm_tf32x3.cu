@@ -6,7 +6,14 @@
 // tile product is accumulated in fp32 TMEM as  lo_P.hi_Q + hi_P.lo_Q + hi_P.hi_Q
 // ("3xTF32").  The dropped lo.lo term is ~2^-22 relative.
 //
-// Kernel shape (one 128 x BQ output tile per CTA, 192 threads):
+// TS variant (default): the operand on the 128-lane axis ("P") never goes back to shared memory --
+// the splitter threads read the raw TMA tile, split it in registers and store hi / lo straight
+// into tensor memory (tcgen05.st); the MMAs take A from TMEM and only B ("Q") from shared memory.
+// That removes the hi/lo write-back and the three A reads per k-step from the shared-memory port,
+// which is what bounded the SS variant (224 KB of shared-memory traffic per 32-wide k-slice of a
+// 128x128 tile).
+//
+// Kernel shape (one 128 x BQ output tile per CTA, 320 threads):
 //   warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) of the raw fp32
 //                              P and Q k-slices into a STAGES-deep ring
 //   warps 2..5  splitter     : rewrite hi in place, write lo beside it, then
@@ -60,7 +67,10 @@ struct Cfg {
   static constexpr int P_BYTES = BP * BK * 4;
   static constexpr int Q_BYTES = BQ * BK * 4;
   static constexpr int STAGE_BYTES = 2 * P_BYTES + 2 * Q_BYTES;
-  static constexpr int MAX_STAGES = (BQ >= 128) ? 3 : (BQ >= 64 ? 4 : 5);
+  static constexpr int MAX_STAGES = (BQ >= 128) ? 3 : 4;
+  // TS variant: accumulator in columns [0, BQ), A-operand stage s (hi 32 cols | lo 32 cols) at 256 + 64 s
+  static constexpr int TS_A_BASE = 256;
+  static constexpr int TS_TMEM_COLS = 512;
   static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
   static constexpr int TMEM_COLS = BQ < 32 ? 32 : BQ;
 };
@@ -144,6 +154,26 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -222,7 +252,7 @@ __device__ __forceinline__ float apply_epi(float acc, const DevSeg &s, float bia
   return v * s.post;
 }
 
-template <int BQ>
+template <int BQ, bool TS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
                    const DevArgs args) {
@@ -264,7 +294,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_ptr_smem)),
-                 "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                 "r"(static_cast<uint32_t>(TS ? C::TS_TMEM_COLS : C::TMEM_COLS))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -307,12 +337,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         const uint64_t dPl = make_desc(stage + C::P_BYTES);
         const uint64_t dQh = make_desc(stage + 2 * C::P_BYTES);
         const uint64_t dQl = make_desc(stage + 2 * C::P_BYTES + C::Q_BYTES);
+        const uint32_t a_hi = tmem_base + C::TS_A_BASE + 64 * s, a_lo = a_hi + 32;
 #pragma unroll
         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
           const uint64_t adv = static_cast<uint64_t>((ks * UMMA_K * 4) >> 4);  // 32 B per k-step
-          tc_mma_tf32(tmem_base, dPl + adv, dQh + adv, idesc, (kb | ks) ? 1u : 0u);
-          tc_mma_tf32(tmem_base, dPh + adv, dQl + adv, idesc, 1u);
-          tc_mma_tf32(tmem_base, dPh + adv, dQh + adv, idesc, 1u);
+          if constexpr (TS) {
+            tc_mma_tf32_ts(tmem_base, a_lo + ks * UMMA_K, dQh + adv, idesc, (kb | ks) ? 1u : 0u);
+            tc_mma_tf32_ts(tmem_base, a_hi + ks * UMMA_K, dQl + adv, idesc, 1u);
+            tc_mma_tf32_ts(tmem_base, a_hi + ks * UMMA_K, dQh + adv, idesc, 1u);
+          } else {
+            tc_mma_tf32(tmem_base, dPl + adv, dQh + adv, idesc, (kb | ks) ? 1u : 0u);
+            tc_mma_tf32(tmem_base, dPh + adv, dQl + adv, idesc, 1u);
+            tc_mma_tf32(tmem_base, dPh + adv, dQh + adv, idesc, 1u);
+          }
         }
         tc_commit(bar_empty + 8 * s);
         if (kb == nk - 1) tc_commit(bar_tmem);
@@ -333,23 +370,61 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       float4 *Pl = reinterpret_cast<float4 *>(stage + C::P_BYTES);
       float4 *Qh = reinterpret_cast<float4 *>(stage + 2 * C::P_BYTES);
       float4 *Ql = reinterpret_cast<float4 *>(stage + 2 * C::P_BYTES + C::Q_BYTES);
-      // all 16-byte loads of this thread first, then the arithmetic, then the stores
-      constexpr int NP4 = C::P_BYTES / 16 / NSPLIT;                 // 4
       constexpr int NQ4 = (C::Q_BYTES / 16 + NSPLIT - 1) / NSPLIT;  // 1 / 2 / 4
-      float4 xp[NP4], xq[NQ4];
+      if constexpr (TS) {
+        // P: this thread owns tile row prow (= its TMEM lane) and 16 of the 32 k-columns.  The TMA
+        // tile is SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7).
+        const int prow = (warp & 3) * 32 + lane;
+        const int ch = (warp - 2) >> 2;
+        const uint8_t *rowp = stage + prow * 128;
+        float4 xp[4], xq[NQ4];
 #pragma unroll
-      for (int i = 0; i < NP4; ++i) xp[i] = Ph[t + i * NSPLIT];
+        for (int i = 0; i < 4; ++i)
+          xp[i] = *reinterpret_cast<const float4 *>(rowp + (((4 * ch + i) ^ (prow & 7)) << 4));
 #pragma unroll
-      for (int i = 0; i < NQ4; ++i) {
-        const int idx = t + i * NSPLIT;
-        xq[i] = (idx < C::Q_BYTES / 16) ? Qh[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int i = 0; i < NQ4; ++i) {
+          const int idx = t + i * NSPLIT;
+          xq[i] = (idx < C::Q_BYTES / 16) ? Qh[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int i = 0; i < NP4; ++i) split_store(xp[i], Ph + t + i * NSPLIT, Pl + t + i * NSPLIT);
+        for (int i = 0; i < 4; ++i) {
+          const float xs[4] = {xp[i].x, xp[i].y, xp[i].z, xp[i].w};
 #pragma unroll
-      for (int i = 0; i < NQ4; ++i) {
-        const int idx = t + i * NSPLIT;
-        if (idx < C::Q_BYTES / 16) split_store(xq[i], Qh + idx, Ql + idx);
+          for (int e = 0; e < 4; ++e) {
+            const float h = rna_tf32(xs[e]);
+            hi[4 * i + e] = __float_as_uint(h);
+            lo[4 * i + e] = __float_as_uint(xs[e] - h);
+          }
+        }
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + C::TS_A_BASE + 64 * s + 16 * ch;
+        tc_st16(ta, hi);
+        tc_st16(ta + 32, lo);
+#pragma unroll
+        for (int i = 0; i < NQ4; ++i) {
+          const int idx = t + i * NSPLIT;
+          if (idx < C::Q_BYTES / 16) split_store(xq[i], Qh + idx, Ql + idx);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+      } else {
+        // all 16-byte loads of this thread first, then the arithmetic, then the stores
+        constexpr int NP4 = C::P_BYTES / 16 / NSPLIT;                 // 4
+        float4 xp[NP4], xq[NQ4];
+#pragma unroll
+        for (int i = 0; i < NP4; ++i) xp[i] = Ph[t + i * NSPLIT];
+#pragma unroll
+        for (int i = 0; i < NQ4; ++i) {
+          const int idx = t + i * NSPLIT;
+          xq[i] = (idx < C::Q_BYTES / 16) ? Qh[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < NP4; ++i) split_store(xp[i], Ph + t + i * NSPLIT, Pl + t + i * NSPLIT);
+#pragma unroll
+        for (int i = 0; i < NQ4; ++i) {
+          const int idx = t + i * NSPLIT;
+          if (idx < C::Q_BYTES / 16) split_store(xq[i], Qh + idx, Ql + idx);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar_split + 8 * s);
@@ -462,7 +537,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                 "r"(static_cast<uint32_t>(TS ? C::TS_TMEM_COLS : C::TMEM_COLS))
                  : "memory");
   }
 }
@@ -548,14 +623,14 @@ int make_map(CUtensorMap *tm, const float *base, int rows, int K, int ld, int bo
   return STAT_OK;
 }
 
-template <int BQ>
+template <int BQ, bool TS>
 int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   CUtensorMap tmP, tmQ;
   STAT_TRY(make_map(&tmP, a.P, a.NP, a.K, a.ldp, BP));
   STAT_TRY(make_map(&tmQ, a.Q, a.NQ, a.K, a.ldq, BQ));
   static bool attr_done = false;
   if (!attr_done) {
-    STAT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    STAT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BQ, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<BQ>::smem_bytes(Cfg<BQ>::MAX_STAGES)));
     attr_done = true;
   }
@@ -563,7 +638,7 @@ int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   const int nk_slice = ((a.K + BK - 1) / BK + da.ksplit - 1) / da.ksplit;
   db.stages = nk_slice < Cfg<BQ>::MAX_STAGES ? nk_slice : Cfg<BQ>::MAX_STAGES;
   dim3 grid((a.NQ + BQ - 1) / BQ, (a.NP + BP - 1) / BP, da.ksplit);
-  gemm_tf32x3_kernel<BQ><<<grid, NTHREADS, Cfg<BQ>::smem_bytes(db.stages), stream>>>(tmP, tmQ, db);
+  gemm_tf32x3_kernel<BQ, TS><<<grid, NTHREADS, Cfg<BQ>::smem_bytes(db.stages), stream>>>(tmP, tmQ, db);
   note_launch();
   STAT_CUDA_CHECK(cudaGetLastError());
   return STAT_OK;
@@ -610,9 +685,14 @@ int gemm_launch(const GemmArgs &a, cudaStream_t stream) {
     STAT_REQUIRE(a.seg[1].f0 % tile == 0, STAT_EINVAL, "gemm: segment boundary %d not a multiple of %d",
                  a.seg[1].f0, tile);
   }
-  if (a.NQ > 64) return launch_tc<128>(a, da, stream);
-  if (a.NQ > 32) return launch_tc<64>(a, da, stream);
-  return launch_tc<32>(a, da, stream);
+  if (g_gemm_impl == 2) {   // SS variant (A and B from shared memory), kept for A/B comparison
+    if (a.NQ > 64) return launch_tc<128, false>(a, da, stream);
+    if (a.NQ > 32) return launch_tc<64, false>(a, da, stream);
+    return launch_tc<32, false>(a, da, stream);
+  }
+  if (a.NQ > 64) return launch_tc<128, true>(a, da, stream);
+  if (a.NQ > 32) return launch_tc<64, true>(a, da, stream);
+  return launch_tc<32, true>(a, da, stream);
 }
 
 }  // namespace stat

@@ -476,7 +476,8 @@ int stat_debug_gemm_trace(void *dev_buffer_64_int64) {
 }
 
 int stat_set_gemm_impl(int impl) {
-  STAT_REQUIRE(impl == 0 || impl == 1, STAT_EINVAL, "gemm impl must be 0 (tcgen05 3xTF32) or 1 (fp32 SIMT)");
+  STAT_REQUIRE(impl >= 0 && impl <= 2, STAT_EINVAL,
+               "gemm impl must be 0 (tcgen05 3xTF32, A from TMEM), 1 (fp32 SIMT) or 2 (tcgen05 3xTF32, A from smem)");
   gemm_set_impl(impl);
   return STAT_OK;
 }
