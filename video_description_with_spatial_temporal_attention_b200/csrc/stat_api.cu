@@ -285,6 +285,47 @@ int dense(const float *x, int ldx, int rows, const float *Wt, int K, int nfeat, 
   return gemm_launch(g, st);
 }
 
+// Fork / join of two side streams around the caller's stream (event based, so it also works while
+// the caller's stream is being captured into a CUDA graph).  Streams and events are created once.
+struct Fork {
+  cudaStream_t main_ = nullptr;
+  bool active_ = false;
+  static cudaStream_t s_side[2];
+  static cudaEvent_t s_fork, s_join[2];
+  static bool s_ready;
+  int open(cudaStream_t st, bool enable) {
+    main_ = st;
+    active_ = false;
+    if (!enable) return STAT_OK;
+    if (!s_ready) {
+      for (int i = 0; i < 2; ++i) {
+        STAT_CUDA_CHECK(cudaStreamCreateWithFlags(&s_side[i], cudaStreamNonBlocking));
+        STAT_CUDA_CHECK(cudaEventCreateWithFlags(&s_join[i], cudaEventDisableTiming));
+      }
+      STAT_CUDA_CHECK(cudaEventCreateWithFlags(&s_fork, cudaEventDisableTiming));
+      s_ready = true;
+    }
+    STAT_CUDA_CHECK(cudaEventRecord(s_fork, st));
+    for (int i = 0; i < 2; ++i) STAT_CUDA_CHECK(cudaStreamWaitEvent(s_side[i], s_fork, 0));
+    active_ = true;
+    return STAT_OK;
+  }
+  cudaStream_t side(int i) const { return active_ ? s_side[i] : main_; }
+  int join() {
+    if (!active_) return STAT_OK;
+    for (int i = 0; i < 2; ++i) {
+      STAT_CUDA_CHECK(cudaEventRecord(s_join[i], s_side[i]));
+      STAT_CUDA_CHECK(cudaStreamWaitEvent(main_, s_join[i], 0));
+    }
+    active_ = false;
+    return STAT_OK;
+  }
+};
+cudaStream_t Fork::s_side[2] = {nullptr, nullptr};
+cudaEvent_t Fork::s_fork = nullptr;
+cudaEvent_t Fork::s_join[2] = {nullptr, nullptr};
+bool Fork::s_ready = false;
+
 // P2, P3: mean-pooled global feature -> h0 | c0   (:618,649,657-660)
 int init_state(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const float *ctxg,
                const float *mask_ctxg, cudaStream_t st) {
@@ -611,47 +652,57 @@ int stat_precompute(const StatDims *d, const void *prepared, const float *ctxg, 
   const float *P = static_cast<const float *>(prepared);
   float *W = static_cast<float *>(ws);
   const int B = d->B, T = d->T, R = d->R, H = d->H;
-  STAT_TRY(init_state(*d, p, P, w, W, ctxg, mask_ctxg, st));
-  // P4: context blocks
+  // Three independent chains: local (main stream), global + init state, motion.  The two short
+  // ones run on side streams forked from / joined to the caller's stream (also under graph
+  // capture); with phase timing on, everything stays on the caller's stream.
+  Fork fk;
+  STAT_TRY(fk.open(st, !g_prof_on));
+  cudaStream_t sg = fk.side(0), sm = fk.side(1);
+  STAT_TRY(init_state(*d, p, P, w, W, ctxg, mask_ctxg, sg));
   {
-    ProfScope ps(PH_K0_GLOBAL, st);
+    ProfScope ps(PH_K0_GLOBAL, sg);
     if (d->flags & STAT_GLOBAL_PROJ) {
       STAT_TRY(dense(ctxg, d->Dg, B * T, P + p.WgT, d->Dg, H, P + p.bg0, W + w.ctxg0, H, 1, 1.f, 1.f, nullptr, 0,
-                     st));
+                     sg));
     } else {
-      STAT_CUDA_CHECK(cudaMemcpyAsync(W + w.ctxg0, ctxg, sizeof(float) * B * T * H, cudaMemcpyDeviceToDevice, st));
+      STAT_CUDA_CHECK(cudaMemcpyAsync(W + w.ctxg0, ctxg, sizeof(float) * B * T * H, cudaMemcpyDeviceToDevice, sg));
     }
+    STAT_TRY(dense(W + w.ctxg0, H, B * T, P + p.WcgT, H, H, P + p.bcg, W + w.pctxg, H, 0, 1.f, 1.f, nullptr, 0,
+                   sg));
   }
   {
-    ProfScope ps(PH_K0_MOTION, st);
+    ProfScope ps(PH_K0_MOTION, sm);
     STAT_TRY(dense(ctxm, d->Dm, B * T, P + p.WmotT, d->Dm, H, P + p.bmot, W + w.ctxm0, H, 1, 1.f, 1.f, nullptr, 0,
-                   st));
+                   sm));
+    STAT_TRY(dense(W + w.ctxm0, H, B * T, P + p.WcmT, H, H, P + p.bcm, W + w.pctxm, H, 0, 1.f, 1.f, nullptr, 0,
+                   sm));
   }
   {
     ProfScope ps(PH_K0_LOCAL, st);
     STAT_TRY(dense(ctxl, d->Dr, B * T * R, P + p.WlocT, d->Dr, H, P + p.bloc, W + w.ctxl0, H, 1, 1.f, 1.f, nullptr,
                    0, st));
   }
-  // P5: projected blocks, and Q = ctxl0.Wclt_att (the :416 product made step-invariant)
-  ProfScope ps5(PH_K0_PROJ, st);
-  STAT_TRY(dense(W + w.ctxg0, H, B * T, P + p.WcgT, H, H, P + p.bcg, W + w.pctxg, H, 0, 1.f, 1.f, nullptr, 0, st));
-  STAT_TRY(dense(W + w.ctxm0, H, B * T, P + p.WcmT, H, H, P + p.bcm, W + w.pctxm, H, 0, 1.f, 1.f, nullptr, 0, st));
-  const int nlr = B * T * R;
-  if (H % 128 == 0 && nlr > 128) {
-    GemmArgs g;
-    memset(&g, 0, sizeof(g));
-    g.P = W + w.ctxl0; g.ldp = H; g.NP = nlr;
-    g.Q = P + p.WclT; g.ldq = H; g.NQ = 2 * H;
-    g.K = H; g.feat_on_p = 0; g.nseg = 2;
-    g.seg[0] = GemmSeg{W + w.pctxl, H, P + p.bcl, nullptr, 0, 1.f, 1.f, 0, 0, H};
-    g.seg[1] = GemmSeg{W + w.qctxl, H, nullptr, nullptr, 0, 1.f, 1.f, 0, H, 2 * H};
-    STAT_TRY(gemm_launch(g, st));
-  } else {
-    STAT_TRY(dense(W + w.ctxl0, H, nlr, P + p.WclT, H, H, P + p.bcl, W + w.pctxl, H, 0, 1.f, 1.f, nullptr, 0, st));
-    STAT_TRY(dense(W + w.ctxl0, H, nlr, P + p.WclT + static_cast<size_t>(H) * H, H, H, nullptr, W + w.qctxl, H, 0,
-                   1.f, 1.f, nullptr, 0, st));
+  // P5 for the local block, and Q = ctxl0.Wclt_att (the :416 product made step-invariant)
+  {
+    ProfScope ps5(PH_K0_PROJ, st);
+    const int nlr = B * T * R;
+    if (H % 128 == 0 && nlr > 128) {
+      GemmArgs g;
+      memset(&g, 0, sizeof(g));
+      g.P = W + w.ctxl0; g.ldp = H; g.NP = nlr;
+      g.Q = P + p.WclT; g.ldq = H; g.NQ = 2 * H;
+      g.K = H; g.feat_on_p = 0; g.nseg = 2;
+      g.seg[0] = GemmSeg{W + w.pctxl, H, P + p.bcl, nullptr, 0, 1.f, 1.f, 0, 0, H};
+      g.seg[1] = GemmSeg{W + w.qctxl, H, nullptr, nullptr, 0, 1.f, 1.f, 0, H, 2 * H};
+      STAT_TRY(gemm_launch(g, st));
+    } else {
+      STAT_TRY(dense(W + w.ctxl0, H, nlr, P + p.WclT, H, H, P + p.bcl, W + w.pctxl, H, 0, 1.f, 1.f, nullptr, 0,
+                     st));
+      STAT_TRY(dense(W + w.ctxl0, H, nlr, P + p.WclT + static_cast<size_t>(H) * H, H, H, nullptr, W + w.qctxl, H,
+                     0, 1.f, 1.f, nullptr, 0, st));
+    }
   }
-  return STAT_OK;
+  return fk.join();
 }
 
 int stat_init_state(const StatDims *d, const void *prepared, const float *ctxg, const float *mask_ctxg, void *ws,

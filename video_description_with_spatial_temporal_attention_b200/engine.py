@@ -228,6 +228,61 @@ class Engine(object):
         graph.replay()
         return out
 
+    def caption_stream(self, host_batches, maxlen, depth=2):
+        """Greedy captions for a stream of host-resident batches, pipelined: the H2D copy of
+        batch i+1 (copy stream, pinned host memory -> staging buffer) overlaps the decode of
+        batch i (compute stream: staging -> graph inputs, graph replay, D2H of the captions).
+
+        host_batches: iterable of (ctxg, mask_ctxg, ctxl, ctxm) float32 torch tensors on the
+        host (pinned memory for a truly asynchronous copy), all of one shape.  Yields
+        (tokens (B,maxlen) int64, lengths (B,) int32, scores (B,) float32) numpy arrays, in
+        order, each as soon as its batch has finished."""
+        self._need_params()
+        compute = torch.cuda.current_stream()
+        copy = self._copy_stream = getattr(self, '_copy_stream', None) or torch.cuda.Stream(device=self.device)
+        slots = None
+        pending = []                      # (slot, done_event)
+
+        def collect(slot, ev):
+            ev.synchronize()
+            return tuple(t.numpy().copy() for t in slots[slot]['out'])
+
+        for i, hb in enumerate(host_batches):
+            ctxg, mask, ctxl, ctxm = hb
+            if slots is None:
+                B, T, R = ctxg.shape[0], ctxg.shape[1], ctxl.shape[2]
+                dev0 = [t.to(self.device) for t in hb]
+                self.greedy_captions(*dev0, maxlen=maxlen, use_graph=True)      # capture once
+                st = self.graph_inputs(B, T, R, maxlen)
+                static = [st['ctxg'], st['mask'], st['ctxl'], st['ctxm']]
+                gout = self._graphs[('greedy', B, T, R, maxlen)][2]
+                slots = [dict(stage=[torch.empty_like(s) for s in static],
+                              out=[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in gout],
+                              ready=torch.cuda.Event(), consumed=torch.cuda.Event(), done=torch.cuda.Event())
+                         for _ in range(depth)]
+                for sl in slots:
+                    sl['consumed'].record(compute)
+            slot = i % depth
+            sl = slots[slot]
+            if len(pending) >= depth:                       # the slot's previous results must be read first
+                yield collect(*pending.pop(0))
+            with torch.cuda.stream(copy):
+                copy.wait_event(sl['consumed'])
+                for dst, src in zip(sl['stage'], hb):
+                    dst.copy_(src, non_blocking=True)
+                sl['ready'].record(copy)
+            compute.wait_event(sl['ready'])
+            for dst, src in zip(static, sl['stage']):
+                dst.copy_(src, non_blocking=True)
+            sl['consumed'].record(compute)
+            out = self.greedy_captions(*static, maxlen=maxlen, use_graph=True)
+            for dst, src in zip(sl['out'], out):
+                dst.copy_(src, non_blocking=True)
+            sl['done'].record(compute)
+            pending.append((slot, sl['done']))
+        while pending:
+            yield collect(*pending.pop(0))
+
     def graph_inputs(self, B, T, R, maxlen):
         """The static input tensors of the captured greedy graph (fill these in place to
         avoid the device-to-device staging copy)."""
