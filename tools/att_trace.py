@@ -38,7 +38,3 @@ for it in range(3):
     e1.record()
     torch.cuda.synchronize()
     print('  10 back-to-back launches: %.1f us each' % (e0.elapsed_time(e1) * 100))
-    for i in range(12):
-        r = [x - t0 for x in t[5 * i:5 * i + 5]]
-        print('  frame %2d top %6d  C+bar %6d (+%5d)  full(i+1) %6d (+%5d)  A(i+1) %6d (+%5d)  D+bar %6d (+%5d)' % (
-            i, r[0], r[1], r[1] - r[0], r[2], r[2] - r[1], r[3], r[3] - r[2], r[4], r[4] - r[3]))

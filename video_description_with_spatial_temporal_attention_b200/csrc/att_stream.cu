@@ -88,6 +88,13 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 512;
 // e^x through the SFU (rel. error 2^-22): soft-max numerators
 __device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * 1.4426950408889634f); }
 
+// acc += u * tanh(x + s) in five instructions: with C = 2 log2(e), sc = s*C and m2u = -2u
+// precomputed, u*tanh(x+s) = u - 2u / (1 + 2^(x*C + sc)); the "+u" terms are pre-summed into acc.
+__device__ __forceinline__ float tanh_acc(float x, float sc, float m2u, float acc) {
+  const float e = ex2_approx(fmaf(x, 2.885390081777927f, sc));
+  return fmaf(rcp_approx(e + 1.0f), m2u, acc);
+}
+
 // largest chunk index whose first frame is <= g, for n equal chunks of F frames:
 // chunk i covers [i*F/n, (i+1)*F/n)
 __host__ __device__ __forceinline__ int chunk_of(long long g, int n, long long F) {
@@ -96,12 +103,12 @@ __host__ __device__ __forceinline__ int chunk_of(long long g, int n, long long F
 
 // NCOL = ceil(H / 512) columns per thread in phases C/D (col = tid + 512 k);
 // NV4  = ceil(H / 256) float4 chunks per lane in phase A (warp = (region, column half));
-// RT   = compile-time R (8) or 0 for a runtime R <= 16.
-template <int NCOL, int NV4, int RT>
+// RT   = compile-time R (8) or 0 for a runtime R <= 16;  HT = compile-time H (512) or 0.
+template <int NCOL, int NV4, int RT, int HT>
 __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a, const int nstages, const int cs) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int RU = RT ? RT : RMAX;              // unroll bound of the region loops
-  const int H = a.H, T = a.T;
+  const int H = HT ? HT : a.H, T = a.T;
   const int R = RT ? RT : a.R;
   const int RH = R * H;
   const int stage_floats = 3 * RH + 4 * H;
@@ -241,39 +248,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
 #pragma unroll
     for (int q = 0; q < 3; ++q) { rm[q] = -INFINITY; rs[q] = 0.f; }
   }
+  // fold the tanh constants into the per-row state (see tanh_acc): s -> s*C, u -> -2u, and the
+  // sum of this thread's u values as the starting value of each score partial
+  constexpr float C2 = 2.885390081777927f;
+  float su_l = 0.f, su_g = 0.f, su_m = 0.f, su_lt = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV4; ++j)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      su_l += ul[j][v];
+      ul[j][v] *= -2.0f;
+      sl[j][v] *= C2;
+    }
+#pragma unroll
+  for (int k = 0; k < NCOL; ++k) {
+    su_g += ug[k]; su_m += um[k]; su_lt += ult[k];
+    ug[k] *= -2.0f; um[k] *= -2.0f; ult[k] *= -2.0f;
+    sg[k] *= C2; sm[k] *= C2; slt[k] *= C2;
+  }
   if (ktrace) ktrace[1] = clock64();
 
-  // phase A of frame i (ring slot sA, score buffers bufA): region scores and g / m partials
+  // phase A of a frame (ring slot st, score buffer bufA): region scores; the g / m score
+  // partials of this thread's columns are returned in pg / pm (reduced later, with lt)
+  float pg = 0.f, pm = 0.f;
   auto phase_a = [&](const float *st, int bufA) {
     const float *pL = st, *pG = st + 3 * RH, *pM = pG + H;
     for (int r = warp & 7; r < R; r += 8) {
-      float part = 0.f;
+      float part = su_l;
 #pragma unroll
       for (int j = 0; j < NV4; ++j) {
         const int c = 4 * lane + 128 * j;
-        if (c < hw) {
+        if (HT || c < hw) {
           const float4 x = *reinterpret_cast<const float4 *>(pL + r * H + half * hw + c);
-          part = fmaf(tanh_fast(x.x + sl[j][0]), ul[j][0], part);
-          part = fmaf(tanh_fast(x.y + sl[j][1]), ul[j][1], part);
-          part = fmaf(tanh_fast(x.z + sl[j][2]), ul[j][2], part);
-          part = fmaf(tanh_fast(x.w + sl[j][3]), ul[j][3], part);
+          part = tanh_acc(x.x, sl[j][0], ul[j][0], part);
+          part = tanh_acc(x.y, sl[j][1], ul[j][1], part);
+          part = tanh_acc(x.z, sl[j][2], ul[j][2], part);
+          part = tanh_acc(x.w, sl[j][3], ul[j][3], part);
         }
       }
       part = warp_sum(part);
       if (lane == 0) s_sc[(bufA * RMAX + r) * 2 + half] = part;
     }
-    float pg = 0.f, pm = 0.f;
+    pg = su_g;
+    pm = su_m;
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) {
       const int col = tid + 512 * k;
-      if (col < H) {
-        pg = fmaf(tanh_fast(pG[col] + sg[k]), ug[k], pg);
-        pm = fmaf(tanh_fast(pM[col] + sm[k]), um[k], pm);
+      if (HT || col < H) {
+        pg = tanh_acc(pG[col], sg[k], ug[k], pg);
+        pm = tanh_acc(pM[col], sm[k], um[k], pm);
       }
     }
-    pg = warp_sum(pg);
-    pm = warp_sum(pm);
-    if (lane == 0) *reinterpret_cast<float2 *>(s_part + (bufA * NWARPS + warp) * 4) = make_float2(pg, pm);
   };
 
   // Software pipeline over the frames of this CTA (two block barriers per frame):
@@ -292,18 +317,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     const float *st = ring + static_cast<size_t>(s) * stage_floats;
     const float *cL0 = st + RH, *qL = st + 2 * RH;
     const float *G0 = st + 3 * RH + 2 * H, *M0 = G0 + H;
-    long long *trace = (a.trace && blockIdx.x == 0 && tid == 0 && i < 12) ? a.trace + 5 * i : nullptr;
-    if (trace) trace[0] = clock64();
 
     // ---- C: softmax over regions, attended local context, its projection, lt partial ---
-    float al[RU];
+    float al[RU];        // un-normalised soft-max numerators e_r; inv = 1 / sum
+    float inv;
     {
       float sc[RU];
       float mx = -INFINITY;
 #pragma unroll
       for (int r = 0; r < RU; ++r) {
         const float2 hs = *reinterpret_cast<const float2 *>(s_sc + (buf * RMAX + r) * 2);
-        sc[r] = (r < R) ? (hs.x + hs.y) + cl : -INFINITY;
+        sc[r] = (RT || r < R) ? (hs.x + hs.y) + cl : -INFINITY;
         mx = fmaxf(mx, sc[r]);
       }
       // lane r evaluates e_r once for the warp; the numerators are then broadcast
@@ -317,35 +341,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
         al[r] = __shfl_sync(0xffffffffu, e_mine, r);
         den += al[r];
       }
-      const float inv = rcp_approx(den);
-#pragma unroll
-      for (int r = 0; r < RU; ++r) {
-        al[r] *= inv;
-        if (a.alpha_l && tid == r && r < R) a.alpha_l[(static_cast<size_t>(row) * T + t) * R + r] = al[r];
-      }
+      inv = rcp_approx(den);
+      if (a.alpha_l && tid < R) a.alpha_l[(static_cast<size_t>(row) * T + t) * R + tid] = e_mine * inv;
     }
     float cLv[NCOL];
-    float plt = 0.f;
+    float plt = su_lt;
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) {
       const int col = tid + 512 * k;
       float c0 = 0.f, p0 = 0.f;
-      if (col < H) {
+      if (HT || col < H) {
 #pragma unroll
         for (int r = 0; r < RU; ++r) {
-          if (r < R) {
+          if (RT || r < R) {
             c0 = fmaf(al[r], cL0[r * H + col], c0);
             p0 = fmaf(al[r], qL[r * H + col], p0);
           }
         }
-        plt = fmaf(tanh_fast(p0 + slt[k]), ult[k], plt);
+        c0 *= inv;
+        plt = tanh_acc(p0 * inv, slt[k], ult[k], plt);
       }
       cLv[k] = c0;
     }
-    plt = warp_sum(plt);
-    if (lane == 0) s_part[(buf * NWARPS + warp) * 4 + 2] = plt;
+    {
+      // one reduction for the three temporal-score partials (pg, pm from phase A of this frame):
+      // xor-16 leaves (pg, pm) sums in lanes < 16 and (plt, -) in lanes >= 16, xor-8 one value per
+      // lane, then xor 4, 2, 1: totals end up in lane 0 (g), 8 (m), 16 (lt)
+      const bool up = lane & 16;
+      const float keep0 = up ? plt : pg, keep1 = up ? 0.f : pm;
+      const float send0 = up ? pg : plt, send1 = up ? pm : 0.f;
+      const float v0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 16);
+      const float v1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 16);
+      const bool up8 = lane & 8;
+      float v = (up8 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, up8 ? v0 : v1, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      if ((lane & 7) == 0 && lane < 24) s_part[(buf * NWARPS + warp) * 4 + (lane >> 3)] = v;
+    }
     consumer_sync();
-    if (trace) trace[1] = clock64();
 
     // ---- A(i+1): next frame's scores, independent of D(i) below ------------------------
     if (i + 1 < nframes) {
@@ -353,10 +387,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
       uint32_t ph1 = ph;
       if (s1 == nstages) { s1 = 0; ph1 ^= 1; }
       mbar_wait(bar_full + 8 * s1, ph1);
-      if (trace) trace[2] = clock64();
       phase_a(ring + static_cast<size_t>(s1) * stage_floats, buf ^ 1);
     }
-    if (trace) trace[3] = clock64();
 
     // ---- D(i): fold the frame into the three running soft-max states --------------------
     float sc3[3];
@@ -411,7 +443,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) att_stream_kernel(const AttArgs a
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8 * s);
     consumer_sync();
-    if (trace) trace[4] = clock64();
     ++t;
     if (++s == nstages) { s = 0; ph ^= 1; }
   }
@@ -507,12 +538,12 @@ int sm_count() {
 
 size_t stage_bytes(int R, int H) { return (static_cast<size_t>(3) * R * H + 4 * static_cast<size_t>(H)) * 4; }
 
-template <int NCOL, int NV4, int RT>
+template <int NCOL, int NV4, int RT, int HT>
 int launch(const AttArgs &a, int cs, int nstages, cudaStream_t stream) {
   const size_t smem = nstages * stage_bytes(a.R, a.H) + (2 * RMAX * 2 + 2 * NWARPS * 4 + 2) * 4 + 2 * 8 * nstages + 64;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    STAT_CUDA_CHECK(cudaFuncSetAttribute(att_stream_kernel<NCOL, NV4, RT>,
+    STAT_CUDA_CHECK(cudaFuncSetAttribute(att_stream_kernel<NCOL, NV4, RT, HT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     smem_set = smem;
   }
@@ -529,7 +560,7 @@ int launch(const AttArgs &a, int cs, int nstages, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_stream_kernel<NCOL, NV4, RT>, a, nstages, cs));
+  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_stream_kernel<NCOL, NV4, RT, HT>, a, nstages, cs));
   note_launch();
   return STAT_OK;
 }
@@ -561,11 +592,11 @@ int att_stream_launch(const AttArgs &a_in, cudaStream_t stream) {
   STAT_REQUIRE(att_stream_plan(a.rows, a.T, a.R, a.H, &nchunks, &max_parts, &nstages), STAT_EINVAL,
                "att_stream: unsupported shape R=%d H=%d", a.R, a.H);
   const int H = a.H;
-  if (H == 512 && a.R == 8) return launch<1, 2, 8>(a, nchunks, nstages, stream);   // BASELINE shape
-  if (H <= 256) return launch<1, 1, 0>(a, nchunks, nstages, stream);
-  if (H <= 512) return launch<1, 2, 0>(a, nchunks, nstages, stream);
-  if (H <= 768) return launch<2, 3, 0>(a, nchunks, nstages, stream);
-  return launch<2, 4, 0>(a, nchunks, nstages, stream);
+  if (H == 512 && a.R == 8) return launch<1, 2, 8, 512>(a, nchunks, nstages, stream);   // BASELINE shape
+  if (H <= 256) return launch<1, 1, 0, 0>(a, nchunks, nstages, stream);
+  if (H <= 512) return launch<1, 2, 0, 0>(a, nchunks, nstages, stream);
+  if (H <= 768) return launch<2, 3, 0, 0>(a, nchunks, nstages, stream);
+  return launch<2, 4, 0, 0>(a, nchunks, nstages, stream);
 }
 
 }  // namespace stat
