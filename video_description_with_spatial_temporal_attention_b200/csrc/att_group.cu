@@ -1,0 +1,669 @@
+// att_group_kernel: the four soft-attentions of one decode step (model_attention.py:370-435,
+// SURVEY App. A S1-S9) -- the HBM/L2-bound kernel of the path.
+//
+// Work split: one thread-block CLUSTER per decode row; the cs CTAs of a cluster (cs = 1, 2, 4
+// or 8, chosen so that rows*cs fills the SMs once) take contiguous slices of the row's T frames.
+// Inside a CTA, G (<= 4) independent GROUPS of four warps each own whole frames (frame j of the
+// slice goes to group j mod G): a group never synchronises with another group while it streams,
+// so the latencies of one frame (shuffle reductions, group barriers, bulk-copy waits) are hidden
+// by the other groups' frames.
+//
+// Per frame a group receives two bulk-copy chunks in its private shared-memory slots
+//   P = pctxl[t] (R*H) | pctxg[t] | pctxm[t]                  -> scores         (S1, S4, S5)
+//   V = ctxl0[t] (R*H) | qctxl[t] (R*H) | ctxg0[t] | ctxm0[t] -> weighted sums  (S3, S6-S8)
+// issued by the group's own thread 0 (cp.async.bulk + mbarrier complete_tx, L2 evict_last: the
+// blocks are re-read every step).  The group barrier that follows the last read of a slot is what
+// frees it, so the copy of P(j+1) flies during the second half of frame j and V(j+1) during the
+// first half of frame j+1; every byte of the seven context blocks is read exactly once per step.
+// Each thread owns a float4 of columns:
+//   A. sum_h tanh(pctxl + h.Wdl) * Ul for the R regions and the g / m scores (four tanh share one
+//      reciprocal); one butterfly reduction for all R (+2) values, group barrier, soft-max over R
+//   C. alpha-weighted sums cL = sum_r a_r ctxl0_r (S3) and pLT = sum_r a_r qctxl_r + h.Wdlt + blt
+//      (S6: the :416 GEMM folded by linearity), the lt score, group barrier            (S7)
+//   D. fold the frame into the running (max, sum, weighted vector) states of the g / m / lt
+//      temporal soft-maxes; the weighted vectors live in registers.
+// At the end the G group states are merged in shared memory, the cluster synchronises, and rank
+// 0 merges the cs parts through distributed shared memory, applies the selector gate and
+// writes ctx (S8, S9).  No global scratch, no atomics; the merge order is fixed, so results
+// are bit-reproducible.
+// The kernel is launched with programmatic stream serialization: barrier set-up, the score
+// vectors and the first context copies overlap the tail of the previous kernel; the
+// h-projections are read after griddepcontrol.wait.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <type_traits>
+
+#include "kernels.cuh"
+#include "stat_common.cuh"
+
+namespace stat {
+namespace {
+
+constexpr int GMAX = 4;                   // groups per CTA
+constexpr int GT = 128;                   // threads per group
+constexpr int NTHREADS = GMAX * GT;       // 512
+constexpr int RMAX = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  uint32_t spins = 0;
+  do {
+    if (++spins > (1u << 26)) __trap();
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// bulk copy global -> shared with an L2 eviction-priority policy
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+// e^x through the SFU (rel. error 2^-22): soft-max numerators
+__device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * 1.4426950408889634f); }
+
+// acc += u * tanh(x + s): with C = 2 log2(e), sc = s*C and m2u = -2u precomputed,
+// u*tanh(x+s) = u - 2u / (1 + 2^(x*C + sc)); the "+u" terms are pre-summed into acc.
+// Four of them with ONE reciprocal: sum_i m2u_i / d_i = (sum_i m2u_i prod_{j != i} d_j) / prod_j d_j with
+// d_i = 1 + 2^(arg_i).  The exponent arguments are clamped to 30 (tanh is 1 to fp32 precision far
+// below that), so the product of the four denominators stays below 2^121.  5 MUFU per 4 tanh.
+__device__ __forceinline__ float tanh_acc4(const float4 x, const float4 sc, const float4 m2u, float acc) {
+  constexpr float C2 = 2.885390081777927f;
+  const float d0 = ex2_approx(fminf(fmaf(x.x, C2, sc.x), 30.0f)) + 1.0f;
+  const float d1 = ex2_approx(fminf(fmaf(x.y, C2, sc.y), 30.0f)) + 1.0f;
+  const float d2 = ex2_approx(fminf(fmaf(x.z, C2, sc.z), 30.0f)) + 1.0f;
+  const float d3 = ex2_approx(fminf(fmaf(x.w, C2, sc.w), 30.0f)) + 1.0f;
+  const float d01 = d0 * d1, d23 = d2 * d3;
+  const float n01 = fmaf(m2u.y, d0, m2u.x * d1), n23 = fmaf(m2u.w, d2, m2u.z * d3);
+  const float num = fmaf(n23, d01, n01 * d23);
+  return fmaf(num, rcp_approx(d01 * d23), acc);
+}
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float sum4(const float4 v) { return (v.x + v.y) + (v.z + v.w); }
+__device__ __forceinline__ void fma4(float4 &acc, float s, const float4 v) {
+  acc.x = fmaf(s, v.x, acc.x);
+  acc.y = fmaf(s, v.y, acc.y);
+  acc.z = fmaf(s, v.z, acc.z);
+  acc.w = fmaf(s, v.w, acc.w);
+}
+
+// Butterfly reduction of N (power of two, <= 16) per-lane values over the warp: halving steps over
+// the lane bits 4, 3, ... fold pairs of values, plain xor steps finish.  Afterwards v[0] of lane l
+// holds the warp total of value  idx(l) = sum_i bit_{4-i}(l) << i  (i < log2 N).
+template <int N>
+__device__ __forceinline__ void warp_multi_reduce(float (&v)[N], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, o >>= 1) {
+    const bool up = lane & o;
+#pragma unroll
+    for (int k = 0; k < n / 2; ++k) {
+      const float keep = up ? v[2 * k + 1] : v[2 * k];
+      const float send = up ? v[2 * k] : v[2 * k + 1];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+#pragma unroll
+  for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+template <int N>
+__device__ __forceinline__ int multi_reduce_index(int lane) {
+  int idx = 0, o = 16, sh = 0;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, o >>= 1, ++sh) idx |= ((lane & o) ? 1 : 0) << sh;
+  return idx;
+}
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a float from the shared memory of CTA `rank` of this cluster (same offset as `local`)
+__device__ __forceinline__ float ld_dsmem(const float *local, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
+  return v;
+}
+
+// NV = ceil(H / 512) float4 column chunks per thread (columns 4*gt + 512*j);
+// RT = compile-time R (8) or 0 for a runtime R <= 16;  HT = compile-time H (512) or 0.
+template <int NV, int RT, int HT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+    att_group_kernel(const AttArgs a, const int G, const int cs, const uint64_t policy, const int stagger) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int RU = RT ? RT : RMAX;              // unroll bound of the region loops
+  const int H = HT ? HT : a.H, T = a.T;
+  const int R = RT ? RT : a.R;
+  const int RH = R * H;
+  const int p_floats = RH + 2 * H, v_floats = 2 * RH + 2 * H;
+  const int slot_floats = p_floats + v_floats;
+  float *slots = reinterpret_cast<float *>(smem_raw);
+  float *s_red = slots + static_cast<size_t>(G) * slot_floats;   // [G][RMAX + 2][4] per-warp score partials
+  float *s_lt = s_red + GMAX * (RMAX + 2) * 4;                    // [G][4]
+  float *s_gms = s_lt + GMAX * 4;                                 // [G][8] group (max, sum) x 3
+  float *s_cms = s_gms + GMAX * 8;                                // [8] CTA (max, sum) x 3
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_cms + 8);       // fullP[G], fullV[G]
+
+  // cluster <-> decode row; CTA rank <-> slice [t0, t0 + nframes) of its T frames
+  const int row = static_cast<int>(blockIdx.x) / cs;
+  const int rank = cs > 1 ? static_cast<int>(cluster_rank()) : 0;
+  const int t0 = (rank * T) / cs;
+  const int nframes = ((rank + 1) * T) / cs - t0;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = tid >> 7, gt = tid & (GT - 1), gw = gt >> 5;
+  const bool active = g < G;
+  const uint32_t bar_p = smem_u32(bars + g), bar_v = smem_u32(bars + GMAX + g);
+  float *slot_p = slots + static_cast<size_t>(active ? g : 0) * slot_floats;
+  float *slot_v = slot_p + p_floats;
+  const int clip = a.row_clip ? a.row_clip[row] : row;
+  // debug trace (stat_debug_gemm_trace): 16 stamps per (CTA, group), written by the group's thread 0
+  long long *tr = (a.trace && gt == 0) ? a.trace + (static_cast<size_t>(blockIdx.x) * GMAX + g) * 16 : nullptr;
+  if (tr) {
+    unsigned long long gtm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gtm));
+    tr[0] = static_cast<long long>(gtm);
+    tr[1] = clock64();
+  }
+
+  if (tid < 2 * GMAX) mbar_init(smem_u32(bars + tid), 1);
+  if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const uint32_t bytes_rh = static_cast<uint32_t>(RH) * 4u, bytes_h = static_cast<uint32_t>(H) * 4u;
+  auto issue_p = [&](int j) {
+    const size_t frame = static_cast<size_t>(clip) * T + t0 + j;
+    const uint32_t dst = smem_u32(slot_p);
+    mbar_expect_tx(bar_p, static_cast<uint32_t>(p_floats) * 4u);
+    bulk_g2s(dst, a.pctxl + frame * RH, bytes_rh, bar_p, policy);
+    bulk_g2s(dst + bytes_rh, a.pctxg + frame * H, bytes_h, bar_p, policy);
+    bulk_g2s(dst + bytes_rh + bytes_h, a.pctxm + frame * H, bytes_h, bar_p, policy);
+  };
+  auto issue_v = [&](int j) {
+    const size_t frame = static_cast<size_t>(clip) * T + t0 + j;
+    const uint32_t dst = smem_u32(slot_v);
+    mbar_expect_tx(bar_v, static_cast<uint32_t>(v_floats) * 4u);
+    bulk_g2s(dst, a.ctxl0 + frame * RH, bytes_rh, bar_v, policy);
+    bulk_g2s(dst + bytes_rh, a.qctxl + frame * RH, bytes_rh, bar_v, policy);
+    bulk_g2s(dst + 2 * bytes_rh, a.ctxg0 + frame * H, bytes_h, bar_v, policy);
+    bulk_g2s(dst + 2 * bytes_rh + bytes_h, a.ctxm0 + frame * H, bytes_h, bar_v, policy);
+  };
+  // The context blocks were written by the prologue of the batch, long before the kernel this launch
+  // programmatically depends on: their first copies start before that kernel has finished.
+  // Groups 2 and 3 ask for their first frame only when the first chunk of group 0 / 1 has landed:
+  // the first copies of a CTA then arrive in two waves and the groups work out of phase from the
+  // start (compute of one pair overlaps the copies of the other) instead of in lock-step.
+  if (active && gt == 0 && g < nframes) {
+    if (stagger && g >= 2) mbar_wait(smem_u32(bars + g - 2), 0);
+    issue_p(g);
+    issue_v(g);
+  }
+
+  // ---- per-row constants of this thread's columns ------------------------------------------
+  // tanh constants folded (see tanh_acc4): s -> s*C, u -> -2u; the sums of the u values are the
+  // starting values of the score partials
+  constexpr float C2 = 2.885390081777927f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ul[NV], ug[NV], um[NV], ult[NV], sl[NV], sg[NV], sm[NV], slt[NV];
+  float su_l = 0.f, su_g = 0.f, su_m = 0.f, su_lt = 0.f;
+  float beta = 1.0f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 4 * gt + 512 * j;
+    const bool ok = HT || c < H;
+    ul[j] = ok ? ld4(a.Ul + c) : z4;
+    ug[j] = ok ? ld4(a.Ug + c) : z4;
+    um[j] = ok ? ld4(a.Um + c) : z4;
+    ult[j] = ok ? ld4(a.Ult + c) : z4;
+    sl[j] = z4; sg[j] = z4; sm[j] = z4; slt[j] = z4;
+  }
+  const float cl = __ldg(a.cl), cg = __ldg(a.cg), cm = __ldg(a.cm), clt = __ldg(a.clt);
+
+  // everything below reads what the previous kernel wrote (the h-projections)
+  pdl_wait();
+  pdl_trigger();
+  {
+    // The h-projections arrive as k-slice planes, summed here in plane order.  The loads of four
+    // planes are issued together before their values are used (one memory round trip).
+    const float *hp = a.hp + static_cast<size_t>(row) * a.ldhp;
+    float bsel = 0.f;
+    for (int q0 = 0; q0 < a.hp_parts; q0 += 4) {
+      float4 x[4][NV][4];
+      float xb[4];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const bool okq = q0 + qq < a.hp_parts;
+        const float *hq = hp + static_cast<size_t>(okq ? q0 + qq : q0) * a.hp_plane;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c = 4 * gt + 512 * j;
+          const bool ok = okq && (HT || c < H);
+          x[qq][j][0] = ok ? ld4(hq + a.off_sl + c) : z4;
+          x[qq][j][1] = ok ? ld4(hq + a.off_sg + c) : z4;
+          x[qq][j][2] = ok ? ld4(hq + a.off_sm + c) : z4;
+          x[qq][j][3] = ok ? ld4(hq + a.off_slt + c) : z4;
+        }
+        xb[qq] = (okq && a.selector) ? hq[a.off_sel] : 0.f;
+      }
+      auto add4 = [](float4 &d, const float4 v) { d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w; };
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          add4(sl[j], x[qq][j][0]);
+          add4(sg[j], x[qq][j][1]);
+          add4(sm[j], x[qq][j][2]);
+          add4(slt[j], x[qq][j][3]);
+        }
+        bsel += xb[qq];
+      }
+    }
+    beta = a.selector ? sigmoid_acc(bsel) : 1.0f;
+    auto fold = [&](float4 &u, float4 &s, float &su) {
+      su += sum4(u);
+      u.x *= -2.0f; u.y *= -2.0f; u.z *= -2.0f; u.w *= -2.0f;
+      s.x *= C2; s.y *= C2; s.z *= C2; s.w *= C2;
+    };
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      fold(ul[j], sl[j], su_l);
+      fold(ug[j], sg[j], su_g);
+      fold(um[j], sm[j], su_m);
+      fold(ult[j], slt[j], su_lt);
+    }
+  }
+  if (tr) tr[2] = clock64();
+
+  float4 acc[3][NV];
+  float rm[3], rs[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    rm[q] = -INFINITY;
+    rs[q] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[q][j] = z4;
+  }
+
+  // ================================ the frames of this group ================================
+  if (active) {
+    float *red = s_red + g * (RMAX + 2) * 4;
+    uint32_t ph = 0;
+    int fi = 0;
+    for (int j = g; j < nframes; j += G, ph ^= 1, ++fi) {
+      const int t = t0 + j;
+      const float *pL = slot_p, *pG = slot_p + RH, *pM = pG + H;
+      const float *cL0 = slot_v, *qL = slot_v + RH, *G0 = slot_v + 2 * RH, *M0 = G0 + H;
+
+      // ---- A: region scores and the g / m scores of the frame -----------------------------
+      mbar_wait(bar_p, ph);
+      if (tr && fi < 4) tr[3 + 3 * fi] = clock64();
+      {
+        float part[RU];
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+          part[r] = (RT || r < R) ? su_l : 0.f;
+          if (RT || r < R) {
+#pragma unroll
+            for (int jj = 0; jj < NV; ++jj) {
+              const int c = 4 * gt + 512 * jj;
+              if (HT || c < H) part[r] = tanh_acc4(ld4(pL + r * H + c), sl[jj], ul[jj], part[r]);
+            }
+          }
+        }
+        float gm[2] = {su_g, su_m};
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) {
+          const int c = 4 * gt + 512 * jj;
+          if (HT || c < H) {
+            gm[0] = tanh_acc4(ld4(pG + c), sg[jj], ug[jj], gm[0]);
+            gm[1] = tanh_acc4(ld4(pM + c), sm[jj], um[jj], gm[1]);
+          }
+        }
+        warp_multi_reduce<RU>(part, lane);
+        warp_multi_reduce<2>(gm, lane);
+        constexpr int STEP = 32 / RU;          // lanes per region value after the reduction
+        if ((lane & (STEP - 1)) == 0) red[multi_reduce_index<RU>(lane) * 4 + gw] = part[0];
+        if ((lane & 15) == 0) red[(RMAX + (lane >> 4)) * 4 + gw] = gm[0];
+      }
+      group_sync(g);                            // scores complete; every thread is done with slot P
+      if (gt == 0 && j + G < nframes) issue_p(j + G);
+
+      // ---- soft-max over the regions ----------------------------------------------------------
+      float al[RU];        // un-normalised numerators e_r; inv = 1 / sum
+      float inv;
+      {
+        float sc[RU];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+          sc[r] = (RT || r < R) ? sum4(ld4(red + r * 4)) + cl : -INFINITY;
+          mx = fmaxf(mx, sc[r]);
+        }
+        // lane r evaluates e_r once for the warp; the numerators are then broadcast
+        float mine = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < RU; ++r) mine = (lane == r) ? sc[r] : mine;
+        const float e_mine = (lane < R) ? exp_fast(mine - mx) : 0.f;
+        float den = 0.f;
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+          al[r] = __shfl_sync(0xffffffffu, e_mine, r);
+          den += al[r];
+        }
+        inv = rcp_approx(den);
+        if (a.alpha_l && gt < R) a.alpha_l[(static_cast<size_t>(row) * T + t) * R + gt] = e_mine * inv;
+      }
+      float sc3[3];
+      sc3[0] = sum4(ld4(red + RMAX * 4)) + cg;
+      sc3[1] = sum4(ld4(red + (RMAX + 1) * 4)) + cm;
+
+      // ---- C: attended local context, its projection, the lt score --------------------------
+      mbar_wait(bar_v, ph);
+      if (tr && fi < 4) tr[4 + 3 * fi] = clock64();
+      float4 cLv[NV], g0[NV], m0[NV];
+      {
+        float plt = su_lt;
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) {
+          const int c = 4 * gt + 512 * jj;
+          float4 c0 = z4, p0 = z4;
+          g0[jj] = z4;
+          m0[jj] = z4;
+          if (HT || c < H) {
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+              if (RT || r < R) {
+                fma4(c0, al[r], ld4(cL0 + r * H + c));
+                fma4(p0, al[r], ld4(qL + r * H + c));
+              }
+            }
+            c0.x *= inv; c0.y *= inv; c0.z *= inv; c0.w *= inv;
+            p0.x *= inv; p0.y *= inv; p0.z *= inv; p0.w *= inv;
+            plt = tanh_acc4(p0, slt[jj], ult[jj], plt);
+            g0[jj] = ld4(G0 + c);
+            m0[jj] = ld4(M0 + c);
+          }
+          cLv[jj] = c0;
+        }
+        plt = warp_sum(plt);
+        if (lane == 0) s_lt[g * 4 + gw] = plt;
+      }
+      group_sync(g);                            // lt score complete; every thread is done with slot V
+      if (gt == 0 && j + G < nframes) issue_v(j + G);
+      sc3[2] = sum4(ld4(s_lt + g * 4)) + clt;
+      if (a.att_scores && gt == 0) {
+        const size_t plane = static_cast<size_t>(a.rows) * T, at = static_cast<size_t>(row) * T + t;
+        a.att_scores[at] = sc3[0];
+        a.att_scores[plane + at] = sc3[1];
+        a.att_scores[2 * plane + at] = sc3[2];
+      }
+
+      // ---- D: fold the frame into the three running soft-max states ---------------------------
+      // (the scores are uniform over the group, so the rescale branch never diverges)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        float e = 1.0f;
+        if (sc3[q] > rm[q]) {
+          const float keep = exp_fast(rm[q] - sc3[q]);      // 0 on the first frame (rm = -inf)
+          rm[q] = sc3[q];
+          rs[q] *= keep;
+#pragma unroll
+          for (int jj = 0; jj < NV; ++jj) {
+            acc[q][jj].x *= keep; acc[q][jj].y *= keep; acc[q][jj].z *= keep; acc[q][jj].w *= keep;
+          }
+        } else {
+          e = exp_fast(sc3[q] - rm[q]);
+        }
+        rs[q] += e;
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) fma4(acc[q][jj], e, q == 0 ? g0[jj] : (q == 1 ? m0[jj] : cLv[jj]));
+      }
+      if (tr && fi < 4) tr[5 + 3 * fi] = clock64();
+    }
+
+    // park the group state in the group's own (drained) V slot
+    if (gt == 0) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { s_gms[g * 8 + 2 * q] = rm[q]; s_gms[g * 8 + 2 * q + 1] = rs[q]; }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int jj = 0; jj < NV; ++jj) {
+        const int c = 4 * gt + 512 * jj;
+        if (HT || c < H) *reinterpret_cast<float4 *>(slot_v + q * H + c) = acc[q][jj];
+      }
+  }
+  __syncthreads();
+
+  // ---- merge of the G group states: thread <-> columns tid + 512 k -------------------------------
+  constexpr int NCOL = NV;
+  float om[3], os[3], ov[3][NCOL];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    float mx = -INFINITY;
+    for (int p = 0; p < G; ++p) mx = fmaxf(mx, s_gms[p * 8 + 2 * q]);
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) ov[q][k] = 0.f;
+    for (int p = 0; p < G; ++p) {
+      const float mp = s_gms[p * 8 + 2 * q];
+      const float w = (mp == -INFINITY) ? 0.f : expf(mp - mx);
+      den = fmaf(w, s_gms[p * 8 + 2 * q + 1], den);
+      const float *vp = slots + static_cast<size_t>(p) * slot_floats + p_floats + q * H;
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) {
+        const int col = tid + 512 * k;
+        if (col < H) ov[q][k] = fmaf(w, vp[col], ov[q][k]);
+      }
+    }
+    om[q] = mx;
+    os[q] = den;
+  }
+  float *ctx = a.ctx + static_cast<size_t>(row) * H;
+  if (cs == 1) {
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) {
+      const int col = tid + 512 * k;
+      if (col < H) ctx[col] = beta * (ov[0][k] / os[0] + ov[1][k] / os[1] + ov[2][k] / os[2]);
+    }
+    return;
+  }
+  // park the CTA state in group 0's P slot (nobody reads it any more) for the cluster merge
+  float *s_vec = slots;               // [3][H]
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { s_cms[2 * q] = om[q]; s_cms[2 * q + 1] = os[q]; }
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) {
+      const int col = tid + 512 * k;
+      if (col < H) s_vec[q * H + col] = ov[q][k];
+    }
+  cluster_sync_all();
+  if (rank == 0) {
+    // all remote values first (independent DSMEM loads), then the arithmetic
+    float pm[3][8], psum[3][8], v[3][8][NCOL];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const bool okp = p < cs;
+        pm[q][p] = okp ? ld_dsmem(s_cms + 2 * q, p) : -INFINITY;
+        psum[q][p] = okp ? ld_dsmem(s_cms + 2 * q + 1, p) : 0.f;
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) {
+          const int col = tid + 512 * k;
+          v[q][p][k] = (okp && col < H) ? ld_dsmem(s_vec + q * H + col, p) : 0.f;
+        }
+      }
+    float o[NCOL];
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) o[k] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) mx = fmaxf(mx, pm[q][p]);
+      float w[8], den = 0.f;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        w[p] = (p < cs) ? expf(pm[q][p] - mx) : 0.f;
+        den = fmaf(w[p], psum[q][p], den);
+      }
+      const float inv = 1.0f / den;
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) {
+        float num = 0.f;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) num = fmaf(w[p], v[q][p][k], num);
+        o[k] = fmaf(num, inv, o[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) {
+      const int col = tid + 512 * k;
+      if (col < H) ctx[col] = beta * o[k];
+    }
+  }
+  if (tr) tr[15] = clock64();
+  cluster_sync_all();       // partners keep their shared memory alive until rank 0 has read it
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;   // B200; also the answer when sizes are queried without a device
+  }
+  return n;
+}
+
+size_t frame_bytes(int R, int H) { return (static_cast<size_t>(3) * R * H + 4 * static_cast<size_t>(H)) * 4; }
+constexpr size_t SMEM_EXTRA = (GMAX * (RMAX + 2) * 4 + GMAX * 4 + GMAX * 8 + 8) * 4 + 2 * GMAX * 8 + 128;
+constexpr size_t SMEM_MAX = 227 * 1024;
+
+// L2 eviction priority of the context-block copies: the blocks are re-read on every decode step,
+// the weights and activations between two attention launches are streamed once.
+//   STAT_ATT_L2 = last (default) | normal | first
+uint64_t l2_policy() {
+  static uint64_t pol = 0;
+  if (pol == 0) {
+    const char *ps = getenv("STAT_L2_PERSIST");
+    if (ps && atoi(ps) > 0) {
+      int dev = 0, mx = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&mx, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      size_t want = static_cast<size_t>(atoi(ps)) << 20;
+      if (want > static_cast<size_t>(mx)) want = mx;
+      cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      fprintf(stderr, "[stat] persisting L2 max %d bytes, set %zu -> %s\n", mx, want, cudaGetErrorString(e));
+    }
+    const char *e = getenv("STAT_ATT_L2");
+    pol = 0x14F0000000000000ull;                               // evict_last
+    if (e && !strcmp(e, "normal")) pol = 0x1000000000000000ull;
+    if (e && !strcmp(e, "first")) pol = 0x12F0000000000000ull;
+  }
+  return pol;
+}
+
+long long *g_group_trace = nullptr;
+
+template <int NV, int RT, int HT>
+int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
+  const size_t smem = G * frame_bytes(a.R, a.H) + SMEM_EXTRA;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    STAT_CUDA_CHECK(cudaFuncSetAttribute(att_group_kernel<NV, RT, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(a.rows) * cs);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1 + pdl_attr(attr + 1);
+  static int stagger = -1;
+  if (stagger < 0) {
+    const char *e = getenv("STAT_ATT_STAGGER");
+    stagger = (e && e[0] == '0') ? 0 : 1;
+  }
+  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_group_kernel<NV, RT, HT>, a, G, cs, l2_policy(), stagger));
+  note_launch();
+  return STAT_OK;
+}
+
+}  // namespace
+
+// plan shared by the launcher and the workspace layout: cluster size (CTAs per decode row) and
+// groups per CTA; the partial soft-max states never leave the cluster (max_parts = 1)
+bool att_group_plan(int rows, int T, int R, int H, int *cluster, int *groups, int *max_parts) {
+  if ((H & 3) != 0 || H > 1024 || R > RMAX || R < 1 || rows < 1 || T < 1) return false;
+  int G = static_cast<int>((SMEM_MAX - SMEM_EXTRA) / frame_bytes(R, H));
+  if (G < 1) return false;
+  if (G > GMAX) G = GMAX;
+  int cs = 1;
+  while (cs < 8 && 2 * cs <= T && static_cast<long long>(rows) * 2 * cs <= sm_count()) cs *= 2;
+  *cluster = cs;
+  *groups = G;
+  *max_parts = 1;
+  return true;
+}
+
+// debug: device buffer of >= ctas * 64 int64 (clock stamps per CTA and group), or null
+void att_group_set_trace(long long *p) { g_group_trace = p; }
+
+int att_group_launch(const AttArgs &a_in, cudaStream_t stream) {
+  AttArgs a = a_in;
+  a.trace = g_group_trace;
+  int cs, G, S;
+  STAT_REQUIRE(att_group_plan(a.rows, a.T, a.R, a.H, &cs, &G, &S), STAT_EINVAL,
+               "att_group: unsupported shape R=%d H=%d", a.R, a.H);
+  const int H = a.H;
+  if (H == 512 && a.R == 8) return launch<1, 8, 512>(a, cs, G, stream);   // BASELINE shape
+  if (H <= 512) return launch<1, 0, 0>(a, cs, G, stream);
+  return launch<2, 0, 0>(a, cs, G, stream);
+}
+
+}  // namespace stat

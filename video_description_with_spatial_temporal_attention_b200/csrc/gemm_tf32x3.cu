@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "stat_common.cuh"
 
@@ -45,6 +46,18 @@ const char *get_error() { return g_err; }
 
 static unsigned long long g_launches = 0;
 void note_launch() { ++g_launches; }
+
+int pdl_attr(cudaLaunchAttribute *attr) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STAT_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!on) return 0;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  return 1;
+}
 unsigned long long launch_count() { return g_launches; }
 
 static long long *g_trace = nullptr;
@@ -303,6 +316,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (trace && threadIdx.x == 0) trace[1] = clock64();
+  // barrier set-up and the tensor-memory allocation above overlap the previous kernel's tail; its
+  // results (an operand, an addend) are read from here on.  The successor may be scheduled now:
+  // this CTA already holds everything it can block on.
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -545,9 +563,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 // ---------------------------------------------------------------------------
 // plain fp32 SIMT version of the same contract (device-side cross-check)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gemm_simt_kernel(const float *__restrict__ P, int ldp,
-                                                        const float *__restrict__ Q, int ldq,
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const float *P, int ldp, const float *Q, int ldq,
                                                         const DevArgs args) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sP[32][33];
   __shared__ float sQ[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -638,9 +657,16 @@ int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   const int nk_slice = ((a.K + BK - 1) / BK + da.ksplit - 1) / da.ksplit;
   db.stages = nk_slice < Cfg<BQ>::MAX_STAGES ? nk_slice : Cfg<BQ>::MAX_STAGES;
   dim3 grid((a.NQ + BQ - 1) / BQ, (a.NP + BP - 1) / BP, da.ksplit);
-  gemm_tf32x3_kernel<BQ, TS><<<grid, NTHREADS, Cfg<BQ>::smem_bytes(db.stages), stream>>>(tmP, tmQ, db);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = Cfg<BQ>::smem_bytes(db.stages);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr(attr);
+  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BQ, TS>, tmP, tmQ, db));
   note_launch();
-  STAT_CUDA_CHECK(cudaGetLastError());
   return STAT_OK;
 }
 
@@ -675,10 +701,7 @@ int gemm_launch(const GemmArgs &a, cudaStream_t stream) {
                       (reinterpret_cast<uintptr_t>(a.Q) & 15) == 0;
   if (g_gemm_impl == 1 || !tma_ok) {
     dim3 grid((a.NQ + 31) / 32, (a.NP + 31) / 32, da.ksplit);
-    gemm_simt_kernel<<<grid, 256, 0, stream>>>(a.P, a.ldp, a.Q, a.ldq, da);
-    note_launch();
-    STAT_CUDA_CHECK(cudaGetLastError());
-    return STAT_OK;
+    return launch_pdl(gemm_simt_kernel, grid, dim3(256), 0, stream, a.P, a.ldp, a.Q, a.ldq, da);
   }
   if (a.nseg == 2) {
     const int tile = a.feat_on_p ? BP : 128;

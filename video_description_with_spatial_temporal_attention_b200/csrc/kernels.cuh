@@ -35,6 +35,11 @@ int att_step_launch(const AttArgs &a, cudaStream_t stream);
 // a.S = capacity (parts per row) of rec_vec / rec_ms; a.Tc unused.
 bool att_stream_plan(int rows, int T, int R, int H, int *nchunks, int *max_parts, int *nstages);
 int att_stream_launch(const AttArgs &a, cudaStream_t stream);
+// att_group.cu: four independent four-warp groups per CTA, each streaming whole frames (H % 4 == 0,
+// one frame fits in shared memory).  a.S = capacity (parts per row) of rec_vec / rec_ms.
+bool att_group_plan(int rows, int T, int R, int H, int *nctas, int *groups, int *max_parts);
+int att_group_launch(const AttArgs &a, cudaStream_t stream);
+void att_group_set_trace(long long *p);
 
 // ---- recurrent.cu --------------------------------------------------------------
 // LSTM gates + state update (model_attention.py:437-457) and the emb / bias part of

@@ -11,6 +11,8 @@ namespace {
 // gates: S10-S13 of SURVEY App. A  (model_attention.py:437-457)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) gates_kernel(const GateArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.y;
   const int j = blockIdx.x * 128 + threadIdx.x;
   const long long tok = a.tok_prev ? a.tok_prev[row] : -1;
@@ -74,6 +76,8 @@ __global__ void __launch_bounds__(128) gates_kernel(const GateArgs a) {
 }
 
 __global__ void __launch_bounds__(256) zact_kernel(const ZactArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= a.rows * a.E) return;
   const int row = i / a.E, e = i - row * a.E;
@@ -88,6 +92,8 @@ __global__ void __launch_bounds__(256) zact_kernel(const ZactArgs a) {
 // gates for even H: two adjacent units per thread, every load of the thread (<= 4 + 4 k-slice
 // planes x 4 gates, the token's table row, the old state) issued before the first use
 __global__ void __launch_bounds__(128) gates2_kernel(const GateArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.y;
   const int j = (blockIdx.x * 128 + threadIdx.x) * 2;
   const long long tok = a.tok_prev ? a.tok_prev[row] : -1;
@@ -186,6 +192,8 @@ __device__ __forceinline__ void pick_fold(float x, int v, float &m, int &bi, flo
 }
 
 __global__ void __launch_bounds__(256) pick_kernel(const PickArgs a) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
   __shared__ float s_sum[8];
@@ -345,30 +353,18 @@ int gates_launch(const GateArgs &a, cudaStream_t stream) {
                     a.hp_parts <= 4 && a.pc_parts <= 4 && (a.hp_plane % 2 == 0) && (a.pc_plane % 2 == 0);
   if (vec2) {
     dim3 grid((w / 2 + 127) / 128 + ((w % 2) ? 1 : 0), a.rows);
-    gates2_kernel<<<grid, 128, 0, stream>>>(a);
-    note_launch();
-    STAT_CUDA_CHECK(cudaGetLastError());
-    return STAT_OK;
+    return launch_pdl(gates2_kernel, grid, dim3(128), 0, stream, a);
   }
   dim3 grid((w + 127) / 128, a.rows);
-  gates_kernel<<<grid, 128, 0, stream>>>(a);
-  note_launch();
-  STAT_CUDA_CHECK(cudaGetLastError());
-  return STAT_OK;
+  return launch_pdl(gates_kernel, grid, dim3(128), 0, stream, a);
 }
 
 int zact_launch(const ZactArgs &a, cudaStream_t stream) {
-  zact_kernel<<<(a.rows * a.E + 255) / 256, 256, 0, stream>>>(a);
-  note_launch();
-  STAT_CUDA_CHECK(cudaGetLastError());
-  return STAT_OK;
+  return launch_pdl(zact_kernel, dim3((a.rows * a.E + 255) / 256), dim3(256), 0, stream, a);
 }
 
 int pick_launch(const PickArgs &a, cudaStream_t stream) {
-  pick_kernel<<<a.rows, 256, 0, stream>>>(a);
-  note_launch();
-  STAT_CUDA_CHECK(cudaGetLastError());
-  return STAT_OK;
+  return launch_pdl(pick_kernel, dim3(a.rows), dim3(256), 0, stream, a);
 }
 
 int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, int T, int D,

@@ -3,6 +3,7 @@
 // gemm_tf32x3.cu / att_step.cu / recurrent.cu.  Everything is enqueued on the
 // caller's stream; nothing here allocates, synchronises or touches the host side
 // of a tensor.
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.cuh"
@@ -152,7 +153,7 @@ struct Ws {
   size_t counters, tok_prev, alive;  // byte-typed regions (still float offsets)
   size_t total;                      // floats
   int ldhp, ldpc, ldl, S, Tc;
-  bool stream_att;   // att_stream_kernel (TMA ring) vs the generic att_step_kernel
+  int att_impl;      // 2 = att_group_kernel, 1 = att_stream_kernel (TMA ring), 0 = the generic att_step_kernel
 };
 
 // k-slices for a skinny (rows <= 128) projection: enough CTAs to cover the SMs once
@@ -194,8 +195,16 @@ Ws ws_layout(const StatDims &d, int rows) {
   };
   int nchunks = 0, nparts = 0, nstages = 0;
   // (the streaming kernel reads the h-projection rows as float4: their offset E must be 16-byte aligned)
-  w.stream_att = (d.E % 4 == 0) && att_stream_plan(rows, d.T, d.R, d.H, &nchunks, &nparts, &nstages);
-  if (w.stream_att) {
+  w.att_impl = 0;
+  if (d.E % 4 == 0) {
+    const char *impl = getenv("STAT_ATT_IMPL");      // "ring": the previous producer/consumer-ring kernel
+    if (impl && !strcmp(impl, "ring")) {
+      if (att_stream_plan(rows, d.T, d.R, d.H, &nchunks, &nparts, &nstages)) w.att_impl = 1;
+    } else if (!(impl && !strcmp(impl, "generic")) && att_group_plan(rows, d.T, d.R, d.H, &nchunks, &nstages, &nparts)) {
+      w.att_impl = 2;
+    }
+  }
+  if (w.att_impl) {
     w.S = nparts;
     w.Tc = 0;
   } else {
@@ -359,6 +368,12 @@ AttArgs att_args(const StatDims &d, const Prep &p, const float *P, const Ws &w, 
   return a;
 }
 
+int att_launch(const Ws &w, const AttArgs &a, cudaStream_t st) {
+  if (w.att_impl == 2) return att_group_launch(a, st);
+  if (w.att_impl == 1) return att_stream_launch(a, st);
+  return att_step_launch(a, st);
+}
+
 struct StepIO {
   int rows;
   const int32_t *row_clip;
@@ -400,7 +415,7 @@ int step_core(const StatDims &d, const Prep &p, const float *P, const Ws &w, flo
   AttArgs a = att_args(d, p, P, w, W, rows, io.row_clip, io.att_scores, io.alpha_l);
   {
     ProfScope ps(PH_ATT, st);
-    STAT_TRY(w.stream_att ? att_stream_launch(a, st) : att_step_launch(a, st));
+    STAT_TRY(att_launch(w, a, st));
   }
   // ctx.Wc (gates, :439) and ctx.ff_logit_ctxglm_W (:691-693) in one pass
   {
@@ -513,6 +528,7 @@ int stat_profile_collect(float *ms_by_phase, int *count_by_phase, int nphase) {
 int stat_debug_gemm_trace(void *dev_buffer_64_int64) {
   gemm_set_trace(static_cast<long long *>(dev_buffer_64_int64));
   att_set_trace(static_cast<long long *>(dev_buffer_64_int64));
+  att_group_set_trace(static_cast<long long *>(dev_buffer_64_int64));
   return STAT_OK;
 }
 
@@ -866,7 +882,7 @@ int stat_attention(const StatDims *d, const void *prepared, void *ws, int rows, 
   AttArgs a = att_args(*d, p, static_cast<const float *>(prepared), w, static_cast<float *>(ws), rows, row_clip,
                        nullptr, nullptr);
   ProfScope ps(PH_ATT, st);
-  return w.stream_att ? att_stream_launch(a, st) : att_step_launch(a, st);
+  return att_launch(w, a, st);
 }
 
 int stat_gemm(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K,

@@ -15,6 +15,12 @@ void set_error(const char *fmt, ...);
 // every kernel launch of the library passes through here (stat_launch_count)
 void note_launch();
 
+// Programmatic dependent launch (STAT_PDL=0 switches it off): fills attr[0] and returns the number
+// of launch attributes (0 or 1).  Kernels launched this way call pdl_wait() before the first read of
+// anything the previous kernel wrote, and pdl_trigger() after it (never before: a kernel whose
+// own dependency is still pending must not let its successor start).
+int pdl_attr(cudaLaunchAttribute *attr);
+
 #define STAT_CUDA_CHECK(expr)                                                      \
   do {                                                                             \
     cudaError_t e__ = (expr);                                                      \
@@ -61,6 +67,25 @@ __device__ __forceinline__ float tanh_fast(float x) {
   float t = ex2_approx(x * 2.885390081777927f);
   return fmaf(-2.0f, rcp_approx(t + 1.0f), 1.0f);
 }
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-serialization attribute
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr(attr);
+  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+  note_launch();
+  return STAT_OK;
+}
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // accurate variants for the few elementwise sites outside the attention loop
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
