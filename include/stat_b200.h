@@ -92,6 +92,16 @@ const char *stat_last_error(void);
  * GEMM (device-side cross-checks used by the GPU tests; never a CPU path). */
 int stat_set_gemm_impl(int impl);
 
+/* ---- L2 residency of the context blocks (no reference counterpart) -----------
+ * The attention kernel re-reads the projected context blocks of the batch on
+ * every decode step and copies them with the L2 evict_last priority; those
+ * lines outlive the weights streamed between two steps only inside the
+ * persisting-L2 carve-out of the device.  Sets that carve-out
+ * (cudaLimitPersistingL2CacheSize, a per-device setting of the calling
+ * process): bytes < 0 = the device maximum (79 MB of the 126 MB on B200),
+ * 0 = none.  Returns the size now in effect, or a negative STAT_E* code. */
+long long stat_set_l2_persist(long long bytes);
+
 /* ---- parameter preparation (once per parameter set) ----------------------
  * Packs the reference tensors into the K-major concatenations the kernels
  * read and builds the token->gate-input table EW = Wemb.decoder_W + decoder_b

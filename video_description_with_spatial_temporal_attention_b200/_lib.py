@@ -54,6 +54,8 @@ def _declare(lib):
     lib.stat_version.restype = i32
     lib.stat_last_error.restype = C.c_char_p
     lib.stat_set_gemm_impl.argtypes = [i32]
+    lib.stat_set_l2_persist.argtypes = [C.c_longlong]
+    lib.stat_set_l2_persist.restype = C.c_longlong
     lib.stat_prepared_bytes.restype = sz
     lib.stat_prepared_bytes.argtypes = [dp]
     lib.stat_prepare_params.argtypes = [dp, C.POINTER(StatParams), vp, vp]

@@ -577,21 +577,12 @@ constexpr size_t SMEM_EXTRA = (GMAX * (RMAX + 2) * 4 + GMAX * 4 + GMAX * 8 + 8) 
 constexpr size_t SMEM_MAX = 227 * 1024;
 
 // L2 eviction priority of the context-block copies: the blocks are re-read on every decode step,
-// the weights and activations between two attention launches are streamed once.
+// the weights and activations between two attention launches are streamed once.  evict_last
+// lines survive only inside the persisting-L2 carve-out (stat_set_l2_persist).
 //   STAT_ATT_L2 = last (default) | normal | first
 uint64_t l2_policy() {
   static uint64_t pol = 0;
   if (pol == 0) {
-    const char *ps = getenv("STAT_L2_PERSIST");
-    if (ps && atoi(ps) > 0) {
-      int dev = 0, mx = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&mx, cudaDevAttrMaxPersistingL2CacheSize, dev);
-      size_t want = static_cast<size_t>(atoi(ps)) << 20;
-      if (want > static_cast<size_t>(mx)) want = mx;
-      cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-      fprintf(stderr, "[stat] persisting L2 max %d bytes, set %zu -> %s\n", mx, want, cudaGetErrorString(e));
-    }
     const char *e = getenv("STAT_ATT_L2");
     pol = 0x14F0000000000000ull;                               // evict_last
     if (e && !strcmp(e, "normal")) pol = 0x1000000000000000ull;
@@ -623,7 +614,15 @@ int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1 + pdl_attr(attr + 1);
+  // An early-launched attention CTA would sit on a whole SM (all of its shared memory) while it waits
+  // for the h-projections, in the way of the readout chain running on the side stream: by default
+  // this kernel is launched with full stream serialization (STAT_PDL_ATT=1 to try otherwise).
+  static int pdl_att = -1;
+  if (pdl_att < 0) {
+    const char *e = getenv("STAT_PDL_ATT");
+    pdl_att = (e && e[0] == '1') ? 1 : 0;
+  }
+  cfg.numAttrs = 1 + (pdl_att ? pdl_attr(attr + 1) : 0);
   static int stagger = -1;
   if (stagger < 0) {
     const char *e = getenv("STAT_ATT_STAGGER");

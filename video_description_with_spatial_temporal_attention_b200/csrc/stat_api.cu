@@ -405,24 +405,31 @@ int h_proj(const StatDims &d, const Prep &p, const float *P, const Ws &w, float 
                w.hpz_plane);
 }
 
-// One decode step given the h-projections of h_in in hpz (S1-S13), then the readout up to the logits
-// (R1-R3 without the softmax).  next_hproj: also leave the h-projections of h_out in hpz for the next
-// step (same pass over h_out as the readout term).
-int step_core(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io,
-              bool next_hproj, cudaStream_t st) {
-  const int H = d.H, E = d.E, V = d.V, rows = io.rows;
-  const bool ctx2out = (d.flags & STAT_CTX2OUT) != 0;
+// One decode step given the h-projections of h_in in hpz, in three launch groups:
+//   step_att   S1-S9 and the context projections (ctx.Wc for the gates, ctx.ff_logit_ctxglm_W)
+//   step_gates S10-S13, then every product of the new hidden state: the readout term and, when
+//              next_hproj, the attention queries / h.U / selector logit of the NEXT step
+//   step_out   R1-R3 without the soft-max: readout activation and the vocabulary logits
+// step_out(t) neither reads anything step_att(t+1) writes nor writes anything it reads, so the
+// decode loops run the two on different streams (Overlap below).
+int step_att(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io,
+             cudaStream_t st) {
+  const int H = d.H, rows = io.rows;
   AttArgs a = att_args(d, p, P, w, W, rows, io.row_clip, io.att_scores, io.alpha_l);
   {
     ProfScope ps(PH_ATT, st);
     STAT_TRY(att_launch(w, a, st));
   }
   // ctx.Wc (gates, :439) and ctx.ff_logit_ctxglm_W (:691-693) in one pass
-  {
-    ProfScope ps(PH_CTXPROJ, st);
-    STAT_TRY(dense(W + w.ctx, H, rows, P + p.WcT, H, p.NC, nullptr, W + w.pre_c, w.ldpc, 0, 1.f, 1.f, nullptr, 0,
-                   st, w.ksc, w.pc_plane));
-  }
+  ProfScope ps(PH_CTXPROJ, st);
+  return dense(W + w.ctx, H, rows, P + p.WcT, H, p.NC, nullptr, W + w.pre_c, w.ldpc, 0, 1.f, 1.f, nullptr, 0, st,
+               w.ksc, w.pc_plane);
+}
+
+int step_gates(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io,
+               bool next_hproj, cudaStream_t st) {
+  const int H = d.H, E = d.E, V = d.V, rows = io.rows;
+  const bool ctx2out = (d.flags & STAT_CTX2OUT) != 0;
   GateArgs g;
   memset(&g, 0, sizeof(g));
   g.rows = rows; g.H = H; g.E = E; g.V = V;
@@ -442,11 +449,6 @@ int step_core(const StatDims &d, const Prep &p, const float *P, const Ws &w, flo
     ProfScope ps(PH_GATES, st);
     STAT_TRY(gates_launch(g, st));
   }
-  // z = tanh(dp_h*h . Wl + b + emb + ctx.Wctx) * dp_z   (:684-696)
-  ZactArgs z;
-  memset(&z, 0, sizeof(z));
-  z.rows = rows; z.E = E;
-  z.zadd = W + w.zadd; z.dp_z = io.dp_z; z.z = W + w.z;
   if (io.dp_h) {
     // explicit dropout mask on h (use_noise=1): the readout multiplies h*mask, the next cell h itself
     {
@@ -454,9 +456,22 @@ int step_core(const StatDims &d, const Prep &p, const float *P, const Ws &w, flo
       STAT_TRY(dense(W + w.hd, H, rows, P + p.WlT, H, E, nullptr, W + w.zpre, E, 0, 1.f, 1.f, nullptr, 0, st));
     }
     if (next_hproj) STAT_TRY(h_proj(d, p, P, w, W, io.h_out, rows, 1, st));
+    return STAT_OK;
+  }
+  return h_proj(d, p, P, w, W, io.h_out, rows, next_hproj ? 3 : 2, st);
+}
+
+int step_out(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io,
+             cudaStream_t st) {
+  const int E = d.E, V = d.V, rows = io.rows;
+  // z = tanh(dp_h*h . Wl + b + emb + ctx.Wctx) * dp_z   (:684-696)
+  ZactArgs z;
+  memset(&z, 0, sizeof(z));
+  z.rows = rows; z.E = E;
+  z.zadd = W + w.zadd; z.dp_z = io.dp_z; z.z = W + w.z;
+  if (io.dp_h) {
     z.zpre = W + w.zpre; z.ldz = E; z.parts = 1; z.plane = 0; z.alpha = 1.0f;
   } else {
-    STAT_TRY(h_proj(d, p, P, w, W, io.h_out, rows, next_hproj ? 3 : 2, st));
     z.zpre = W + w.hpz; z.ldz = w.ldhp; z.parts = w.ksa; z.plane = w.hpz_plane; z.alpha = 0.5f;
   }
   {
@@ -465,8 +480,64 @@ int step_core(const StatDims &d, const Prep &p, const float *P, const Ws &w, flo
   }
   // logits = z . ff_logit_W + b  (:704-705)
   ProfScope pl(PH_LOGITS, st);
-  STAT_TRY(dense(W + w.z, E, rows, P + p.WvT, E, V, P + p.bv, W + w.logits, w.ldl, 0, 1.f, 1.f, nullptr, 0, st));
-  return STAT_OK;
+  return dense(W + w.z, E, rows, P + p.WvT, E, V, P + p.bv, W + w.logits, w.ldl, 0, 1.f, 1.f, nullptr, 0, st);
+}
+
+// The readout chain of step t (step_out + the vocabulary reduction) on a side stream, next to the
+// attention of step t+1 on the caller's stream; the two meet again at the gates of step t+1, which
+// need the token picked in step t.  Event based, so it also works under stream capture.
+struct Overlap {
+  cudaStream_t main_ = nullptr;
+  bool on_ = false, side_busy_ = false;
+  static cudaStream_t s_side;
+  static cudaEvent_t s_state, s_done;
+  int open(cudaStream_t st, bool enable) {
+    main_ = st;
+    on_ = false;
+    side_busy_ = false;
+    if (!enable) return STAT_OK;
+    if (!s_side) {
+      STAT_CUDA_CHECK(cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking));
+      STAT_CUDA_CHECK(cudaEventCreateWithFlags(&s_state, cudaEventDisableTiming));
+      STAT_CUDA_CHECK(cudaEventCreateWithFlags(&s_done, cudaEventDisableTiming));
+    }
+    on_ = true;
+    return STAT_OK;
+  }
+  cudaStream_t side() const { return on_ ? s_side : main_; }
+  // the new hidden state and its products are enqueued on the caller's stream: the side stream may go on
+  int state_ready() {
+    if (!on_) return STAT_OK;
+    STAT_CUDA_CHECK(cudaEventRecord(s_state, main_));
+    STAT_CUDA_CHECK(cudaStreamWaitEvent(s_side, s_state, 0));
+    return STAT_OK;
+  }
+  // the readout chain of this step is enqueued on the side stream
+  int side_enqueued() {
+    if (!on_) return STAT_OK;
+    STAT_CUDA_CHECK(cudaEventRecord(s_done, s_side));
+    side_busy_ = true;
+    return STAT_OK;
+  }
+  // the caller's stream needs what the side stream produced (picked token, free readout buffers)
+  int join() {
+    if (!on_ || !side_busy_) return STAT_OK;
+    STAT_CUDA_CHECK(cudaStreamWaitEvent(main_, s_done, 0));
+    side_busy_ = false;
+    return STAT_OK;
+  }
+};
+cudaStream_t Overlap::s_side = nullptr;
+cudaEvent_t Overlap::s_state = nullptr;
+cudaEvent_t Overlap::s_done = nullptr;
+
+bool overlap_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STAT_OVERLAP");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on && !g_prof_on;
 }
 
 }  // namespace
@@ -530,6 +601,16 @@ int stat_debug_gemm_trace(void *dev_buffer_64_int64) {
   att_set_trace(static_cast<long long *>(dev_buffer_64_int64));
   att_group_set_trace(static_cast<long long *>(dev_buffer_64_int64));
   return STAT_OK;
+}
+
+long long stat_set_l2_persist(long long bytes) {
+  if (check_device() != STAT_OK) return STAT_ECUDA;
+  int dev = 0, mx = 0;
+  STAT_CUDA_CHECK(cudaGetDevice(&dev));
+  STAT_CUDA_CHECK(cudaDeviceGetAttribute(&mx, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  size_t want = (bytes < 0 || bytes > mx) ? static_cast<size_t>(mx) : static_cast<size_t>(bytes);
+  STAT_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+  return static_cast<long long>(want);
 }
 
 int stat_set_gemm_impl(int impl) {
@@ -761,6 +842,8 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
   STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
                                     sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
   STAT_TRY(h_proj(*d, p, P, w, W, W + w.h, B, 1, st));
+  Overlap ov;
+  STAT_TRY(ov.open(st, overlap_enabled()));
   for (int t = 0; t < L; ++t) {
     StepIO io;
     memset(&io, 0, sizeof(io));
@@ -774,7 +857,11 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
     io.h_all = out_h ? out_h + static_cast<size_t>(t) * B * H : nullptr;
     io.alpha_l = out_alpha_l ? out_alpha_l + static_cast<size_t>(t) * B * T * R : nullptr;
     io.att_scores = want_t ? W + w.att_scores : nullptr;
-    STAT_TRY(step_core(*d, p, P, w, W, io, t + 1 < L, st));
+    STAT_TRY(step_att(*d, p, P, w, W, io, st));
+    STAT_TRY(ov.join());
+    STAT_TRY(step_gates(*d, p, P, w, W, io, t + 1 < L, st));
+    STAT_TRY(ov.state_ready());
+    STAT_TRY(step_out(*d, p, P, w, W, io, ov.side()));
     if (want_t) {
       const size_t n = static_cast<size_t>(B) * T;
       if (out_alpha_g) STAT_TRY(softmax_rows_launch(W + w.att_scores, out_alpha_g + t * n, B, T, st));
@@ -788,11 +875,12 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
     k.mask_t = mask + static_cast<size_t>(t) * B;
     k.logprob = out_logprob;
     {
-      ProfScope ps(PH_PICK, st);
-      STAT_TRY(pick_launch(k, st));
+      ProfScope ps(PH_PICK, ov.side());
+      STAT_TRY(pick_launch(k, ov.side()));
     }
+    STAT_TRY(ov.side_enqueued());
   }
-  return STAT_OK;
+  return ov.join();
 }
 
 int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws, int maxlen, int64_t *out_tokens,
@@ -816,24 +904,31 @@ int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws, int ma
   STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
                                     sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
   STAT_TRY(h_proj(*d, p, P, w, W, W + w.h, B, 1, st));
+  Overlap ov;
+  STAT_TRY(ov.open(st, overlap_enabled()));
   for (int t = 0; t < maxlen; ++t) {
     StepIO io;
     memset(&io, 0, sizeof(io));
     io.rows = B;
     io.tok_prev = tok_prev;   // -1 on the first step: no previous word (:893, :803-804)
     io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.h; io.c_out = W + w.c;
-    STAT_TRY(step_core(*d, p, P, w, W, io, t + 1 < maxlen, st));
+    STAT_TRY(step_att(*d, p, P, w, W, io, st));
+    STAT_TRY(ov.join());
+    STAT_TRY(step_gates(*d, p, P, w, W, io, t + 1 < maxlen, st));
+    STAT_TRY(ov.state_ready());
+    STAT_TRY(step_out(*d, p, P, w, W, io, ov.side()));
     PickArgs k;
     memset(&k, 0, sizeof(k));
     k.rows = B; k.V = d->V; k.ldl = w.ldl; k.logits = W + w.logits;
     k.tokens = out_tokens; k.maxlen = maxlen; k.t = t;
     k.lengths = out_lengths; k.scores = out_scores; k.alive = alive; k.tok_prev = tok_prev;
     {
-      ProfScope ps(PH_PICK, st);
-      STAT_TRY(pick_launch(k, st));
+      ProfScope ps(PH_PICK, ov.side());
+      STAT_TRY(pick_launch(k, ov.side()));
     }
+    STAT_TRY(ov.side_enqueued());
   }
-  return STAT_OK;
+  return ov.join();
 }
 
 int stat_step(const StatDims *d, const void *prepared, void *ws, int rows, const int32_t *row_clip,
@@ -857,7 +952,9 @@ int stat_step(const StatDims *d, const void *prepared, void *ws, int rows, const
   io.tok_prev = x;
   io.h_in = h_in; io.c_in = c_in; io.h_out = out_h; io.c_out = out_c;
   STAT_TRY(h_proj(*d, p, P, w, W, h_in, rows, 1, st));
-  STAT_TRY(step_core(*d, p, P, w, W, io, false, st));
+  STAT_TRY(step_att(*d, p, P, w, W, io, st));
+  STAT_TRY(step_gates(*d, p, P, w, W, io, false, st));
+  STAT_TRY(step_out(*d, p, P, w, W, io, st));
   PickArgs k;
   memset(&k, 0, sizeof(k));
   k.rows = rows; k.V = d->V; k.ldl = w.ldl; k.logits = W + w.logits;

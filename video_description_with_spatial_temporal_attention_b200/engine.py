@@ -7,6 +7,7 @@ in this package) and the C ABI; all arithmetic happens in the CUDA kernels.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -36,6 +37,12 @@ class Engine(object):
         if not o.get('global_proj') and o['ctxg_dim'] != o['dim']:
             raise ValueError('the reference graph needs ctxg_dim == dim; set global_proj=True otherwise')
         self.flags = _lib.flags_of(o)
+        # keep the projected context blocks of a batch resident in L2 across the decode steps: the
+        # attention kernel copies them with evict_last priority, which only outlives the weight
+        # traffic between two steps inside the persisting carve-out (STAT_L2_PERSIST=<MB>, 0 = off)
+        mb = os.environ.get('STAT_L2_PERSIST')
+        with torch.cuda.device(self.device):
+            self.l2_persist_bytes = int(self.lib.stat_set_l2_persist(-1 if mb is None else int(mb) << 20))
         self.prepared = None
         self._dev_params = None
         self._ws = {}
