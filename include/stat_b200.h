@@ -162,6 +162,20 @@ int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws,
                        int maxlen, int64_t *out_tokens, int32_t *out_lengths,
                        float *out_scores, void *stream);
 
+/* ---- beam search = gen_sample(k > 1) for B clips at once ---------------------
+ * (model_attention.py:852-994, stochastic=False).  `ws` must have been sized for
+ * rows = B*k (stat_workspace_bytes) and hold the stat_precompute results of the
+ * B clips.  Per clip and step: the k - dead cheapest continuations
+ * (cumulative -log p, fp32) of the live hypotheses, hypotheses ending in token 0
+ * retire, the search stops when none is live, k have retired or maxlen steps are
+ * done; the survivors follow the retired ones, exactly the reference's order.
+ * out_tokens (B,k,maxlen) int64, -1 padded; out_lengths (B,k) int32 (incl. the
+ * eos when there is one); out_scores (B,k) cumulative -log p; out_count (B)
+ * hypotheses returned per clip (<= k).  1 <= k <= 16, 1 <= maxlen <= 64. */
+int stat_decode_beam(const StatDims *d, const void *prepared, void *ws, int k,
+                     int maxlen, int64_t *out_tokens, int32_t *out_lengths,
+                     float *out_scores, int32_t *out_count, void *stream);
+
 /* ---- f_next (model_attention.py:845-848): one step for `rows` hypotheses ---
  * row_clip (rows) int32 maps a hypothesis to its clip in `ws` (NULL = row i
  * uses clip i).  x (rows) int64, -1 = no previous word.  h_in/c_in (rows,H).

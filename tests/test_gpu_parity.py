@@ -139,6 +139,21 @@ def test_golden_greedy_batch(torch_cuda, name, use_graph):
         np.testing.assert_allclose(scores[b], want_sc[0], atol=TOL_LP)
 
 
+@pytest.mark.parametrize('name', NAMES)
+def test_golden_beam_batch(torch_cuda, name):
+    """stat_decode_beam (all clips of the batch at once, bookkeeping on the device) against the
+    hypotheses the reference's gen_sample produced clip by clip: same hypotheses, same order."""
+    g = Golden(name)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = g.batch
+    model, tp, _, _, _, _ = _build(g.options, g.params)
+    for k in g.ks:
+        got = model.beam_batch(tp, g.options, ctxg, mg, ctxl, ctxm, k=k, maxlen=g.maxlen)
+        for b in range(ctxg.shape[0]):
+            want, want_sc = g.hyps(k, b)
+            assert got[b][0] == want, (name, k, b)
+            np.testing.assert_allclose(np.asarray(got[b][1]), want_sc, atol=TOL_LP)
+
+
 # ---------------------------------------------------------------------------
 # BASELINE width against the oracle, both Dg == H (faithful) and Dg = 2048 (D1)
 # ---------------------------------------------------------------------------
@@ -204,6 +219,49 @@ def test_full_width_greedy_vs_oracle(torch_cuda, kind):
         if upto == n:
             assert lens[b] == n
             np.testing.assert_allclose(scores[b], ws[b], atol=TOL_LP)
+
+
+@pytest.mark.parametrize('kind,k', [('faithful', 5), ('baseline', 3), ('baseline', 5)])
+def test_full_width_beam_vs_host_search(torch_cuda, kind, k):
+    """Device beam search for a batch == the reference-shaped host search (gen_sample over f_next)
+    clip by clip, and both == the fp64 oracle where no two candidates are within rounding."""
+    o, params, batch = _case(kind, B=5, seed=13)
+    params['ff_logit_b'] = params['ff_logit_b'].copy()
+    params['ff_logit_b'][0] += 1.5          # hypotheses retire at different steps: the beam shrinks
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+    model, tp, _, _, f_init, f_next = _build(o, params)
+    maxlen = 10
+    got = model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=k, maxlen=maxlen)
+    fi, fn = so.make_sampler(params, o, dtype=np.float64, hoist=True)
+    n_exact = 0
+    for b in range(ctxg.shape[0]):
+        hyp, sc, _, _ = model.gen_sample(tp, f_init, f_next, ctxg[b], mg[b], ctxl[b], ml[b], ctxm[b], mm[b], o, None,
+                                         k, maxlen, False)
+        assert got[b][0] == hyp, (b, got[b][0], hyp)
+        np.testing.assert_allclose(np.asarray(got[b][1]), np.asarray(sc), atol=2e-5)
+        assert 1 <= len(hyp) <= k
+        want, want_sc = so.gen_sample(fi, fn, ctxg[b], mg[b], ctxl[b], ml[b], ctxm[b], mm[b], k=k, maxlen=maxlen)[:2]
+        if got[b][0] == want:
+            n_exact += 1
+            # cumulative fp32 scores (the reference accumulates in fp32 too): 1e-4 plus a few ulp of the sum
+            np.testing.assert_allclose(np.asarray(got[b][1]), np.asarray(want_sc, 'float64'), atol=TOL_LP, rtol=4e-6)
+    assert n_exact >= ctxg.shape[0] - 1     # an fp32 near-tie may reorder one beam at most
+
+
+def test_beam_k1_equals_greedy_and_limits(torch_cuda):
+    o, params, batch = _case('baseline', B=4, seed=17)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+    model, tp, _, _, _, _ = _build(o, params)
+    toks, lens, scores = model.greedy_batch(tp, o, ctxg, mg, ctxl, ctxm, maxlen=8)
+    got = model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=1, maxlen=8)
+    for b in range(4):
+        assert got[b][0] == [[int(t) for t in toks[b, :lens[b]]]]
+        np.testing.assert_allclose(got[b][1][0], scores[b], atol=1e-5)
+    from video_description_with_spatial_temporal_attention_b200 import _lib
+    with pytest.raises(_lib.StatError):
+        model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=17, maxlen=8)
+    with pytest.raises(_lib.StatError):
+        model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=2, maxlen=65)
 
 
 # ---------------------------------------------------------------------------

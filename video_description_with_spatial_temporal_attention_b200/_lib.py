@@ -66,6 +66,7 @@ def _declare(lib):
     lib.stat_init_state.argtypes = [dp] + [vp] * 7
     lib.stat_forward_teacher.argtypes = [dp, vp, vp, i32] + [vp] * 12
     lib.stat_decode_greedy.argtypes = [dp, vp, vp, i32, vp, vp, vp, vp]
+    lib.stat_decode_beam.argtypes = [dp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.stat_step.argtypes = [dp, vp, vp, i32] + [vp] * 8
     lib.stat_attention.argtypes = [dp, vp, vp, i32, vp, vp]
     lib.stat_gemm.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, C.c_float, C.c_float, i32, i32, vp]
@@ -76,7 +77,7 @@ def _declare(lib):
     lib.stat_profile_phase_name.argtypes = [i32]
     lib.stat_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int), i32]
     for n in ('stat_attention', 'stat_profile_enable', 'stat_profile_collect', 'stat_set_gemm_impl', 'stat_prepare_params', 'stat_init_state', 'stat_workspace_region', 'stat_precompute',
-              'stat_forward_teacher', 'stat_decode_greedy', 'stat_step', 'stat_gemm'):
+              'stat_forward_teacher', 'stat_decode_greedy', 'stat_decode_beam', 'stat_step', 'stat_gemm'):
         getattr(lib, n).restype = i32
 
 

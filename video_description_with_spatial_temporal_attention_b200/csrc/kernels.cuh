@@ -100,8 +100,43 @@ struct PickArgs {
   float *logprob;            // (rows) accumulated
   // f_next
   float *probs;              // (rows,V) or null
+  // beam search: the beam_k most probable words of every live row and their cumulative costs
+  int beam_k;                // 0 = off
+  const int32_t *row_alive;  // (rows)
+  const float *row_score;    // (rows) cumulative -log p of the hypothesis in this row
+  float *cand_cost;          // (rows,BEAM_KMAX): row_score - log p[word], ascending; +inf when absent
+  int32_t *cand_word;        // (rows,BEAM_KMAX)
 };
+constexpr int BEAM_KMAX = 16;      // beam width limit
+constexpr int BEAM_LMAX = 64;      // hypothesis length limit (maxlen)
 int pick_launch(const PickArgs &a, cudaStream_t stream);
+
+// Beam bookkeeping of one step for every clip (model_attention.py:905-973): the k - dead best of the
+// live hypotheses' candidates, retirement on token 0, survivors compacted to the front of the
+// clip's k row slots.  One warp per clip.
+struct BeamArgs {
+  int B, k, V, maxlen, t;
+  const float *cand_cost;    // (B*k,BEAM_KMAX)
+  const int32_t *cand_word;  // (B*k,BEAM_KMAX)
+  int32_t *alive;            // (B*k) live flag of a row slot
+  float *score;              // (B*k) cumulative cost of the live hypothesis
+  int32_t *hist;             // (B*k,BEAM_LMAX) its words so far
+  int32_t *hist_len;         // (B*k)
+  int32_t *src_row;          // (B*k) out: row whose LSTM state the slot continues from
+  int64_t *tok_prev;         // (B*k) out: last word of the slot (input of the next step)
+  int32_t *dead_k;           // (B)
+  int32_t *done;             // (B)
+  int64_t *out_tokens;       // (B,k,maxlen), -1 padded
+  int32_t *out_lengths;      // (B,k)
+  float *out_scores;         // (B,k)
+  int32_t *out_count;        // (B) finished hypotheses so far
+};
+int beam_select_launch(const BeamArgs &a, cudaStream_t stream);
+int beam_init_launch(const BeamArgs &a, const float *h0c0, float *h, float *c, int H, int32_t *row_clip,
+                     cudaStream_t stream);
+// dst_h[r] = src_h[src_row[r]], same for c   (rows,H)
+int gather_state_launch(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h, float *dst_c,
+                        int rows, int H, cudaStream_t stream);
 
 int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, int T, int D,
                     cudaStream_t stream);

@@ -276,6 +276,184 @@ __global__ void __launch_bounds__(256) pick_kernel(const PickArgs a) {
     float *p = a.probs + static_cast<size_t>(row) * a.V;
     for (int v = threadIdx.x; v < a.V; v += 256) p[v] = expf(l[v] - mm) * inv;
   }
+  if (a.beam_k > 0) {
+    // The cost score - log p[v] falls as the logit rises: the beam_k cheapest continuations of the row
+    // are its beam_k largest logits (lower index first among equals), found by beam_k arg-max rounds.
+    __shared__ int s_taken[BEAM_KMAX];
+    __syncthreads();
+    float *cc = a.cand_cost + static_cast<size_t>(row) * BEAM_KMAX;
+    int32_t *cw = a.cand_word + static_cast<size_t>(row) * BEAM_KMAX;
+    if (!a.row_alive[row]) {
+      if (threadIdx.x < BEAM_KMAX) { cc[threadIdx.x] = INFINITY; cw[threadIdx.x] = 0; }
+      return;
+    }
+    const float mm = s_bm, inv = 1.0f / s_bs, sc = a.row_score[row];
+    for (int r = 0; r < a.beam_k; ++r) {
+      float bm = -INFINITY;
+      int bv = 0x7fffffff;
+      for (int v = threadIdx.x; v < a.V; v += 256) {
+        bool taken = false;
+        for (int q = 0; q < r; ++q) taken |= (s_taken[q] == v);
+        const float x = l[v];
+        if (!taken && x > bm) { bm = x; bv = v; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, bm, o);
+        const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        if (om > bm || (om == bm && ov < bv)) { bm = om; bv = ov; }
+      }
+      __syncthreads();                       // previous round's readers of s_val / s_idx are done
+      if (lane == 0) { s_val[warp] = bm; s_idx[warp] = bv; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float b = s_val[0];
+        int i = s_idx[0];
+        for (int w = 1; w < 8; ++w)
+          if (s_val[w] > b || (s_val[w] == b && s_idx[w] < i)) { b = s_val[w]; i = s_idx[w]; }
+        s_taken[r] = i;
+        const bool ok = i < a.V;             // V < beam_k: no candidate left
+        cc[r] = ok ? sc - logf(expf(b - mm) * inv) : INFINITY;   // as the reference: -log of the fp32 probability
+        cw[r] = ok ? i : 0;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x >= a.beam_k && threadIdx.x < BEAM_KMAX) { cc[threadIdx.x] = INFINITY; cw[threadIdx.x] = 0; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// beam search bookkeeping (model_attention.py:852-994), one warp per clip
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) beam_select_kernel(const BeamArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ int s_hist[BEAM_KMAX][BEAM_LMAX];
+  __shared__ int s_len[BEAM_KMAX];
+  __shared__ int s_src[BEAM_KMAX], s_word[BEAM_KMAX];
+  __shared__ float s_cost[BEAM_KMAX];
+  __shared__ int s_nsel;
+  const int b = blockIdx.x, lane = threadIdx.x, k = a.k;
+  const int r0 = b * k;
+  if (a.done[b]) {
+    for (int j = lane; j < k; j += 32) { a.src_row[r0 + j] = r0 + j; a.tok_prev[r0 + j] = 0; }
+    return;
+  }
+  // old histories of the clip's slots
+  for (int j = 0; j < k; ++j) {
+    const int n = a.hist_len[r0 + j];
+    for (int i = lane; i < n; i += 32) s_hist[j][i] = a.hist[static_cast<size_t>(r0 + j) * BEAM_LMAX + i];
+    if (lane == 0) s_len[j] = n;
+  }
+  if (lane == 0) {
+    // the k - dead cheapest of the live slots' candidates: ascending cost, lower flat index (slot*V + word) first
+    const int want = k - a.dead_k[b];
+    int head[BEAM_KMAX];                      // every slot's candidates are already in ascending order
+    for (int j = 0; j < k; ++j) head[j] = 0;
+    int n = 0;
+    for (; n < want; ++n) {
+      float bc = INFINITY;
+      int bj = -1;
+      long long bf = 0;
+      for (int j = 0; j < k; ++j) {
+        if (!a.alive[r0 + j] || head[j] >= k) continue;
+        const float c = a.cand_cost[static_cast<size_t>(r0 + j) * BEAM_KMAX + head[j]];
+        const long long f = static_cast<long long>(j) * a.V + a.cand_word[static_cast<size_t>(r0 + j) * BEAM_KMAX + head[j]];
+        if (c < bc || (c == bc && bj >= 0 && f < bf)) { bc = c; bj = j; bf = f; }
+      }
+      if (bj < 0 || bc == INFINITY) break;
+      s_src[n] = bj;
+      s_word[n] = a.cand_word[static_cast<size_t>(r0 + bj) * BEAM_KMAX + head[bj]];
+      s_cost[n] = bc;
+      ++head[bj];
+    }
+    s_nsel = n;
+  }
+  __syncwarp();
+  const int nsel = s_nsel;
+  // new hypotheses in rank order: token 0 retires one, the others become the live slots 0, 1, ...
+  int n_live = 0, n_out = a.out_count[b], dead = a.dead_k[b];
+  for (int n = 0; n < nsel; ++n) {
+    const int src = s_src[n], word = s_word[n], len = s_len[src];
+    if (word == 0) {
+      int64_t *ot = a.out_tokens + (static_cast<size_t>(b) * k + n_out) * a.maxlen;
+      for (int i = lane; i < a.maxlen; i += 32) ot[i] = i < len ? s_hist[src][i] : (i == len ? 0 : -1);
+      if (lane == 0) { a.out_lengths[b * k + n_out] = len + 1; a.out_scores[b * k + n_out] = s_cost[n]; }
+      ++n_out;
+      ++dead;
+    } else {
+      const int row = r0 + n_live;
+      int32_t *h = a.hist + static_cast<size_t>(row) * BEAM_LMAX;
+      for (int i = lane; i < len; i += 32) h[i] = s_hist[src][i];
+      if (lane == 0) {
+        h[len] = word;
+        a.hist_len[row] = len + 1;
+        a.score[row] = s_cost[n];
+        a.src_row[row] = r0 + src;
+        a.tok_prev[row] = word;
+        a.alive[row] = 1;
+      }
+      ++n_live;
+    }
+  }
+  __syncwarp();
+  const bool finished = n_live < 1 || dead >= k || a.t + 1 >= a.maxlen;   // :969-972 and the end of the loop
+  if (finished) {
+    // the survivors follow the retired hypotheses (:975-979)
+    for (int j = 0; j < n_live; ++j) {
+      const int row = r0 + j;
+      const int len = a.hist_len[row];
+      int64_t *ot = a.out_tokens + (static_cast<size_t>(b) * k + n_out) * a.maxlen;
+      for (int i = lane; i < a.maxlen; i += 32) ot[i] = i < len ? a.hist[static_cast<size_t>(row) * BEAM_LMAX + i] : -1;
+      if (lane == 0) { a.out_lengths[b * k + n_out] = len; a.out_scores[b * k + n_out] = a.score[row]; }
+      ++n_out;
+    }
+    n_live = 0;
+  }
+  for (int j = n_live + lane; j < k; j += 32) {
+    a.alive[r0 + j] = 0;
+    a.src_row[r0 + j] = r0 + j;
+    a.tok_prev[r0 + j] = 0;
+  }
+  if (lane == 0) {
+    a.out_count[b] = n_out;
+    a.dead_k[b] = dead;
+    a.done[b] = finished ? 1 : 0;
+  }
+}
+
+// slot 0 of every clip starts from (h0, c0) with the empty hypothesis, "no previous word" (:881-893)
+__global__ void beam_init_kernel(const BeamArgs a, const float *h0c0, float *h, float *c, int H, int32_t *row_clip) {
+  const int row = blockIdx.x, b = row / a.k, j = row - b * a.k;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    h[static_cast<size_t>(row) * H + i] = j == 0 ? h0c0[static_cast<size_t>(b) * 2 * H + i] : 0.f;
+    c[static_cast<size_t>(row) * H + i] = j == 0 ? h0c0[static_cast<size_t>(b) * 2 * H + H + i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < a.maxlen; i += blockDim.x)
+    a.out_tokens[static_cast<size_t>(row) * a.maxlen + i] = -1;
+  if (threadIdx.x == 0) {
+    row_clip[row] = b;
+    a.alive[row] = j == 0;
+    a.score[row] = 0.f;
+    a.hist_len[row] = 0;
+    a.src_row[row] = row;
+    a.tok_prev[row] = -1;
+    a.out_lengths[row] = 0;
+    a.out_scores[row] = 0.f;
+    if (j == 0) { a.dead_k[b] = 0; a.done[b] = 0; a.out_count[b] = 0; }
+  }
+}
+
+__global__ void gather_state_kernel(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h,
+                                    float *dst_c, int H) {
+  pdl_wait();
+  pdl_trigger();
+  const int row = blockIdx.x;
+  const size_t s = static_cast<size_t>(src_row[row]) * H, d = static_cast<size_t>(row) * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    dst_h[d + i] = src_h[s + i];
+    dst_c[d + i] = src_c[s + i];
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -365,6 +543,23 @@ int zact_launch(const ZactArgs &a, cudaStream_t stream) {
 
 int pick_launch(const PickArgs &a, cudaStream_t stream) {
   return launch_pdl(pick_kernel, dim3(a.rows), dim3(256), 0, stream, a);
+}
+
+int beam_select_launch(const BeamArgs &a, cudaStream_t stream) {
+  return launch_pdl(beam_select_kernel, dim3(a.B), dim3(32), 0, stream, a);
+}
+
+int beam_init_launch(const BeamArgs &a, const float *h0c0, float *h, float *c, int H, int32_t *row_clip,
+                     cudaStream_t stream) {
+  beam_init_kernel<<<a.B * a.k, 128, 0, stream>>>(a, h0c0, h, c, H, row_clip);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int gather_state_launch(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h, float *dst_c,
+                        int rows, int H, cudaStream_t stream) {
+  return launch_pdl(gather_state_kernel, dim3(rows), dim3(128), 0, stream, src_h, src_c, src_row, dst_h, dst_c, H);
 }
 
 int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, int T, int D,

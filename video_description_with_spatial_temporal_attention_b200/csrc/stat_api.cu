@@ -151,6 +151,7 @@ struct Ws {
   size_t hpz_plane, pc_plane;        // floats between planes
   size_t rec_vec, rec_ms, att_scores, alpha_l;
   size_t counters, tok_prev, alive;  // byte-typed regions (still float offsets)
+  size_t hb, cb, cand_cost, cand_word, hist, hist_len, bscore, src_row, row_clip, dead_k, bdone;   // beam search
   size_t total;                      // floats
   int ldhp, ldpc, ldl, S, Tc;
   int att_impl;      // 2 = att_group_kernel, 1 = att_stream_kernel (TMA ring), 0 = the generic att_step_kernel
@@ -243,6 +244,17 @@ Ws ws_layout(const StatDims &d, int rows) {
   w.counters = take(n);
   w.tok_prev = take(2 * n);
   w.alive = take(n);
+  w.hb = take(n * H);
+  w.cb = take(n * H);
+  w.cand_cost = take(n * BEAM_KMAX);
+  w.cand_word = take(n * BEAM_KMAX);
+  w.hist = take(n * BEAM_LMAX);
+  w.hist_len = take(n);
+  w.bscore = take(n);
+  w.src_row = take(n);
+  w.row_clip = take(n);
+  w.dead_k = take(n);
+  w.bdone = take(n);
   w.total = o;
   return w;
 }
@@ -929,6 +941,69 @@ int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws, int ma
     STAT_TRY(ov.side_enqueued());
   }
   return ov.join();
+}
+
+int stat_decode_beam(const StatDims *d, const void *prepared, void *ws, int k, int maxlen, int64_t *out_tokens,
+                     int32_t *out_lengths, float *out_scores, int32_t *out_count, void *stream) {
+  STAT_TRY(check_dims(d));
+  STAT_TRY(check_device());
+  STAT_REQUIRE(prepared && ws && out_tokens && out_lengths && out_scores && out_count, STAT_EINVAL,
+               "decode_beam: bad argument");
+  STAT_REQUIRE(k >= 1 && k <= BEAM_KMAX && maxlen >= 1 && maxlen <= BEAM_LMAX, STAT_EINVAL,
+               "decode_beam: need 1 <= k <= %d and 1 <= maxlen <= %d (k=%d maxlen=%d)", BEAM_KMAX, BEAM_LMAX, k, maxlen);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int B = d->B, rows = B * k;
+  const Prep p = prep_layout(*d);
+  const Ws w = ws_layout(*d, rows);
+  const float *P = static_cast<const float *>(prepared);
+  float *W = static_cast<float *>(ws);
+  int32_t *row_clip = reinterpret_cast<int32_t *>(W + w.row_clip);
+  BeamArgs b;
+  memset(&b, 0, sizeof(b));
+  b.B = B; b.k = k; b.V = d->V; b.maxlen = maxlen;
+  b.cand_cost = W + w.cand_cost;
+  b.cand_word = reinterpret_cast<int32_t *>(W + w.cand_word);
+  b.alive = reinterpret_cast<int32_t *>(W + w.alive);
+  b.score = W + w.bscore;
+  b.hist = reinterpret_cast<int32_t *>(W + w.hist);
+  b.hist_len = reinterpret_cast<int32_t *>(W + w.hist_len);
+  b.src_row = reinterpret_cast<int32_t *>(W + w.src_row);
+  b.tok_prev = reinterpret_cast<int64_t *>(W + w.tok_prev);
+  b.dead_k = reinterpret_cast<int32_t *>(W + w.dead_k);
+  b.done = reinterpret_cast<int32_t *>(W + w.bdone);
+  b.out_tokens = out_tokens; b.out_lengths = out_lengths; b.out_scores = out_scores; b.out_count = out_count;
+  STAT_CUDA_CHECK(cudaMemsetAsync(W + w.counters, 0, sizeof(float) * rows, st));
+  STAT_TRY(beam_init_launch(b, W + w.h0c0, W + w.h, W + w.c, d->H, row_clip, st));
+  STAT_TRY(h_proj(*d, p, P, w, W, W + w.h, rows, 1, st));
+  for (int t = 0; t < maxlen; ++t) {
+    // the k row slots of a clip share its context blocks; slot order changes every step, so the new
+    // state is written next to the old one and gathered back in the new order after the selection
+    StepIO io;
+    memset(&io, 0, sizeof(io));
+    io.rows = rows;
+    io.row_clip = row_clip;
+    io.tok_prev = b.tok_prev;
+    io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.hb; io.c_out = W + w.cb;
+    STAT_TRY(step_att(*d, p, P, w, W, io, st));
+    STAT_TRY(step_gates(*d, p, P, w, W, io, false, st));
+    STAT_TRY(step_out(*d, p, P, w, W, io, st));
+    PickArgs pk;
+    memset(&pk, 0, sizeof(pk));
+    pk.rows = rows; pk.V = d->V; pk.ldl = w.ldl; pk.logits = W + w.logits;
+    pk.beam_k = k; pk.row_alive = b.alive; pk.row_score = b.score;
+    pk.cand_cost = W + w.cand_cost; pk.cand_word = reinterpret_cast<int32_t *>(W + w.cand_word);
+    {
+      ProfScope ps(PH_PICK, st);
+      STAT_TRY(pick_launch(pk, st));
+      b.t = t;
+      STAT_TRY(beam_select_launch(b, st));
+    }
+    if (t + 1 < maxlen) {
+      STAT_TRY(gather_state_launch(W + w.hb, W + w.cb, b.src_row, W + w.h, W + w.c, rows, d->H, st));
+      STAT_TRY(h_proj(*d, p, P, w, W, W + w.h, rows, 1, st));
+    }
+  }
+  return STAT_OK;
 }
 
 int stat_step(const StatDims *d, const void *prepared, void *ws, int rows, const int32_t *row_clip,

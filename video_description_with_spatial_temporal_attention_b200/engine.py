@@ -178,6 +178,27 @@ class Engine(object):
                                           _ptr(lengths), _ptr(scores), _stream()))
         return tokens, lengths, scores
 
+    # ---- beam search ---------------------------------------------------------
+    def decode_beam(self, ws, d, k, maxlen):
+        """ws: precompute(..., rows=B*k).  -> tokens (B,k,maxlen) i64, lengths (B,k) i32,
+        scores (B,k) f32, count (B,) i32, device tensors in the reference's hypothesis order."""
+        B = d.B
+        if self.lib.stat_workspace_bytes(C.byref(d), B * k) > ws.numel() * 4:
+            raise _lib.StatError('workspace too small for %d x %d beam rows' % (B, k))
+        tokens = torch.empty((B, k, maxlen), dtype=torch.int64, device=self.device)
+        lengths = torch.empty((B, k), dtype=torch.int32, device=self.device)
+        scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        count = torch.empty(B, dtype=torch.int32, device=self.device)
+        check(self.lib.stat_decode_beam(C.byref(d), _ptr(self.prepared), _ptr(ws), k, maxlen, _ptr(tokens),
+                                        _ptr(lengths), _ptr(scores), _ptr(count), _stream()))
+        return tokens, lengths, scores, count
+
+    def beam_captions(self, ctxg, mask_ctxg, ctxl, ctxm, k, maxlen):
+        """Features on the device -> decode_beam outputs (K0 + maxlen beam steps)."""
+        B = ctxg.shape[0]
+        ws, d = self.precompute(ctxg, mask_ctxg, ctxl, ctxm, rows=B * k)
+        return self.decode_beam(ws, d, k, maxlen)
+
     # ---- f_next ----------------------------------------------------------------
     def step(self, ws, d, x, h, c, row_clip=None):
         rows = x.shape[0]

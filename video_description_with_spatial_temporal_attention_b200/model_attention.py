@@ -361,6 +361,29 @@ class Attention(object):
         perp = 2 ** (numpy.sum(nll) / numpy.sum(lens) / numpy.log(2))
         return -1 * numpy.mean(probs), perp
 
+    # ---- batched extension (not in the reference): beam search for B clips at once ----
+    def beam_batch(self, tparams, options, ctxg, mask_ctxg, ctxl, ctxm, k=5, maxlen=30):
+        """gen_sample(k) for every clip of a batch in one device pass.  Host arrays
+        in; returns per clip (sample, sample_score) exactly as gen_sample does: lists of word-id
+        lists and of cumulative -log p, retired hypotheses first, then the survivors."""
+        model = getattr(self, '_model', None)
+        if model is None or model.tparams is not tparams:
+            model = _Model(tparams, dict(options), Shared(numpy.float32(0.)), common.rng_seed)
+            self._model = model
+        eng = model.engine()
+        f32 = torch.float32
+        gd = eng.to_device(ctxg, f32, 'ctxg')
+        gm = eng.to_device(mask_ctxg, f32, 'mask_ctxg')
+        ld = eng.to_device(ctxl, f32, 'ctxl')
+        md = eng.to_device(ctxm, f32, 'ctxm')
+        tokens, lengths, scores, count = [t.cpu().numpy() for t in eng.beam_captions(gd, gm, ld, md, k, maxlen)]
+        out = []
+        for b in range(tokens.shape[0]):
+            n = int(count[b])
+            out.append(([tokens[b, j, :lengths[b, j]].tolist() for j in range(n)],
+                        [numpy.float32(scores[b, j]) for j in range(n)]))
+        return out
+
     # ---- batched extension (not in the reference): B clips at once -----------------
     def greedy_batch(self, tparams, options, ctxg, mask_ctxg, ctxl, ctxm, maxlen=30, use_graph=True):
         """gen_sample(k=1) for every clip of a batch in one device pass.  Host arrays in,
