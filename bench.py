@@ -239,7 +239,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- the attention kernel alone: cold (L2 flushed before every launch) and warm ----
     ws, d = eng.precompute(*devf)
     eng.decode_greedy(ws, d, 1)                      # leaves a valid h-projection row set in ws
-    flush = torch.empty(96 * 1024 * 1024, dtype=torch.float32, device=dev)   # 384 MB > 126 MB L2
+    flush = torch.zeros(96 * 1024 * 1024, dtype=torch.float32, device=dev)   # 384 MB > 126 MB L2
     n_att = 20
     for _ in range(3):
         eng.attention(ws, d)
@@ -247,7 +247,7 @@ def run_ours(args, rank, world, local_rank):
     pairs = []
     torch.cuda._sleep(4000000)
     for _ in range(n_att):
-        flush.zero_()
+        flush.sum()                                   # read-only flush: no dirty lines left to write back
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         eng.attention(ws, d)
@@ -264,6 +264,29 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     att_warm_us = a.elapsed_time(b) / n_att * 1e3
     del flush
+
+    # ---- secondary (BASELINE configs[4] per GPU): beam search k=5, 32 clips, maxlen 30, on the device ----
+    beam = None
+    try:
+        bB, bk, bL = 32, 5, 30
+        bf = [t[:bB].contiguous() for t in devf]
+        for _ in range(2):
+            eng.beam_captions(*bf, k=bk, maxlen=bL)
+        torch.cuda.synchronize()
+        n_beam = 5
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(n_beam):
+            bout = eng.beam_captions(*bf, k=bk, maxlen=bL)
+        b1.record()
+        torch.cuda.synchronize()
+        ms_beam = b0.elapsed_time(b1) / n_beam
+        beam = {'workload': 'configs[4] per-GPU share: beam k=5, B=32 clips (160 decode rows), maxlen=30, K0 from raw '
+                            'features, bookkeeping on the device, eager launches',
+                'captions_per_s': bB / (ms_beam * 1e-3), 'ms_per_batch': ms_beam,
+                'hypotheses_returned': int(bout[3].sum().item())}
+    except Exception as e:                                   # secondary: never fail the headline line
+        beam = {'error': str(e)[:200]}
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -314,7 +337,9 @@ def run_ours(args, rank, world, local_rank):
                                    'features every batch',
                        'batch_per_gpu': B, 'parallelism': 'clips sharded, %d rank(s), no data-path collective' % world,
                        'l2': 'inputs 259 MB/step > 126 MB L2, no flush', 'params': 'random, trained-like scale',
-                       'precision': 'fp32 in/out, 3xTF32 tensor-core GEMMs, fp32 attention'},
+                       'precision': 'fp32 in/out, 3xTF32 tensor-core GEMMs, fp32 attention',
+                       'l2_carve_out': 'context blocks copied evict_last into a %.0f MB persisting-L2 carve-out'
+                                       % (eng.l2_persist_bytes / 1048576.0)},
             'e2e': {'value': world * B * k_e2e / (ms_e2e * 1e-3), 'unit': 'captions/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'steps': k_e2e, 'ms_per_step': ms_e2e / k_e2e},
             'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
@@ -322,6 +347,7 @@ def run_ours(args, rank, world, local_rank):
             'whole_path': {'algorithmic_bytes_per_step': total_bytes,
                            'achieved_GBps': total_bytes / (ms / args.steps * 1e-3) / 1e9,
                            'frac_of_hbm_peak': total_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+            'beam5': beam, 'l2_persist_bytes': eng.l2_persist_bytes,
             'tokens_checksum': int(tokens.astype(np.int64).sum())}
     print(json.dumps(line))
     if world > 1:

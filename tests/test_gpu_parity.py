@@ -351,3 +351,37 @@ def test_edge_cases(torch_cuda):
         lp = f_log_probs(*batch)
         want = so.forward_teacher(params, o, *batch, dtype=np.float64)
         np.testing.assert_allclose(lp, want, atol=TOL_LP, err_msg=str((B, T, R, L)))
+
+
+# ---------------------------------------------------------------------------
+# the callers either side of the path: pred_probs over prepare_data batches,
+# parameters through the reference's checkpoint files
+# ---------------------------------------------------------------------------
+def test_pred_probs_over_prepare_data_and_checkpoint(torch_cuda, tmp_path):
+    from video_description_with_spatial_temporal_attention_b200 import checkpoint as ck, data_engine as de
+    o = stat.default_options(dim=64, dim_word=64, ctxg_dim=64, ctxl_dim=96, ctxm_dim=80, n_words=50)
+    params = so.trained_like_params(o, seed=4)
+    eng = de.synthetic_engine(o, n_videos=8, caps_per_video=3, T=7, R=3, seed=4, mb_size_test=5)
+    model, tp, f_log_probs, _, _, _ = _build(o, params)
+    model.engine = eng
+    cost, perp = model.pred_probs('valid', f_log_probs, verbose=False)
+    # the same numbers from the oracle, batch by batch (model_attention.py:996-1032)
+    lps, lens = [], []
+    for index in eng.kf_valid:
+        batch = de.prepare_data(eng, [eng.valid[i] for i in index])
+        lps.extend((-so.forward_teacher(params, o, *batch, dtype=np.float64)).tolist())
+        lens.extend(batch[1].sum(0).tolist())
+    want_cost = np.mean(lps)
+    want_perp = 2 ** (np.sum(lps) / np.sum(lens) / np.log(2))
+    assert abs(cost - want_cost) < TOL_LP
+    assert abs(perp - want_perp) < 1e-4 * want_perp
+    # save in the reference's archive layout, reload into a fresh model: identical log-probs
+    path = str(tmp_path / 'model_best_so_far.npz')
+    ck.save_params(path, tp, history_errs=[[0.0, float(cost), 0.0]])
+    ck.save_options(str(tmp_path), o)
+    o2 = ck.load_options(str(tmp_path))
+    m2 = ma.Attention()
+    p2 = m2.load_params(path, m2.init_params(o2))
+    _, _, f2, _, _, _ = _build(o2, p2)
+    batch = de.prepare_data(eng, eng.test)
+    assert np.array_equal(f2(*batch), f_log_probs(*batch))

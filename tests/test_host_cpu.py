@@ -117,3 +117,70 @@ def test_shared_and_function_plumbing():
     with pytest.raises(TypeError):
         f(1, 2, 3)
     assert common.generate_minibatch_idx(10, 4) == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+
+
+# ---------------------------------------------------------------------------
+# minibatch layout (data_engine.py:258-337) and checkpoint files (N3, N4)
+# ---------------------------------------------------------------------------
+def test_prepare_data_layout_matches_reference_rules():
+    import video_description_with_spatial_temporal_attention_b200 as stat
+    from video_description_with_spatial_temporal_attention_b200 import data_engine as de
+    o = stat.default_options(dim=16, dim_word=16, ctxg_dim=16, ctxl_dim=24, ctxm_dim=20, n_words=30)
+    eng = de.synthetic_engine(o, n_videos=6, caps_per_video=2, T=5, R=3, seed=3)
+    ids = eng.train[:4]
+    x, xm, yg, ygm, yl, ylm, ym, ymm = de.prepare_data(eng, ids)
+    assert x.dtype == np.int64 and xm.dtype == np.float32 and x.shape == xm.shape
+    assert yg.shape == (4, 5, 16) and yl.shape == (4, 5, 3, 24) and ym.shape == (4, 5, 20)
+    assert ygm.shape == (4, 5) and ylm.shape == (4, 5, 3) and ymm.shape == (4, 5)
+    for i, ID in enumerate(ids):
+        vid, cap = ID.split('_')
+        words = [c for c in eng.CAP[vid] if c['cap_id'] == cap][0]['tokenized'].split(' ')
+        want = [eng.worddict[w] if eng.worddict[w] < eng.n_words else 1 for w in words]
+        n = len(want)
+        assert x[:n, i].tolist() == want and (x[n:, i] == 0).all()          # 0 = eos padding
+        assert xm[:n + 1, i].tolist() == [1.0] * (n + 1) and (xm[n + 1:, i] == 0).all()
+        assert (ygm[i] == (yg[i].sum(-1) != 0)).all()
+    assert x.shape[0] == max(int(xm[:, i].sum()) for i in range(4))          # longest caption + eos
+    assert (x < eng.n_words).all()                                            # ids beyond n_words -> UNK (1)
+    # captions of length >= maxlen are dropped; nothing left -> five Nones
+    eng.maxlen = 2
+    assert de.prepare_data(eng, ids) == (None, None, None, None, None)
+    eng.maxlen = 6
+    r = de.prepare_data(eng, eng.train)
+    assert r[0].shape[0] <= 6 and r[0].shape[1] == sum(
+        len([c for c in eng.CAP[i.split('_')[0]] if c['cap_id'] == i.split('_')[1]][0]['tokenized'].split(' ')) < 6
+        for i in eng.train)
+    assert [len(b) for b in eng.kf_train] == [4] * (len(eng.train) // 4) + ([len(eng.train) % 4] if len(eng.train) % 4 else [])
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    import video_description_with_spatial_temporal_attention_b200 as stat
+    from video_description_with_spatial_temporal_attention_b200 import checkpoint as ck, model_attention as ma
+    o = stat.default_options(dim=8, dim_word=8, ctxg_dim=8, ctxl_dim=12, ctxm_dim=10, n_words=11)
+    model = ma.Attention()
+    params = model.init_params(o)
+    tp = model.init_tparams(params)
+    path = str(tmp_path / 'model_best_so_far.npz')
+    ck.save_params(path, tp, history_errs=[[1.0, 2.0, 3.0]], train_err=0.5, valid_err=0.6, test_err=0.7)
+    ck.save_options(str(tmp_path), o)
+    o2 = ck.load_options(str(tmp_path))
+    assert o2 == dict(o)
+    fresh = model.init_params(o2)
+    got = ck.load_params(path, fresh)
+    assert list(got.keys()) == list(params.keys())
+    for k in params:
+        assert got[k].dtype == np.float32 and np.array_equal(got[k], params[k])
+    ex = ck.archive_extras(path)
+    assert float(ex['valid_err']) == pytest.approx(0.6) and ex['history_errs'].shape == (1, 3)
+    # the reference's own loader contract: a missing key / a wrong shape is an error
+    bad = dict(params)
+    bad.pop('Wemb')
+    np.savez(str(tmp_path / 'bad.npz'), **bad)
+    with pytest.raises(Exception):
+        ck.load_params(str(tmp_path / 'bad.npz'), model.init_params(o))
+    o3 = dict(o, n_words=12)
+    with pytest.raises(ValueError):
+        ck.load_params(path, model.init_params(o3))
+    # model.load_params (model_attention.py:1109-1113) reads the same archive
+    again = model.load_params(path, model.init_params(o))
+    assert np.array_equal(again['decoder_U'], params['decoder_U'])
