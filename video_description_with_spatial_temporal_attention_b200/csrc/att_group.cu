@@ -159,7 +159,8 @@ __device__ __forceinline__ float ld_dsmem(const float *local, uint32_t rank) {
 // RT = compile-time R (8) or 0 for a runtime R <= 16;  HT = compile-time H (512) or 0.
 template <int NV, int RT, int HT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-    att_group_kernel(const AttArgs a, const int G, const int cs, const uint64_t policy, const int stagger) {
+    att_group_kernel(const AttArgs a, const int G, const int cs, const uint64_t policy, const uint64_t policy_q,
+                     const int stagger) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int RU = RT ? RT : RMAX;              // unroll bound of the region loops
   const int H = HT ? HT : a.H, T = a.T;
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const uint32_t dst = smem_u32(slot_v);
     mbar_expect_tx(bar_v, static_cast<uint32_t>(v_floats) * 4u);
     bulk_g2s(dst, a.ctxl0 + frame * RH, bytes_rh, bar_v, policy);
-    bulk_g2s(dst + bytes_rh, a.qctxl + frame * RH, bytes_rh, bar_v, policy);
+    bulk_g2s(dst + bytes_rh, a.qctxl + frame * RH, bytes_rh, bar_v, policy_q);
     bulk_g2s(dst + 2 * bytes_rh, a.ctxg0 + frame * H, bytes_h, bar_v, policy);
     bulk_g2s(dst + 2 * bytes_rh + bytes_h, a.ctxm0 + frame * H, bytes_h, bar_v, policy);
   };
@@ -592,6 +593,20 @@ uint64_t l2_policy() {
 }
 
 long long *g_group_trace = nullptr;
+size_t g_persist_bytes = 0;
+
+// The seven blocks of a B=64 batch (95 MB) are more than the L2 keeps across a step (about 90 MB, less
+// the weights and activations streamed in between): cyclically re-reading all of them with one
+// priority would miss everywhere.  One block, qctxl, is therefore streamed (evict_first) every step and
+// leaves the L2 to the other six (68 MB).   STAT_ATT_Q_L2 = first (default) | same
+uint64_t l2_policy_q() {
+  static uint64_t pol = 0;
+  if (pol == 0) {
+    const char *e = getenv("STAT_ATT_Q_L2");
+    pol = (e && !strcmp(e, "same")) ? l2_policy() : 0x12F0000000000000ull;
+  }
+  return pol;
+}
 
 template <int NV, int RT, int HT>
 int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
@@ -608,7 +623,7 @@ int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
@@ -623,12 +638,30 @@ int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
     pdl_att = (e && e[0] == '1') ? 1 : 0;
   }
   cfg.numAttrs = 1 + (pdl_att ? pdl_attr(attr + 1) : 0);
+  // The context blocks of the batch are re-read by every decode step: inside this launch their address
+  // range is an L2 access-policy window whose lines are allocated as persisting -- as many of them as
+  // the carve-out holds (hitRatio), the rest as streaming so that they do not push the others out.
+  static int window = -1;
+  if (window < 0) {
+    const char *e = getenv("STAT_ATT_WINDOW");
+    window = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (window && g_persist_bytes > 0 && a.blocks_bytes > 0) {
+    cudaLaunchAttribute &w = attr[cfg.numAttrs++];
+    w.id = cudaLaunchAttributeAccessPolicyWindow;
+    w.val.accessPolicyWindow.base_ptr = const_cast<void *>(a.blocks_base);
+    w.val.accessPolicyWindow.num_bytes = a.blocks_bytes;
+    const double r = 0.92 * static_cast<double>(g_persist_bytes) / static_cast<double>(a.blocks_bytes);
+    w.val.accessPolicyWindow.hitRatio = static_cast<float>(r > 1.0 ? 1.0 : r);
+    w.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    w.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  }
   static int stagger = -1;
   if (stagger < 0) {
     const char *e = getenv("STAT_ATT_STAGGER");
     stagger = (e && e[0] == '0') ? 0 : 1;
   }
-  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_group_kernel<NV, RT, HT>, a, G, cs, l2_policy(), stagger));
+  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_group_kernel<NV, RT, HT>, a, G, cs, l2_policy(), l2_policy_q(), stagger));
   note_launch();
   return STAT_OK;
 }
@@ -652,6 +685,7 @@ bool att_group_plan(int rows, int T, int R, int H, int *cluster, int *groups, in
 
 // debug: device buffer of >= ctas * 64 int64 (clock stamps per CTA and group), or null
 void att_group_set_trace(long long *p) { g_group_trace = p; }
+void att_group_set_persist(size_t carve_out_bytes) { g_persist_bytes = carve_out_bytes; }
 
 int att_group_launch(const AttArgs &a_in, cudaStream_t stream) {
   AttArgs a = a_in;

@@ -105,8 +105,14 @@ struct DevArgs {
   int stages;               // depth of the shared-memory ring
   long long plane;          // floats between output planes
   long long *trace;         // debug: per-phase clock64 stamps of CTA (0,0,0), or null
+  unsigned long long pol_p, pol_q;   // L2 eviction-priority policies of the two operand streams
   DevSeg seg[2];
 };
+
+// L2 cache-hint policy words (the encodings createpolicy.fractional.L2::evict_* 1.0 produces)
+constexpr unsigned long long L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr unsigned long long L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr unsigned long long L2_EVICT_LAST = 0x14F0000000000000ull;
 
 // ---- PTX wrappers ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -139,11 +145,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1,
-                                            uint32_t bar) {
+                                            uint32_t bar, unsigned long long policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
@@ -331,8 +337,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         const uint32_t stage = smem_u32(smem + s * C::STAGE_BYTES);
         mbar_expect_tx(bar_full + 8 * s, C::P_BYTES + C::Q_BYTES);
-        tma_load_2d(stage, &tmP, (kb0 + kb) * BK, p0, bar_full + 8 * s);
-        tma_load_2d(stage + 2 * C::P_BYTES, &tmQ, (kb0 + kb) * BK, q0, bar_full + 8 * s);
+        tma_load_2d(stage, &tmP, (kb0 + kb) * BK, p0, bar_full + 8 * s, args.pol_p);
+        tma_load_2d(stage + 2 * C::P_BYTES, &tmQ, (kb0 + kb) * BK, q0, bar_full + 8 * s, args.pol_q);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -686,6 +692,17 @@ int gemm_launch(const GemmArgs &a, cudaStream_t stream) {
   da.stages = 1;
   da.plane = static_cast<long long>(a.plane);
   da.trace = g_trace;
+  // Skinny activations ("swap": the weights ride the 128-lane axis): each weight tile is read by one CTA
+  // and not again before the next decode step, with the whole context-block stream of the attention
+  // kernel in between -- mark it evict_first so that it does not push those blocks out of the L2; the
+  // activation rows are re-read by every CTA.  Wide problems (K0) keep the default priority.
+  static int hint = -1;
+  if (hint < 0) {
+    const char *e = getenv("STAT_GEMM_L2");
+    hint = (e && e[0] == '0') ? 0 : 1;
+  }
+  da.pol_p = (hint && a.feat_on_p && a.NQ <= 128) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+  da.pol_q = (hint && a.feat_on_p && a.NQ <= 128) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
   if (da.ksplit > 1) {
     STAT_REQUIRE(a.nseg == 1 && a.seg[0].act == 0, STAT_EINVAL,
                  "gemm: k-split needs a single linear segment (partial sums are combined by the consumer)");
