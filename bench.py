@@ -309,7 +309,11 @@ def run_ours(args, rank, world, local_rank):
         tp = os.path.join(ROOT, 'profiles', 'att_step_traffic.json')
         if os.path.isfile(tp):
             with open(tp) as fh:
-                traffic = json.load(fh).get('dram_bytes_per_launch')
+                tj = json.load(fh)
+                ins = tj.get('in_situ')
+                # in situ (one ncu pass per launch, caches untouched) when captured, else the cold capture
+                traffic = (ins['dram_read_bytes_per_launch'] + ins['dram_write_bytes_per_launch']) if ins else \
+                    tj.get('dram_bytes_per_launch')
         roof = {'bound': 'hbm', 'kernel': 'att_stream_kernel (4 soft-attentions of one decode step, all rows)',
                 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic,
                 'peak_source': peak_src, 'algorithmic_bytes_per_launch': ctx_step_bytes,

@@ -108,6 +108,79 @@ def launch_list(tag, md):
     md.append('')
 
 
+def sass_profile(md):
+    """Instruction mix and stall reasons of the attention kernel from the source page of its capture."""
+    path = os.path.join(SRC, 'att_sass.csv')
+    if not os.path.isfile(path):
+        return
+    rows = list(csv.reader(open(path)))
+    hdr, data = rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    stallcols = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
+    byop, stall, tot, nsamp = collections.Counter(), collections.Counter(), 0, 0
+    for r in data:
+        if len(r) < len(hdr):
+            continue
+        toks = r[ix['Source']].split()
+        op = (toks[1] if toks[0].startswith('@') else toks[0]).split('.')[0]
+        n = int(r[ix['Instructions Executed']] or 0)
+        byop[op] += n
+        tot += n
+        nsamp += int(r[ix['# Samples']] or 0)
+        for c in stallcols:
+            stall[c] += int(r[ix[c]] or 0)
+    md.append('### att_group_kernel: executed warp instructions by opcode and warp-state samples (`--page source`)\n')
+    md.append('%d warp instructions in the launch; ' % tot + ', '.join('%s %.1f%%' % (o, 100.0 * n / tot)
+                                                                    for o, n in byop.most_common(10)) + '.\n')
+    md.append('%d samples: ' % nsamp + ', '.join('%s %d' % (c, n) for c, n in stall.most_common(8)) + '.\n')
+    mufu, ublk = byop.get('MUFU', 0), byop.get('UBLKCP', 0)
+    md.append('MUFU %d (5 per 4 tanh), UBLKCP (cp.async.bulk) %d, no tensor-pipe instructions (HBM-bound '
+              'streaming kernel).\n' % (mufu, ublk))
+
+
+def step_traffic(tag, md):
+    """Per-kernel DRAM bytes of the decode steps measured in situ: one ncu pass per launch, no replay,
+    caches left alone (tools/ncu_full.sh step 2 / the step_dram capture)."""
+    path = os.path.join(SRC, 'step_dram.csv')
+    if not os.path.isfile(path):
+        return None
+    rows = [r for r in csv.reader(l for l in open(path) if not l.startswith('=='))]
+    hdr = rows[0]
+    ix = {h: i for i, h in enumerate(hdr)}
+    d = collections.OrderedDict()
+    for r in rows[1:]:
+        e = d.setdefault(int(r[ix['ID']]), {'name': re.sub(r'\(.*', '', r[ix['Kernel Name']]).split('::')[-1],
+                                            'grid': r[ix['Grid Size']]})
+        e[r[ix['Metric Name']]] = float(r[ix['Metric Value']].replace(',', ''))
+    att = [i for i in d if d[i]['name'].startswith('att_group')]
+    if len(att) < 12:
+        return None
+    s, e = att[8], att[10]
+    md.append('## DRAM traffic of two decode steps in situ (`%s_step_dram.csv`)\n' % tag)
+    md.append('`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct '
+              '--cache-control none --clock-control none` on `tools/one_step.py`: one pass per launch, nothing replayed, '
+              'caches as the preceding kernels left them.\n')
+    md.append('| # | kernel | grid | us | DRAM read MB | DRAM write MB | L2 hit % |\n|---|---|---|---|---|---|---|')
+    with open(os.path.join(OUT, '%s_step_dram.csv' % tag), 'w') as f:
+        f.write('index,kernel,grid,duration_us,dram_read_bytes,dram_write_bytes,l2_hit_pct\n')
+        for i in d:
+            x = d[i]
+            f.write('%d,"%s","%s",%.2f,%.0f,%.0f,%.2f\n' % (i, x['name'], x['grid'], x['gpu__time_duration.sum'] / 1e3,
+                                                         x['dram__bytes_read.sum'], x['dram__bytes_write.sum'],
+                                                         x['lts__t_sector_hit_rate.pct']))
+            if s <= i < e:
+                md.append('| %d | %s | %s | %.1f | %.2f | %.2f | %.1f |' % (
+                    i, x['name'], x['grid'], x['gpu__time_duration.sum'] / 1e3, x['dram__bytes_read.sum'] / 1e6,
+                    x['dram__bytes_write.sum'] / 1e6, x['lts__t_sector_hit_rate.pct']))
+    md.append('')
+    a = [d[i] for i in att[2:]]
+    n = len(a)
+    return {'launches': n, 'dram_read_bytes_per_launch': sum(x['dram__bytes_read.sum'] for x in a) / n,
+            'dram_write_bytes_per_launch': sum(x['dram__bytes_write.sum'] for x in a) / n,
+            'l2_hit_pct': sum(x['lts__t_sector_hit_rate.pct'] for x in a) / n,
+            'source': '%s_step_dram.csv (one ncu pass per launch, --cache-control none)' % tag}
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
     os.makedirs(OUT, exist_ok=True)
@@ -116,7 +189,9 @@ def main():
           'on `tools/one_step.py` (one eager pass of the bench workload).  Numbers under a profiler are evidence '
           'of *where* time and bytes go; throughput claims come from `bench.py`.\n']
     launch_list(tag, md)
-    att = summarize(os.path.join(SRC, 'prof_att.ncu-rep'), 'att_stream_kernel — the HBM-bound attention kernel', md)
+    att = summarize(os.path.join(SRC, 'prof_att.ncu-rep'), 'att_group_kernel — the HBM/L2-bound attention kernel (full set: replayed, caches flushed between passes = cold numbers)', md)
+    insitu = step_traffic(tag, md)
+    sass_profile(md)
     summarize(os.path.join(SRC, 'prof_gemm.ncu-rep'), 'gemm_tf32x3_kernel — K0 projections and per-step GEMMs', md)
     with open(os.path.join(OUT, '%s_ncu_summary.md' % tag), 'w') as f:
         f.write('\n'.join(md) + '\n')
@@ -124,10 +199,13 @@ def main():
         a = att[-1]
         rd = to_bytes(*a['dram__bytes_read.sum'])
         wr = to_bytes(*a['dram__bytes_write.sum'])
+        rec = {'kernel': a['kernel'], 'dram_bytes_per_launch': rd + wr, 'dram_read': rd, 'dram_write': wr,
+               'source': '%s_ncu_summary.md (ncu --set full, one launch, caches flushed by ncu: every byte from DRAM; '
+                         'B=64 T=26 R=8 H=512)' % tag}
+        if insitu:
+            rec['in_situ'] = insitu
         with open(os.path.join(OUT, 'att_step_traffic.json'), 'w') as f:
-            json.dump({'kernel': a['kernel'], 'dram_bytes_per_launch': rd + wr, 'dram_read': rd, 'dram_write': wr,
-                       'source': '%s_ncu_summary.md (ncu --set full, one launch, B=64 T=26 R=8 H=512)' % tag}, f,
-                      indent=1)
+            json.dump(rec, f, indent=1)
     print('\n'.join(md[:60]))
 
 
