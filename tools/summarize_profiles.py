@@ -120,6 +120,10 @@ def sass_profile(md):
     byop, stall, tot, nsamp = collections.Counter(), collections.Counter(), 0, 0
     for r in data:
         if len(r) < len(hdr):
+            if r and r[0] == 'Kernel Name':
+                break                     # the second captured launch: one is enough
+            continue
+        if r[ix['Source']] == 'Source':
             continue
         toks = r[ix['Source']].split()
         op = (toks[1] if toks[0].startswith('@') else toks[0]).split('.')[0]
