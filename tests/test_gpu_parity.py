@@ -254,6 +254,12 @@ def test_beam_k1_equals_greedy_and_limits(torch_cuda):
     model, tp, _, _, _, _ = _build(o, params)
     toks, lens, scores = model.greedy_batch(tp, o, ctxg, mg, ctxl, ctxm, maxlen=8)
     got = model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=1, maxlen=8)
+    # graph replay == direct launches, twice (the second replay reuses the captured buffers)
+    want3 = model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=3, maxlen=8)
+    for _ in range(2):
+        got3 = model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=3, maxlen=8, use_graph=True)
+        assert [h for h, _ in got3] == [h for h, _ in want3]
+        assert all(np.array_equal(np.asarray(a[1]), np.asarray(b[1])) for a, b in zip(got3, want3))
     for b in range(4):
         assert got[b][0] == [[int(t) for t in toks[b, :lens[b]]]]
         np.testing.assert_allclose(got[b][1][0], scores[b], atol=1e-5)

@@ -193,11 +193,42 @@ class Engine(object):
                                         _ptr(lengths), _ptr(scores), _ptr(count), _stream()))
         return tokens, lengths, scores, count
 
-    def beam_captions(self, ctxg, mask_ctxg, ctxl, ctxm, k, maxlen):
-        """Features on the device -> decode_beam outputs (K0 + maxlen beam steps)."""
-        B = ctxg.shape[0]
-        ws, d = self.precompute(ctxg, mask_ctxg, ctxl, ctxm, rows=B * k)
-        return self.decode_beam(ws, d, k, maxlen)
+    def beam_captions(self, ctxg, mask_ctxg, ctxl, ctxm, k, maxlen, use_graph=False):
+        """Features on the device -> decode_beam outputs (K0 + maxlen beam steps).  With use_graph the
+        launch sequence is captured once per shape and replayed (outputs are then reused buffers)."""
+        self._need_params()
+        B, T, R = ctxg.shape[0], ctxg.shape[1], ctxl.shape[2]
+        if not use_graph:
+            ws, d = self.precompute(ctxg, mask_ctxg, ctxl, ctxm, rows=B * k)
+            return self.decode_beam(ws, d, k, maxlen)
+        key = ('beam', B, T, R, k, maxlen)
+        g = self._graphs.get(key)
+        if g is None:
+            st = [torch.empty_like(t) for t in (ctxg, mask_ctxg, ctxl, ctxm)]
+            for dst, src in zip(st, (ctxg, mask_ctxg, ctxl, ctxm)):
+                dst.copy_(src)
+            holder = {}
+
+            def run():
+                ws, d = self.precompute(*st, rows=B * k)
+                holder['out'] = self.decode_beam(ws, d, k, maxlen)
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                run()                       # warm-up: function attributes, workspace allocation
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run()
+            g = (graph, st, holder['out'])
+            self._graphs[key] = g
+        graph, st, out = g
+        for dst, src in zip(st, (ctxg, mask_ctxg, ctxl, ctxm)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        graph.replay()
+        return out
 
     # ---- f_next ----------------------------------------------------------------
     def step(self, ws, d, x, h, c, row_clip=None):

@@ -362,7 +362,7 @@ class Attention(object):
         return -1 * numpy.mean(probs), perp
 
     # ---- batched extension (not in the reference): beam search for B clips at once ----
-    def beam_batch(self, tparams, options, ctxg, mask_ctxg, ctxl, ctxm, k=5, maxlen=30):
+    def beam_batch(self, tparams, options, ctxg, mask_ctxg, ctxl, ctxm, k=5, maxlen=30, use_graph=False):
         """gen_sample(k) for every clip of a batch in one device pass.  Host arrays
         in; returns per clip (sample, sample_score) exactly as gen_sample does: lists of word-id
         lists and of cumulative -log p, retired hypotheses first, then the survivors."""
@@ -376,7 +376,7 @@ class Attention(object):
         gm = eng.to_device(mask_ctxg, f32, 'mask_ctxg')
         ld = eng.to_device(ctxl, f32, 'ctxl')
         md = eng.to_device(ctxm, f32, 'ctxm')
-        tokens, lengths, scores, count = [t.cpu().numpy() for t in eng.beam_captions(gd, gm, ld, md, k, maxlen)]
+        tokens, lengths, scores, count = [t.cpu().numpy() for t in eng.beam_captions(gd, gm, ld, md, k, maxlen, use_graph=use_graph)]
         out = []
         for b in range(tokens.shape[0]):
             n = int(count[b])
