@@ -27,16 +27,11 @@ struct AttArgs {
   unsigned int *counters;                        // (rows) tickets, zero between launches
   float *att_scores;                             // (3,rows,T) raw temporal scores or null
   float *alpha_l;                                // (rows,T,R) spatial weights or null
-  long long *trace;                              // debug: clock64 stamps of CTA 0 (att_stream), or null
+  long long *trace;                              // debug: clock stamps per CTA and group (att_group), or null
   const void *blocks_base;                       // address range that holds the seven context blocks
   size_t blocks_bytes;                           // (L2 access-policy window of the launch), 0 = none
 };
-void att_set_trace(long long *p);
 int att_step_launch(const AttArgs &a, cudaStream_t stream);
-// att_stream.cu: persistent TMA-fed variant (H % 4 == 0, two ring slots fit in shared memory).
-// a.S = capacity (parts per row) of rec_vec / rec_ms; a.Tc unused.
-bool att_stream_plan(int rows, int T, int R, int H, int *nchunks, int *max_parts, int *nstages);
-int att_stream_launch(const AttArgs &a, cudaStream_t stream);
 // att_group.cu: four independent four-warp groups per CTA, each streaming whole frames (H % 4 == 0,
 // one frame fits in shared memory).  a.S = capacity (parts per row) of rec_vec / rec_ms.
 bool att_group_plan(int rows, int T, int R, int H, int *nctas, int *groups, int *max_parts);

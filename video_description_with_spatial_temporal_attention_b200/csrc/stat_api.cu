@@ -154,7 +154,7 @@ struct Ws {
   size_t hb, cb, cand_cost, cand_word, hist, hist_len, bscore, src_row, row_clip, dead_k, bdone;   // beam search
   size_t total;                      // floats
   int ldhp, ldpc, ldl, S, Tc;
-  int att_impl;      // 2 = att_group_kernel, 1 = att_stream_kernel (TMA ring), 0 = the generic att_step_kernel
+  int att_impl;      // 2 = att_group_kernel (bulk-copy streaming), 0 = the generic att_step_kernel
 };
 
 // k-slices for a skinny (rows <= 128) projection: enough CTAs to cover the SMs once
@@ -198,12 +198,9 @@ Ws ws_layout(const StatDims &d, int rows) {
   // (the streaming kernel reads the h-projection rows as float4: their offset E must be 16-byte aligned)
   w.att_impl = 0;
   if (d.E % 4 == 0) {
-    const char *impl = getenv("STAT_ATT_IMPL");      // "ring": the previous producer/consumer-ring kernel
-    if (impl && !strcmp(impl, "ring")) {
-      if (att_stream_plan(rows, d.T, d.R, d.H, &nchunks, &nparts, &nstages)) w.att_impl = 1;
-    } else if (!(impl && !strcmp(impl, "generic")) && att_group_plan(rows, d.T, d.R, d.H, &nchunks, &nstages, &nparts)) {
+    const char *impl = getenv("STAT_ATT_IMPL");      // "generic": force the plain kernel (cross-checks)
+    if (!(impl && !strcmp(impl, "generic")) && att_group_plan(rows, d.T, d.R, d.H, &nchunks, &nstages, &nparts))
       w.att_impl = 2;
-    }
   }
   if (w.att_impl) {
     w.S = nparts;
@@ -385,7 +382,6 @@ AttArgs att_args(const StatDims &d, const Prep &p, const float *P, const Ws &w, 
 
 int att_launch(const Ws &w, const AttArgs &a, cudaStream_t st) {
   if (w.att_impl == 2) return att_group_launch(a, st);
-  if (w.att_impl == 1) return att_stream_launch(a, st);
   return att_step_launch(a, st);
 }
 
@@ -613,7 +609,6 @@ int stat_profile_collect(float *ms_by_phase, int *count_by_phase, int nphase) {
 
 int stat_debug_gemm_trace(void *dev_buffer_64_int64) {
   gemm_set_trace(static_cast<long long *>(dev_buffer_64_int64));
-  att_set_trace(static_cast<long long *>(dev_buffer_64_int64));
   att_group_set_trace(static_cast<long long *>(dev_buffer_64_int64));
   return STAT_OK;
 }
