@@ -288,35 +288,72 @@ __global__ void __launch_bounds__(256) pick_kernel(const PickArgs a) {
       return;
     }
     const float mm = s_bm, inv = 1.0f / s_bs, sc = a.row_score[row];
-    for (int r = 0; r < a.beam_k; ++r) {
-      float bm = -INFINITY;
-      int bv = 0x7fffffff;
-      for (int v = threadIdx.x; v < a.V; v += 256) {
-        bool taken = false;
-        for (int q = 0; q < r; ++q) taken |= (s_taken[q] == v);
-        const float x = l[v];
-        if (!taken && x > bm) { bm = x; bv = v; }
+    // Every thread holds its own words (v = tid, tid + 256, ...) in registers -- one batch of independent
+    // loads -- and keeps the best not-yet-taken one; after a round only the owner of the winner looks at
+    // its words again.  Vocabularies beyond 256 * PICK_NB words re-read theirs from L2 instead.
+    constexpr int PICK_NB = 64;
+    const bool in_regs = a.V <= 256 * PICK_NB;
+    float xv[PICK_NB];
+    float bm = -INFINITY;
+    int bv = 0x7fffffff;
+    if (in_regs) {
+#pragma unroll
+      for (int s = 0; s < PICK_NB; ++s) {
+        const int v = threadIdx.x + 256 * s;
+        xv[s] = v < a.V ? l[v] : -INFINITY;
       }
 #pragma unroll
+      for (int s = 0; s < PICK_NB; ++s)
+        if (xv[s] > bm) { bm = xv[s]; bv = threadIdx.x + 256 * s; }
+    } else {
+      for (int v = threadIdx.x; v < a.V; v += 256) {
+        const float x = l[v];
+        if (x > bm) { bm = x; bv = v; }
+      }
+    }
+    for (int r = 0; r < a.beam_k; ++r) {
+      float wm = bm;
+      int wv = bv;
+#pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const float om = __shfl_xor_sync(0xffffffffu, bm, o);
-        const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        if (om > bm || (om == bm && ov < bv)) { bm = om; bv = ov; }
+        const float om = __shfl_xor_sync(0xffffffffu, wm, o);
+        const int ov = __shfl_xor_sync(0xffffffffu, wv, o);
+        if (om > wm || (om == wm && ov < wv)) { wm = om; wv = ov; }
       }
       __syncthreads();                       // previous round's readers of s_val / s_idx are done
-      if (lane == 0) { s_val[warp] = bm; s_idx[warp] = bv; }
+      if (lane == 0) { s_val[warp] = wm; s_idx[warp] = wv; }
       __syncthreads();
+      float b = s_val[0];
+      int i = s_idx[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w)
+        if (s_val[w] > b || (s_val[w] == b && s_idx[w] < i)) { b = s_val[w]; i = s_idx[w]; }
+      const bool ok = i < a.V;               // V < beam_k: no candidate left
       if (threadIdx.x == 0) {
-        float b = s_val[0];
-        int i = s_idx[0];
-        for (int w = 1; w < 8; ++w)
-          if (s_val[w] > b || (s_val[w] == b && s_idx[w] < i)) { b = s_val[w]; i = s_idx[w]; }
         s_taken[r] = i;
-        const bool ok = i < a.V;             // V < beam_k: no candidate left
         cc[r] = ok ? sc - logf(expf(b - mm) * inv) : INFINITY;   // as the reference: -log of the fp32 probability
         cw[r] = ok ? i : 0;
       }
-      __syncthreads();
+      if (ok && (i & 255) == static_cast<int>(threadIdx.x)) {
+        // my best word was taken: next best of my words
+        bm = -INFINITY;
+        bv = 0x7fffffff;
+        if (in_regs) {
+          const int slot = i >> 8;
+#pragma unroll
+          for (int s = 0; s < PICK_NB; ++s) {
+            if (s == slot) xv[s] = -INFINITY;
+            if (xv[s] > bm) { bm = xv[s]; bv = threadIdx.x + 256 * s; }
+          }
+        } else {
+          for (int v = threadIdx.x; v < a.V; v += 256) {
+            bool taken = (v == i);
+            for (int q = 0; q < r; ++q) taken |= (s_taken[q] == v);
+            const float x = l[v];
+            if (!taken && x > bm) { bm = x; bv = v; }
+          }
+        }
+      }
     }
     if (threadIdx.x >= a.beam_k && threadIdx.x < BEAM_KMAX) { cc[threadIdx.x] = INFINITY; cw[threadIdx.x] = 0; }
   }
@@ -345,9 +382,22 @@ __global__ void __launch_bounds__(32) beam_select_kernel(const BeamArgs a) {
     for (int i = lane; i < n; i += 32) s_hist[j][i] = a.hist[static_cast<size_t>(r0 + j) * BEAM_LMAX + i];
     if (lane == 0) s_len[j] = n;
   }
+  // candidates and flags of the clip into shared memory with all lanes (the selection below walks them
+  // serially: from global memory every probe would be a dependent L2 round trip)
+  __shared__ float s_cc[BEAM_KMAX][BEAM_KMAX];
+  __shared__ int s_cw[BEAM_KMAX][BEAM_KMAX];
+  __shared__ int s_alive[BEAM_KMAX];
+  for (int e = lane; e < k * k; e += 32) {
+    const int j = e / k, c = e - j * k;
+    s_cc[j][c] = a.cand_cost[static_cast<size_t>(r0 + j) * BEAM_KMAX + c];
+    s_cw[j][c] = a.cand_word[static_cast<size_t>(r0 + j) * BEAM_KMAX + c];
+  }
+  for (int j = lane; j < k; j += 32) s_alive[j] = a.alive[r0 + j];
+  const int dead0 = a.dead_k[b], nout0 = a.out_count[b];
+  __syncwarp();
   if (lane == 0) {
     // the k - dead cheapest of the live slots' candidates: ascending cost, lower flat index (slot*V + word) first
-    const int want = k - a.dead_k[b];
+    const int want = k - dead0;
     int head[BEAM_KMAX];                      // every slot's candidates are already in ascending order
     for (int j = 0; j < k; ++j) head[j] = 0;
     int n = 0;
@@ -356,14 +406,14 @@ __global__ void __launch_bounds__(32) beam_select_kernel(const BeamArgs a) {
       int bj = -1;
       long long bf = 0;
       for (int j = 0; j < k; ++j) {
-        if (!a.alive[r0 + j] || head[j] >= k) continue;
-        const float c = a.cand_cost[static_cast<size_t>(r0 + j) * BEAM_KMAX + head[j]];
-        const long long f = static_cast<long long>(j) * a.V + a.cand_word[static_cast<size_t>(r0 + j) * BEAM_KMAX + head[j]];
+        if (!s_alive[j] || head[j] >= k) continue;
+        const float c = s_cc[j][head[j]];
+        const long long f = static_cast<long long>(j) * a.V + s_cw[j][head[j]];
         if (c < bc || (c == bc && bj >= 0 && f < bf)) { bc = c; bj = j; bf = f; }
       }
       if (bj < 0 || bc == INFINITY) break;
       s_src[n] = bj;
-      s_word[n] = a.cand_word[static_cast<size_t>(r0 + bj) * BEAM_KMAX + head[bj]];
+      s_word[n] = s_cw[bj][head[bj]];
       s_cost[n] = bc;
       ++head[bj];
     }
@@ -372,7 +422,7 @@ __global__ void __launch_bounds__(32) beam_select_kernel(const BeamArgs a) {
   __syncwarp();
   const int nsel = s_nsel;
   // new hypotheses in rank order: token 0 retires one, the others become the live slots 0, 1, ...
-  int n_live = 0, n_out = a.out_count[b], dead = a.dead_k[b];
+  int n_live = 0, n_out = nout0, dead = dead0;
   for (int n = 0; n < nsel; ++n) {
     const int src = s_src[n], word = s_word[n], len = s_len[src];
     if (word == 0) {
