@@ -146,6 +146,11 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// same rendezvous without the release fence: for a CTA that has published nothing the others read
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // read a float from the shared memory of CTA `rank` of this cluster (same offset as `local`)
 __device__ __forceinline__ float ld_dsmem(const float *local, uint32_t rank) {
   uint32_t ra;
@@ -223,10 +228,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // Groups 2 and 3 ask for their first frame only when the first chunk of group 0 / 1 has landed:
   // the first copies of a CTA then arrive in two waves and the groups work out of phase from the
   // start (compute of one pair overlaps the copies of the other) instead of in lock-step.
+  // Only chunk P goes out here: chunk V (needed a phase later) is requested below, after the loads of
+  // the per-row constants have been issued, which would otherwise queue behind it.
   if (active && gt == 0 && g < nframes) {
     if (stagger && g >= 2) mbar_wait(smem_u32(bars + g - 2), 0);
     issue_p(g);
-    issue_v(g);
   }
 
   // ---- per-row constants of this thread's columns ------------------------------------------
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         }
         xb[qq] = (okq && a.selector) ? hq[a.off_sel] : 0.f;
       }
+      if (q0 == 0 && active && gt == 0 && g < nframes) issue_v(g);
       auto add4 = [](float4 &d, const float4 v) { d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w; };
 #pragma unroll
       for (int qq = 0; qq < 4; ++qq) {
@@ -559,7 +566,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
   }
   if (tr) tr[15] = clock64();
-  cluster_sync_all();       // partners keep their shared memory alive until rank 0 has read it
+  cluster_sync_relaxed();   // partners keep their shared memory alive until rank 0 has read it
 }
 
 int sm_count() {
