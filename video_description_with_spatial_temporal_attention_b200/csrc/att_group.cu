@@ -142,22 +142,43 @@ __device__ __forceinline__ uint32_t cluster_rank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ void cluster_sync_all() {
+__device__ __forceinline__ void cluster_arrive() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// same rendezvous without the release fence: for a CTA that has published nothing the others read
-__device__ __forceinline__ void cluster_sync_relaxed() {
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// read a float from the shared memory of CTA `rank` of this cluster (same offset as `local`)
-__device__ __forceinline__ float ld_dsmem(const float *local, uint32_t rank) {
+// address of `local` (a shared-memory location of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void *local, uint32_t rank) {
   uint32_t ra;
-  float v;
   asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
-  return v;
+  return ra;
+}
+// 16 bytes from registers into another CTA's shared memory; the write signals that CTA's mbarrier
+// (complete_tx), so no fence or cluster barrier is needed on either side
+__device__ __forceinline__ void st_async_v4(uint32_t remote_dst, float x, float y, float z, float w,
+                                            uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::
+                   "r"(remote_dst),
+               "r"(__float_as_uint(x)), "r"(__float_as_uint(y)), "r"(__float_as_uint(z)), "r"(__float_as_uint(w)),
+               "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  uint32_t spins = 0;
+  do {
+    if (++spins > (1u << 26)) __trap();
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
 }
 
 // NV = ceil(H / 512) float4 column chunks per thread (columns 4*gt + 512*j);
@@ -171,14 +192,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const int H = HT ? HT : a.H, T = a.T;
   const int R = RT ? RT : a.R;
   const int RH = R * H;
-  const int p_floats = RH + 2 * H, v_floats = 2 * RH + 2 * H;
+  const int p_floats = RH + 2 * H, v_floats = 2 * RH;
   const int slot_floats = p_floats + v_floats;
   float *slots = reinterpret_cast<float *>(smem_raw);
   float *s_red = slots + static_cast<size_t>(G) * slot_floats;   // [G][RMAX + 2][4] per-warp score partials
   float *s_lt = s_red + GMAX * (RMAX + 2) * 4;                    // [G][4]
   float *s_gms = s_lt + GMAX * 4;                                 // [G][8] group (max, sum) x 3
-  float *s_cms = s_gms + GMAX * 8;                                // [8] CTA (max, sum) x 3
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_cms + 8);       // fullP[G], fullV[G]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_gms + GMAX * 8);   // fullP[G], fullV[G], merge
+  // landing pads of rank 0 for the partial states of the other CTAs of the cluster:
+  // [cs - 1] x ([NV * 512][4] weighted sums of a column (g, m, lt, -) | [8] (max, sum) x 3)
+  float *s_pad = reinterpret_cast<float *>(bars + 2 * GMAX + 2);
+  constexpr int PAD_FLOATS = NV * 512 * 4 + 8;
 
   // cluster <-> decode row; CTA rank <-> slice [t0, t0 + nframes) of its T frames
   const int row = static_cast<int>(blockIdx.x) / cs;
@@ -202,8 +226,16 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
 
   if (tid < 2 * GMAX) mbar_init(smem_u32(bars + tid), 1);
-  if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (tid == 0) {
+    if (cs > 1 && rank == 0) {
+      // every other CTA of the cluster sends H x 16 bytes of weighted sums and 32 bytes of (max, sum)
+      mbar_init(smem_u32(bars + 2 * GMAX), 1);
+      mbar_expect_tx(smem_u32(bars + 2 * GMAX), static_cast<uint32_t>(cs - 1) * (static_cast<uint32_t>(H) * 16u + 32u));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  if (cs > 1) cluster_arrive();     // matched by cluster_wait() before the first remote write (end of kernel)
 
   const uint32_t bytes_rh = static_cast<uint32_t>(RH) * 4u, bytes_h = static_cast<uint32_t>(H) * 4u;
   auto issue_p = [&](int j) {
@@ -220,8 +252,6 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     mbar_expect_tx(bar_v, static_cast<uint32_t>(v_floats) * 4u);
     bulk_g2s(dst, a.ctxl0 + frame * RH, bytes_rh, bar_v, policy);
     bulk_g2s(dst + bytes_rh, a.qctxl + frame * RH, bytes_rh, bar_v, policy_q);
-    bulk_g2s(dst + 2 * bytes_rh, a.ctxg0 + frame * H, bytes_h, bar_v, policy);
-    bulk_g2s(dst + 2 * bytes_rh + bytes_h, a.ctxm0 + frame * H, bytes_h, bar_v, policy);
   };
   // The context blocks were written by the prologue of the batch, long before the kernel this launch
   // programmatically depends on: their first copies start before that kernel has finished.
@@ -329,7 +359,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     for (int j = g; j < nframes; j += G, ph ^= 1, ++fi) {
       const int t = t0 + j;
       const float *pL = slot_p, *pG = slot_p + RH, *pM = pG + H;
-      const float *cL0 = slot_v, *qL = slot_v + RH, *G0 = slot_v + 2 * RH, *M0 = G0 + H;
+      const float *cL0 = slot_v, *qL = slot_v + RH;
+      // the g / m values of the frame (2 x H floats) come straight from global memory: requested at the
+      // top of phase C, used after its barrier -- that keeps 4 KB per group of shared memory free
+      const float *G0 = a.ctxg0 + (static_cast<size_t>(clip) * T + t) * H;
+      const float *M0 = a.ctxm0 + (static_cast<size_t>(clip) * T + t) * H;
 
       // ---- A: region scores and the g / m scores of the frame -----------------------------
       mbar_wait(bar_p, ph);
@@ -398,14 +432,19 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       mbar_wait(bar_v, ph);
       if (tr && fi < 4) tr[4 + 3 * fi] = clock64();
       float4 cLv[NV], g0[NV], m0[NV];
+#pragma unroll
+      for (int jj = 0; jj < NV; ++jj) {
+        const int c = 4 * gt + 512 * jj;
+        const bool ok = HT || c < H;
+        g0[jj] = ok ? __ldg(reinterpret_cast<const float4 *>(G0 + c)) : z4;
+        m0[jj] = ok ? __ldg(reinterpret_cast<const float4 *>(M0 + c)) : z4;
+      }
       {
         float plt = su_lt;
 #pragma unroll
         for (int jj = 0; jj < NV; ++jj) {
           const int c = 4 * gt + 512 * jj;
           float4 c0 = z4, p0 = z4;
-          g0[jj] = z4;
-          m0[jj] = z4;
           if (HT || c < H) {
 #pragma unroll
             for (int r = 0; r < RU; ++r) {
@@ -417,8 +456,6 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             c0.x *= inv; c0.y *= inv; c0.z *= inv; c0.w *= inv;
             p0.x *= inv; p0.y *= inv; p0.z *= inv; p0.w *= inv;
             plt = tanh_acc4(p0, slt[jj], ult[jj], plt);
-            g0[jj] = ld4(G0 + c);
-            m0[jj] = ld4(M0 + c);
           }
           cLv[jj] = c0;
         }
@@ -506,58 +543,52 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
     return;
   }
-  // park the CTA state in group 0's P slot (nobody reads it any more) for the cluster merge
-  float *s_vec = slots;               // [3][H]
-  if (tid == 0) {
-#pragma unroll
-    for (int q = 0; q < 3; ++q) { s_cms[2 * q] = om[q]; s_cms[2 * q + 1] = os[q]; }
-  }
-#pragma unroll
-  for (int q = 0; q < 3; ++q)
+  cluster_wait();           // every CTA of the cluster has initialised its barriers (arrive: top of the kernel)
+  if (rank != 0) {
+    // push this CTA's state into its landing pad in rank 0 and leave: the data travel from registers
+    // and complete rank 0's merge barrier on arrival
+    float *pad = s_pad + static_cast<size_t>(rank - 1) * PAD_FLOATS;
+    const uint32_t rbar = dsmem_addr(bars + 2 * GMAX, 0);
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) {
       const int col = tid + 512 * k;
-      if (col < H) s_vec[q * H + col] = ov[q][k];
+      if (col < H) st_async_v4(dsmem_addr(pad + 4 * col, 0), ov[0][k], ov[1][k], ov[2][k], 0.f, rbar);
     }
-  cluster_sync_all();
-  if (rank == 0) {
-    // all remote values first (independent DSMEM loads), then the arithmetic
-    float pm[3][8], psum[3][8], v[3][8][NCOL];
-#pragma unroll
-    for (int q = 0; q < 3; ++q)
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const bool okp = p < cs;
-        pm[q][p] = okp ? ld_dsmem(s_cms + 2 * q, p) : -INFINITY;
-        psum[q][p] = okp ? ld_dsmem(s_cms + 2 * q + 1, p) : 0.f;
-#pragma unroll
-        for (int k = 0; k < NCOL; ++k) {
-          const int col = tid + 512 * k;
-          v[q][p][k] = (okp && col < H) ? ld_dsmem(s_vec + q * H + col, p) : 0.f;
-        }
-      }
+    if (tid == 0) {
+      st_async_v4(dsmem_addr(pad + NV * 512 * 4, 0), om[0], os[0], om[1], os[1], rbar);
+      st_async_v4(dsmem_addr(pad + NV * 512 * 4 + 4, 0), om[2], os[2], 0.f, 0.f, rbar);
+    }
+    if (tr) tr[15] = clock64();
+    return;
+  }
+  mbar_wait_cluster(smem_u32(bars + 2 * GMAX), 0);
+  {
+    // fixed order: this CTA first, then the pads by rank
     float o[NCOL];
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) o[k] = 0.f;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      float mx = -INFINITY;
+      float mx = om[q];
+      for (int p = 0; p + 1 < cs; ++p) mx = fmaxf(mx, s_pad[p * PAD_FLOATS + NV * 512 * 4 + 2 * q]);
+      const float w0 = expf(om[q] - mx);
+      float den = w0 * os[q];
+      float num[NCOL];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) mx = fmaxf(mx, pm[q][p]);
-      float w[8], den = 0.f;
+      for (int k = 0; k < NCOL; ++k) num[k] = w0 * ov[q][k];
+      for (int p = 0; p + 1 < cs; ++p) {
+        const float *pad = s_pad + static_cast<size_t>(p) * PAD_FLOATS;
+        const float w = expf(pad[NV * 512 * 4 + 2 * q] - mx);
+        den = fmaf(w, pad[NV * 512 * 4 + 2 * q + 1], den);
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        w[p] = (p < cs) ? expf(pm[q][p] - mx) : 0.f;
-        den = fmaf(w[p], psum[q][p], den);
+        for (int k = 0; k < NCOL; ++k) {
+          const int col = tid + 512 * k;
+          if (col < H) num[k] = fmaf(w, pad[4 * col + q], num[k]);
+        }
       }
       const float inv = 1.0f / den;
 #pragma unroll
-      for (int k = 0; k < NCOL; ++k) {
-        float num = 0.f;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) num = fmaf(w[p], v[q][p][k], num);
-        o[k] = fmaf(num, inv, o[k]);
-      }
+      for (int k = 0; k < NCOL; ++k) o[k] = fmaf(num[k], inv, o[k]);
     }
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) {
@@ -566,7 +597,6 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
   }
   if (tr) tr[15] = clock64();
-  cluster_sync_relaxed();   // partners keep their shared memory alive until rank 0 has read it
 }
 
 int sm_count() {
@@ -580,8 +610,9 @@ int sm_count() {
   return n;
 }
 
-size_t frame_bytes(int R, int H) { return (static_cast<size_t>(3) * R * H + 4 * static_cast<size_t>(H)) * 4; }
-constexpr size_t SMEM_EXTRA = (GMAX * (RMAX + 2) * 4 + GMAX * 4 + GMAX * 8 + 8) * 4 + 2 * GMAX * 8 + 128;
+size_t frame_bytes(int R, int H) { return (static_cast<size_t>(3) * R * H + 2 * static_cast<size_t>(H)) * 4; }
+size_t pad_bytes(int H) { return (static_cast<size_t>(H <= 512 ? 1 : 2) * 512 * 4 + 8) * 4; }
+constexpr size_t SMEM_EXTRA = (GMAX * (RMAX + 2) * 4 + GMAX * 4 + GMAX * 8) * 4 + (2 * GMAX + 2) * 8 + 128;
 constexpr size_t SMEM_MAX = 227 * 1024;
 
 // L2 eviction priority of the context-block copies: the blocks are re-read on every decode step,
@@ -617,7 +648,7 @@ uint64_t l2_policy_q() {
 
 template <int NV, int RT, int HT>
 int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
-  const size_t smem = G * frame_bytes(a.R, a.H) + SMEM_EXTRA;
+  const size_t smem = G * frame_bytes(a.R, a.H) + SMEM_EXTRA + (cs - 1) * pad_bytes(a.H);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     STAT_CUDA_CHECK(cudaFuncSetAttribute(att_group_kernel<NV, RT, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -679,11 +710,13 @@ int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
 // groups per CTA; the partial soft-max states never leave the cluster (max_parts = 1)
 bool att_group_plan(int rows, int T, int R, int H, int *cluster, int *groups, int *max_parts) {
   if ((H & 3) != 0 || H > 1024 || R > RMAX || R < 1 || rows < 1 || T < 1) return false;
-  int G = static_cast<int>((SMEM_MAX - SMEM_EXTRA) / frame_bytes(R, H));
-  if (G < 1) return false;
-  if (G > GMAX) G = GMAX;
   int cs = 1;
   while (cs < 8 && 2 * cs <= T && static_cast<long long>(rows) * 2 * cs <= sm_count()) cs *= 2;
+  // rank 0 of a cluster also holds one landing pad per partner
+  while (cs > 1 && SMEM_EXTRA + (cs - 1) * pad_bytes(H) + frame_bytes(R, H) > SMEM_MAX) cs /= 2;
+  if (SMEM_EXTRA + (cs - 1) * pad_bytes(H) + frame_bytes(R, H) > SMEM_MAX) return false;
+  int G = static_cast<int>((SMEM_MAX - SMEM_EXTRA - (cs - 1) * pad_bytes(H)) / frame_bytes(R, H));
+  if (G > GMAX) G = GMAX;
   *cluster = cs;
   *groups = G;
   *max_parts = 1;
