@@ -15,3 +15,5 @@ tail -2 gpurun_out/ncu_gemm.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python tools/one_step.py > gpurun_out/ncu_stdout.log 2>&1
 tail -1 gpurun_out/ncu_stdout.log
 ncu -i gpurun_out/prof_att.ncu-rep --page source --csv --print-source sass > gpurun_out/att_sass.csv 2>/dev/null
+# 5. DRAM bytes / L2 hit rate of every launch of the step in situ (one pass each, caches untouched)
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct --cache-control none --clock-control none -c 400 --csv --log-file gpurun_out/step_dram.csv python tools/one_step.py > /dev/null 2>&1
