@@ -359,6 +359,33 @@ def test_edge_cases(torch_cuda):
         np.testing.assert_allclose(lp, want, atol=TOL_LP, err_msg=str((B, T, R, L)))
 
 
+@pytest.mark.parametrize('H,B,T,R', [(1024, 3, 5, 2),     # two float4 chunks per thread, clusters of 2
+                                     (768, 70, 4, 3),     # H not a power of two, one CTA per row
+                                     (520, 9, 26, 8),     # runtime H <= 1024 with a partial second chunk
+                                     (256, 20, 9, 16),    # R = 16, clusters of 2..4, fewer columns than threads
+                                     (512, 5, 26, 8),     # BASELINE width, clusters of 8 (push-merge from 7 partners)
+                                     (36, 4, 6, 3),       # H % 4 == 0 but tiny: most threads of a group idle
+                                     (30, 4, 6, 3)])      # H % 4 != 0: the generic kernel
+def test_attention_kernel_variants(torch_cuda, H, B, T, R):
+    """Every instantiation / cluster size / merge width of the attention kernel against the fp64 oracle:
+    log-probs, all four attention weights, greedy tokens."""
+    o = stat.default_options(dim=H, dim_word=32, ctxg_dim=H, ctxl_dim=40, ctxm_dim=24, n_words=61)
+    params = so.trained_like_params(o, seed=H % 97)
+    batch = synthetic.make_batch(o, B=B, T=T, R=R, L=4, seed=H % 89, zero_tail=True)
+    model, tp, f_log_probs, f_alphas, _, _ = _build(o, params)
+    want, aux = so.forward_teacher(params, o, *batch, dtype=np.float64, return_all=True)
+    np.testing.assert_allclose(f_log_probs(*batch), want, atol=TOL_LP)
+    got = f_alphas(*batch)
+    for g_, k_ in zip(got, ('alphaL', 'alphaG', 'alphaM', 'alphaLT')):
+        np.testing.assert_allclose(g_, np.stack([s_[k_] for s_ in aux['steps']]), atol=TOL_A_WIDE, err_msg=k_)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+    toks, lens, scores = model.greedy_batch(tp, o, ctxg, mg, ctxl, ctxm, maxlen=5)
+    wt, wl, ws = so.greedy_decode_batch(params, o, ctxg, mg, ctxl, ctxm, 5, dtype=np.float64)[:3]
+    for b in range(B):
+        assert [int(t) for t in toks[b, :lens[b]]] == [int(t) for t in wt[b, :wl[b]]], b
+    np.testing.assert_allclose(scores, ws, atol=TOL_LP)
+
+
 # ---------------------------------------------------------------------------
 # the callers either side of the path (SURVEY N3, N4): pred_probs over prepare_data batches,
 # parameters through the reference's checkpoint files
