@@ -185,6 +185,46 @@ def step_traffic(tag, md):
             'source': '%s_step_dram.csv (one ncu pass per launch, --cache-control none)' % tag}
 
 
+def bench_launch_list(tag, md):
+    """Launch list of bench.py itself (first 1200 launches): one replay of the captured K0 + 20-step graph."""
+    path = os.path.join(SRC, 'bench_launches.csv')
+    if not os.path.isfile(path):
+        return
+    rows = [r for r in csv.reader(l for l in open(path) if not l.startswith('=='))]
+    hdr = rows[0]
+    ki, vi, ui, gi = (hdr.index(k) for k in ('Kernel Name', 'Metric Value', 'Metric Unit', 'Grid Size'))
+    seq = []
+    for row in rows[1:]:
+        if len(row) <= vi:
+            continue
+        v = float(row[vi].replace(',', ''))
+        seq.append((re.sub(r'\(.*', '', row[ki]).split('::')[-1], row[gi], v / 1000 if row[ui] == 'ns' else v))
+    with open(os.path.join(OUT, '%s_bench_launches.csv' % tag), 'w') as f:
+        f.write('index,kernel,grid,duration_us\n')
+        for i, (n, g, v) in enumerate(seq):
+            f.write('%d,"%s","%s",%.2f\n' % (i, n, g, v))
+    starts = [i for i, x in enumerate(seq) if x[0].startswith('meanpool')]
+    if len(starts) < 4:
+        return
+    a, b = starts[2], starts[3]               # a graph replay (the first two passes are the eager warm-up / capture)
+    step = seq[a:b]
+    tot = sum(v for _, _, v in step)
+    agg = collections.OrderedDict()
+    for n, g, v in step:
+        e = agg.setdefault((n, g), [0, 0.0])
+        e[0] += 1
+        e[1] += v
+    md.append('## Launch list of `bench.py --steps 2 --warmup 3` itself — `%s_bench_launches.csv`\n' % tag)
+    md.append('`ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 python bench.py --steps 2 --warmup 3`: the '
+              'first 1200 launches of the bench command (parameter packing, eager warm-up, then replays of the captured '
+              'K0 + 20-step graph, 150 kernel nodes each).  One replay = launches %d..%d, %.0f us in total under the '
+              'profiler (serialised); shares agree with the eager list above.\n' % (a, b - 1, tot))
+    md.append('| kernel | grid | launches | total us | avg us | share |\n|---|---|---|---|---|---|')
+    for (n, g), (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
+        md.append('| %s | %s | %d | %.1f | %.2f | %.1f%% |' % (n, g, c, t, t / c, 100 * t / tot))
+    md.append('')
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
     os.makedirs(OUT, exist_ok=True)
@@ -193,6 +233,7 @@ def main():
           'on `tools/one_step.py` (one eager pass of the bench workload).  Numbers under a profiler are evidence '
           'of *where* time and bytes go; throughput claims come from `bench.py`.\n']
     launch_list(tag, md)
+    bench_launch_list(tag, md)
     att = summarize(os.path.join(SRC, 'prof_att.ncu-rep'), 'att_group_kernel — the HBM/L2-bound attention kernel (full set: replayed, caches flushed between passes = cold numbers)', md)
     insitu = step_traffic(tag, md)
     sass_profile(md)
