@@ -9,31 +9,32 @@
 // by the other groups' frames.
 //
 // Per frame a group receives two bulk-copy chunks in its private shared-memory slots
-//   P = pctxl[t] (R*H) | pctxg[t] | pctxm[t]                  -> scores         (S1, S4, S5)
-//   V = ctxl0[t] (R*H) | qctxl[t] (R*H) | ctxg0[t] | ctxm0[t] -> weighted sums  (S3, S6-S8)
-// issued by the group's own thread 0 (cp.async.bulk + mbarrier complete_tx, L2 evict_last: the
-// blocks are re-read every step).  The group barrier that follows the last read of a slot is what
-// frees it, so the copy of P(j+1) flies during the second half of frame j and V(j+1) during the
-// first half of frame j+1; every byte of the seven context blocks is read exactly once per step.
-// Each thread owns a float4 of columns:
+//   P = pctxl[t] (R*H) | pctxg[t] | pctxm[t]   -> scores         (S1, S4, S5)
+//   V = ctxl0[t] (R*H) | qctxl[t] (R*H)        -> weighted sums  (S3, S6-S7)
+// issued by the group's own thread 0 (cp.async.bulk + mbarrier complete_tx; L2 priorities: qctxl is
+// streamed evict_first, the other blocks evict_last -- they are re-read every step and together with
+// the weights of the step do not all fit in the L2).  The group barrier that follows the last read
+// of a slot is what frees it, so the copy of P(j+1) flies during the second half of frame j and
+// V(j+1) during the first half of frame j+1; ctxg0[t] / ctxm0[t] (2 x H floats) are read straight from
+// global memory at the top of phase C.  Every byte of the seven blocks is read once per step.
+// Groups 2 and 3 request their first frame when the first chunk of groups 0 / 1 has landed, so the
+// groups work out of phase rather than in lock-step.  Each thread owns a float4 of columns:
 //   A. sum_h tanh(pctxl + h.Wdl) * Ul for the R regions and the g / m scores (four tanh share one
 //      reciprocal); one butterfly reduction for all R (+2) values, group barrier, soft-max over R
 //   C. alpha-weighted sums cL = sum_r a_r ctxl0_r (S3) and pLT = sum_r a_r qctxl_r + h.Wdlt + blt
 //      (S6: the :416 GEMM folded by linearity), the lt score, group barrier            (S7)
 //   D. fold the frame into the running (max, sum, weighted vector) states of the g / m / lt
 //      temporal soft-maxes; the weighted vectors live in registers.
-// At the end the G group states are merged in shared memory, the cluster synchronises, and rank
-// 0 merges the cs parts through distributed shared memory, applies the selector gate and
-// writes ctx (S8, S9).  No global scratch, no atomics; the merge order is fixed, so results
-// are bit-reproducible.
-// The kernel is launched with programmatic stream serialization: barrier set-up, the score
-// vectors and the first context copies overlap the tail of the previous kernel; the
-// h-projections are read after griddepcontrol.wait.
+// At the end the G group states are merged in shared memory; the other CTAs of the cluster push
+// their state from registers into landing pads of rank 0 (st.async + mbarrier complete_tx: no
+// fence, no cluster barrier on the way out) and exit; rank 0 waits on its mbarrier, merges in rank
+// order, applies the selector gate and writes ctx (S8, S9).  No global scratch, no atomics; the
+// merge order is fixed, so results are bit-reproducible.
+// The kernel calls griddepcontrol.wait before it reads the h-projections, so it may be launched with
+// programmatic stream serialization (STAT_PDL_ATT=1); by default it is not, see launch().
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-
-#include <type_traits>
 
 #include "kernels.cuh"
 #include "stat_common.cuh"
