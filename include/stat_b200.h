@@ -185,6 +185,25 @@ int stat_step(const StatDims *d, const void *prepared, void *ws, int rows,
               const float *h_in, const float *c_in,
               float *out_probs, float *out_h, float *out_c, void *stream);
 
+/* ---- parameter update of the training step (common.py:178-230, ---------------
+ * model_attention.py:1194-1203).  All parameters / gradients / optimizer states
+ * live in flat fp32 buffers of n elements in init_params order (the layout the
+ * data-parallel all-reduce uses); buffers 16-byte aligned.
+ * stat_grad_clip: g2 = sum g^2; if g2 > clip_c^2 every gradient is scaled by
+ *   clip_c / sqrt(g2) (clip_c <= 0: no clipping).  `scratch` holds
+ *   stat_clip_scratch_bytes() bytes; out_g2 (optional, 2 floats) receives g2 and
+ *   the factor applied.  Deterministic (fixed-shape two-stage reduction).
+ * stat_adam_step: the reference's adam, constants as in common.py:204-207
+ *   (lr0 = 2e-4 -- the lr argument of f_update is ignored there -- b1 = 0.1 and
+ *   b2 = 0.001 weight the NEW gradient, e = 1e-8), `step` = 1-based update count.
+ * stat_adadelta_step: phase 0 = the running-gradient update f_grad_shared does
+ *   (rg2 <- 0.95 rg2 + 0.05 g^2), phase 1 = f_update's step. */
+size_t stat_clip_scratch_bytes(void);
+int stat_grad_clip(float *grads, size_t n, float clip_c, void *scratch, float *out_g2, void *stream);
+int stat_adam_step(float *params, const float *grads, float *m, float *v, size_t n, int step, void *stream);
+int stat_adadelta_step(float *params, const float *grads, float *rg2, float *ru2, size_t n, int phase,
+                       void *stream);
+
 /* ---- the attention fragment of one step alone (model_attention.py:370-435) ---
  * S1-S9 for `rows` decode rows whose hidden-state projections (h.Wd*_att, selector
  * logit) already sit in the "hp" region of `ws` (left there by the previous

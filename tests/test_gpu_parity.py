@@ -418,3 +418,38 @@ def test_pred_probs_over_prepare_data_and_checkpoint(torch_cuda, tmp_path):
     _, _, f2, _, _, _ = _build(o2, p2)
     batch = de.prepare_data(eng, eng.test)
     assert np.array_equal(f2(*batch), f_log_probs(*batch))
+
+
+# ---------------------------------------------------------------------------
+# the parameter update of the training step (second half): clipping, adam, adadelta
+# ---------------------------------------------------------------------------
+def test_optimizers_match_reference_update_rules(torch_cuda):
+    torch = torch_cuda
+    from oracle import optim_oracle as oo
+    from video_description_with_spatial_temporal_attention_b200 import optim
+    o = stat.default_options(dim=24, dim_word=20, ctxg_dim=24, ctxl_dim=36, ctxm_dim=28, n_words=103)
+    params = ma.Attention().init_params(o)
+    rng = np.random.RandomState(5)
+    for cls, ocls in ((optim.Adam, oo.Adam), (optim.Adadelta, oo.Adadelta)):
+        flat = optim.FlatParams(params)
+        assert list(flat.views.keys()) == list(params.keys()) and flat.n == sum(int(np.prod(v.shape)) for v in params.values())
+        opt, ref = cls(flat), ocls(flat.n)
+        p_ref = flat.flat.cpu().numpy().copy()
+        for step in range(6):
+            g = (rng.randn(flat.n) * (10.0 if step % 2 else 0.01)).astype('float32')
+            opt.grads.copy_(torch.from_numpy(g))
+            info = opt.clip(10.0).cpu().numpy()
+            g_ref, g2 = oo.clip(g, 10.0)
+            np.testing.assert_allclose(info[0], g2, rtol=2e-6)
+            assert (info[1] < 1.0) == (g2 > 100.0)
+            np.testing.assert_allclose(opt.grads.cpu().numpy(), g_ref, rtol=2e-6, atol=1e-12)
+            if cls is optim.Adadelta:
+                opt.grad_shared()
+                ref.grad_shared(g_ref)
+            opt.f_update(0.01)
+            p_ref = ref.update(p_ref, g_ref)
+            np.testing.assert_allclose(flat.flat.cpu().numpy(), p_ref, rtol=3e-6, atol=2e-8, err_msg='%s step %d' % (cls.__name__, step))
+        # the views are the parameters: what unzip() returns is what was updated
+        un = flat.unzip()
+        assert np.array_equal(un['Wemb'].reshape(-1), flat.flat[:un['Wemb'].size].cpu().numpy())
+        assert un['decoder_b_sel'].shape == params['decoder_b_sel'].shape

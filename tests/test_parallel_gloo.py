@@ -65,3 +65,40 @@ def test_gather_and_max_world2():
         assert l == [i % 4 + 1 for i in range(n_total)]
         assert s == [i * 0.5 for i in range(n_total)]
         assert mx == [2.0, 5.0]
+
+
+def _allreduce_worker(rank, world, port, q):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import optim_oracle as oo
+    from video_description_with_spatial_temporal_attention_b200 import optim
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    n = 1003
+    local = np.random.RandomState(100 + rank).randn(n).astype('float32')
+    g = torch.from_numpy(local.copy())
+    optim.allreduce_grads(g)                              # SUM over the ranks, in place
+    total = sum(np.random.RandomState(100 + r).randn(n).astype('float32') for r in range(world))
+    ok = bool(np.allclose(g.numpy(), total, rtol=1e-6, atol=1e-6))
+    # clipping happens after the all-reduce and the update is the same on every rank: identical parameters
+    gc, _ = oo.clip(g.numpy(), 5.0)
+    p = oo.Adam(n).update(np.zeros(n, 'float32'), gc)
+    gathered = [torch.zeros(n) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(p))
+    same = all(torch.equal(gathered[0], t) for t in gathered)
+    q.put((rank, ok, same))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_then_clip_then_update_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok and same for _, ok, same in res), res

@@ -136,6 +136,12 @@ int beam_init_launch(const BeamArgs &a, const float *h0c0, float *h, float *c, i
 int gather_state_launch(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h, float *dst_c,
                         int rows, int H, cudaStream_t stream);
 
+// ---- optim.cu: gradient clipping and the reference's optimizers over one flat parameter buffer ----
+size_t clip_scratch_bytes();
+int grad_clip_launch(float *grads, size_t n, float clip_c, void *scratch, cudaStream_t stream);
+int adam_launch(float *p, const float *g, float *m, float *v, size_t n, int step, cudaStream_t stream);
+int adadelta_launch(float *p, const float *g, float *rg2, float *ru2, size_t n, int phase, cudaStream_t stream);
+
 int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, int T, int D,
                     cudaStream_t stream);
 // dst (rows_out, ld_dst) [r0 + n][k] = src (K, N) [k][n]   (weights -> K-major)

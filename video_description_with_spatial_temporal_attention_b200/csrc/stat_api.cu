@@ -624,6 +624,37 @@ long long stat_set_l2_persist(long long bytes) {
   return static_cast<long long>(want);
 }
 
+size_t stat_clip_scratch_bytes(void) { return clip_scratch_bytes(); }
+
+int stat_grad_clip(float *grads, size_t n, float clip_c, void *scratch, float *out_g2, void *stream) {
+  STAT_TRY(check_device());
+  STAT_REQUIRE(grads && scratch && n > 0, STAT_EINVAL, "grad_clip: bad argument");
+  STAT_REQUIRE((reinterpret_cast<uintptr_t>(grads) & 15) == 0 && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0,
+               STAT_EALIGN, "grad_clip: buffers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  STAT_TRY(grad_clip_launch(grads, n, clip_c, scratch, st));
+  if (out_g2)
+    STAT_CUDA_CHECK(cudaMemcpyAsync(out_g2, static_cast<char *>(scratch) + clip_scratch_bytes() - 16, 2 * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+  return STAT_OK;
+}
+
+int stat_adam_step(float *params, const float *grads, float *m, float *v, size_t n, int step, void *stream) {
+  STAT_TRY(check_device());
+  STAT_REQUIRE(params && grads && m && v && n > 0 && step >= 1, STAT_EINVAL, "adam_step: bad argument (step is 1-based)");
+  STAT_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(m) |
+                 reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+               STAT_EALIGN, "adam_step: buffers must be 16-byte aligned");
+  return adam_launch(params, grads, m, v, n, step, static_cast<cudaStream_t>(stream));
+}
+
+int stat_adadelta_step(float *params, const float *grads, float *rg2, float *ru2, size_t n, int phase, void *stream) {
+  STAT_TRY(check_device());
+  STAT_REQUIRE(params && grads && rg2 && ru2 && n > 0 && (phase == 0 || phase == 1), STAT_EINVAL,
+               "adadelta_step: bad argument");
+  return adadelta_launch(params, grads, rg2, ru2, n, phase, static_cast<cudaStream_t>(stream));
+}
+
 int stat_set_gemm_impl(int impl) {
   STAT_REQUIRE(impl >= 0 && impl <= 2, STAT_EINVAL,
                "gemm impl must be 0 (tcgen05 3xTF32, A from TMEM), 1 (fp32 SIMT) or 2 (tcgen05 3xTF32, A from smem)");
