@@ -453,3 +453,23 @@ def test_optimizers_match_reference_update_rules(torch_cuda):
         un = flat.unzip()
         assert np.array_equal(un['Wemb'].reshape(-1), flat.flat[:un['Wemb'].size].cpu().numpy())
         assert un['decoder_b_sel'].shape == params['decoder_b_sel'].shape
+
+
+def test_beam_edge_cases_vs_host_search(torch_cuda):
+    """Tiny vocabulary (fewer words than beam slots squared), a single clip, maxlen 1 and 2, a model that
+    ends every caption at once: the device bookkeeping must still equal the reference-shaped host search."""
+    o = stat.default_options(dim=16, dim_word=12, ctxg_dim=16, ctxl_dim=20, ctxm_dim=12, n_words=5)
+    for seed, eos_bias in ((1, 0.0), (2, 6.0), (3, -6.0)):
+        params = so.trained_like_params(o, seed=seed)
+        params['ff_logit_b'] = params['ff_logit_b'].copy()
+        params['ff_logit_b'][0] += eos_bias
+        for (B, k, maxlen) in ((1, 4, 1), (1, 4, 2), (3, 5, 6), (2, 16, 4)):
+            batch = synthetic.make_batch(o, B=B, T=3, R=2, L=3, seed=seed + B)
+            x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+            model, tp, _, _, f_init, f_next = _build(o, params)
+            got = model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=k, maxlen=maxlen)
+            for b in range(B):
+                hyp, sc, _, _ = model.gen_sample(tp, f_init, f_next, ctxg[b], mg[b], ctxl[b], ml[b], ctxm[b], mm[b], o,
+                                                 None, k, maxlen, False)
+                assert got[b][0] == hyp, (seed, B, k, maxlen, b, got[b][0], hyp)
+                np.testing.assert_allclose(np.asarray(got[b][1]), np.asarray(sc), atol=2e-5, rtol=2e-6)
