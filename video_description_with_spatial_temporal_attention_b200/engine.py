@@ -6,8 +6,10 @@ in this package) and the C ABI; all arithmetic happens in the CUDA kernels.
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -18,6 +20,25 @@ from ._lib import StatDims, StatParams, check
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+# Engines alive in this process.  Their captured CUDA graphs are released (after a device
+# synchronisation) before the interpreter starts tearing modules down: graph-exec objects destroyed in
+# arbitrary order during finalisation, possibly after the CUDA context, are a known way to die at exit.
+_ENGINES = weakref.WeakSet()
+
+
+def _release_graphs():
+    try:
+        if torch.cuda.is_available() and torch.cuda.is_initialized():
+            torch.cuda.synchronize()
+    except Exception:
+        pass
+    for e in list(_ENGINES):
+        e._graphs.clear()
+
+
+atexit.register(_release_graphs)
 
 
 def _stream():
@@ -48,6 +69,7 @@ class Engine(object):
         self._ws = {}
         self._pinned = {}
         self._graphs = {}
+        _ENGINES.add(self)
 
     # ---- dims / buffers --------------------------------------------------
     def dims(self, B, T, R):
