@@ -27,3 +27,19 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if 'gpu' in it.keywords:
             it.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Drop the engines (captured CUDA graphs, workspaces) while the CUDA context is still healthy instead
+    of leaving them to interpreter finalisation."""
+    import gc
+    try:
+        import torch
+        if not (torch.cuda.is_available() and torch.cuda.is_initialized()):
+            return
+        from video_description_with_spatial_temporal_attention_b200 import engine
+        engine._release_graphs()
+        gc.collect()
+        torch.cuda.synchronize()
+    except Exception:
+        pass
