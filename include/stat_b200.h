@@ -197,8 +197,13 @@ int stat_step(const StatDims *d, const void *prepared, void *ws, int rows,
  *   (lr0 = 2e-4 -- the lr argument of f_update is ignored there -- b1 = 0.1 and
  *   b2 = 0.001 weight the NEW gradient, e = 1e-8), `step` = 1-based update count.
  * stat_adadelta_step: phase 0 = the running-gradient update f_grad_shared does
- *   (rg2 <- 0.95 rg2 + 0.05 g^2), phase 1 = f_update's step. */
+ *   (rg2 <- 0.95 rg2 + 0.05 g^2), phase 1 = f_update's step.
+ * stat_alpha_coverage: the attention-coverage regulariser of the training cost
+ *   (model_attention.py:1138-1147) without its alpha_c factor: for alphas
+ *   (L, rows, n) out[0] = ((1 - alphas.sum(0))**2).sum(0).mean(), i.e. the sum over
+ *   rows and mean over the n attended positions; `scratch` as for stat_grad_clip. */
 size_t stat_clip_scratch_bytes(void);
+int stat_alpha_coverage(const float *alphas, int L, int rows, int n, void *scratch, float *out, void *stream);
 int stat_grad_clip(float *grads, size_t n, float clip_c, void *scratch, float *out_g2, void *stream);
 int stat_adam_step(float *params, const float *grads, float *m, float *v, size_t n, int step, void *stream);
 int stat_adadelta_step(float *params, const float *grads, float *rg2, float *ru2, size_t n, int phase,

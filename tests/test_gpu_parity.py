@@ -473,3 +473,17 @@ def test_beam_edge_cases_vs_host_search(torch_cuda):
                                                  None, k, maxlen, False)
                 assert got[b][0] == hyp, (seed, B, k, maxlen, b, got[b][0], hyp)
                 np.testing.assert_allclose(np.asarray(got[b][1]), np.asarray(sc), atol=2e-5, rtol=2e-6)
+
+
+def test_training_cost_with_regularisers(torch_cuda):
+    """The first output of f_grad_shared: mean NLL + weight decay + attention-coverage terms
+    (model_attention.py:1129-1147) against the gradient oracle's cost."""
+    from oracle import grad_oracle as go
+    o = stat.default_options(dim=32, dim_word=24, ctxg_dim=48, ctxl_dim=40, ctxm_dim=28, n_words=53, global_proj=True)
+    params = so.trained_like_params(o, seed=8)
+    batch = synthetic.make_batch(o, B=6, T=7, R=3, L=5, seed=8, zero_tail=True)
+    model, tp, _, _, _, _ = _build(o, params)
+    for alpha_c, decay_c in ((0., 0.), (0.70602, 0.), (0., 1e-4), (0.70602, 1e-4)):
+        want = go.cost_and_grads(params, o, batch, alpha_c=alpha_c, decay_c=decay_c)[0]
+        got = model.train_cost(tp, o, batch, alpha_c=alpha_c, decay_c=decay_c)
+        assert abs(got - want) < 1e-4 * max(1.0, abs(want)), (alpha_c, decay_c, got, want)

@@ -74,6 +74,7 @@ def _declare(lib):
     lib.stat_clip_scratch_bytes.restype = sz
     lib.stat_grad_clip.argtypes = [vp, sz, C.c_float, vp, vp, vp]
     lib.stat_adam_step.argtypes = [vp, vp, vp, vp, sz, i32, vp]
+    lib.stat_alpha_coverage.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     lib.stat_adadelta_step.argtypes = [vp, vp, vp, vp, sz, i32, vp]
     lib.stat_profile_enable.argtypes = [i32]
     lib.stat_profile_phases.restype = i32
@@ -82,7 +83,7 @@ def _declare(lib):
     lib.stat_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int), i32]
     for n in ('stat_attention', 'stat_profile_enable', 'stat_profile_collect', 'stat_set_gemm_impl', 'stat_prepare_params', 'stat_init_state', 'stat_workspace_region', 'stat_precompute',
               'stat_forward_teacher', 'stat_decode_greedy', 'stat_decode_beam', 'stat_step', 'stat_gemm', 'stat_grad_clip',
-              'stat_adam_step', 'stat_adadelta_step'):
+              'stat_adam_step', 'stat_adadelta_step', 'stat_alpha_coverage'):
         getattr(lib, n).restype = i32
 
 

@@ -140,6 +140,7 @@ int gather_state_launch(const float *src_h, const float *src_c, const int32_t *s
 size_t clip_scratch_bytes();
 int grad_clip_launch(float *grads, size_t n, float clip_c, void *scratch, cudaStream_t stream);
 int adam_launch(float *p, const float *g, float *m, float *v, size_t n, int step, cudaStream_t stream);
+int coverage_launch(const float *alphas, int L, int rows, int n, void *scratch, float *out, cudaStream_t stream);
 int adadelta_launch(float *p, const float *g, float *rg2, float *ru2, size_t n, int phase, cudaStream_t stream);
 
 int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, int T, int D,

@@ -115,7 +115,53 @@ __global__ void __launch_bounds__(OPT_THREADS) adadelta_kernel(float *p, const f
   }
 }
 
+// ---- attention-coverage regulariser (model_attention.py:1138-1147): for alphas (L, rows, n),
+// ((1 - alphas.sum(0))**2).sum(0).mean() = (1/n) sum_{b,j} (1 - sum_l alphas[l,b,j])^2; same two
+// fixed-shape stages as the sum of squares
+__global__ void __launch_bounds__(OPT_THREADS) coverage_partial_kernel(const float *alphas, int L, size_t rows_n,
+                                                                      double *partial) {
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(OPT_THREADS) + threadIdx.x; i < rows_n;
+       i += static_cast<size_t>(OPT_BLOCKS) * OPT_THREADS) {
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += alphas[static_cast<size_t>(l) * rows_n + i];
+    const double dlt = 1.0 - static_cast<double>(s);
+    acc += dlt * dlt;
+  }
+  __shared__ double sm[OPT_THREADS];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = OPT_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+
+__global__ void __launch_bounds__(OPT_THREADS) coverage_final_kernel(const double *partial, double inv_n, float *out) {
+  __shared__ double sm[OPT_THREADS];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < OPT_BLOCKS; i += OPT_THREADS) acc += partial[i];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = OPT_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = static_cast<float>(sm[0] * inv_n);
+}
+
 }  // namespace
+
+int coverage_launch(const float *alphas, int L, int rows, int n, void *scratch, float *out, cudaStream_t stream) {
+  double *partial = static_cast<double *>(scratch);
+  coverage_partial_kernel<<<OPT_BLOCKS, OPT_THREADS, 0, stream>>>(alphas, L, static_cast<size_t>(rows) * n, partial);
+  note_launch();
+  coverage_final_kernel<<<1, OPT_THREADS, 0, stream>>>(partial, 1.0 / n, out);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
 
 size_t clip_scratch_bytes() { return OPT_BLOCKS * sizeof(double) + 16; }
 

@@ -639,6 +639,12 @@ int stat_grad_clip(float *grads, size_t n, float clip_c, void *scratch, float *o
   return STAT_OK;
 }
 
+int stat_alpha_coverage(const float *alphas, int L, int rows, int n, void *scratch, float *out, void *stream) {
+  STAT_TRY(check_device());
+  STAT_REQUIRE(alphas && scratch && out && L >= 1 && rows >= 1 && n >= 1, STAT_EINVAL, "alpha_coverage: bad argument");
+  return coverage_launch(alphas, L, rows, n, scratch, out, static_cast<cudaStream_t>(stream));
+}
+
 int stat_adam_step(float *params, const float *grads, float *m, float *v, size_t n, int step, void *stream) {
   STAT_TRY(check_device());
   STAT_REQUIRE(params && grads && m && v && n > 0 && step >= 1, STAT_EINVAL, "adam_step: bad argument (step is 1-based)");

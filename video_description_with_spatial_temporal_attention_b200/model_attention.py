@@ -361,6 +361,35 @@ class Attention(object):
         perp = 2 ** (numpy.sum(nll) / numpy.sum(lens) / numpy.log(2))
         return -1 * numpy.mean(probs), perp
 
+    # ---- training objective (model_attention.py:1129-1147), the first output of f_grad_shared ----
+    def train_cost(self, tparams, options, batch, alpha_c=0., decay_c=0.):
+        """cost = mean_b(-f_log_probs) + decay_c * sum_params sum(p^2) + alpha_c * sum over the four attentions
+        of ((1 - alphas.sum(0))**2).sum(0).mean(), with the current use_noise setting (dropout masks drawn on the
+        device when it is 1).  The gradients of this cost (the rest of f_grad_shared) are not built yet."""
+        import ctypes as C
+        model = getattr(self, '_model', None)
+        if model is None or model.tparams is not tparams:
+            raise RuntimeError('call build_model(tparams, options) first')
+        lp, alphas, _ = model.run_teacher(batch, want_alphas=alpha_c > 0.)
+        cost = float((-lp.cpu().numpy().astype('float64')).mean())                       # :1129
+        if decay_c > 0.:                                                                  # :1130-1136
+            cost += float(decay_c) * sum(float((numpy.asarray(v.get_value(), 'float64') ** 2).sum())
+                                         for v in tparams.values())
+        if alpha_c > 0.:                                                                  # :1138-1147
+            eng = model.engine()
+            lib = eng.lib
+            scratch = torch.empty((int(lib.stat_clip_scratch_bytes()) + 3) // 4, dtype=torch.float32, device=eng.device)
+            out = torch.zeros(4, dtype=torch.float32, device=eng.device)
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            for i, a in enumerate(alphas):
+                L, rows = a.shape[0], a.shape[1]
+                n = int(a.numel() // (L * rows))
+                from ._lib import check
+                check(lib.stat_alpha_coverage(C.c_void_p(a.data_ptr()), L, rows, n, C.c_void_p(scratch.data_ptr()),
+                                              C.c_void_p(out[i:].data_ptr()), stream))
+            cost += float(alpha_c) * float(out.cpu().numpy().astype('float64').sum())
+        return cost
+
     # ---- batched extension (not in the reference): beam search for B clips at once ----
     def beam_batch(self, tparams, options, ctxg, mask_ctxg, ctxl, ctxm, k=5, maxlen=30, use_graph=False):
         """gen_sample(k) for every clip of a batch in one device pass.  Host arrays
