@@ -86,6 +86,7 @@ class Var(object):
     def __rtruediv__(self, o): return self._bin(o, np.true_divide, True)
     __div__ = __truediv__
     def __pow__(self, o): return self._bin(o, np.power)
+    def __rpow__(self, o): return self._bin(o, np.power, True)
     def __lt__(self, o): return self._bin(o, np.less)
     def __gt__(self, o): return self._bin(o, np.greater)
     def __neg__(self): return Var(lambda env: -self.ev(env), self.ndim)
