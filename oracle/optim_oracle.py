@@ -1,7 +1,7 @@
 """CPU restatement (test infrastructure only) of the reference's parameter update: gradient clipping
 (model_attention.py:1194-1203) and the optimizers of common.py:178-230, in float32 like the Theano graph
 (floatX = float32).  Flat arrays stand for the per-tensor lists: the update is elementwise, and the clip
-norm is a sum over all tensors.  Pinned to the reference: tests/golden/ref_optim.npz (trajectories from the
+norm is a sum over all tensors.  Pinned to the reference: tests/golden/optim_ref.npz (trajectories from the
 reference's own adam / adadelta source run on oracle/mini_theano) is replayed in tests/test_optim_golden.py."""
 import numpy as np
 

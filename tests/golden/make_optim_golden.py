@@ -2,7 +2,7 @@
 executed on oracle/mini_theano via oracle/ref_exec._load) for a few updates on seeded gradients and stores
 the parameter trajectories.  Authoring container only (needs /root/reference):
 
-    python tests/golden/make_optim_golden.py        # -> tests/golden/ref_optim.npz
+    python tests/golden/make_optim_golden.py        # -> tests/golden/optim_ref.npz
 """
 import os
 import sys
@@ -39,5 +39,5 @@ def trajectories(n=257, steps=6, seed=3):
 
 if __name__ == '__main__':
     o = trajectories()
-    np.savez(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ref_optim.npz'), **o)
+    np.savez(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'optim_ref.npz'), **o)
     print({k: v.shape for k, v in o.items()})

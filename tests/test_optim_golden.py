@@ -1,5 +1,5 @@
 """The optimizer oracle is pinned to the reference's own adam / adadelta source (common.py:178-230): the
-trajectories in tests/golden/ref_optim.npz were produced by executing that source text
+trajectories in tests/golden/optim_ref.npz were produced by executing that source text
 (tests/golden/make_optim_golden.py); here the restatement oracle/optim_oracle.py must reproduce them, and --
 where /root/reference is mounted -- the fixture is regenerated live and compared."""
 import os
@@ -9,7 +9,7 @@ import pytest
 
 from oracle import optim_oracle as oo, ref_exec
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_optim.npz')
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'optim_ref.npz')
 
 
 def _replay(z, name):
