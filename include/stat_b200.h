@@ -19,6 +19,12 @@
  *   - return 0 on success, a negative STAT_E* code otherwise;
  *     stat_last_error() gives a thread-local message;
  *   - all tensors fp32 row-major, tokens int64 (model_attention.py:587,798);
+ *   - threads and devices: entry points may be called from several host
+ *     threads and on several devices of one process as long as concurrent calls
+ *     use different streams and different workspaces; the library keeps its
+ *     internal side streams / events per host thread and device.  Process-wide
+ *     state: the launch counter, the profiling and trace hooks, the GEMM
+ *     implementation switch, the persisting-L2 size (per device);
  *   - there is no CPU fallback: without a CUDA device every compute entry
  *     point fails with STAT_ECUDA.
  */

@@ -650,12 +650,8 @@ uint64_t l2_policy_q() {
 template <int NV, int RT, int HT>
 int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
   const size_t smem = G * frame_bytes(a.R, a.H) + SMEM_EXTRA + (cs - 1) * pad_bytes(a.H);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    STAT_CUDA_CHECK(cudaFuncSetAttribute(att_group_kernel<NV, RT, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    smem_set = smem;
-  }
+  static size_t smem_set[STAT_MAX_DEV] = {};
+  STAT_TRY(ensure_dyn_smem(att_group_kernel<NV, RT, HT>, smem, smem_set));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(a.rows) * cs);

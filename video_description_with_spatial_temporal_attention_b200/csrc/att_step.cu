@@ -276,12 +276,8 @@ template <int VEC, int NV, int RMAX>
 int launch(const AttArgs &a, cudaStream_t stream) {
   const int nwarps = a.Tc < 16 ? a.Tc : 16;
   const size_t smem = sizeof(float) * (8 * a.H + static_cast<size_t>(a.Tc) * a.H + 6 * a.Tc + 6) + 16;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    STAT_CUDA_CHECK(cudaFuncSetAttribute(att_step_kernel<VEC, NV, RMAX>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    smem_set = smem;
-  }
+  static size_t smem_set[STAT_MAX_DEV] = {};
+  if (smem > 48 * 1024) STAT_TRY(ensure_dyn_smem(att_step_kernel<VEC, NV, RMAX>, smem, smem_set));
   dim3 grid(a.S, a.rows);
   att_step_kernel<VEC, NV, RMAX><<<grid, nwarps * 32, smem, stream>>>(a);
   note_launch();

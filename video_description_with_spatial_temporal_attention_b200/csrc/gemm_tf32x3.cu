@@ -653,12 +653,8 @@ int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   CUtensorMap tmP, tmQ;
   STAT_TRY(make_map(&tmP, a.P, a.NP, a.K, a.ldp, BP));
   STAT_TRY(make_map(&tmQ, a.Q, a.NQ, a.K, a.ldq, BQ));
-  static bool attr_done = false;
-  if (!attr_done) {
-    STAT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BQ, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BQ>::smem_bytes(Cfg<BQ>::MAX_STAGES)));
-    attr_done = true;
-  }
+  static size_t smem_set[STAT_MAX_DEV] = {};
+  STAT_TRY(ensure_dyn_smem(gemm_tf32x3_kernel<BQ, TS>, Cfg<BQ>::smem_bytes(Cfg<BQ>::MAX_STAGES), smem_set));
   DevArgs db = da;
   const int nk_slice = ((a.K + BK - 1) / BK + da.ksplit - 1) / da.ksplit;
   db.stages = nk_slice < Cfg<BQ>::MAX_STAGES ? nk_slice : Cfg<BQ>::MAX_STAGES;

@@ -303,46 +303,63 @@ int dense(const float *x, int ldx, int rows, const float *Wt, int K, int nfeat, 
   return gemm_launch(g, st);
 }
 
+// Side streams and events of the internal fork/join points: one set per host thread and device, created
+// on first use and never destroyed (they may be part of captured graphs).
+constexpr int MAX_DEVICES = 64;
+struct SideSet {
+  cudaStream_t k0[2] = {nullptr, nullptr};      // K0 chains
+  cudaStream_t readout = nullptr;               // readout chain of a decode step
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr}, state = nullptr, done = nullptr;
+  bool ready = false;
+};
+int side_set(SideSet **out) {
+  thread_local SideSet tab[MAX_DEVICES];
+  int dev = 0;
+  STAT_CUDA_CHECK(cudaGetDevice(&dev));
+  STAT_REQUIRE(dev >= 0 && dev < MAX_DEVICES, STAT_EINVAL, "device ordinal %d out of range", dev);
+  SideSet &t = tab[dev];
+  if (!t.ready) {
+    for (int i = 0; i < 2; ++i) {
+      STAT_CUDA_CHECK(cudaStreamCreateWithFlags(&t.k0[i], cudaStreamNonBlocking));
+      STAT_CUDA_CHECK(cudaEventCreateWithFlags(&t.join[i], cudaEventDisableTiming));
+    }
+    STAT_CUDA_CHECK(cudaStreamCreateWithFlags(&t.readout, cudaStreamNonBlocking));
+    STAT_CUDA_CHECK(cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming));
+    STAT_CUDA_CHECK(cudaEventCreateWithFlags(&t.state, cudaEventDisableTiming));
+    STAT_CUDA_CHECK(cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
+    t.ready = true;
+  }
+  *out = &t;
+  return STAT_OK;
+}
+
 // Fork / join of two side streams around the caller's stream (event based, so it also works while
-// the caller's stream is being captured into a CUDA graph).  Streams and events are created once.
+// the caller's stream is being captured into a CUDA graph).
 struct Fork {
   cudaStream_t main_ = nullptr;
   bool active_ = false;
-  static cudaStream_t s_side[2];
-  static cudaEvent_t s_fork, s_join[2];
-  static bool s_ready;
+  SideSet *s_ = nullptr;
   int open(cudaStream_t st, bool enable) {
     main_ = st;
     active_ = false;
     if (!enable) return STAT_OK;
-    if (!s_ready) {
-      for (int i = 0; i < 2; ++i) {
-        STAT_CUDA_CHECK(cudaStreamCreateWithFlags(&s_side[i], cudaStreamNonBlocking));
-        STAT_CUDA_CHECK(cudaEventCreateWithFlags(&s_join[i], cudaEventDisableTiming));
-      }
-      STAT_CUDA_CHECK(cudaEventCreateWithFlags(&s_fork, cudaEventDisableTiming));
-      s_ready = true;
-    }
-    STAT_CUDA_CHECK(cudaEventRecord(s_fork, st));
-    for (int i = 0; i < 2; ++i) STAT_CUDA_CHECK(cudaStreamWaitEvent(s_side[i], s_fork, 0));
+    STAT_TRY(side_set(&s_));
+    STAT_CUDA_CHECK(cudaEventRecord(s_->fork, st));
+    for (int i = 0; i < 2; ++i) STAT_CUDA_CHECK(cudaStreamWaitEvent(s_->k0[i], s_->fork, 0));
     active_ = true;
     return STAT_OK;
   }
-  cudaStream_t side(int i) const { return active_ ? s_side[i] : main_; }
+  cudaStream_t side(int i) const { return active_ ? s_->k0[i] : main_; }
   int join() {
     if (!active_) return STAT_OK;
     for (int i = 0; i < 2; ++i) {
-      STAT_CUDA_CHECK(cudaEventRecord(s_join[i], s_side[i]));
-      STAT_CUDA_CHECK(cudaStreamWaitEvent(main_, s_join[i], 0));
+      STAT_CUDA_CHECK(cudaEventRecord(s_->join[i], s_->k0[i]));
+      STAT_CUDA_CHECK(cudaStreamWaitEvent(main_, s_->join[i], 0));
     }
     active_ = false;
     return STAT_OK;
   }
 };
-cudaStream_t Fork::s_side[2] = {nullptr, nullptr};
-cudaEvent_t Fork::s_fork = nullptr;
-cudaEvent_t Fork::s_join[2] = {nullptr, nullptr};
-bool Fork::s_ready = false;
 
 // P2, P3: mean-pooled global feature -> h0 | c0   (:618,649,657-660)
 int init_state(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const float *ctxg,
@@ -500,47 +517,39 @@ int step_out(const StatDims &d, const Prep &p, const float *P, const Ws &w, floa
 struct Overlap {
   cudaStream_t main_ = nullptr;
   bool on_ = false, side_busy_ = false;
-  static cudaStream_t s_side;
-  static cudaEvent_t s_state, s_done;
+  SideSet *s_ = nullptr;
   int open(cudaStream_t st, bool enable) {
     main_ = st;
     on_ = false;
     side_busy_ = false;
     if (!enable) return STAT_OK;
-    if (!s_side) {
-      STAT_CUDA_CHECK(cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking));
-      STAT_CUDA_CHECK(cudaEventCreateWithFlags(&s_state, cudaEventDisableTiming));
-      STAT_CUDA_CHECK(cudaEventCreateWithFlags(&s_done, cudaEventDisableTiming));
-    }
+    STAT_TRY(side_set(&s_));
     on_ = true;
     return STAT_OK;
   }
-  cudaStream_t side() const { return on_ ? s_side : main_; }
+  cudaStream_t side() const { return on_ ? s_->readout : main_; }
   // the new hidden state and its products are enqueued on the caller's stream: the side stream may go on
   int state_ready() {
     if (!on_) return STAT_OK;
-    STAT_CUDA_CHECK(cudaEventRecord(s_state, main_));
-    STAT_CUDA_CHECK(cudaStreamWaitEvent(s_side, s_state, 0));
+    STAT_CUDA_CHECK(cudaEventRecord(s_->state, main_));
+    STAT_CUDA_CHECK(cudaStreamWaitEvent(s_->readout, s_->state, 0));
     return STAT_OK;
   }
   // the readout chain of this step is enqueued on the side stream
   int side_enqueued() {
     if (!on_) return STAT_OK;
-    STAT_CUDA_CHECK(cudaEventRecord(s_done, s_side));
+    STAT_CUDA_CHECK(cudaEventRecord(s_->done, s_->readout));
     side_busy_ = true;
     return STAT_OK;
   }
   // the caller's stream needs what the side stream produced (picked token, free readout buffers)
   int join() {
     if (!on_ || !side_busy_) return STAT_OK;
-    STAT_CUDA_CHECK(cudaStreamWaitEvent(main_, s_done, 0));
+    STAT_CUDA_CHECK(cudaStreamWaitEvent(main_, s_->done, 0));
     side_busy_ = false;
     return STAT_OK;
   }
 };
-cudaStream_t Overlap::s_side = nullptr;
-cudaEvent_t Overlap::s_state = nullptr;
-cudaEvent_t Overlap::s_done = nullptr;
 
 bool overlap_enabled() {
   static int on = -1;

@@ -68,6 +68,22 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return fmaf(-2.0f, rcp_approx(t + 1.0f), 1.0f);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: raise it once per (kernel
+// instantiation, device) and only when a launch needs more than was configured before.  `table` is a
+// zero-initialised static array of MAX_DEV entries owned by the caller (one per instantiation).
+constexpr int STAT_MAX_DEV = 64;
+template <typename K>
+int ensure_dyn_smem(K kernel, size_t bytes, size_t *table) {
+  int dev = 0;
+  STAT_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= STAT_MAX_DEV) dev = 0;
+  if (bytes > table[dev]) {
+    STAT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    table[dev] = bytes;
+  }
+  return STAT_OK;
+}
+
 // kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-serialization attribute
 template <typename... KArgs, typename... Args>
 int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
