@@ -632,7 +632,6 @@ uint64_t l2_policy() {
 }
 
 long long *g_group_trace = nullptr;
-size_t g_persist_bytes = 0;
 
 // The seven blocks of a B=64 batch (95 MB) are more than the L2 keeps across a step (about 90 MB, less
 // the weights and activations streamed in between): cyclically re-reading all of them with one
@@ -658,7 +657,7 @@ int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[3];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
@@ -673,24 +672,6 @@ int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
     pdl_att = (e && e[0] == '1') ? 1 : 0;
   }
   cfg.numAttrs = 1 + (pdl_att ? pdl_attr(attr + 1) : 0);
-  // The context blocks of the batch are re-read by every decode step: inside this launch their address
-  // range is an L2 access-policy window whose lines are allocated as persisting -- as many of them as
-  // the carve-out holds (hitRatio), the rest as streaming so that they do not push the others out.
-  static int window = -1;
-  if (window < 0) {
-    const char *e = getenv("STAT_ATT_WINDOW");
-    window = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (window && g_persist_bytes > 0 && a.blocks_bytes > 0) {
-    cudaLaunchAttribute &w = attr[cfg.numAttrs++];
-    w.id = cudaLaunchAttributeAccessPolicyWindow;
-    w.val.accessPolicyWindow.base_ptr = const_cast<void *>(a.blocks_base);
-    w.val.accessPolicyWindow.num_bytes = a.blocks_bytes;
-    const double r = 0.92 * static_cast<double>(g_persist_bytes) / static_cast<double>(a.blocks_bytes);
-    w.val.accessPolicyWindow.hitRatio = static_cast<float>(r > 1.0 ? 1.0 : r);
-    w.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    w.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  }
   static int stagger = -1;
   if (stagger < 0) {
     const char *e = getenv("STAT_ATT_STAGGER");
@@ -722,7 +703,6 @@ bool att_group_plan(int rows, int T, int R, int H, int *cluster, int *groups, in
 
 // debug: device buffer of >= ctas * 64 int64 (clock stamps per CTA and group), or null
 void att_group_set_trace(long long *p) { g_group_trace = p; }
-void att_group_set_persist(size_t carve_out_bytes) { g_persist_bytes = carve_out_bytes; }
 
 int att_group_launch(const AttArgs &a_in, cudaStream_t stream) {
   AttArgs a = a_in;

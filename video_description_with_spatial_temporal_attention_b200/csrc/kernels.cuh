@@ -28,8 +28,6 @@ struct AttArgs {
   float *att_scores;                             // (3,rows,T) raw temporal scores or null
   float *alpha_l;                                // (rows,T,R) spatial weights or null
   long long *trace;                              // debug: clock stamps per CTA and group (att_group), or null
-  const void *blocks_base;                       // address range that holds the seven context blocks
-  size_t blocks_bytes;                           // (L2 access-policy window of the launch), 0 = none
 };
 int att_step_launch(const AttArgs &a, cudaStream_t stream);
 // att_group.cu: four independent four-warp groups per CTA, each streaming whole frames (H % 4 == 0,
@@ -37,7 +35,6 @@ int att_step_launch(const AttArgs &a, cudaStream_t stream);
 bool att_group_plan(int rows, int T, int R, int H, int *nctas, int *groups, int *max_parts);
 int att_group_launch(const AttArgs &a, cudaStream_t stream);
 void att_group_set_trace(long long *p);
-void att_group_set_persist(size_t carve_out_bytes);   // persisting-L2 carve-out the launches may count on
 
 // ---- recurrent.cu --------------------------------------------------------------
 // LSTM gates + state update (model_attention.py:437-457) and the emb / bias part of

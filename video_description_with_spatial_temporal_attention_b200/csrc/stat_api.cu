@@ -391,9 +391,6 @@ AttArgs att_args(const StatDims &d, const Prep &p, const float *P, const Ws &w, 
   a.counters = reinterpret_cast<unsigned int *>(W + w.counters);
   a.att_scores = att_scores;
   a.alpha_l = alpha_l;
-  // ctxg0 .. qctxl are laid out back to back at the start of the workspace
-  a.blocks_base = W + w.ctxg0;
-  a.blocks_bytes = (w.qctxl + static_cast<size_t>(d.B) * d.T * d.R * H - w.ctxg0) * sizeof(float);
   return a;
 }
 
@@ -629,7 +626,6 @@ long long stat_set_l2_persist(long long bytes) {
   STAT_CUDA_CHECK(cudaDeviceGetAttribute(&mx, cudaDevAttrMaxPersistingL2CacheSize, dev));
   size_t want = (bytes < 0 || bytes > mx) ? static_cast<size_t>(mx) : static_cast<size_t>(bytes);
   STAT_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-  att_group_set_persist(want);
   return static_cast<long long>(want);
 }
 
