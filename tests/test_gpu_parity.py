@@ -487,3 +487,21 @@ def test_training_cost_with_regularisers(torch_cuda):
         want = go.cost_and_grads(params, o, batch, alpha_c=alpha_c, decay_c=decay_c)[0]
         got = model.train_cost(tp, o, batch, alpha_c=alpha_c, decay_c=decay_c)
         assert abs(got - want) < 1e-4 * max(1.0, abs(want)), (alpha_c, decay_c, got, want)
+
+
+def test_stochastic_sampling_on_the_device_sampler(torch_cuda):
+    """gen_sample(stochastic=True) over the device f_next: draws from the step's own probabilities
+    (reproducible per sampler), sums the drawn words' probabilities, stops at the eos."""
+    o, params, batch = _case('faithful', B=2, seed=23)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+    model, tp, _, _, f_init, f_next = _build(o, params)
+    a = model.gen_sample(tp, f_init, f_next, ctxg[0], mg[0], ctxl[0], ml[0], ctxm[0], mm[0], o, None, 1, 12, True)
+    assert 1 <= len(a[0]) <= 12 and all(0 <= t < o['n_words'] for t in a[0]) and 0.0 < a[1] <= len(a[0])
+    assert f_next.draw is False                                       # switched back after the call
+    # a fresh sampler with the same seed repeats the draw sequence; the deterministic search is unaffected
+    _, _, _, _, f_init2, f_next2 = _build(o, params)
+    b = model.gen_sample(tp, f_init2, f_next2, ctxg[0], mg[0], ctxl[0], ml[0], ctxm[0], mm[0], o, None, 1, 12, True)
+    assert a[0] == b[0] and abs(a[1] - b[1]) < 1e-6
+    det = model.gen_sample(tp, f_init, f_next, ctxg[0], mg[0], ctxl[0], ml[0], ctxm[0], mm[0], o, None, 1, 12, False)
+    want = so.greedy_decode_batch(params, o, ctxg[:1], mg[:1], ctxl[:1], ctxm[:1], 12)
+    assert det[0][0] == [int(t) for t in want[0][0, :want[1][0]]]

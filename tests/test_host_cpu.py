@@ -184,3 +184,31 @@ def test_checkpoint_roundtrip(tmp_path):
     # model.load_params (model_attention.py:1109-1113) reads the same archive
     again = model.load_params(path, model.init_params(o))
     assert np.array_equal(again['decoder_U'], params['decoder_U'])
+
+
+def test_stochastic_branch_of_gen_sample_and_token_draws():
+    """gen_sample(stochastic=True) follows f_next's own next_sample (model_attention.py:914-918): with the
+    oracle callables (whose next_sample is the mode) it walks the greedy path and sums PROBABILITIES."""
+    g = Golden(NAMES[0])
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = g.batch
+    f_init, f_next = so.make_sampler(g.params, g.options, hoist=True)
+    model = ma.Attention()
+    sample, score, _, _ = model.gen_sample(None, f_init, f_next, ctxg[0], mg[0], ctxl[0], ml[0], ctxm[0], mm[0],
+                                           g.options, None, 1, g.maxlen, True)
+    want, _ = g.hyps(1, 0)
+    assert sample == want[0]
+    # replay the path by hand: score = sum_t p_t[w_t]
+    r = f_init(ctxg[0], mg[0])
+    h, c, w, tot = r[1][None], r[2][None], -np.ones((1,), 'int64'), 0.0
+    for tok in sample:
+        p, _, h, c = f_next(w, r[0], mg[0], ctxl[0], ml[0], ctxm[0], mm[0], h, c)
+        tot += p[0, tok]
+        w = np.array([tok], 'int64')
+    assert abs(score - tot) < 1e-6
+    # the draw helper: right distribution, valid ids, reproducible
+    p = np.array([[0.1, 0.2, 0.7], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]], 'float32')
+    d = np.stack([ma.draw_tokens(p, np.random.RandomState(s)) for s in range(4000)])
+    assert (d[:, 1] == 0).all() and (d[:, 2] == 2).all()
+    freq = np.bincount(d[:, 0], minlength=3) / 4000.0
+    assert np.abs(freq - p[0]).max() < 0.03
+    assert np.array_equal(ma.draw_tokens(p, np.random.RandomState(5)), ma.draw_tokens(p, np.random.RandomState(5)))

@@ -139,6 +139,15 @@ def function(inps, out, **kw):
     return fn
 
 
+def draw_tokens(p, rng):
+    """One multinomial draw per row of the probability matrix p (k, V) -> (k,) int64
+    (`trng.multinomial(pvals=next_probs).argmax(1)`, model_attention.py:841)."""
+    p = numpy.asarray(p, 'float64')
+    c = numpy.cumsum(p, axis=1)
+    u = rng.random_sample(p.shape[0]) * c[:, -1]
+    return numpy.minimum((c < u[:, None]).sum(1), p.shape[1] - 1).astype('int64')
+
+
 def validate_options(options):
     if options.get('ctx2out') and not options.get('ctxglm_dim', options['dim']) == options['dim']:
         raise ValueError('ctxglm_dim must equal dim (fusion is a sum, model_attention.py:430)')
@@ -284,10 +293,15 @@ class Attention(object):
             rc = torch.zeros(k, dtype=torch.int32, device=eng.device)
             probs, h2, c2 = eng.step(cc['ws'], cc['d'], xd, hd, cd, row_clip=rc)
             p = probs.cpu().numpy()
-            # next_sample is an MRG multinomial draw every caller discards
-            # (stochastic=False everywhere): return the mode.
-            return [p, p.argmax(1), h2.cpu().numpy(), c2.cpu().numpy()]
+            # next_sample (:841) is an MRG multinomial draw that every shipped caller discards
+            # (stochastic=False everywhere): the mode is returned unless a caller switches
+            # f_next.draw on (gen_sample(stochastic=True) does), then it is a draw from p with numpy's
+            # generator (same distribution, not Theano's MRG stream).
+            nxt = draw_tokens(p, f_next.rng) if f_next.draw else p.argmax(1)
+            return [p, nxt, h2.cpu().numpy(), c2.cpu().numpy()]
 
+        f_next.draw = False
+        f_next.rng = numpy.random.RandomState(common.rng_seed)
         return f_init, f_next
 
     # ---- search (model_attention.py:852-994) ---------------------------------------
@@ -297,7 +311,8 @@ class Attention(object):
         reference: un-normalised cumulative -log p, the k - dead_k best of the flattened
         (live, V) table, hypotheses retire on token 0, survivors appended at the end."""
         if stochastic:
-            raise NotImplementedError('stochastic sampling is never used by the reference callers (SURVEY F8)')
+            return self._sample_stochastic(f_init, f_next, ctxg_0, ctxg_mask, ctxl_0, ctxl_mask, ctxm_0, ctxm_mask,
+                                           maxlen)
         done, done_scores = [], []
         live = [[]]
         live_scores = numpy.zeros(1, 'float32')
@@ -337,6 +352,31 @@ class Attention(object):
             done.append(hyp)
             done_scores.append(sc)
         return done, done_scores, state, memory
+
+    def _sample_stochastic(self, f_init, f_next, ctxg_0, ctxg_mask, ctxl_0, ctxl_mask, ctxm_0, ctxm_mask, maxlen):
+        """The stochastic branch of gen_sample (model_attention.py:914-918): follow f_next's own
+        next_sample, one hypothesis; `sample` is a flat list of word ids and `sample_score` the SUM OF THE
+        PROBABILITIES of the drawn words (as the reference computes it, not a log-likelihood)."""
+        sample, score = [], 0.0
+        r = f_init(ctxg_0, ctxg_mask)
+        ctxg_0, state, memory = r[0], r[1].reshape(1, -1), r[2].reshape(1, -1)
+        words = -1 * numpy.ones((1,), 'int64')
+        had = getattr(f_next, 'draw', None)
+        if had is not None:
+            f_next.draw = True
+        try:
+            for _ in range(maxlen):
+                probs, words, state, memory = f_next(words, ctxg_0, ctxg_mask, ctxl_0, ctxl_mask, ctxm_0, ctxm_mask,
+                                                     state, memory)
+                words = numpy.asarray(words, 'int64')
+                sample.append(int(words[0]))
+                score += probs[0, words[0]]
+                if words[0] == 0:
+                    break
+        finally:
+            if had is not None:
+                f_next.draw = had
+        return sample, score, state, memory
 
     # ---- evaluation loop (model_attention.py:996-1032) -------------------------------
     def pred_probs(self, whichset, f_log_probs, verbose=True, prepare_data=None):
