@@ -215,6 +215,42 @@ int stat_adam_step(float *params, const float *grads, float *m, float *v, size_t
 int stat_adadelta_step(float *params, const float *grads, float *rg2, float *ru2, size_t n, int phase,
                        void *stream);
 
+/* ---- f_grad_shared: the gradients of the training cost -------------
+ * Replaces `grads = tensor.grad(cost, wrt=itemlist(tparams))` (model_attention.py:1193) for
+ *   cost = inv_batch * sum_b( -sum_t mask*log(p[x]+1e-8) )                    (:1129)
+ *        + decay_c * sum_params sum(p^2)                                      (:1130-1136)
+ *        + alpha_c * sum over the four attentions of
+ *              ((1 - alphas.sum(0))**2).sum(0).mean()                         (:1138-1147)
+ * (clipping, :1194-1203, is stat_grad_clip).  Call order of one training step:
+ * stat_prepare_params, stat_precompute, stat_forward_teacher with every optional output
+ * requested, then this.
+ *   p          the reference tensors themselves (not the prepared block);
+ *   f          the forward's step-invariant blocks inside its workspace (offsets from
+ *              stat_workspace_region: "ctxg0","pctxg","ctxm0","pctxm","ctxl0","pctxl","qctxl";
+ *              h0c0 = the "h0" region, (B,2H) rows of [h0 | c0]);
+ *   x, mask, ctxg, mask_ctxg, ctxl, ctxm, dp_*   the inputs the forward saw (dp_* NULL = eval factors 0.5);
+ *   alpha_l (L,B,T,R), alpha_g/m/lt (L,B,T), h_all (L,B,H)   stat_forward_teacher's outputs;
+ *   inv_batch  1 / (clips in the GLOBAL batch): with data parallelism every rank passes the same
+ *              value, adds decay_c on one rank only (or decay_c/world on each) and SUM-all-reduces;
+ *   grads      a StatParams whose pointers name the OUTPUT buffers (written, not read), one per
+ *              parameter in the reference's shapes -- e.g. views into the flat gradient buffer the
+ *              optimizer entry points use;
+ *   gws        stat_grad_workspace_bytes(d, L) bytes of scratch.
+ * Deterministic: no atomics, fixed summation orders.  H <= 1024, R <= 16. */
+typedef struct StatFwdBlocks {
+  const float *ctxg0, *pctxg, *ctxm0, *pctxm;   /* (B,T,H)    */
+  const float *ctxl0, *pctxl, *qctxl;           /* (B,T,R,H)  */
+  const float *h0c0;                            /* (B,2H)     */
+} StatFwdBlocks;
+size_t stat_grad_workspace_bytes(const StatDims *d, int L);
+int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks *f, int L,
+                     const int64_t *x, const float *mask, const float *ctxg, const float *mask_ctxg,
+                     const float *ctxl, const float *ctxm, const float *dp_gates, const float *dp_h,
+                     const float *dp_z, const float *alpha_l, const float *alpha_g,
+                     const float *alpha_m, const float *alpha_lt, const float *h_all,
+                     float inv_batch, float alpha_c, float decay_c, const StatParams *grads,
+                     void *gws, void *stream);
+
 /* ---- the attention fragment of one step alone (model_attention.py:370-435) ---
  * S1-S9 for `rows` decode rows whose hidden-state projections (h.Wd*_att, selector
  * logit) already sit in the "hp" region of `ws` (left there by the previous

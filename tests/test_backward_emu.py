@@ -1,0 +1,124 @@
+"""The backward pass (csrc/backward.cu: kernels + host orchestration of stat_grad_shared) executed on the CPU
+through tests/emu (threads-as-CUDA-threads emulation, the GEMM replaced by a loop with the same contract)
+and compared with the gradient oracle (torch fp64 autograd over the restated forward, oracle/grad_oracle.py).
+The forward products the entry point consumes (context blocks, attention weights, hidden states) come from the
+numpy oracle in float32, as the CUDA forward would leave them.  This checks the derivation, the indexing,
+the reductions and the launch sequence; what it cannot check (nvcc code generation, the tensor-core GEMM on
+these operand layouts) is covered by tests/test_gpu_parity.py::test_grad_shared_* on the GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import video_description_with_spatial_temporal_attention_b200 as stat
+from video_description_with_spatial_temporal_attention_b200 import _lib, synthetic
+from oracle import grad_oracle as go, stat_oracle as so
+from tests.emu import build_emu
+
+
+class FwdBlocks(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('ctxg0', 'pctxg', 'ctxm0', 'pctxm', 'ctxl0', 'pctxl', 'qctxl', 'h0c0')]
+
+
+@pytest.fixture(scope='module')
+def emu():
+    lib = C.CDLL(build_emu.build())
+    lib.stat_grad_workspace_bytes.restype = C.c_size_t
+    lib.stat_grad_workspace_bytes.argtypes = [C.POINTER(_lib.StatDims), C.c_int]
+    lib.stat_grad_shared.restype = C.c_int
+    lib.stat_grad_shared.argtypes = ([C.POINTER(_lib.StatDims), C.POINTER(_lib.StatParams), C.POINTER(FwdBlocks), C.c_int]
+                                     + [C.c_void_p] * 14 + [C.c_float] * 3
+                                     + [C.POINTER(_lib.StatParams), C.c_void_p, C.c_void_p])
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def run_emu(lib, o, params, batch, alpha_c, decay_c, dp=None):
+    x, mask, ctxg, mask_ctxg, ctxl, _ml, ctxm, _mm = batch
+    L, B = x.shape
+    T, R = ctxl.shape[1], ctxl.shape[2]
+    H, E, V = o['dim'], o['dim_word'], o['n_words']
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    dp = dp or {}
+    dpk = {k: (f32(v) if v is not None else None) for k, v in dp.items()}
+    _, allv = so.forward_teacher(params, o, *batch, dtype=np.float32, return_all=True, **dpk)
+    blk = allv['blk']
+    P32 = {k: f32(v) for k, v in params.items()}
+    keep = dict(ctxg0=f32(blk['G']), pctxg=f32(blk['pG']), ctxm0=f32(blk['M']), pctxm=f32(blk['pM']),
+                ctxl0=f32(blk['Lc']), pctxl=f32(blk['pL']), qctxl=f32(blk['Lc'] @ P32['decoder_Wclt_att']),
+                h0c0=f32(np.concatenate([allv['h0'], allv['c0']], 1)))
+    fb = FwdBlocks(**{k: _ptr(v) for k, v in keep.items()})
+    al = f32(np.stack([s['alphaL'] for s in allv['steps']]))
+    ag = f32(np.stack([s['alphaG'] for s in allv['steps']]))
+    am = f32(np.stack([s['alphaM'] for s in allv['steps']]))
+    alt = f32(np.stack([s['alphaLT'] for s in allv['steps']]))
+    hall = f32(np.stack([s['h'] for s in allv['steps']]))
+    d = _lib.StatDims(B, T, R, ctxg.shape[2], ctxm.shape[2], ctxl.shape[3], H, E, V, _lib.flags_of(o))
+    sp, sg = _lib.StatParams(), _lib.StatParams()
+    grads = {k: np.full_like(v, np.nan) for k, v in P32.items()}           # every element must be written
+    for k in _lib.PARAM_FIELDS:
+        setattr(sp, k, _ptr(P32[k]) if k in P32 else None)
+        setattr(sg, k, _ptr(grads[k]) if k in grads else None)
+    nbytes = lib.stat_grad_workspace_bytes(C.byref(d), L)
+    assert nbytes > 0
+    gws = np.full(nbytes // 4, np.nan, np.float32)                         # nothing may rely on a zeroed workspace
+    x64 = np.ascontiguousarray(x, dtype=np.int64)
+    args = [f32(mask), f32(ctxg), f32(mask_ctxg), f32(ctxl), f32(ctxm)]
+    rc = lib.stat_grad_shared(C.byref(d), C.byref(sp), C.byref(fb), L, _ptr(x64), *[_ptr(a) for a in args],
+                              _ptr(dpk.get('dp_gates')), _ptr(dpk.get('dp_h')), _ptr(dpk.get('dp_z')),
+                              _ptr(al), _ptr(ag), _ptr(am), _ptr(alt), _ptr(hall),
+                              1.0 / B, alpha_c, decay_c, C.byref(sg), _ptr(gws), None)
+    assert rc == 0
+    return grads
+
+
+def _case(global_proj, selector=True, ctx2out=True, prev2out=True):
+    kw = dict(dim=8, dim_word=8, ctxl_dim=12, ctxm_dim=16, n_words=11, selector=selector, ctx2out=ctx2out,
+              prev2out=prev2out)
+    o = stat.default_options(ctxg_dim=12, global_proj=True, **kw) if global_proj else \
+        stat.default_options(ctxg_dim=8, **kw)
+    params = so.trained_like_params(o, seed=5)
+    batch = synthetic.make_batch(o, B=3, T=4, R=2, L=5, seed=5, zero_tail=True)
+    return o, params, batch
+
+
+def _compare(grads, want, rtol=2e-5):
+    assert list(grads.keys()) == list(want.keys())
+    for k, w in want.items():
+        g = grads[k]
+        assert np.isfinite(g).all(), k
+        scale = max(float(np.abs(w).max()), 1e-6)
+        err = float(np.abs(g.astype('float64') - w).max())
+        assert err <= rtol * scale + 1e-6, (k, err, scale)
+
+
+@pytest.mark.parametrize('global_proj', [False, True])
+def test_grads_match_oracle(emu, global_proj):
+    o, params, batch = _case(global_proj)
+    kw = dict(alpha_c=0.70602, decay_c=1e-4)
+    grads = run_emu(emu, o, params, batch, **kw)
+    _, want, _ = go.cost_and_grads(params, o, batch, **kw)
+    _compare(grads, want)
+
+
+def test_grads_without_regularisers_and_options_off(emu):
+    o, params, batch = _case(False, selector=False, ctx2out=False, prev2out=False)
+    grads = run_emu(emu, o, params, batch, 0., 0.)
+    _, want, _ = go.cost_and_grads(params, o, batch)
+    _compare(grads, want)
+
+
+def test_grads_with_dropout_factors(emu):
+    o, params, batch = _case(True)
+    L, B = batch[0].shape
+    H, E = o['dim'], o['dim_word']
+    rng = np.random.RandomState(2)
+    dp = dict(dp_gates=rng.binomial(1, 0.5, (L, B, 3 * H)).astype('float32'),
+              dp_h=rng.binomial(1, 0.5, (L, B, H)).astype('float32'),
+              dp_z=rng.binomial(1, 0.5, (L, B, E)).astype('float32'))
+    grads = run_emu(emu, o, params, batch, 0.3, 1e-4, dp=dp)
+    _, want, _ = go.cost_and_grads(params, o, batch, alpha_c=0.3, decay_c=1e-4, **dp)
+    _compare(grads, want)
