@@ -122,3 +122,15 @@ def test_grads_with_dropout_factors(emu):
     grads = run_emu(emu, o, params, batch, 0.3, 1e-4, dp=dp)
     _, want, _ = go.cost_and_grads(params, o, batch, alpha_c=0.3, decay_c=1e-4, **dp)
     _compare(grads, want)
+
+
+def test_grads_wider_than_a_block(emu):
+    """H = 160 > the 128 threads of the per-frame blocks (strided column loops, two columns per thread for some
+    threads only), R = 3, a vocabulary that is not a multiple of 4, a single-frame tail."""
+    kw = dict(dim=160, dim_word=12, ctxl_dim=20, ctxm_dim=12, n_words=37)
+    o = stat.default_options(ctxg_dim=24, global_proj=True, **kw)
+    params = so.trained_like_params(o, seed=9)
+    batch = synthetic.make_batch(o, B=2, T=5, R=3, L=3, seed=9, zero_tail=True)
+    grads = run_emu(emu, o, params, batch, 0.70602, 1e-4)
+    _, want, _ = go.cost_and_grads(params, o, batch, alpha_c=0.70602, decay_c=1e-4)
+    _compare(grads, want)

@@ -1,0 +1,133 @@
+"""GPU parity of the training step (BASELINE config 3): gradients of the cost of
+model_attention.py:1129-1147 from stat_grad_shared (through train.Trainer, i.e. the real forward kernels
+followed by csrc/backward.cu) against the fp64 gradient oracle, then the whole step -- clip, adam /
+adadelta -- against the oracle's update rules.  Tolerance: 1e-4 of the largest entry of each gradient
+tensor ("rel 1e-4 vs fp64 oracle").
+
+The same backward code is checked on the CPU, kernel for kernel, in tests/test_backward_emu.py."""
+import numpy as np
+import pytest
+
+import video_description_with_spatial_temporal_attention_b200 as stat
+from video_description_with_spatial_temporal_attention_b200 import synthetic
+from oracle import grad_oracle as go, optim_oracle as oo, stat_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _compare(got, want, rtol=RTOL, atol=5e-6):
+    assert list(got.keys()) == list(want.keys())
+    worst = ('', 0.0)
+    for k, w in want.items():
+        g = got[k].astype('float64')
+        assert g.shape == w.shape, k
+        assert np.isfinite(g).all(), k
+        scale = max(float(np.abs(w).max()), 1e-6)
+        err = float(np.abs(g - w).max())
+        if err / scale > worst[1]:
+            worst = (k, err / scale)
+        assert err <= rtol * scale + atol, (k, err, scale)
+    return worst
+
+
+def _toy(global_proj, **kw):
+    base = dict(dim=8, dim_word=8, ctxl_dim=12, ctxm_dim=16, n_words=11)
+    base.update(kw)
+    o = stat.default_options(ctxg_dim=12, global_proj=True, **base) if global_proj else \
+        stat.default_options(ctxg_dim=8, **base)
+    params = so.trained_like_params(o, seed=5)
+    batch = synthetic.make_batch(o, B=3, T=4, R=2, L=5, seed=5, zero_tail=True)
+    return o, params, batch
+
+
+@pytest.mark.parametrize('global_proj', [False, True])
+def test_grad_shared_toy_vs_oracle(torch_cuda, global_proj):
+    from video_description_with_spatial_temporal_attention_b200.train import Trainer
+    o, params, batch = _toy(global_proj)
+    kw = dict(alpha_c=0.70602, decay_c=1e-4)
+    tr = Trainer(params, o, use_noise=False, **kw)
+    cost = tr.f_grad_shared(*batch)[0]
+    want_cost, want, _ = go.cost_and_grads(params, o, batch, **kw)
+    assert abs(cost - want_cost) < 1e-4 * max(1.0, abs(want_cost))
+    _compare(tr.grads(), want)
+
+
+def test_grad_shared_options_off_and_dropout(torch_cuda):
+    from video_description_with_spatial_temporal_attention_b200.train import Trainer
+    o, params, batch = _toy(False, selector=False, ctx2out=False, prev2out=False)
+    tr = Trainer(params, o, use_noise=False)
+    tr.f_grad_shared(*batch)
+    _compare(tr.grads(), go.cost_and_grads(params, o, batch)[1])
+    o, params, batch = _toy(True)
+    L, B = batch[0].shape
+    rng = np.random.RandomState(2)
+    dp = dict(dp_gates=rng.binomial(1, 0.5, (L, B, 3 * o['dim'])).astype('float32'),
+              dp_h=rng.binomial(1, 0.5, (L, B, o['dim'])).astype('float32'),
+              dp_z=rng.binomial(1, 0.5, (L, B, o['dim_word'])).astype('float32'))
+    tr = Trainer(params, o, alpha_c=0.3, decay_c=1e-4)
+    tr.f_grad_shared(*batch, dropout=(dp['dp_gates'], dp['dp_h'], dp['dp_z']))
+    _compare(tr.grads(), go.cost_and_grads(params, o, batch, alpha_c=0.3, decay_c=1e-4, **dp)[1])
+
+
+def test_grad_shared_wide_vs_oracle(torch_cuda):
+    """Tensor-core path: every operand 16-byte aligned (H = E = 128, BASELINE-like feature widths / 8,
+    a vocabulary that is not a multiple of 4), ragged captions, zeroed trailing frames."""
+    from video_description_with_spatial_temporal_attention_b200.train import Trainer
+    o = stat.default_options(dim=128, dim_word=128, ctxg_dim=256, ctxl_dim=512, ctxm_dim=512, n_words=1574,
+                             global_proj=True)
+    params = so.trained_like_params(o, seed=3)
+    batch = synthetic.make_batch(o, B=8, T=6, R=4, L=8, seed=3, zero_tail=True)
+    kw = dict(alpha_c=0.70602, decay_c=1e-4)
+    tr = Trainer(params, o, use_noise=False, **kw)
+    cost = tr.f_grad_shared(*batch)[0]
+    want_cost, want, _ = go.cost_and_grads(params, o, batch, **kw)
+    assert abs(cost - want_cost) < 1e-4 * max(1.0, abs(want_cost))
+    worst = _compare(tr.grads(), want)
+    print('worst relative gradient error', worst)
+    # bit-reproducible: no atomics, fixed summation orders
+    g1 = {k: v.copy() for k, v in tr.grads().items()}
+    tr.f_grad_shared(*batch)
+    g2 = tr.grads()
+    assert all(np.array_equal(g1[k], g2[k]) for k in g1)
+
+
+@pytest.mark.parametrize('optimizer', ['adam', 'adadelta'])
+def test_training_steps_follow_the_reference_update(torch_cuda, optimizer):
+    """Three full steps (gradients -> global-norm clip -> update).  Per step: the clipped device gradients equal
+    the oracle's at the parameters the device currently holds, and the device update equals the oracle's
+    restatement of common.py:178-230 applied to those gradients (adam's m / sqrt(v) amplifies fp32 rounding
+    of near-zero gradients, so a three-step trajectory from fp64 gradients is not a usable yardstick); the
+    cost goes down on the repeated batch."""
+    from video_description_with_spatial_temporal_attention_b200.train import Trainer
+    o, params, batch = _toy(True)
+    kw = dict(alpha_c=0.70602, decay_c=1e-4)
+    clip_c = 1.0                                            # active: the gradient norm of this batch is 11.4
+    tr = Trainer(params, o, optimizer=optimizer, clip_c=clip_c, use_noise=False, **kw)
+    n = tr.flat.n
+    ref = oo.Adam(n) if optimizer == 'adam' else oo.Adadelta(n)
+    costs = []
+    for step in range(3):
+        before = tr.unzip()
+        costs.append(tr.f_grad_shared(*batch)[0])
+        want_cost, g, ex = go.cost_and_grads(before, o, batch, clip_c=clip_c, **kw)
+        assert ex['g2'] > clip_c ** 2
+        assert abs(costs[-1] - want_cost) < 1e-4 * max(1.0, abs(want_cost))
+        got_g = tr.grads()
+        _compare(got_g, g)
+        gflat = np.concatenate([v.reshape(-1) for v in got_g.values()]).astype('float32')
+        if optimizer == 'adadelta':
+            ref.grad_shared(gflat)
+        pflat = ref.update(np.concatenate([v.reshape(-1) for v in before.values()]), gflat)
+        tr.f_update(0.01)
+        got = np.concatenate([v.reshape(-1) for v in tr.unzip().values()])
+        np.testing.assert_allclose(got, pflat, rtol=3e-6, atol=2e-8, err_msg='step %d' % step)
+    assert costs[-1] < costs[0]

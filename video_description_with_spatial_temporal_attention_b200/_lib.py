@@ -41,6 +41,12 @@ class StatParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
 
 
+class StatFwdBlocks(C.Structure):
+    """include/stat_b200.h StatFwdBlocks: the forward's step-invariant blocks the backward pass reads"""
+    FIELDS = ('ctxg0', 'pctxg', 'ctxm0', 'pctxm', 'ctxl0', 'pctxl', 'qctxl', 'h0c0')
+    _fields_ = [(n, C.c_void_p) for n in FIELDS]
+
+
 class StatError(RuntimeError):
     pass
 
@@ -76,6 +82,10 @@ def _declare(lib):
     lib.stat_adam_step.argtypes = [vp, vp, vp, vp, sz, i32, vp]
     lib.stat_alpha_coverage.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     lib.stat_adadelta_step.argtypes = [vp, vp, vp, vp, sz, i32, vp]
+    lib.stat_grad_workspace_bytes.restype = sz
+    lib.stat_grad_workspace_bytes.argtypes = [dp, i32]
+    lib.stat_grad_shared.argtypes = ([dp, C.POINTER(StatParams), C.POINTER(StatFwdBlocks), i32] + [vp] * 14
+                                     + [C.c_float] * 3 + [C.POINTER(StatParams), vp, vp])
     lib.stat_profile_enable.argtypes = [i32]
     lib.stat_profile_phases.restype = i32
     lib.stat_profile_phase_name.restype = C.c_char_p
@@ -83,7 +93,7 @@ def _declare(lib):
     lib.stat_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int), i32]
     for n in ('stat_attention', 'stat_profile_enable', 'stat_profile_collect', 'stat_set_gemm_impl', 'stat_prepare_params', 'stat_init_state', 'stat_workspace_region', 'stat_precompute',
               'stat_forward_teacher', 'stat_decode_greedy', 'stat_decode_beam', 'stat_step', 'stat_gemm', 'stat_grad_clip',
-              'stat_adam_step', 'stat_adadelta_step', 'stat_alpha_coverage'):
+              'stat_adam_step', 'stat_adadelta_step', 'stat_alpha_coverage', 'stat_grad_shared'):
         getattr(lib, n).restype = i32
 
 

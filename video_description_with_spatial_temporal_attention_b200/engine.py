@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import StatDims, StatParams, check
+from ._lib import StatDims, StatFwdBlocks, StatParams, check
 
 
 def _ptr(t):
@@ -187,6 +187,40 @@ class Engine(object):
                                             _ptr(dp_gates), _ptr(dp_h), _ptr(dp_z), _ptr(out), _ptr(al), _ptr(ag),
                                             _ptr(am), _ptr(alt), _ptr(hh), _stream()))
         return out, (al, ag, am, alt), hh
+
+    # ---- f_grad_shared (gradients only; clipping / update live in optim.py) ----------
+    def grad_shared(self, ws, d, batch_dev, alphas, h_all, grad_views, inv_batch, alpha_c=0., decay_c=0.,
+                    dp_gates=None, dp_h=None, dp_z=None):
+        """Gradients of the training cost (model_attention.py:1129-1147, :1193) for the batch whose forward
+        (precompute + forward_teacher with alphas and hidden states) has just run in `ws`.
+        batch_dev = (x, mask, ctxg, mask_ctxg, ctxl, ctxm) device tensors; grad_views: name -> writable fp32
+        device tensor per parameter (e.g. views into the optimizer's flat gradient buffer)."""
+        self._need_params()
+        x, mask, ctxg, mask_ctxg, ctxl, ctxm = batch_dev
+        L, B = x.shape
+        T, R = d.T, d.R
+        blocks = StatFwdBlocks()
+        for name in StatFwdBlocks.FIELDS:
+            setattr(blocks, name, self.region(ws, B, T, R, 'h0' if name == 'h0c0' else name).data_ptr())
+        sp, sg = StatParams(), StatParams()
+        for f in _lib.PARAM_FIELDS:
+            if f in self._dev_params:
+                setattr(sp, f, self._dev_params[f].data_ptr())
+                setattr(sg, f, grad_views[f].data_ptr())
+        n = self.lib.stat_grad_workspace_bytes(C.byref(d), L)
+        if n == 0:
+            check(-1)
+        key = ('grad', B, T, R, L)
+        gws = self._ws.get(key)
+        if gws is None:
+            gws = torch.empty((n + 3) // 4, dtype=torch.float32, device=self.device)
+            self._ws[key] = gws
+        al, ag, am, alt = alphas
+        check(self.lib.stat_grad_shared(C.byref(d), C.byref(sp), C.byref(blocks), L, _ptr(x), _ptr(mask), _ptr(ctxg),
+                                        _ptr(mask_ctxg), _ptr(ctxl), _ptr(ctxm), _ptr(dp_gates), _ptr(dp_h),
+                                        _ptr(dp_z), _ptr(al), _ptr(ag), _ptr(am), _ptr(alt), _ptr(h_all),
+                                        float(inv_batch), float(alpha_c), float(decay_c), C.byref(sg), _ptr(gws),
+                                        _stream()))
 
     # ---- greedy ----------------------------------------------------------------
     def decode_greedy(self, ws, d, maxlen, out=None):

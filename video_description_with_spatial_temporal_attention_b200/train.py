@@ -1,0 +1,140 @@
+"""The training step of train() on the device: what the reference builds at
+model_attention.py:1129-1147 (cost), :1193-1203 (gradients, global-norm clipping) and :1206-1209
+(`f_grad_shared, f_update = optimizer(lr, tparams, grads, inps, cost, extra)`, common.py:178-230), and
+calls at :1259-1278 as
+
+    rvals = f_grad_shared(x, mask, ctxg, mask_ctxg, ctxl, mask_ctxl, ctxm, mask_ctxm)
+    cost, alphas = rvals[0], rvals[2:6]
+    f_update(lrate)
+
+Parameters, gradients and optimizer state live in flat fp32 device buffers (optim.py); one step is
+stat_prepare_params -> stat_precompute -> stat_forward_teacher -> stat_grad_shared -> (SUM all-reduce over
+the data-parallel ranks) -> stat_grad_clip -> stat_adam_step / stat_adadelta_step.  Data parallelism
+(SURVEY 8e): every rank scales its NLL sum by 1 / B_global, the coverage regulariser is a sum over clips,
+weight decay is added on rank 0 only, clipping runs after the all-reduce, every rank applies the same update.
+There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+
+from . import optim
+from ._lib import check
+from .engine import Engine
+
+
+class Trainer(object):
+    def __init__(self, params, options, optimizer='adam', alpha_c=0., decay_c=0., clip_c=0., device=None,
+                 group=None, use_noise=True, seed=1234):
+        self.options = dict(options)
+        self.engine = Engine(self.options, device)
+        self.flat = optim.FlatParams(params, self.engine.device)
+        if optimizer == 'adam':
+            self.opt = optim.Adam(self.flat)
+        elif optimizer == 'adadelta':
+            self.opt = optim.Adadelta(self.flat)
+        else:
+            raise ValueError('optimizer must be adam or adadelta (the two the reference config offers)')
+        self.alpha_c, self.decay_c, self.clip_c = float(alpha_c), float(decay_c), float(clip_c)
+        self.group = group
+        self.use_noise = bool(use_noise)
+        self.gen = torch.Generator(device=self.engine.device)
+        self.gen.manual_seed(seed)
+        self._dirty = True
+        self.grad_views = OrderedDict()
+        for k, shp in self.flat.shapes.items():
+            o = self.flat.offsets[k]
+            self.grad_views[k] = self.opt.grads[o:o + self.flat.views[k].numel()]
+        self._cov = torch.zeros(4, dtype=torch.float32, device=self.engine.device)
+        self.last = {}
+
+    # ---- distributed helpers -------------------------------------------------------------------
+    def _world(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(self.group), dist.get_world_size(self.group)
+        return 0, 1
+
+    def dropout_masks(self, L, B):
+        """Bernoulli(0.5) keep masks (common.py:94-99, model_attention.py:469-477, :684-696) drawn on the device."""
+        if not self.use_noise:
+            return None, None, None
+        H, E = self.options['dim'], self.options['dim_word']
+        dev = self.engine.device
+        draw = lambda *s: (torch.rand(*s, device=dev, generator=self.gen) < 0.5).float()
+        return draw(L, B, 3 * H), draw(L, B, H), draw(L, B, E)
+
+    # ---- f_grad_shared -------------------------------------------------------------------------
+    def f_grad_shared(self, x, mask, ctxg, mask_ctxg, ctxl, mask_ctxl, ctxm, mask_ctxm, dropout=None,
+                      global_batch=None):
+        """Returns [cost, None, alphals, alphags, alphams, alphalts] (the reference's `probs` output, a
+        (L*B, V) matrix nothing downstream reads, is not materialised); cost is a python float, the alphas
+        device tensors.  The clipped, all-reduced gradients stay in the optimizer's flat buffer, as the
+        reference stashes them in shared variables (common.py:198-201).  `dropout` = explicit
+        (dp_gates, dp_h, dp_z) factors instead of drawn masks (parity tests)."""
+        eng = self.engine
+        if self._dirty:
+            eng.set_params(self.flat.views)
+            self._dirty = False
+        f32, i64 = torch.float32, torch.int64
+        xd = eng.to_device(x, i64, 'x')
+        md = eng.to_device(mask, f32, 'mask')
+        gd = eng.to_device(ctxg, f32, 'ctxg')
+        gmd = eng.to_device(mask_ctxg, f32, 'mask_ctxg')
+        ld = eng.to_device(ctxl, f32, 'ctxl')
+        mmd = eng.to_device(ctxm, f32, 'ctxm')
+        L, B = xd.shape
+        rank, world = self._world()
+        inv_batch = 1.0 / float(global_batch if global_batch is not None else B * world)
+        ws, d = eng.precompute(gd, gmd, ld, mmd)
+        if dropout is not None:
+            dpg, dph, dpz = (None if a is None else eng.to_device(a, f32) for a in dropout)
+        else:
+            dpg, dph, dpz = self.dropout_masks(L, B)
+        lp, alphas, h_all = eng.forward_teacher(ws, d, xd, md, dpg, dph, dpz, want_alphas=True, want_h=True)
+        eng.grad_shared(ws, d, (xd, md, gd, gmd, ld, mmd), alphas, h_all, self.grad_views, inv_batch,
+                        alpha_c=self.alpha_c, decay_c=self.decay_c if rank == 0 else 0.,
+                        dp_gates=dpg, dp_h=dph, dp_z=dpz)
+        optim.allreduce_grads(self.opt.grads, self.group)
+        g2 = self.opt.clip(self.clip_c) if self.clip_c > 0. else None
+        if isinstance(self.opt, optim.Adadelta):
+            self.opt.grad_shared()
+        # the cost itself (:1129-1147)
+        cost = (-lp.double().sum()) * inv_batch
+        if self.alpha_c > 0.:
+            lib = eng.lib
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            for i, a in enumerate(alphas):
+                n = int(a.numel() // (a.shape[0] * a.shape[1]))
+                check(lib.stat_alpha_coverage(C.c_void_p(a.data_ptr()), a.shape[0], a.shape[1], n,
+                                              C.c_void_p(self.opt._scratch.data_ptr()),
+                                              C.c_void_p(self._cov[i:].data_ptr()), stream))
+            cost = cost + self.alpha_c * self._cov.double().sum()
+        if world > 1:
+            import torch.distributed as dist
+            cost = cost.reshape(1)
+            dist.all_reduce(cost, op=dist.ReduceOp.SUM, group=self.group)
+            cost = cost[0]
+        if self.decay_c > 0.:
+            cost = cost + self.decay_c * self.flat.flat.double().square().sum()
+        self.last = dict(logp=lp, g2=g2, tokens=md.sum())
+        return [float(cost), None] + list(alphas)
+
+    # ---- f_update ----------------------------------------------------------------------------
+    def f_update(self, lr=None):
+        """common.py:190-195 / :216-230: applies the stashed gradients; `lr` is accepted and (for adam, as in the
+        reference) ignored."""
+        self.opt.f_update(lr)
+        self._dirty = True
+        return []
+
+    def grads(self):
+        """host copies of the current (clipped, all-reduced) gradients, init_params order"""
+        return OrderedDict((k, v.detach().cpu().numpy().reshape(self.flat.shapes[k]))
+                           for k, v in self.grad_views.items())
+
+    def unzip(self):
+        return self.flat.unzip()
