@@ -91,7 +91,8 @@ def test_grad_shared_wide_vs_oracle(torch_cuda):
     cost = tr.f_grad_shared(*batch)[0]
     want_cost, want, _ = go.cost_and_grads(params, o, batch, **kw)
     assert abs(cost - want_cost) < 1e-4 * max(1.0, abs(want_cost))
-    worst = _compare(tr.grads(), want)
+    # the forward's attention weights carry the 3xTF32 / fast-tanh error of the wide path (4e-5, test_gpu_parity.py)
+    worst = _compare(tr.grads(), want, rtol=5e-4)
     print('worst relative gradient error', worst)
     # bit-reproducible: no atomics, fixed summation orders
     g1 = {k: v.copy() for k, v in tr.grads().items()}
