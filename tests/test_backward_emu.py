@@ -20,8 +20,7 @@ class FwdBlocks(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('ctxg0', 'pctxg', 'ctxm0', 'pctxm', 'ctxl0', 'pctxl', 'qctxl', 'h0c0')]
 
 
-@pytest.fixture(scope='module')
-def emu():
+def load_emu():
     lib = C.CDLL(build_emu.build())
     lib.stat_grad_workspace_bytes.restype = C.c_size_t
     lib.stat_grad_workspace_bytes.argtypes = [C.POINTER(_lib.StatDims), C.c_int]
@@ -32,11 +31,16 @@ def emu():
     return lib
 
 
+@pytest.fixture(scope='module')
+def emu():
+    return load_emu()
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
-def run_emu(lib, o, params, batch, alpha_c, decay_c, dp=None):
+def run_emu(lib, o, params, batch, alpha_c, decay_c, dp=None, inv_batch=None):
     x, mask, ctxg, mask_ctxg, ctxl, _ml, ctxm, _mm = batch
     L, B = x.shape
     T, R = ctxl.shape[1], ctxl.shape[2]
@@ -70,7 +74,8 @@ def run_emu(lib, o, params, batch, alpha_c, decay_c, dp=None):
     rc = lib.stat_grad_shared(C.byref(d), C.byref(sp), C.byref(fb), L, _ptr(x64), *[_ptr(a) for a in args],
                               _ptr(dpk.get('dp_gates')), _ptr(dpk.get('dp_h')), _ptr(dpk.get('dp_z')),
                               _ptr(al), _ptr(ag), _ptr(am), _ptr(alt), _ptr(hall),
-                              1.0 / B, alpha_c, decay_c, C.byref(sg), _ptr(gws), None)
+                              inv_batch if inv_batch is not None else 1.0 / B, alpha_c, decay_c, C.byref(sg),
+                              _ptr(gws), None)
     assert rc == 0
     return grads
 
@@ -134,3 +139,56 @@ def test_grads_wider_than_a_block(emu):
     grads = run_emu(emu, o, params, batch, 0.70602, 1e-4)
     _, want, _ = go.cost_and_grads(params, o, batch, alpha_c=0.70602, decay_c=1e-4)
     _compare(grads, want)
+
+
+# ---- data parallelism: two ranks over gloo, each with half of the clips ------------------------
+def _dp_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    from video_description_with_spatial_temporal_attention_b200 import optim, parallel
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        o, params, _ = _case(True)
+        batch = synthetic.make_batch(o, B=4, T=4, R=2, L=5, seed=6, zero_tail=True)
+        B = batch[0].shape[1]
+        lo, hi = parallel.shard_range(B, rank, world)
+        shard = tuple(a[:, lo:hi] if i < 2 else a[lo:hi] for i, a in enumerate(batch))
+        # every rank: NLL scaled by 1 / B_global, coverage summed over its clips, decay on rank 0 only
+        g = run_emu(load_emu(), o, params, shard, 0.70602, 1e-4 if rank == 0 else 0., inv_batch=1.0 / B)
+        flat = torch.from_numpy(np.concatenate([v.reshape(-1) for v in g.values()]))
+        optim.allreduce_grads(flat)                       # the product's collective: one SUM over the flat buffer
+        q.put((rank, flat.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_data_parallel_gradients_equal_the_global_batch():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0], res[1])                 # every rank holds the same reduced gradient
+    o, params, _ = _case(True)
+    batch = synthetic.make_batch(o, B=4, T=4, R=2, L=5, seed=6, zero_tail=True)
+    _, want, _ = go.cost_and_grads(params, o, batch, alpha_c=0.70602, decay_c=1e-4)
+    off = 0
+    got = {}
+    for k, w in want.items():
+        got[k] = res[0][off:off + w.size].reshape(w.shape)
+        off += w.size
+    _compare(got, want)

@@ -25,6 +25,8 @@ from . import optim
 from ._lib import check
 from .engine import Engine
 
+__all__ = ['Trainer']
+
 
 class Trainer(object):
     def __init__(self, params, options, optimizer='adam', alpha_c=0., decay_c=0., clip_c=0., device=None,
@@ -138,3 +140,18 @@ class Trainer(object):
 
     def unzip(self):
         return self.flat.unzip()
+
+    # ---- hand-over to the reference-shaped validation / sampling callables -------------------------
+    @classmethod
+    def from_tparams(cls, tparams, options, **kw):
+        """Trainer over the current values of the shared parameters (`unzip(tparams)`, common.py:84-88)."""
+        from . import common
+        return cls(common.unzip(tparams), options, **kw)
+
+    def sync_tparams(self, tparams):
+        """`zipp(self.unzip(), tparams)` (common.py:78-81): what train() gets for free from Theano's in-place updates
+        of the shared variables -- call before pred_probs / gen_sample / numpy.savez(**unzip(tparams)) so that
+        f_log_probs, f_init / f_next and the checkpoint see the trained values (one device-to-host copy of the
+        parameters, at validation frequency)."""
+        from . import common
+        common.zipp(self.unzip(), tparams)
