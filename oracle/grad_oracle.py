@@ -9,7 +9,8 @@ yields in the reference (model_attention.py:1193), for the training cost of mode
 
 followed by the global-norm clipping of :1194-1203.  The forward is checked against the numpy oracle
 (itself pinned to the reference's source) in tests/test_grad_oracle.py; the gradients against central
-differences.  The CUDA backward pass (not built yet) will be compared with this.
+differences.  The CUDA backward pass (csrc/backward.cu, stat_grad_shared) is compared with this in
+tests/test_gpu_train.py (GPU) and tests/test_backward_emu.py (the same code under the CPU launch emulation).
 """
 from __future__ import annotations
 

@@ -405,7 +405,7 @@ class Attention(object):
     def train_cost(self, tparams, options, batch, alpha_c=0., decay_c=0.):
         """cost = mean_b(-f_log_probs) + decay_c * sum_params sum(p^2) + alpha_c * sum over the four attentions
         of ((1 - alphas.sum(0))**2).sum(0).mean(), with the current use_noise setting (dropout masks drawn on the
-        device when it is 1).  The gradients of this cost (the rest of f_grad_shared) are not built yet."""
+        device when it is 1).  The gradients of this cost (the rest of f_grad_shared) are train.Trainer's."""
         import ctypes as C
         model = getattr(self, '_model', None)
         if model is None or model.tparams is not tparams:

@@ -1,5 +1,5 @@
-"""Parameter update of the training step on the device (second half; the backward pass that
-produces the gradients is not built yet): the reference's `f_update` for adam / adadelta
+"""Parameter update of the training step on the device (second half; the gradients come from
+stat_grad_shared, driven by train.Trainer): the reference's `f_update` for adam / adadelta
 (common.py:178-230), global-norm clipping (model_attention.py:1194-1203) and the data-parallel
 gradient all-reduce, all over ONE flat fp32 buffer in init_params order.
 
