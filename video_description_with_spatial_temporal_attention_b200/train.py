@@ -141,6 +141,15 @@ class Trainer(object):
     def unzip(self):
         return self.flat.unzip()
 
+    def load_params(self, params):
+        """Overwrite the device parameters (e.g. `zipp(best_p, ...)`, model_attention.py:1522-1523); optimizer
+        state is kept, like the reference's shared m / v / running averages."""
+        import numpy
+        for k, v in params.items():
+            self.flat.views[k].copy_(torch.from_numpy(numpy.ascontiguousarray(numpy.asarray(v, 'float32')))
+                                     .reshape(self.flat.views[k].shape))
+        self._dirty = True
+
     # ---- hand-over to the reference-shaped validation / sampling callables -------------------------
     @classmethod
     def from_tparams(cls, tparams, options, **kw):
