@@ -251,6 +251,14 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
                      float inv_batch, float alpha_c, float decay_c, const StatParams *grads,
                      void *gws, void *stream);
 
+/* Phase timing of stat_grad_shared (measurement hook, no reference counterpart): when enabled, CUDA
+ * events on the caller's stream bracket each launch group; collect synchronises on them and returns the
+ * summed milliseconds / occurrences per phase.  Process-wide; not while capturing a graph. */
+int         stat_grad_profile_enable(int on);
+int         stat_grad_profile_phases(void);
+const char *stat_grad_profile_phase_name(int phase);
+int         stat_grad_profile_collect(float *ms_by_phase, int *count_by_phase, int nphase);
+
 /* ---- the attention fragment of one step alone (model_attention.py:370-435) ---
  * S1-S9 for `rows` decode rows whose hidden-state projections (h.Wd*_att, selector
  * logit) already sit in the "hp" region of `ws` (left there by the previous

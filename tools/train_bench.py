@@ -24,6 +24,7 @@ def main():
     ap.add_argument('--R', type=int, default=8)
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=1)
+    ap.add_argument('--phases', action='store_true', help='one extra step with the per-phase timing of stat_grad_shared')
     a = ap.parse_args()
     o = stat.baseline_options()
     params = ma.Attention().init_params(o)
@@ -55,12 +56,24 @@ def main():
         if it == 0:
             lc1 = tr.engine.launch_count()
     ms = float(np.mean([t[0] + t[1] for t in times]))
+    phases = None
+    if a.phases:
+        import ctypes as C
+        lib = tr.engine.lib
+        lib.stat_grad_profile_enable(1)
+        tr.f_grad_shared(*batch)
+        n = lib.stat_grad_profile_phases()
+        msv, cnt = (C.c_float * n)(), (C.c_int * n)()
+        lib.stat_grad_profile_collect(msv, cnt, n)
+        lib.stat_grad_profile_enable(0)
+        phases = {lib.stat_grad_profile_phase_name(i).decode(): {'ms': round(float(msv[i]), 4), 'n': int(cnt[i])}
+                  for i in range(n)}
     tokens = float(mask.sum())
     print(json.dumps({'metric': 'training tokens/sec (config 3: fwd+bwd+clip+adam, dropout on)', 'value': tokens / ms * 1e3,
                       'unit': 'tokens/s', 'ms_per_step': ms, 'ms_grad_shared': float(np.mean([t[0] for t in times])),
                       'ms_update': float(np.mean([t[1] for t in times])), 'cost': cost, 'B': B, 'L': L, 'T': T, 'R': R,
                       'launches_per_step': int(lc1 - lc0), 'steps': a.steps, 'warmup': a.warmup,
-                      'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}))
+                      'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30, 'backward_phases': phases}))
 
 
 if __name__ == '__main__':

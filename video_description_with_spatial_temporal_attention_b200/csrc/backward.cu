@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "kernels.cuh"
 #include "stat_common.cuh"
@@ -52,6 +53,42 @@ int bw_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stre
   return STAT_OK;
 }
 #define BW_LAUNCH(kernel, grid, block, stream, ...) bw_launch(kernel, grid, block, stream, __VA_ARGS__)
+#endif
+
+// ---------------------------------------------------------------------------
+// optional phase timing (stat_grad_profile_*): CUDA events on the caller's stream around each group of
+// launches.  Off by default; process-wide, not for concurrent use, not under stream capture.
+// ---------------------------------------------------------------------------
+enum BwPhase { BP_LAYOUT = 0, BP_RECOMPUTE, BP_LOGITS, BP_READOUT_BW, BP_CELL_BW, BP_DCTX_GEMM, BP_SELECTOR_BW,
+               BP_ATT_DOTS, BP_ATT_SOFT, BP_ATT_MAIN, BP_REDUCE_T, BP_DH_GEMM, BP_WGRAD_STEPS, BP_EMBEDDING,
+               BP_CTX_BLOCKS, BP_INIT_STATE, BP_DECAY, BP_COUNT };
+const char *const kBwPhaseNames[BP_COUNT] = {
+    "operand_layouts", "recompute", "logits", "readout_backward", "loop_cell_backward", "loop_dctx_gemm",
+    "loop_selector_backward", "loop_att_dots", "loop_att_soft", "loop_att_main", "loop_reduce_frames",
+    "loop_dh_gemm", "weight_grads_steps", "embedding", "context_blocks", "init_state", "weight_decay"};
+// bw_mark(phase, st): closes the phase that was open and opens `phase` (BP_COUNT = just close)
+#ifdef STAT_EMU
+inline void bw_mark(int, cudaStream_t) {}
+#else
+struct BwRec { int phase; cudaEvent_t a, b; };
+bool g_bw_prof_on = false;
+bool g_bw_open = false;
+BwRec g_bw_cur;
+std::vector<BwRec> g_bw_recs;
+inline void bw_mark(int phase, cudaStream_t st) {
+  if (!g_bw_prof_on) return;
+  if (g_bw_open) {
+    cudaEventRecord(g_bw_cur.b, st);
+    g_bw_recs.push_back(g_bw_cur);
+    g_bw_open = false;
+  }
+  if (phase >= BP_COUNT) return;
+  g_bw_cur.phase = phase;
+  cudaEventCreate(&g_bw_cur.a);
+  cudaEventCreate(&g_bw_cur.b);
+  cudaEventRecord(g_bw_cur.a, st);
+  g_bw_open = true;
+}
 #endif
 
 // ---------------------------------------------------------------------------
@@ -613,6 +650,49 @@ using namespace stat::bw;
 
 extern "C" {
 
+int stat_grad_profile_phases(void) { return BP_COUNT; }
+
+const char *stat_grad_profile_phase_name(int phase) {
+  return (phase >= 0 && phase < BP_COUNT) ? kBwPhaseNames[phase] : nullptr;
+}
+
+int stat_grad_profile_enable(int on) {
+#ifndef STAT_EMU
+  for (auto &r : g_bw_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_bw_recs.clear();
+  g_bw_open = false;
+  g_bw_prof_on = on != 0;
+#else
+  (void)on;
+#endif
+  return STAT_OK;
+}
+
+int stat_grad_profile_collect(float *ms_by_phase, int *count_by_phase, int nphase) {
+  STAT_REQUIRE(ms_by_phase && count_by_phase && nphase >= BP_COUNT, STAT_EINVAL,
+               "grad_profile_collect: need arrays of %d entries", static_cast<int>(BP_COUNT));
+  for (int i = 0; i < nphase; ++i) {
+    ms_by_phase[i] = 0.f;
+    count_by_phase[i] = 0;
+  }
+#ifndef STAT_EMU
+  for (auto &r : g_bw_recs) {
+    STAT_CUDA_CHECK(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    STAT_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_phase[r.phase] += ms;
+    count_by_phase[r.phase] += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_bw_recs.clear();
+#endif
+  return STAT_OK;
+}
+
 size_t stat_grad_workspace_bytes(const StatDims *d, int L) {
   if (!d || L < 1 || d->B < 1 || d->H < 1) return 0;
   return gw_layout(*d, L).total * sizeof(float);
@@ -663,6 +743,7 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
   };
   auto zero = [&](size_t off, size_t n) { return cudaMemsetAsync(W + off, 0, n * F, st); };
 
+  bw_mark(BP_LAYOUT, st);
   // ---- operand layouts --------------------------------------------------------------------
   // Whcat (H, ldq) = [Wdl | Wdg | Wdm | Wdlt | U | W_sel | 0]: K-major operand of the dh_{t-1} product;
   // its transpose is the operand of the hidden-state projections
@@ -687,6 +768,7 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
   STAT_CUDA_CHECK(cp2d(W + w.WvP, Vp, p->ff_logit_W, V, V, E));
   STAT_TRY(transpose(p->decoder_W, E, 4 * H, 4 * H, W + w.WdT, E, st));
 
+  bw_mark(BP_RECOMPUTE, st);
   // ---- A: recompute over all (step, clip) rows -------------------------------------------------
   const size_t NHs = static_cast<size_t>(N) * H, NEs = static_cast<size_t>(N) * E;
   STAT_TRY(BW_LAUNCH(k_gather_prev, g1(NHs), dim3(256), st, f->h0c0, h_all, W + w.Hprev, L, B, H));
@@ -706,9 +788,11 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
   if (c2o) STAT_TRY(mm(W + w.ctx, H, W + w.WctxT, H, W + w.ZC, E, N, E, H, p->ff_logit_ctxglm_b, st));
   STAT_TRY(BW_LAUNCH(k_zact, g1(NEs), dim3(256), st, W + w.DZ, p2o ? W + w.EMB : nullptr, c2o ? W + w.ZC : nullptr,
                      dp_z, W + w.ZT, W + w.Z, NEs));
+  bw_mark(BP_LOGITS, st);
   STAT_CUDA_CHECK(zero(w.LOG, static_cast<size_t>(N) * Vp));
   STAT_TRY(mm(W + w.Z, E, W + w.WvT, E, W + w.LOG, Vp, N, V, E, p->ff_logit_b, st));                 // :704-705
 
+  bw_mark(BP_READOUT_BW, st);
   // ---- B: readout backward ---------------------------------------------------------------------
   STAT_TRY(BW_LAUNCH(k_softmax_nll, dim3(N), dim3(256), st, W + w.LOG, Vp, V, x, mask, inv_batch));
   STAT_TRY(colsum(W + w.LOG, N, V, Vp, GRAD(ff_logit_b), W + w.CS, st));
@@ -755,17 +839,23 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
   STAT_CUDA_CHECK(zero(w.DCACC, static_cast<size_t>(BT) * 4));
   for (int t = L - 1; t >= 0; --t) {
     float *DHQt = W + w.DHQ + static_cast<size_t>(t) * B * ldq;
+    bw_mark(BP_CELL_BW, st);
     STAT_TRY(BW_LAUNCH(k_cell_backward, g1(static_cast<size_t>(B) * H), dim3(256), st, t, W + w.DHc, W + w.DCc,
                        W + w.DHR, W + w.GATES, W + w.Call, f->h0c0, mask, dp_gates, W + w.DHQ, ldq, 4 * H, W + w.DHm,
                        B, H));
+    bw_mark(BP_DCTX_GEMM, st);
     // dctx_t = dpre . Wc^T (:439); decoder_Wc (H,4H) is K-major for this product as it stands
     STAT_TRY(mm(DHQt + 4 * H, ldq, p->decoder_Wc, 4 * H, W + w.DCTX, H, B, H, 4 * H, nullptr, st));
+    bw_mark(BP_SELECTOR_BW, st);
     STAT_TRY(BW_LAUNCH(k_selector_bw, dim3(B), dim3(NT), st, t, W + w.DCTX, W + w.DCR, W + w.csum, W + w.beta,
                        W + w.DHQ, ldq, 8 * H, W + w.DC, B, H, sel ? 1 : 0));
+    bw_mark(BP_ATT_DOTS, st);
     STAT_TRY(BW_LAUNCH(k_att_dots, dim3(BT), dim3(NT), st, t, alpha_l, f->ctxl0, f->ctxg0, f->ctxm0, W + w.DC,
                        W + w.CL, W + w.DA3, B, T, R, H));
+    bw_mark(BP_ATT_SOFT, st);
     STAT_TRY(BW_LAUNCH(k_att_soft, g1(3 * B, 128), dim3(128), st, t, alpha_g, alpha_m, alpha_lt, W + w.DA3,
                        W + w.COV3, W + w.DS3, W + w.DCACC, B, T));
+    bw_mark(BP_ATT_MAIN, st);
     AttBw a;
     memset(&a, 0, sizeof(a));
     a.t_step = t; a.B = B; a.T = T; a.R = R; a.H = H; a.ldq = ldq; a.global_proj = gp ? 1 : 0;
@@ -778,14 +868,17 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     a.DPG = W + w.DPG; a.DPM = W + w.DPM; a.DG = W + w.DG; a.DM = W + w.DM;
     a.DUACC = W + w.DUACC; a.DCACC = W + w.DCACC; a.DSQP = W + w.DSQP;
     STAT_TRY(BW_LAUNCH(k_att_main, dim3(BT), dim3(NT), st, a));
+    bw_mark(BP_REDUCE_T, st);
     STAT_TRY(BW_LAUNCH(k_reduce_t, g1(static_cast<size_t>(B) * 4 * H), dim3(256), st, t, W + w.DSQP, W + w.DHQ, ldq,
                        B, T, 4 * H));
+    bw_mark(BP_DH_GEMM, st);
     // dh_{t-1} = [dsl | dsg | dsm | dslt | dpre | dsel] . Whcat^T + the masked bypass
     STAT_TRY(mm(DHQt, ldq, W + w.Whcat, ldq, W + w.TMPH, H, B, H, ldq, nullptr, st));
     STAT_TRY(BW_LAUNCH(k_add2, g1(static_cast<size_t>(B) * H), dim3(256), st, W + w.DHc, W + w.TMPH, W + w.DHm,
                        static_cast<size_t>(B) * H));
   }
 
+  bw_mark(BP_WGRAD_STEPS, st);
   // ---- D: weight gradients over the stacked steps ----------------------------------------------------
   float *T1 = W + w.T1, *T2 = W + w.T2, *T3 = W + w.T3, *CS = W + w.CS, *SM = W + w.SMALL;
   STAT_TRY(transpose(W + w.Hprev, N, H, H, T1, N, st));
@@ -805,11 +898,13 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
   STAT_TRY(mm(T1, N, DPREt, N, GRAD(decoder_W), 4 * H, E, 4 * H, N, nullptr, st));
   STAT_TRY(transpose(W + w.ctx, N, H, H, T1, N, st));
   STAT_TRY(mm(T1, N, DPREt, N, GRAD(decoder_Wc), 4 * H, H, 4 * H, N, nullptr, st));
+  bw_mark(BP_EMBEDDING, st);
   // embedding: dEMB = dpre . W^T (+ the readout's prev2out term), scattered to the rows of Wemb
   STAT_TRY(mm(W + w.DHQ + 4 * H, ldq, p->decoder_W, 4 * H, W + w.DEMB, E, N, E, 4 * H, nullptr, st));
   if (p2o) STAT_TRY(BW_LAUNCH(k_add_inplace, g1(NEs), dim3(256), st, W + w.DEMB, W + w.DZP, NEs));
   STAT_CUDA_CHECK(cudaMemsetAsync(GRAD(Wemb), 0, F * V * E, st));
   STAT_TRY(BW_LAUNCH(k_scatter_emb, g1(E, 128), dim3(128), st, W + w.DEMB, x, GRAD(Wemb), L, B, E));
+  bw_mark(BP_CTX_BLOCKS, st);
   // score vectors and biases
   STAT_TRY(colsum(W + w.DUACC, BT, 4 * H, 4 * H, SM, CS, st));
   STAT_CUDA_CHECK(cudaMemcpyAsync(GRAD(decoder_Ul_att), SM, F * H, cudaMemcpyDeviceToDevice, st));
@@ -861,6 +956,7 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     STAT_TRY(BW_LAUNCH(k_add_inplace, g1(cnt), dim3(256), st, W + w.DLC, T3, cnt));
   }
   STAT_TRY(feat_path(f->ctxl0, W + w.DLC, BTR, ctxl, Dr, GRAD(ff_local_W), GRAD(ff_local_b)));
+  bw_mark(BP_INIT_STATE, st);
   // init state (:618,:649,:657-660)
   STAT_TRY(BW_LAUNCH(k_meanpool, g1(static_cast<size_t>(B) * Dg), dim3(256), st, ctxg, mask_ctxg, W + w.GBAR, B, T, Dg));
   STAT_TRY(BW_LAUNCH(k_init_bw, g1(static_cast<size_t>(B) * H), dim3(256), st, W + w.DHc, W + w.DCc, f->h0c0,
@@ -871,6 +967,7 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
   STAT_TRY(mm(T1, B, T2 + static_cast<size_t>(H) * B, B, GRAD(ff_memory_W), H, Dg, H, B, nullptr, st));
   STAT_TRY(colsum(W + w.DP0, B, H, 2 * H, GRAD(ff_state_b), CS, st));
   STAT_TRY(colsum(W + w.DP0 + H, B, H, 2 * H, GRAD(ff_memory_b), CS, st));
+  bw_mark(BP_DECAY, st);
   // weight decay (:1130-1136): every parameter, biases included
   if (decay_c > 0.f) {
     const float c2 = 2.0f * decay_c;
@@ -898,6 +995,7 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
 #undef DEC
   }
 #undef GRAD
+  bw_mark(BP_COUNT, st);
   return STAT_OK;
 }
 
