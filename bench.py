@@ -36,9 +36,16 @@ METRIC = 'captions/sec (B=64, T=26, R=8, len=20)'
 
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.isfile(p):
+    try:
         with open(p) as fh:
-            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+            v = json.load(fh).get('hbm_gbs')
+        if isinstance(v, dict):                      # tolerate {"hbm_gbs": {"value": ...}}
+            v = v.get('value', v.get('gbs'))
+        v = float(v)
+        if v > 0:
+            return v, 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        pass
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
