@@ -178,24 +178,31 @@ struct GemmArgs {
   size_t plane;
 };
 
-// out = post * act(alpha * P.Q^T + bias + addend), routing exactly as documented in stat_common.cuh
+// out = post * act(alpha * P.Q^T + bias + addend), routing exactly as documented in stat_common.cuh; k-split:
+// slice z of the 32-wide k-blocks (the kernels' partition) goes to plane z, bias / addend ride on plane 0
 inline int gemm_launch(const GemmArgs &a, cudaStream_t) {
   STAT_REQUIRE(a.NP > 0 && a.NQ > 0 && a.K > 0, STAT_EINVAL, "gemm: empty problem");
-  STAT_REQUIRE(a.ksplit <= 1, STAT_EINVAL, "emu gemm: no k-split");
-  for (int i = 0; i < a.NP; ++i)
-    for (int j = 0; j < a.NQ; ++j) {
-      float acc = 0.f;
-      for (int k = 0; k < a.K; ++k)
-        acc = fmaf(a.P[static_cast<size_t>(i) * a.ldp + k], a.Q[static_cast<size_t>(j) * a.ldq + k], acc);
-      const int feat = a.feat_on_p ? i : j, row = a.feat_on_p ? j : i;
-      const GemmSeg &s = a.seg[(a.nseg > 1 && feat >= a.seg[1].f0) ? 1 : 0];
-      if (feat < s.f0 || feat >= s.f1) continue;
-      const int f = feat - s.f0;
-      float x = s.alpha * acc + (s.bias ? s.bias[f] : 0.f);
-      if (s.addend) x += s.addend[static_cast<size_t>(row) * s.ld_add + f];
-      if (s.act) x = tanhf(x);
-      s.C[static_cast<size_t>(row) * s.ldc + f] = x * s.post;
-    }
+  const int nk_all = (a.K + 31) / 32;
+  const int ks = a.ksplit < 1 ? 1 : (a.ksplit > nk_all ? nk_all : a.ksplit);
+  if (ks > 1) STAT_REQUIRE(a.nseg == 1 && a.seg[0].act == 0, STAT_EINVAL, "gemm: k-split needs a single linear segment");
+  for (int kz = 0; kz < ks; ++kz) {
+    const int kbeg = ((kz * nk_all) / ks) * 32;
+    const int kend = std::min(a.K, (((kz + 1) * nk_all) / ks) * 32);
+    for (int i = 0; i < a.NP; ++i)
+      for (int j = 0; j < a.NQ; ++j) {
+        float acc = 0.f;
+        for (int k = kbeg; k < kend; ++k)
+          acc = fmaf(a.P[static_cast<size_t>(i) * a.ldp + k], a.Q[static_cast<size_t>(j) * a.ldq + k], acc);
+        const int feat = a.feat_on_p ? i : j, row = a.feat_on_p ? j : i;
+        const GemmSeg &s = a.seg[(a.nseg > 1 && feat >= a.seg[1].f0) ? 1 : 0];
+        if (feat < s.f0 || feat >= s.f1) continue;
+        const int f = feat - s.f0;
+        float x = s.alpha * acc + ((s.bias && kz == 0) ? s.bias[f] : 0.f);
+        if (s.addend && kz == 0) x += s.addend[static_cast<size_t>(row) * s.ld_add + f];
+        if (s.act) x = tanhf(x);
+        s.C[static_cast<size_t>(kz) * a.plane + static_cast<size_t>(row) * s.ldc + f] = x * s.post;
+      }
+  }
   return STAT_OK;
 }
 

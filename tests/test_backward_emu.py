@@ -40,7 +40,7 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
-def run_emu(lib, o, params, batch, alpha_c, decay_c, dp=None, inv_batch=None):
+def run_emu(lib, o, params, batch, alpha_c, decay_c, dp=None, inv_batch=None, flat=False):
     x, mask, ctxg, mask_ctxg, ctxl, _ml, ctxm, _mm = batch
     L, B = x.shape
     T, R = ctxl.shape[1], ctxl.shape[2]
@@ -51,6 +51,16 @@ def run_emu(lib, o, params, batch, alpha_c, decay_c, dp=None, inv_batch=None):
     _, allv = so.forward_teacher(params, o, *batch, dtype=np.float32, return_all=True, **dpk)
     blk = allv['blk']
     P32 = {k: f32(v) for k, v in params.items()}
+    if flat:
+        # one contiguous buffer in init_params order, like optim.FlatParams: everything after the first scalar
+        # parameter is only 4-byte aligned
+        buf = np.zeros(sum(v.size for v in P32.values()) + 4, np.float32)
+        off = 0
+        for k, v in list(P32.items()):
+            buf[off:off + v.size] = v.reshape(-1)
+            P32[k] = buf[off:off + v.size].reshape(v.shape)
+            off += v.size
+        assert any(v.ctypes.data % 16 for v in P32.values())
     keep = dict(ctxg0=f32(blk['G']), pctxg=f32(blk['pG']), ctxm0=f32(blk['M']), pctxm=f32(blk['pM']),
                 ctxl0=f32(blk['Lc']), pctxl=f32(blk['pL']), qctxl=f32(blk['Lc'] @ P32['decoder_Wclt_att']),
                 h0c0=f32(np.concatenate([allv['h0'], allv['c0']], 1)))
@@ -109,9 +119,12 @@ def test_grads_match_oracle(emu, global_proj):
     _compare(grads, want)
 
 
-def test_grads_without_regularisers_and_options_off(emu):
+@pytest.mark.parametrize('fast', [False, True])
+def test_grads_without_regularisers_and_options_off(emu, fast, monkeypatch):
+    if fast:
+        monkeypatch.setenv('STAT_BW_FAST', '1')
     o, params, batch = _case(False, selector=False, ctx2out=False, prev2out=False)
-    grads = run_emu(emu, o, params, batch, 0., 0.)
+    grads = run_emu(emu, o, params, batch, 0., 0., flat=fast)
     _, want, _ = go.cost_and_grads(params, o, batch)
     _compare(grads, want)
 
@@ -129,14 +142,19 @@ def test_grads_with_dropout_factors(emu):
     _compare(grads, want)
 
 
-def test_grads_wider_than_a_block(emu):
-    """H = 160 > the 128 threads of the per-frame blocks (strided column loops, two columns per thread for some
+@pytest.mark.parametrize('fast', [False, True])
+def test_grads_wider_than_a_block(emu, fast, monkeypatch):
+    """(fast: the STAT_BW_FAST=1 variants -- k-split products summed from planes, row-wise embedding scatter, aligned
+    copies of the weights that sit 4-byte aligned in a flat parameter buffer.)
+    H = 160 > the 128 threads of the per-frame blocks (strided column loops, two columns per thread for some
     threads only), R = 3, a vocabulary that is not a multiple of 4, a single-frame tail."""
     kw = dict(dim=160, dim_word=12, ctxl_dim=20, ctxm_dim=12, n_words=37)
     o = stat.default_options(ctxg_dim=24, global_proj=True, **kw)
     params = so.trained_like_params(o, seed=9)
     batch = synthetic.make_batch(o, B=2, T=5, R=3, L=3, seed=9, zero_tail=True)
-    grads = run_emu(emu, o, params, batch, 0.70602, 1e-4)
+    if fast:
+        monkeypatch.setenv('STAT_BW_FAST', '1')
+    grads = run_emu(emu, o, params, batch, 0.70602, 1e-4, flat=fast)
     _, want, _ = go.cost_and_grads(params, o, batch, alpha_c=0.70602, decay_c=1e-4)
     _compare(grads, want)
 

@@ -554,9 +554,42 @@ __global__ void k_scatter_emb(const float *DEMB, const int64_t *x, float *dWemb,
     dWemb[static_cast<size_t>(x[n - B]) * E + e] += DEMB[n * E + e];
 }
 
+// STAT_BW_FAST variant of k_scatter_emb: one block per vocabulary row scans the tokens in order (still
+// deterministic) and writes its whole row, zeros included
+__global__ void k_scatter_emb_rows(const float *DEMB, const int64_t *x, float *dWemb, int L, int B, int E) {
+  const int64_t v = blockIdx.x;
+  const size_t n1 = static_cast<size_t>(L) * B;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float acc = 0.f;
+    for (size_t n = B; n < n1; ++n)
+      if (x[n - B] == v) acc += DEMB[n * E + e];
+    dWemb[static_cast<size_t>(v) * E + e] = acc;
+  }
+}
+
+// C[m][n] = sum over the k-slice planes, in order (STAT_BW_FAST: k-split products)
+__global__ void k_sum_planes(float *C, int ldc, const float *planes, size_t plane, int ks, int M, int N) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(M) * N) return;
+  float s = 0.f;
+  for (int z = 0; z < ks; ++z) s += planes[static_cast<size_t>(z) * plane + i];
+  C[(i / N) * ldc + (i % N)] = s;
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// STAT_BW_FAST=1 (default off until measured on the GPU): products whose output has too few
+// tiles to fill the SMs are k-split into planes and summed in order; the embedding scatter runs one block per
+// vocabulary row; weights that sit 4-byte aligned in the caller's flat buffer are copied to 16-byte aligned
+// scratch so that they take the tensor-core path.
+struct MmCtx {
+  bool fast = false;
+  float *planes = nullptr;
+};
+thread_local MmCtx g_mm;
+constexpr size_t PLANES_FLOATS = static_cast<size_t>(148) * 128 * 128 + 64 * 64;
+
 inline dim3 g1(size_t n, int bs = 256) { return dim3(static_cast<unsigned>((n + bs - 1) / bs)); }
 
 // C (M,N) = alpha * A (M,K) . Bt (N,K)^T + bias[N]
@@ -568,6 +601,23 @@ int mm(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int
   g.Q = Bt; g.ldq = ldb; g.NQ = N;
   g.K = K; g.feat_on_p = 0; g.nseg = 1; g.ksplit = 1;
   g.seg[0] = GemmSeg{C, ldc, bias, nullptr, 0, 1.f, 1.f, 0, 0, N};
+  if (g_mm.fast && g_mm.planes) {
+    const int bq = N > 64 ? 128 : (N > 32 ? 64 : 32);
+    const int tiles = ((M + 127) / 128) * ((N + bq - 1) / bq);
+    const int nk = (K + 31) / 32;
+    int ks = 148 / tiles;
+    if (ks > 32) ks = 32;
+    if (ks > nk) ks = nk;
+    const size_t plane = up(static_cast<size_t>(M) * N, 64);
+    if (ks >= 2 && plane * ks <= PLANES_FLOATS) {
+      g.ksplit = ks;
+      g.plane = plane;
+      g.seg[0].C = g_mm.planes;
+      g.seg[0].ldc = N;
+      STAT_TRY(gemm_launch(g, st));
+      return BW_LAUNCH(k_sum_planes, g1(static_cast<size_t>(M) * N), dim3(256), st, C, ldc, g_mm.planes, plane, ks, M, N);
+    }
+  }
   return gemm_launch(g, st);
 }
 
@@ -595,7 +645,7 @@ struct GW {   // float offsets into the gradient workspace
   size_t Hprev, EMB, HQ, csum, beta, ctx, XW, CW, ZC, GATES, Call, HD, ZT, Z, LOG, DLT;
   size_t DZ, DZP, DHR, DCR, DHQ, DHc, DCc, DHm, DCTX, DC, TMPH, CL, DA3, DS3, COV3, COVL, DSQP;
   size_t DPG, DPM, DG, DM, DPL, DLC, DQ, DUACC, DCACC;
-  size_t T1, T2, T3, DEMB, DWH, GBAR, DP0, SMALL, CS;
+  size_t T1, T2, T3, DEMB, DWH, GBAR, DP0, SMALL, CS, PLANES, ALN;
   size_t total;
   int ldq, Vp;
 };
@@ -638,6 +688,8 @@ GW gw_layout(const StatDims &d, int L) {
   w.SMALL = take(up(4 * H + 4, 64) + 64);
   const size_t cmax = std::max(std::max(ldq, Vp), 4 * H);
   w.CS = take(2 * ((kmax + 63) / 64 + 1) * cmax);
+  w.PLANES = take(PLANES_FLOATS);
+  w.ALN = take(8 * H * H + 6 * H * E + 8 * 64);
   w.total = o;
   return w;
 }
@@ -742,6 +794,24 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     return cudaMemcpy2DAsync(dst, F * ldd, src, F * lds, F * width, rows, cudaMemcpyDeviceToDevice, st);
   };
   auto zero = [&](size_t off, size_t n) { return cudaMemsetAsync(W + off, 0, n * F, st); };
+  const char *fast_env = getenv("STAT_BW_FAST");
+  const bool fast = fast_env && fast_env[0] == '1';
+  g_mm.fast = fast;
+  g_mm.planes = W + w.PLANES;
+  // weight operands read in the caller's layout: 16-byte aligned copies when needed (fast mode only)
+  size_t aln_used = 0;
+  auto aligned = [&](const float *src, size_t n) -> const float * {
+    if (!fast || (reinterpret_cast<uintptr_t>(src) & 15) == 0) return src;
+    float *dst = W + w.ALN + aln_used;
+    aln_used += up(n, 64);
+    if (cudaMemcpyAsync(dst, src, n * F, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return src;
+    return dst;
+  };
+  const size_t HH = static_cast<size_t>(H) * H, HE = static_cast<size_t>(H) * E;
+  const float *Wc_a = aligned(p->decoder_Wc, 4 * HH), *Wctx_a = c2o ? aligned(p->ff_logit_ctxglm_W, HE) : nullptr;
+  const float *Wl_a = aligned(p->ff_logit_lstm_W, HE), *Wd_a = aligned(p->decoder_W, 4 * HE);
+  const float *Wcg_a = aligned(p->decoder_Wcg_att, HH), *Wcm_a = aligned(p->decoder_Wcm_att, HH);
+  const float *Wcl_a = aligned(p->decoder_Wcl_att, HH), *Wclt_a = aligned(p->decoder_Wclt_att, HH);
 
   bw_mark(BP_LAYOUT, st);
   // ---- operand layouts --------------------------------------------------------------------
@@ -809,11 +879,11 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     STAT_CUDA_CHECK(cudaMemcpyAsync(GRAD(ff_logit_ctxglm_b), GRAD(ff_logit_lstm_b), F * E, cudaMemcpyDeviceToDevice, st));
     STAT_TRY(transpose(W + w.ctx, N, H, H, W + w.T1, N, st));
     STAT_TRY(mm(W + w.T1, N, W + w.T2, N, GRAD(ff_logit_ctxglm_W), E, H, E, N, nullptr, st));
-    STAT_TRY(mm(W + w.DZP, E, p->ff_logit_ctxglm_W, E, W + w.DCR, H, N, H, E, nullptr, st));
+    STAT_TRY(mm(W + w.DZP, E, Wctx_a, E, W + w.DCR, H, N, H, E, nullptr, st));
   } else {
     STAT_CUDA_CHECK(zero(w.DCR, NHs));
   }
-  STAT_TRY(mm(W + w.DZP, E, p->ff_logit_lstm_W, E, W + w.DHR, H, N, H, E, nullptr, st));
+  STAT_TRY(mm(W + w.DZP, E, Wl_a, E, W + w.DHR, H, N, H, E, nullptr, st));
   STAT_TRY(BW_LAUNCH(k_scale_dp, g1(NHs), dim3(256), st, W + w.DHR, W + w.DHR, dp_h, NHs));
   // coverage terms of the four attentions (:1138-1147): mean over T (T*R for alpha_l), sum over clips
   {
@@ -845,7 +915,7 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
                        B, H));
     bw_mark(BP_DCTX_GEMM, st);
     // dctx_t = dpre . Wc^T (:439); decoder_Wc (H,4H) is K-major for this product as it stands
-    STAT_TRY(mm(DHQt + 4 * H, ldq, p->decoder_Wc, 4 * H, W + w.DCTX, H, B, H, 4 * H, nullptr, st));
+    STAT_TRY(mm(DHQt + 4 * H, ldq, Wc_a, 4 * H, W + w.DCTX, H, B, H, 4 * H, nullptr, st));
     bw_mark(BP_SELECTOR_BW, st);
     STAT_TRY(BW_LAUNCH(k_selector_bw, dim3(B), dim3(NT), st, t, W + w.DCTX, W + w.DCR, W + w.csum, W + w.beta,
                        W + w.DHQ, ldq, 8 * H, W + w.DC, B, H, sel ? 1 : 0));
@@ -900,10 +970,14 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
   STAT_TRY(mm(T1, N, DPREt, N, GRAD(decoder_Wc), 4 * H, H, 4 * H, N, nullptr, st));
   bw_mark(BP_EMBEDDING, st);
   // embedding: dEMB = dpre . W^T (+ the readout's prev2out term), scattered to the rows of Wemb
-  STAT_TRY(mm(W + w.DHQ + 4 * H, ldq, p->decoder_W, 4 * H, W + w.DEMB, E, N, E, 4 * H, nullptr, st));
+  STAT_TRY(mm(W + w.DHQ + 4 * H, ldq, Wd_a, 4 * H, W + w.DEMB, E, N, E, 4 * H, nullptr, st));
   if (p2o) STAT_TRY(BW_LAUNCH(k_add_inplace, g1(NEs), dim3(256), st, W + w.DEMB, W + w.DZP, NEs));
-  STAT_CUDA_CHECK(cudaMemsetAsync(GRAD(Wemb), 0, F * V * E, st));
-  STAT_TRY(BW_LAUNCH(k_scatter_emb, g1(E, 128), dim3(128), st, W + w.DEMB, x, GRAD(Wemb), L, B, E));
+  if (fast) {
+    STAT_TRY(BW_LAUNCH(k_scatter_emb_rows, dim3(V), dim3(128), st, W + w.DEMB, x, GRAD(Wemb), L, B, E));
+  } else {
+    STAT_CUDA_CHECK(cudaMemsetAsync(GRAD(Wemb), 0, F * V * E, st));
+    STAT_TRY(BW_LAUNCH(k_scatter_emb, g1(E, 128), dim3(128), st, W + w.DEMB, x, GRAD(Wemb), L, B, E));
+  }
   bw_mark(BP_CTX_BLOCKS, st);
   // score vectors and biases
   STAT_TRY(colsum(W + w.DUACC, BT, 4 * H, 4 * H, SM, CS, st));
@@ -939,19 +1013,19 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     STAT_TRY(mm(T1, rows, T2, rows, gWf, H, D, H, rows, nullptr, st));
     return colsum(DY, rows, H, H, gbf, CS, st);
   };
-  STAT_TRY(ctx_path(f->ctxg0, W + w.DPG, W + w.DG, BT, p->decoder_Wcg_att, GRAD(decoder_Wcg_att),
+  STAT_TRY(ctx_path(f->ctxg0, W + w.DPG, W + w.DG, BT, Wcg_a, GRAD(decoder_Wcg_att),
                     GRAD(decoder_bg_att), gp));
   if (gp) STAT_TRY(feat_path(f->ctxg0, W + w.DG, BT, ctxg, Dg, GRAD(ff_global_W), GRAD(ff_global_b)));
-  STAT_TRY(ctx_path(f->ctxm0, W + w.DPM, W + w.DM, BT, p->decoder_Wcm_att, GRAD(decoder_Wcm_att),
+  STAT_TRY(ctx_path(f->ctxm0, W + w.DPM, W + w.DM, BT, Wcm_a, GRAD(decoder_Wcm_att),
                     GRAD(decoder_bm_att), true));
   STAT_TRY(feat_path(f->ctxm0, W + w.DM, BT, ctxm, Dm, GRAD(ff_motion_W), GRAD(ff_motion_b)));
-  STAT_TRY(ctx_path(f->ctxl0, W + w.DPL, W + w.DLC, BTR, p->decoder_Wcl_att, GRAD(decoder_Wcl_att),
+  STAT_TRY(ctx_path(f->ctxl0, W + w.DPL, W + w.DLC, BTR, Wcl_a, GRAD(decoder_Wcl_att),
                     GRAD(decoder_bl_att), true));
   {   // Q = ctxl0 . Wclt_att (the :416 product made step-invariant): dWclt = ctxl0^T . dQ, dctxl0 += dQ . Wclt^T
     STAT_TRY(transpose(f->ctxl0, BTR, H, H, T1, BTR, st));
     STAT_TRY(transpose(W + w.DQ, BTR, H, H, T2, BTR, st));
     STAT_TRY(mm(T1, BTR, T2, BTR, GRAD(decoder_Wclt_att), H, H, H, BTR, nullptr, st));
-    STAT_TRY(mm(W + w.DQ, H, p->decoder_Wclt_att, H, T3, H, BTR, H, H, nullptr, st));
+    STAT_TRY(mm(W + w.DQ, H, Wclt_a, H, T3, H, BTR, H, H, nullptr, st));
     const size_t cnt = static_cast<size_t>(BTR) * H;
     STAT_TRY(BW_LAUNCH(k_add_inplace, g1(cnt), dim3(256), st, W + w.DLC, T3, cnt));
   }
