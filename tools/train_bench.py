@@ -56,24 +56,27 @@ def main():
         if it == 0:
             lc1 = tr.engine.launch_count()
     ms = float(np.mean([t[0] + t[1] for t in times]))
-    phases = None
-    if a.phases:
-        import ctypes as C
-        lib = tr.engine.lib
-        lib.stat_grad_profile_enable(1)
-        tr.f_grad_shared(*batch)
-        n = lib.stat_grad_profile_phases()
-        msv, cnt = (C.c_float * n)(), (C.c_int * n)()
-        lib.stat_grad_profile_collect(msv, cnt, n)
-        lib.stat_grad_profile_enable(0)
-        phases = {lib.stat_grad_profile_phase_name(i).decode(): {'ms': round(float(msv[i]), 4), 'n': int(cnt[i])}
-                  for i in range(n)}
-    tokens = float(mask.sum())
     print(json.dumps({'metric': 'training tokens/sec (config 3: fwd+bwd+clip+adam, dropout on)', 'value': tokens / ms * 1e3,
                       'unit': 'tokens/s', 'ms_per_step': ms, 'ms_grad_shared': float(np.mean([t[0] for t in times])),
                       'ms_update': float(np.mean([t[1] for t in times])), 'cost': cost, 'B': B, 'L': L, 'T': T, 'R': R,
                       'launches_per_step': int(lc1 - lc0), 'steps': a.steps, 'warmup': a.warmup,
-                      'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30, 'backward_phases': phases}))
+                      'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+    if a.phases:
+        # second line: per-phase device time of stat_grad_shared (CUDA events recorded inside the library)
+        try:
+            import ctypes as C
+            lib = tr.engine.lib
+            lib.stat_grad_profile_enable(1)
+            tr.f_grad_shared(*batch)
+            n = lib.stat_grad_profile_phases()
+            msv, cnt = (C.c_float * n)(), (C.c_int * n)()
+            lib.stat_grad_profile_collect(msv, cnt, n)
+            lib.stat_grad_profile_enable(0)
+            phases = {lib.stat_grad_profile_phase_name(i).decode(): {'ms': round(float(msv[i]), 4), 'n': int(cnt[i])}
+                      for i in range(n)}
+        except Exception as e:
+            phases = {'error': str(e)[:200]}
+        print(json.dumps({'backward_phases': phases}), flush=True)
 
 
 if __name__ == '__main__':
