@@ -443,6 +443,10 @@ struct AttBw {
   float *DUACC;                           // (B,T,4H) += [l | g | m | lt]
   float *DCACC;                           // (B,T,4)  += column 0
   float *DSQP;                            // (B,T,4H) = [dsl | dsg | dsm | dslt]
+  // STAT_BW_FAST: instead of read-modify-writing DPL / DLC / DQ every step, keep this step's small factors
+  // (k_att_accum sums all steps in registers after the loop); null = accumulate in place
+  float *DAL;                             // (L,B,T,R) spatial score gradients of every step
+  float *DPLT;                            // (L,B,T,H) dpLT of every step
 };
 
 __global__ void k_att_main(const AttBw a) {
@@ -488,6 +492,7 @@ __global__ void k_att_main(const AttBw a) {
     const float dcL = aLT * dc;
     dcl[k] = dcL;
     dpl[k] = dp;
+    if (a.DPLT) a.DPLT[nt * H + h] = dp;
     for (int r = 0; r < R; ++r) {
       const size_t ol = (static_cast<size_t>(bt) * R + r) * H + h;
       part[r] = fmaf(dcL, a.Lc[ol], fmaf(dp, a.Q[ol], part[r]));
@@ -505,6 +510,7 @@ __global__ void k_att_main(const AttBw a) {
     dsum += dal[r];
   }
   if (threadIdx.x == 0) a.DCACC[static_cast<size_t>(bt) * 4] += dsum;
+  if (a.DAL && threadIdx.x < R) a.DAL[nt * R + threadIdx.x] = dal[threadIdx.x];
   k = 0;
   for (int h = threadIdx.x; h < H; h += blockDim.x, ++k) {
     const float sl = hq[h], ul = a.Ul[h];
@@ -513,15 +519,45 @@ __global__ void k_att_main(const AttBw a) {
       const size_t ol = (static_cast<size_t>(bt) * R + r) * H + h;
       const float tl = tanhf(a.pL[ol] + sl);
       const float dq = dal[r] * ul * (1.0f - tl * tl);
-      a.DPL[ol] += dq;
       dsl += dq;
       dul = fmaf(dal[r], tl, dul);
-      a.DLC[ol] = fmaf(alr[r], dcl[k], a.DLC[ol]);
-      a.DQ[ol] = fmaf(alr[r], dpl[k], a.DQ[ol]);
+      if (!a.DAL) {
+        a.DPL[ol] += dq;
+        a.DLC[ol] = fmaf(alr[r], dcl[k], a.DLC[ol]);
+        a.DQ[ol] = fmaf(alr[r], dpl[k], a.DQ[ol]);
+      }
     }
     const size_t o4 = static_cast<size_t>(bt) * 4 * H + h;
     a.DSQP[o4] = dsl;
     a.DUACC[o4] += dul;
+  }
+}
+
+// STAT_BW_FAST: the step-invariant local gradient blocks in one pass after the loop -- per (clip, frame, region,
+// column) the sum over all steps, in registers, of what k_att_main otherwise read-modify-writes every step:
+//   DPL = sum_s dal_r(s) Ul (1 - tanh^2(pL + sl_s)),  DLC = sum_s alpha_l,r(s) alpha_lt(s) dC_s,  DQ = sum_s alpha_l,r(s) dpLT_s
+__global__ void k_att_accum(int L, int B, int T, int R, int H, int ldq, const float *al, const float *alt,
+                            const float *DAL, const float *DPLT, const float *DCS, const float *HQ, const float *pL,
+                            const float *Ul, float *DPL, float *DLC, float *DQ) {
+  const int bt = blockIdx.x, b = bt / T, t = bt % T;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const float ul = Ul[h];
+    for (int r = 0; r < R; ++r) {
+      const size_t ol = (static_cast<size_t>(bt) * R + r) * H + h;
+      const float pl = pL[ol];
+      float apl = 0.f, alc = 0.f, aq = 0.f;
+      for (int s = L - 1; s >= 0; --s) {
+        const size_t n = static_cast<size_t>(s) * B + b, nt = n * T + t;
+        const float ar = al[nt * R + r];
+        const float tl = tanhf(pl + HQ[n * ldq + h]);
+        apl = fmaf(DAL[nt * R + r] * ul, 1.0f - tl * tl, apl);
+        alc = fmaf(ar, alt[nt] * DCS[n * H + h], alc);
+        aq = fmaf(ar, DPLT[nt * H + h], aq);
+      }
+      DPL[ol] = apl;
+      DLC[ol] = alc;
+      DQ[ol] = aq;
+    }
   }
 }
 
@@ -645,7 +681,7 @@ struct GW {   // float offsets into the gradient workspace
   size_t Hprev, EMB, HQ, csum, beta, ctx, XW, CW, ZC, GATES, Call, HD, ZT, Z, LOG, DLT;
   size_t DZ, DZP, DHR, DCR, DHQ, DHc, DCc, DHm, DCTX, DC, TMPH, CL, DA3, DS3, COV3, COVL, DSQP;
   size_t DPG, DPM, DG, DM, DPL, DLC, DQ, DUACC, DCACC;
-  size_t T1, T2, T3, DEMB, DWH, GBAR, DP0, SMALL, CS, PLANES, ALN;
+  size_t T1, T2, T3, DEMB, DWH, GBAR, DP0, SMALL, CS, PLANES, ALN, DAL, DPLT, DCS;
   size_t total;
   int ldq, Vp;
 };
@@ -690,6 +726,9 @@ GW gw_layout(const StatDims &d, int L) {
   w.CS = take(2 * ((kmax + 63) / 64 + 1) * cmax);
   w.PLANES = take(PLANES_FLOATS);
   w.ALN = take(8 * H * H + 6 * H * E + 8 * 64);
+  w.DAL = take(N * T * R);
+  w.DPLT = take(N * T * H);
+  w.DCS = take(N * H);
   w.total = o;
   return w;
 }
@@ -909,6 +948,8 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
   STAT_CUDA_CHECK(zero(w.DCACC, static_cast<size_t>(BT) * 4));
   for (int t = L - 1; t >= 0; --t) {
     float *DHQt = W + w.DHQ + static_cast<size_t>(t) * B * ldq;
+    // fast mode keeps dC of every step (k_att_accum reads them after the loop)
+    float *DCt = fast ? W + w.DCS + static_cast<size_t>(t) * B * H : W + w.DC;
     bw_mark(BP_CELL_BW, st);
     STAT_TRY(BW_LAUNCH(k_cell_backward, g1(static_cast<size_t>(B) * H), dim3(256), st, t, W + w.DHc, W + w.DCc,
                        W + w.DHR, W + w.GATES, W + w.Call, f->h0c0, mask, dp_gates, W + w.DHQ, ldq, 4 * H, W + w.DHm,
@@ -918,9 +959,9 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     STAT_TRY(mm(DHQt + 4 * H, ldq, Wc_a, 4 * H, W + w.DCTX, H, B, H, 4 * H, nullptr, st));
     bw_mark(BP_SELECTOR_BW, st);
     STAT_TRY(BW_LAUNCH(k_selector_bw, dim3(B), dim3(NT), st, t, W + w.DCTX, W + w.DCR, W + w.csum, W + w.beta,
-                       W + w.DHQ, ldq, 8 * H, W + w.DC, B, H, sel ? 1 : 0));
+                       W + w.DHQ, ldq, 8 * H, DCt, B, H, sel ? 1 : 0));
     bw_mark(BP_ATT_DOTS, st);
-    STAT_TRY(BW_LAUNCH(k_att_dots, dim3(BT), dim3(NT), st, t, alpha_l, f->ctxl0, f->ctxg0, f->ctxm0, W + w.DC,
+    STAT_TRY(BW_LAUNCH(k_att_dots, dim3(BT), dim3(NT), st, t, alpha_l, f->ctxl0, f->ctxg0, f->ctxm0, DCt,
                        W + w.CL, W + w.DA3, B, T, R, H));
     bw_mark(BP_ATT_SOFT, st);
     STAT_TRY(BW_LAUNCH(k_att_soft, g1(3 * B, 128), dim3(128), st, t, alpha_g, alpha_m, alpha_lt, W + w.DA3,
@@ -933,10 +974,11 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     a.HQ = W + w.HQ;
     a.pL = f->pctxl; a.Lc = f->ctxl0; a.Q = f->qctxl; a.pG = f->pctxg; a.pM = f->pctxm;
     a.Ul = p->decoder_Ul_att; a.Ug = p->decoder_Ug_att; a.Um = p->decoder_Um_att; a.Ult = p->decoder_Ult_att;
-    a.DC = W + w.DC; a.DS3 = W + w.DS3; a.COVL = W + w.COVL;
+    a.DC = DCt; a.DS3 = W + w.DS3; a.COVL = W + w.COVL;
     a.DPL = W + w.DPL; a.DLC = W + w.DLC; a.DQ = W + w.DQ;
     a.DPG = W + w.DPG; a.DPM = W + w.DPM; a.DG = W + w.DG; a.DM = W + w.DM;
     a.DUACC = W + w.DUACC; a.DCACC = W + w.DCACC; a.DSQP = W + w.DSQP;
+    if (fast) { a.DAL = W + w.DAL; a.DPLT = W + w.DPLT; }
     STAT_TRY(BW_LAUNCH(k_att_main, dim3(BT), dim3(NT), st, a));
     bw_mark(BP_REDUCE_T, st);
     STAT_TRY(BW_LAUNCH(k_reduce_t, g1(static_cast<size_t>(B) * 4 * H), dim3(256), st, t, W + w.DSQP, W + w.DHQ, ldq,
@@ -948,6 +990,11 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
                        static_cast<size_t>(B) * H));
   }
 
+  if (fast) {
+    bw_mark(BP_ATT_MAIN, st);
+    STAT_TRY(BW_LAUNCH(k_att_accum, dim3(BT), dim3(NT), st, L, B, T, R, H, ldq, alpha_l, alpha_lt, W + w.DAL, W + w.DPLT,
+                       W + w.DCS, W + w.HQ, f->pctxl, p->decoder_Ul_att, W + w.DPL, W + w.DLC, W + w.DQ));
+  }
   bw_mark(BP_WGRAD_STEPS, st);
   // ---- D: weight gradients over the stacked steps ----------------------------------------------------
   float *T1 = W + w.T1, *T2 = W + w.T2, *T3 = W + w.T3, *CS = W + w.CS, *SM = W + w.SMALL;
