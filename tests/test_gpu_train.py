@@ -132,3 +132,23 @@ def test_training_steps_follow_the_reference_update(torch_cuda, optimizer):
         got = np.concatenate([v.reshape(-1) for v in tr.unzip().values()])
         np.testing.assert_allclose(got, pflat, rtol=3e-6, atol=2e-8, err_msg='step %d' % step)
     assert costs[-1] < costs[0]
+
+
+@pytest.mark.xfail(strict=False, reason='STAT_BW_FAST variants (k-split products, deferred accumulation, row-wise scatter) were '
+                                        'written after the round-1 GPU budget was spent: checked under the CPU emulation only. '
+                                        'Non-strict and last in the suite: reports xpass / xfail without gating anything.')
+def test_zz_fast_variants_match_oracle(torch_cuda, monkeypatch):
+    from video_description_with_spatial_temporal_attention_b200.train import Trainer
+    monkeypatch.setenv('STAT_BW_FAST', '1')
+    kw = dict(alpha_c=0.70602, decay_c=1e-4)
+    o, params, batch = _toy(True)
+    tr = Trainer(params, o, use_noise=False, **kw)
+    tr.f_grad_shared(*batch)
+    _compare(tr.grads(), go.cost_and_grads(params, o, batch, **kw)[1])
+    o = stat.default_options(dim=128, dim_word=128, ctxg_dim=256, ctxl_dim=512, ctxm_dim=512, n_words=1574,
+                             global_proj=True)
+    params = so.trained_like_params(o, seed=3)
+    batch = synthetic.make_batch(o, B=8, T=6, R=4, L=8, seed=3, zero_tail=True)
+    tr = Trainer(params, o, use_noise=False, **kw)
+    tr.f_grad_shared(*batch)
+    _compare(tr.grads(), go.cost_and_grads(params, o, batch, **kw)[1], rtol=5e-4)
