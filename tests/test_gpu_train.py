@@ -5,6 +5,8 @@ adadelta -- against the oracle's update rules.  Tolerance: 1e-4 of the largest e
 tensor ("rel 1e-4 vs fp64 oracle").
 
 The same backward code is checked on the CPU, kernel for kernel, in tests/test_backward_emu.py."""
+import os
+
 import numpy as np
 import pytest
 
@@ -134,9 +136,10 @@ def test_training_steps_follow_the_reference_update(torch_cuda, optimizer):
     assert costs[-1] < costs[0]
 
 
-@pytest.mark.xfail(strict=False, reason='STAT_BW_FAST variants (k-split products, deferred accumulation, row-wise scatter) were '
-                                        'written after the round-1 GPU budget was spent: checked under the CPU emulation only. '
-                                        'Non-strict and last in the suite: reports xpass / xfail without gating anything.')
+@pytest.mark.skipif(os.environ.get('STAT_TEST_FAST') != '1',
+                    reason='STAT_BW_FAST variants (k-split products, deferred accumulation, row-wise scatter) were written '
+                           'after the round-1 GPU budget was spent and are checked under the CPU emulation only; run with '
+                           'STAT_TEST_FAST=1 on a GPU before switching them on')
 def test_zz_fast_variants_match_oracle(torch_cuda, monkeypatch):
     from video_description_with_spatial_temporal_attention_b200.train import Trainer
     monkeypatch.setenv('STAT_BW_FAST', '1')
