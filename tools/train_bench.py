@@ -1,6 +1,7 @@
 """Timing of one training step (BASELINE config 3: B=128 clips, L=20, BASELINE widths; fwd + bwd + clip + adam)
 with CUDA events, per phase.  Synthetic features drawn on the device, random-init parameters.
-    python tools/train_bench.py [--B 128] [--steps 2] [--warmup 1]  ->  one JSON line"""
+    python tools/train_bench.py [--B 128] [--steps 2] [--warmup 1] [--phases]  ->  one JSON line (+ the phase table)
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_bench.py   (config 4: B per rank)"""
 import argparse
 import json
 import os
@@ -26,11 +27,18 @@ def main():
     ap.add_argument('--warmup', type=int, default=1)
     ap.add_argument('--phases', action='store_true', help='one extra step with the per-phase timing of stat_grad_shared')
     a = ap.parse_args()
+    # data parallel (BASELINE config 4) under torchrun: one rank per GPU, B clips per rank, one SUM all-reduce of the
+    # flat gradient per step inside Trainer.f_grad_shared
+    world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        dist.init_process_group('nccl')
     o = stat.baseline_options()
     params = ma.Attention().init_params(o)
-    tr = Trainer(params, o, optimizer='adam', alpha_c=0.70602, decay_c=1e-4, clip_c=10., use_noise=True)
+    tr = Trainer(params, o, optimizer='adam', alpha_c=0.70602, decay_c=1e-4, clip_c=10., use_noise=True, seed=1234 + rank)
     dev = tr.engine.device
-    g = torch.Generator(device=dev).manual_seed(1234)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
     B, L, T, R = a.B, a.L, a.T, a.R
     ctxg = torch.randn(B, T, o['ctxg_dim'], device=dev, generator=g) * 0.5
     ctxl = torch.randn(B, T, R, o['ctxl_dim'], device=dev, generator=g) * 0.5
@@ -56,9 +64,16 @@ def main():
         if it == 0:
             lc1 = tr.engine.launch_count()
     ms = float(np.mean([t[0] + t[1] for t in times]))
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)              # device time, max over ranks
+        ms = float(tmax[0])
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     print(json.dumps({'metric': 'training tokens/sec (config 3: fwd+bwd+clip+adam, dropout on)', 'value': tokens / ms * 1e3,
                       'unit': 'tokens/s', 'ms_per_step': ms, 'ms_grad_shared': float(np.mean([t[0] for t in times])),
-                      'ms_update': float(np.mean([t[1] for t in times])), 'cost': cost, 'B': B, 'L': L, 'T': T, 'R': R,
+                      'ms_update': float(np.mean([t[1] for t in times])), 'cost': cost, 'n_gpus': world, 'B': B, 'L': L, 'T': T, 'R': R,
                       'launches_per_step': int(lc1 - lc0), 'steps': a.steps, 'warmup': a.warmup,
                       'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
     if a.phases:
