@@ -176,3 +176,18 @@ def test_fit_keeps_the_shared_parameters_in_step_with_the_trainer(tmp_path):
     # validations after updates 2, 4, ... saw exactly those parameter values; the closing one the best (update 4)
     assert seen == [2.0, 4.0, 6.0, 8.0, 10.0, 4.0]
     assert float(tparams['w'].get_value()[0]) == 4.0 and (h.params['w'] == 4).all()
+
+
+def test_reload_continues_the_history(tmp_path):
+    """reload_ (:1109-1113, :1215-1218): parameters and history of model_best_so_far.npz feed the next run, whose
+    validations are judged against the reloaded history."""
+    h = Harness(tmp_path, [5.0, 4.0, 4.5, 4.6, 4.7, 4.0])
+    h.run()
+    params, hist = train_loop.reload(h.dir, OrderedDict(w=np.zeros(3, 'float32'), b=np.zeros((), 'float32')))
+    assert (params['w'] == 4).all() and len(hist) == 2 and hist[-1][train_loop.COL_VALID_ERR] == 4.0
+    h2 = Harness(tmp_path, [3.9, 5.0, 5.0, 5.0, 3.9])
+    h2.set_params(params)
+    h2.run(history_errs=hist, patience=1)
+    out = np.loadtxt(h2.dir + 'train_valid_test.txt', ndmin=2)
+    # two reloaded rows, then 3.9 is an improvement at once (the history is longer than one row), then two bad ones
+    assert out.shape[0] == 2 + 3 and (np.load(h2.dir + 'model_best_so_far.npz')['w'] == 2).all()

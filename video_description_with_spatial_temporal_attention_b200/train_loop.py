@@ -40,6 +40,16 @@ def alpha_ratio(alphas):
     return float(a.min(-1).mean() / a.max(-1).mean())
 
 
+def reload(from_dir, params):
+    """`reload_=True` (:1109-1113, :1215-1218): parameters and the error history of `from_dir/model_best_so_far.npz`.
+    Returns (params filled from the archive, history_errs as a list of rows) -- pass the latter to train()."""
+    path = os.path.join(from_dir, 'model_best_so_far.npz')
+    params = checkpoint.load_params(path, params)
+    extras = checkpoint.archive_extras(path)
+    hist = extras.get('history_errs')
+    return params, (numpy.asarray(hist).tolist() if hist is not None and numpy.size(hist) else [])
+
+
 def _zero_scores():
     return {s: dict((k, 0.) for k in SCORE_KEYS) for s in ('valid', 'test')}
 
