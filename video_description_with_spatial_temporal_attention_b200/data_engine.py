@@ -45,6 +45,9 @@ class MemoryEngine(object):
         self.word_idict = OrderedDict((v, k) for k, v in worddict.items())
         self.word_idict[0] = '<eos>'
         self.word_idict[1] = 'UNK'
+        # clip ids of each split, in order of first appearance (data_engine.py:229-232: vid1..1200 / 1201..1300 / ...)
+        uniq = lambda ids: list(OrderedDict((i.rsplit('_', 1)[0], None) for i in ids))
+        self.train_ids, self.valid_ids, self.test_ids = uniq(self.train), uniq(self.valid), uniq(self.test)
         self.kf_train = common.generate_minibatch_idx(len(self.train), min(mb_size_train, len(self.train)))
         self.kf_valid = common.generate_minibatch_idx(len(self.valid), min(mb_size_test, len(self.valid)))
         self.kf_test = common.generate_minibatch_idx(len(self.test), min(mb_size_test, len(self.test)))
@@ -69,6 +72,15 @@ class MemoryEngine(object):
 
     def prepare_data(self, engine, IDs):
         return prepare_data(engine, IDs)
+
+    def prepare_data_for_blue(self, whichset):
+        """Features and masks of every clip of a split, one entry per clip (data_engine.py:137-167)."""
+        ids = {'valid': self.valid_ids, 'test': self.test_ids, 'train': self.train_ids}[whichset]
+        g = [self.get_video_global_features(v) for v in ids]
+        l = [self.get_video_local_features(v) for v in ids]
+        m = [self.get_video_motion_features(v) for v in ids]
+        return (g, [self.get_ctxg_mask(a) for a in g], l, [self.get_ctxl_mask(a) for a in l],
+                m, [self.get_ctxm_mask(a) for a in m])
 
 
 def prepare_data(engine, IDs):

@@ -169,7 +169,7 @@ def train(model, data_engine_module, f_grad_shared, f_update, f_log_probs, f_alp
 
 
 def fit(model, tparams, model_options, trainer, f_log_probs, f_alphas, save_model_dir, use_noise=None,
-        data_engine_module=None, **kw):
+        data_engine_module=None, caption_scorer=None, decode_samples=False, **kw):
     """train() wired to a device trainer (train.Trainer or anything with f_grad_shared / f_update / unzip /
     load_params): the shared parameters `tparams` -- what f_log_probs, f_init / f_next and the checkpoints read --
     are refreshed from the trainer's device buffers at the top of every validation block and receive the best
@@ -187,5 +187,15 @@ def fit(model, tparams, model_options, trainer, f_log_probs, f_alphas, save_mode
         trainer.load_params(p)
         common.zipp(p, tparams)
 
+    if (caption_scorer is not None or decode_samples) and 'score_fn' not in kw:
+        # what the reference does at every validation (:1432-1446): beam-5 captions of the validation and test clips
+        # (device search for 32 clips at a time), valid_samples.txt / test_samples.txt, scores from the COCO scorer
+        from . import metrics
+
+        def score_fn(params):
+            return metrics.compute_score('attention', params, model_options, model.engine, save_model_dir, 5, 5,
+                                         whichset='both', on_cpu=False, one_time=True, model=model,
+                                         scorer=caption_scorer, tparams=tparams)
+        kw['score_fn'] = score_fn
     return train(model, data_engine_module, trainer.f_grad_shared, trainer.f_update, f_log_probs, f_alphas,
                  get_params, set_params, model_options, save_model_dir, use_noise=use_noise, **kw)
