@@ -117,6 +117,11 @@ def test_grads_match_oracle(emu, global_proj):
     grads = run_emu(emu, o, params, batch, **kw)
     _, want, _ = go.cost_and_grads(params, o, batch, **kw)
     _compare(grads, want)
+    # and against the committed fixture of the same case (tests/golden/grad_toy.npz)
+    import os
+    from collections import OrderedDict
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'grad_toy.npz'))
+    _compare(grads, OrderedDict((k, gold['gp%d/%s' % (int(global_proj), k)]) for k in want))
 
 
 @pytest.mark.parametrize('fast', [False, True])

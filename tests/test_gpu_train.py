@@ -6,6 +6,7 @@ tensor ("rel 1e-4 vs fp64 oracle").
 
 The same backward code is checked on the CPU, kernel for kernel, in tests/test_backward_emu.py."""
 import os
+from collections import OrderedDict
 
 import numpy as np
 import pytest
@@ -61,6 +62,11 @@ def test_grad_shared_toy_vs_oracle(torch_cuda, global_proj):
     want_cost, want, _ = go.cost_and_grads(params, o, batch, **kw)
     assert abs(cost - want_cost) < 1e-4 * max(1.0, abs(want_cost))
     _compare(tr.grads(), want)
+    # and against the committed fixture of the same case (tests/golden/grad_toy.npz)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'grad_toy.npz'))
+    tag = 'gp%d/' % int(global_proj)
+    assert abs(cost - float(gold[tag + 'cost'])) < 1e-4 * max(1.0, abs(want_cost))
+    _compare(tr.grads(), OrderedDict((k, gold[tag + k]) for k in want))
 
 
 def test_grad_shared_options_off_and_dropout(torch_cuda):

@@ -66,3 +66,15 @@ def test_clip_and_regularisers():
     got = np.concatenate([g.reshape(-1) for g in gc.values()])
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-9)
     assert abs(exc['g2'] - float(g2)) < 1e-5 * exc['g2']
+
+
+def test_oracle_reproduces_the_committed_gradient_fixture():
+    """tests/golden/grad_toy.npz (tests/golden/make_grad_golden.py) freezes the target of the CUDA backward pass."""
+    import os
+    from tests.golden import make_grad_golden as mg
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'grad_toy.npz')
+    want = np.load(path)
+    got = mg.build()
+    assert sorted(want.files) == sorted(got.keys())
+    for k in want.files:
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=1e-12, err_msg=k)
