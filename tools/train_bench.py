@@ -71,6 +71,7 @@ def main():
         if rank != 0:
             dist.destroy_process_group()
             return
+    tokens = float(mask.sum()) * world
     print(json.dumps({'metric': 'training tokens/sec (config 3: fwd+bwd+clip+adam, dropout on)', 'value': tokens / ms * 1e3,
                       'unit': 'tokens/s', 'ms_per_step': ms, 'ms_grad_shared': float(np.mean([t[0] for t in times])),
                       'ms_update': float(np.mean([t[1] for t in times])), 'cost': cost, 'n_gpus': world, 'B': B, 'L': L, 'T': T, 'R': R,
