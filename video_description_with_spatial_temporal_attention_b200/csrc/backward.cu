@@ -803,6 +803,9 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
                "grad_shared: need 1<=R<=%d and H<=%d (R=%d H=%d)", RMAX, NT * HMAX_PT, d->R, d->H);
   STAT_REQUIRE(f->ctxg0 && f->pctxg && f->ctxm0 && f->pctxm && f->ctxl0 && f->pctxl && f->qctxl && f->h0c0,
                STAT_EINVAL, "grad_shared: forward blocks missing");
+  STAT_REQUIRE((reinterpret_cast<uintptr_t>(gws) & 15) == 0, STAT_EALIGN, "grad_shared: workspace must be 16-byte aligned");
+  STAT_REQUIRE(d->B >= 1 && d->T >= 1 && d->E >= 1 && d->V >= 2 && d->Dg >= 1 && d->Dm >= 1 && d->Dr >= 1, STAT_EINVAL,
+               "grad_shared: bad dims");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int B = d->B, T = d->T, R = d->R, H = d->H, E = d->E, V = d->V, Dg = d->Dg, Dm = d->Dm, Dr = d->Dr;
   const bool sel = d->flags & STAT_SELECTOR, c2o = d->flags & STAT_CTX2OUT, p2o = d->flags & STAT_PREV2OUT,
