@@ -58,6 +58,28 @@ def test_sizes_and_argument_errors_without_gpu():
     assert b'ctxg_dim == dim' in lib.stat_last_error()
 
 
+def test_training_entry_points_without_gpu():
+    """Sizes, phase names and argument errors of the backward-pass ABI (no compute without a GPU)."""
+    lib = _lib.load()
+    o = stat.baseline_options()
+    d = _lib.StatDims(B=128, T=26, R=8, Dg=o['ctxg_dim'], Dm=o['ctxm_dim'], Dr=o['ctxl_dim'], H=o['dim'],
+                      E=o['dim_word'], V=o['n_words'], flags=_lib.flags_of(o))
+    n20 = lib.stat_grad_workspace_bytes(ctypes.byref(d), 20)
+    n10 = lib.stat_grad_workspace_bytes(ctypes.byref(d), 10)
+    # transposed raw local features (4096 x 26624 floats) and their H-wide partner dominate; a few GB at most
+    assert 1.5e9 < n10 < n20 < 4e9
+    assert lib.stat_grad_workspace_bytes(ctypes.byref(d), 0) == 0
+    names = [lib.stat_grad_profile_phase_name(i).decode() for i in range(lib.stat_grad_profile_phases())]
+    assert 'loop_att_main' in names and 'readout_backward' in names and len(set(names)) == len(names)
+    assert lib.stat_grad_profile_phase_name(len(names)) is None
+    sp, blocks = _lib.StatParams(), _lib.StatFwdBlocks()
+    rc = lib.stat_grad_shared(ctypes.byref(d), ctypes.byref(sp), ctypes.byref(blocks), 20, *([None] * 14), 1.0, 0.0, 0.0,
+                              ctypes.byref(sp), None, None)
+    assert rc == -1 and b'NULL' in lib.stat_last_error()
+    with pytest.raises(_lib.StatError):
+        _lib.check(rc)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
