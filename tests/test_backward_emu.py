@@ -192,6 +192,7 @@ def _dp_worker(rank, world, port, q):
 def test_data_parallel_gradients_equal_the_global_batch():
     import socket
     import torch.multiprocessing as mp
+    build_emu.build()                                    # once, before the ranks load it
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
     port = s.getsockname()[1]
