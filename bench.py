@@ -129,6 +129,24 @@ def cpu_reference_rate(options, params, feats, n_clips, repeats=1):
     return n / dt, dt
 
 
+def cpu_train_rate(options, params, n_clips=32, repeats=2):
+    """CPU figure beside the secondary train_step line: forward + backward + clipping of the gradient oracle
+    (oracle/grad_oracle.py: the reference's cost graph restated in torch, autograd for `tensor.grad`; fp32, all
+    host cores) on a bounded sample of the config-3 workload.  Returns (tokens/s, seconds per step)."""
+    import torch
+    from oracle import grad_oracle as go
+    from video_description_with_spatial_temporal_attention_b200 import synthetic
+    all_host_threads()
+    batch = synthetic.make_batch(options, B=n_clips, T=T, R=R, L=MAXLEN, seed=99, ragged=False)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        go.cost_and_grads(params, options, batch, alpha_c=0.70602, decay_c=1e-4, clip_c=10., dtype=torch.float32)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    return float(np.asarray(batch[1]).sum()) / best, best
+
+
 def run_reference(args, rank):
     import video_description_with_spatial_temporal_attention_b200 as stat
     from video_description_with_spatial_temporal_attention_b200 import synthetic
@@ -363,6 +381,15 @@ def run_ours(args, rank, world, local_rank):
         cpu['hoisted_batched'] = {'value': B / dth, 'unit': 'captions/s',
                                   'sample': 'one B=64 batch (%.1f s): projections computed once per batch, all clips '
                                             'stepped together; numpy fp32 BLAS on all host cores' % dth}
+    if cpu is not None:
+        try:
+            rate_t, dt_t = cpu_train_rate(o, params)
+            cpu['train_step'] = {'value': rate_t, 'unit': 'tokens/s',
+                                 'sample': '32 clips x 20 steps of the config-3 workload (%.1f s per step): forward + '
+                                           'backward + clipping of the gradient oracle, torch fp32 on all host cores'
+                                           % dt_t}
+        except Exception as e:
+            cpu['train_step'] = {'error': str(e)[:200]}
     # secondary (BASELINE config 3): one training step -- forward, backward, clip, adam -- at B=128, timed by
     # tools/train_bench.py in its own process so that nothing it does can cost the headline line
     train = None
