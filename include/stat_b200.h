@@ -236,7 +236,9 @@ int stat_adadelta_step(float *params, const float *grads, float *rg2, float *ru2
  *              parameter in the reference's shapes -- e.g. views into the flat gradient buffer the
  *              optimizer entry points use;
  *   gws        stat_grad_workspace_bytes(d, L) bytes of scratch.
- * Deterministic: no atomics, fixed summation orders.  H <= 1024, R <= 16. */
+ * Deterministic: no atomics, fixed summation orders.  H <= 1024, R <= 16.
+ * Environment: STAT_BW_FAST=1 selects the optimised variants (k-split products, deferred accumulation of the
+ * step-invariant gradient blocks, row-wise embedding scatter); same results up to fp32 summation order. */
 typedef struct StatFwdBlocks {
   const float *ctxg0, *pctxg, *ctxm0, *pctxm;   /* (B,T,H)    */
   const float *ctxl0, *pctxl, *qctxl;           /* (B,T,R,H)  */

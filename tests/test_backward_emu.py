@@ -216,3 +216,14 @@ def test_data_parallel_gradients_equal_the_global_batch():
         got[k] = res[0][off:off + w.size].reshape(w.shape)
         off += w.size
     _compare(got, want)
+
+
+@pytest.mark.parametrize('B,T,R,L', [(1, 1, 1, 1), (2, 1, 3, 2), (1, 3, 1, 4), (2, 2, 16, 2)])
+def test_grads_edge_shapes(emu, B, T, R, L):
+    """One clip, one frame, one region (soft-maxes over a single element: alpha = 1, zero score gradients), a single
+    step (no recurrence), the maximum region count."""
+    o, params, _ = _case(True)
+    batch = synthetic.make_batch(o, B=B, T=T, R=R, L=L, seed=B + 10 * T + 100 * R)
+    grads = run_emu(emu, o, params, batch, 0.70602, 1e-4)
+    _, want, _ = go.cost_and_grads(params, o, batch, alpha_c=0.70602, decay_c=1e-4)
+    _compare(grads, want)

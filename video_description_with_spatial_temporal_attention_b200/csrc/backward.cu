@@ -16,7 +16,10 @@
 //      backward (tanh feature projections), the init-state path, the embedding scatter, decay.
 //
 // First, correctness-oriented version: plain SIMT kernels around gemm_launch, no fusion, no
-// tuning (per-step products run as single 128-row tiles).  The same translation unit compiles
+// tuning (per-step products run as single 128-row tiles).  STAT_BW_FAST=1 switches on the first round of
+// optimisations (k-split products, deferred accumulation of the step-invariant blocks, row-wise embedding
+// scatter, aligned weight copies), default off until they have been measured on the GPU; stat_grad_profile_*
+// gives the per-phase device time of either mode.  The same translation unit compiles
 // under g++ with -DSTAT_EMU against tests/emu/cuda_emu.h (threads-as-CUDA-threads emulation,
 // test infrastructure) so that kernels and orchestration can be checked against the gradient
 // oracle without a GPU; the product build never defines STAT_EMU.
