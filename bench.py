@@ -392,20 +392,26 @@ def run_ours(args, rank, world, local_rank):
             cpu['train_step'] = {'error': str(e)[:200]}
     # secondary (BASELINE config 3): one training step -- forward, backward, clip, adam -- at B=128, timed by
     # tools/train_bench.py in its own process so that nothing it does can cost the headline line
-    train = None
+    train = train_fast = None
     if world == 1 and os.environ.get('STAT_BENCH_TRAIN', '1') != '0':
-        try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'train_bench.py'), '--steps', '3',
-                                '--warmup', '2', '--phases'], capture_output=True, text=True, timeout=240)
-            rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith('{')]
-            if rows:
-                train = rows[0]
+        def train_line(extra_env):
+            try:
+                env = dict(os.environ)
+                env.update(extra_env)
+                r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'train_bench.py'), '--steps', '3',
+                                    '--warmup', '2', '--phases'], capture_output=True, text=True, timeout=240, env=env)
+                rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith('{')]
+                if not rows:
+                    return {'error': (r.stderr or 'no output')[-300:]}
+                out = rows[0]
                 for extra in rows[1:]:
-                    train.update(extra)
-            else:
-                train = {'error': (r.stderr or 'no output')[-300:]}
-        except Exception as e:
-            train = {'error': str(e)[:200]}
+                    out.update(extra)
+                return out
+            except Exception as e:
+                return {'error': str(e)[:200]}
+        train = train_line({'STAT_BW_FAST': '0'})
+        # the same step with the optimised backward variants (parity-checked on the GPU, not yet the default)
+        train_fast = train_line({'STAT_BW_FAST': '1'})
     total_bytes = B * 4 * T * (o['ctxg_dim'] + o['ctxm_dim'] + R * o['ctxl_dim']) + MAXLEN * (
         ctx_step_bytes + 41571528) + 8 * B * MAXLEN
     line = {'metric': METRIC, 'value': world * B * args.steps / (ms * 1e-3), 'unit': 'captions/s',
@@ -426,7 +432,7 @@ def run_ours(args, rank, world, local_rank):
             'whole_path': {'algorithmic_bytes_per_step': total_bytes,
                            'achieved_GBps': total_bytes / (ms / args.steps * 1e-3) / 1e9,
                            'frac_of_hbm_peak': total_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
-            'beam5': beam, 'train_step': train, 'l2_persist_bytes': eng.l2_persist_bytes,
+            'beam5': beam, 'train_step': train, 'train_step_fast': train_fast, 'l2_persist_bytes': eng.l2_persist_bytes,
             'tokens_checksum': int(tokens.astype(np.int64).sum())}
     print(json.dumps(line))
     if world > 1:
