@@ -3,7 +3,6 @@
 # both modes.  usage: gpurun --timeout 600 -- 'bash tools/gpu_train_check.sh'
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_train.py -q --tb=short -p no:cacheprovider 2>&1 | tail -15 | tee gpurun_out/t_train.log
-STAT_TEST_FAST=1 timeout 300 python -m pytest tests/test_gpu_train.py -q --tb=short -p no:cacheprovider -k fast_variants 2>&1 | tail -15 | tee gpurun_out/t_train_fast.log
 timeout 200 python tools/train_bench.py --steps 5 --warmup 2 --phases > gpurun_out/train_default.json 2> gpurun_out/train_default.err
 STAT_BW_FAST=1 timeout 200 python tools/train_bench.py --steps 5 --warmup 2 --phases > gpurun_out/train_fast.json 2> gpurun_out/train_fast.err
 python - <<'PY'
