@@ -134,7 +134,10 @@ def test_grads_without_regularisers_and_options_off(emu, fast, monkeypatch):
     _compare(grads, want)
 
 
-def test_grads_with_dropout_factors(emu):
+@pytest.mark.parametrize('fast', [False, True])
+def test_grads_with_dropout_factors(emu, fast, monkeypatch):
+    if fast:
+        monkeypatch.setenv('STAT_BW_FAST', '1')
     o, params, batch = _case(True)
     L, B = batch[0].shape
     H, E = o['dim'], o['dim_word']
@@ -142,7 +145,7 @@ def test_grads_with_dropout_factors(emu):
     dp = dict(dp_gates=rng.binomial(1, 0.5, (L, B, 3 * H)).astype('float32'),
               dp_h=rng.binomial(1, 0.5, (L, B, H)).astype('float32'),
               dp_z=rng.binomial(1, 0.5, (L, B, E)).astype('float32'))
-    grads = run_emu(emu, o, params, batch, 0.3, 1e-4, dp=dp)
+    grads = run_emu(emu, o, params, batch, 0.3, 1e-4, dp=dp, flat=fast)
     _, want, _ = go.cost_and_grads(params, o, batch, alpha_c=0.3, decay_c=1e-4, **dp)
     _compare(grads, want)
 
