@@ -399,7 +399,7 @@ def run_ours(args, rank, world, local_rank):
                 env = dict(os.environ)
                 env.update(extra_env)
                 r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'train_bench.py'), '--steps', '3',
-                                    '--warmup', '2', '--phases'], capture_output=True, text=True, timeout=240, env=env)
+                                    '--warmup', '2', '--phases'], capture_output=True, text=True, timeout=90, env=env)
                 rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith('{')]
                 if not rows:
                     return {'error': (r.stderr or 'no output')[-300:]}
@@ -411,7 +411,7 @@ def run_ours(args, rank, world, local_rank):
                 return {'error': str(e)[:200]}
         train = train_line({'STAT_BW_FAST': '0'})
         # the same step with the optimised backward variants (parity-checked on the GPU, not yet the default)
-        train_fast = train_line({'STAT_BW_FAST': '1'})
+        train_fast = train_line({'STAT_BW_FAST': '1'}) if 'error' not in train else None
     total_bytes = B * 4 * T * (o['ctxg_dim'] + o['ctxm_dim'] + R * o['ctxl_dim']) + MAXLEN * (
         ctx_step_bytes + 41571528) + 8 * B * MAXLEN
     line = {'metric': METRIC, 'value': world * B * args.steps / (ms * 1e-3), 'unit': 'captions/s',
