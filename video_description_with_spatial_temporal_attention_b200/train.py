@@ -71,12 +71,14 @@ class Trainer(object):
 
     # ---- f_grad_shared -------------------------------------------------------------------------
     def f_grad_shared(self, x, mask, ctxg, mask_ctxg, ctxl, mask_ctxl, ctxm, mask_ctxm, dropout=None,
-                      global_batch=None):
+                      global_batch=None, return_grads=False):
         """Returns [cost, None, alphals, alphags, alphams, alphalts] (the reference's `probs` output, a
         (L*B, V) matrix nothing downstream reads, is not materialised); cost is a python float, the alphas
         device tensors.  The clipped, all-reduced gradients stay in the optimizer's flat buffer, as the
         reference stashes them in shared variables (common.py:198-201).  `dropout` = explicit
-        (dp_gates, dp_h, dp_z) factors instead of drawn masks (parity tests)."""
+        (dp_gates, dp_h, dp_z) factors instead of drawn masks (parity tests).  return_grads=True appends host copies
+        of the clipped gradients in init_params order, i.e. the reference's `rvals[6:]` (one device-to-host copy of
+        every parameter-sized array per step: what train() pays for its NaN report, :1263-1269)."""
         eng = self.engine
         if self._dirty:
             eng.set_params(self.flat.views)
@@ -123,7 +125,10 @@ class Trainer(object):
         if self.decay_c > 0.:
             cost = cost + self.decay_c * self.flat.flat.double().square().sum()
         self.last = dict(logp=lp, g2=g2, tokens=md.sum())
-        return [float(cost), None] + list(alphas)
+        out = [float(cost), None] + list(alphas)
+        if return_grads:
+            out += list(self.grads().values())
+        return out
 
     # ---- f_update ----------------------------------------------------------------------------
     def f_update(self, lr=None):
