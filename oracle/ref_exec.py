@@ -12,8 +12,11 @@ header, parameter initialisers, ``lstm_cond_layer``, ``build_model``,
 ``build_sampler``, ``gen_sample``, ``pred_probs``) is read at run time, given
 the minimal Python-2 -> 3 token fixes listed in ``_py3`` (print statement,
 xrange, iteritems, cPickle, integer ``/`` in gen_sample, tab expansion), and
-exec'd with ``oracle/mini_theano`` registered as ``theano``.  No reference
-source is copied into this repository.
+exec'd with ``oracle/mini_theano`` registered as ``theano``.  For options with
+``global_proj`` (decision D1) the three commented-out ``ff_global`` statements of the
+reference are un-commented in memory first (``_enable_ff_global``), so the D1 fixtures
+come from the reference's own lines too.  No reference source is copied into this
+repository.
 """
 from __future__ import annotations
 
@@ -29,8 +32,16 @@ from . import mini_theano
 REF = os.environ.get('STAT_REFERENCE_DIR', '/root/reference')
 
 
-def available():
+def mounted():
+    """The reference sources are present (authoring container only)."""
     return os.path.isfile(os.path.join(REF, 'model_attention.py'))
+
+
+def available():
+    """Executing the reference's source text in-process is OPT-IN: it runs third-party code, so the
+    build entry point and the default test run never do it.  Set STAT_RUN_REFERENCE=1 to enable the
+    live re-execution tests (the fixture generators under tests/golden/ call _load() explicitly)."""
+    return mounted() and os.environ.get('STAT_RUN_REFERENCE', '0') == '1'
 
 
 def _py3(src):
@@ -58,7 +69,24 @@ def _py3(src):
     return src
 
 
-def _load():
+def _enable_ff_global(lines):
+    """Decision D1 from the reference's own text: the `ff_global` layer (a tanh projection of the global
+    features to `dim`) exists in /root/reference/model_attention.py only as three commented-out
+    two-line statements -- the parameter (:553-554), its use in build_model (:661-662) and in
+    build_sampler (:780-781).  Un-comment exactly those six lines, in memory."""
+    out = list(lines)
+    hits = 0
+    for i, line in enumerate(out):
+        if "prefix='ff_global'" in line and line.lstrip().startswith('#'):
+            assert out[i - 1].lstrip().startswith('#') and "get_layer('ff')" in out[i - 1], out[i - 1]
+            out[i - 1] = out[i - 1].replace('# ', '', 1)
+            out[i] = out[i].replace('# ', '', 1)
+            hits += 1
+    assert hits == 3, 'expected the three commented ff_global sites, found %d' % hits
+    return out
+
+
+def _load(global_proj=False):
     th = mini_theano.install()
     for stub in ('data_engine', 'metrics'):
         if stub not in sys.modules:
@@ -73,6 +101,8 @@ def _load():
     with open(os.path.join(REF, 'model_attention.py')) as f:
         lines = f.read().split('\n')
     cut = next(i for i, l in enumerate(lines) if re.match(r'\s+def train\(self', l))
+    if global_proj:
+        lines = _enable_ff_global(lines[:cut]) + lines[cut:]
     msrc = _py3('\n'.join(lines[:cut]))
     mod = types.ModuleType('ref_model_attention')
     mod.__file__ = os.path.join(REF, 'model_attention.py')
@@ -92,7 +122,7 @@ class RefModel(object):
     def __init__(self, options, params=None, quiet=True):
         import contextlib
         import io
-        self.th, self.common, self.mod = _load()
+        self.th, self.common, self.mod = _load(global_proj=bool(options.get('global_proj')))
         self.options = dict(options)
         self.options.setdefault('encoder', 'none')
         sink = io.StringIO() if quiet else sys.stdout

@@ -79,7 +79,13 @@ def run_case(name, opt_kw, B, T, R, L, params_kind, seed, ks=(1, 3, 5), maxlen=8
 
 
 if __name__ == '__main__':
-    assert ref_exec.available(), 'needs /root/reference'
+    assert ref_exec.mounted(), 'needs /root/reference'
+    only = sys.argv[1:]            # optional: fixture names to (re)generate
+    _run = run_case
+
+    def run_case(name, *a, **kw):  # noqa: F811
+        if not only or name in only:
+            _run(name, *a, **kw)
     tiny = dict(dim_word=8, dim=8, ctxg_dim=8, ctxl_dim=12, ctxm_dim=10, n_words=11)
     run_case('ref_tiny_trained', tiny, B=3, T=4, R=2, L=5, params_kind='trained',
              seed=11, eos_bias=1.5)
@@ -89,3 +95,11 @@ if __name__ == '__main__':
     mid = dict(dim_word=24, dim=32, ctxg_dim=32, ctxl_dim=40, ctxm_dim=36, n_words=50)
     run_case('ref_mid_trained', mid, B=4, T=6, R=3, L=7, params_kind='trained',
              seed=14, eos_bias=2.5, maxlen=10, nonneg=True)
+    # decision D1 (ctxg_dim != dim): the reference's own commented-out ff_global lines
+    # (model_attention.py:553-554, 661-662, 780-781), un-commented in memory by ref_exec
+    run_case('ref_tiny_globalproj', dict(tiny, ctxg_dim=20, global_proj=True), B=3, T=4, R=2, L=5,
+             params_kind='trained', seed=21, eos_bias=1.5)
+    run_case('ref_tiny_globalproj_init', dict(tiny, ctxg_dim=20, global_proj=True), B=2, T=4, R=2, L=5,
+             params_kind='init', seed=22)
+    run_case('ref_mid_globalproj', dict(mid, ctxg_dim=48, global_proj=True), B=4, T=6, R=3, L=7,
+             params_kind='trained', seed=23, eos_bias=0.8, maxlen=10, nonneg=True)

@@ -175,6 +175,45 @@ def test_prepare_data_layout_matches_reference_rules():
     assert [len(b) for b in eng.kf_train] == [4] * (len(eng.train) // 4) + ([len(eng.train) % 4] if len(eng.train) % 4 else [])
 
 
+def test_pred_probs_with_an_engine_that_has_no_prepare_data_method():
+    """The reference's Movie2Caption engine has no prepare_data method (it is a module function,
+    data_engine.py:258): pred_probs -- called by train() with the reference's 3-argument signature --
+    must fall back to the module function."""
+    import video_description_with_spatial_temporal_attention_b200 as stat
+    from video_description_with_spatial_temporal_attention_b200 import data_engine as de, model_attention as ma
+    o = stat.default_options(dim=16, dim_word=16, ctxg_dim=16, ctxl_dim=24, ctxm_dim=20, n_words=30)
+    real = de.synthetic_engine(o, n_videos=6, caps_per_video=2, T=5, R=3, seed=3)
+
+    class Movie2CaptionLike(object):          # attribute access only, like the reference's engine object
+        def __init__(self, inner):
+            self.__dict__.update({k: v for k, v in inner.__dict__.items()})
+            self.signature = inner.signature
+            for m in ('get_video_global_features', 'get_video_local_features', 'get_video_motion_features',
+                      'get_ctxg_mask', 'get_ctxl_mask', 'get_ctxm_mask'):
+                setattr(self, m, getattr(inner, m))
+    eng = Movie2CaptionLike(real)
+    assert not hasattr(eng, 'prepare_data')
+    model = ma.Attention()
+    model.engine = eng
+    seen = []
+
+    def f_log_probs(*batch):
+        assert len(batch) == 8
+        seen.append(batch[0].shape)
+        return -np.ones(batch[0].shape[1], 'float32')
+    err, perp = model.pred_probs('valid', f_log_probs, verbose=False)
+    assert seen and err == 1.0 and perp > 1.0
+
+
+def test_use_dropout_false_is_rejected():
+    import video_description_with_spatial_temporal_attention_b200 as stat
+    from video_description_with_spatial_temporal_attention_b200 import model_attention as ma
+    o = stat.default_options(dim=16, dim_word=16, ctxg_dim=16, ctxl_dim=24, ctxm_dim=20, n_words=30)
+    o['use_dropout'] = False
+    with pytest.raises(ValueError):
+        ma.validate_options(o)
+
+
 def test_checkpoint_roundtrip(tmp_path):
     import video_description_with_spatial_temporal_attention_b200 as stat
     from video_description_with_spatial_temporal_attention_b200 import checkpoint as ck, model_attention as ma

@@ -64,7 +64,7 @@ def test_gen_sample_tokens_and_scores(name):
             np.testing.assert_allclose(np.asarray(got_sc), want_sc, atol=2e-5)
             n_dead_early += sum(len(h) < g.maxlen for h in want)
             n_maxlen += sum(len(h) == g.maxlen and h[-1] != 0 for h in want)
-    if name == 'ref_tiny_init':
+    if name.endswith('_init'):
         assert n_maxlen > 0          # a hypothesis that hits maxlen
     else:
         assert n_dead_early > 0      # a hypothesis that retires early (shrinking beam)
@@ -99,13 +99,21 @@ def test_init_params_matches_reference_layout():
                             ctxl_dim=12, ctxm_dim=10)
     p2 = so.init_params(o2)
     assert len(p2) == 43 and list(p2)[5:7] == ['ff_global_W', 'ff_global_b']
+    # D1: the reference's own init_params with its ff_global lines un-commented (ref_exec) draws the
+    # same 43 tensors in the same order, bit for bit
+    g2 = Golden('ref_tiny_globalproj_init')
+    assert list(g2.params) == list(p2)
+    for k in p2:
+        np.testing.assert_array_equal(np.asarray(p2[k]), g2.params[k])
 
 
-@pytest.mark.skipif(not ref_exec.available(), reason='/root/reference not mounted')
-def test_live_reference_execution_matches_fixture():
+@pytest.mark.skipif(not ref_exec.available(),
+                    reason='opt-in (STAT_RUN_REFERENCE=1 with /root/reference mounted): executes reference source')
+@pytest.mark.parametrize('name', ['ref_tiny_trained', 'ref_tiny_globalproj'])
+def test_live_reference_execution_matches_fixture(name):
     """In the authoring container: re-run the reference source and check the
     committed fixture is what it produces (fixtures are not stale)."""
-    g = Golden('ref_tiny_trained')
+    g = Golden(name)
     rm = ref_exec.RefModel(g.options, params=g.params)
     np.testing.assert_allclose(rm.f_log_probs(*g.batch), g.out('f_log_probs'), atol=1e-6)
 

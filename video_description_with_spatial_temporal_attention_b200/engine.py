@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import atexit
 import ctypes as C
+import functools
 import os
 import weakref
 
@@ -45,6 +46,19 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_device(fn):
+    """Run an Engine method with the engine's device current: the ABI enqueues on the CURRENT device's
+    stream and the library picks its side streams / events by cudaGetDevice(), so an Engine created for
+    cuda:1 must not launch while cuda:0 is current."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapper
+
+
 class Engine(object):
     """One parameter set on one GPU."""
 
@@ -54,9 +68,16 @@ class Engine(object):
         self.lib = _lib.load()
         self.options = dict(options)
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         o = self.options
         if not o.get('global_proj') and o['ctxg_dim'] != o['dim']:
             raise ValueError('the reference graph needs ctxg_dim == dim; set global_proj=True otherwise')
+        if not o.get('use_dropout', True):
+            # the kernels implement the dropout graph (0.5 factors at eval, masks when training); the
+            # reference's use_dropout=False branch calls _step with a stale signature and cannot run
+            # (model_attention.py:480-488)
+            raise ValueError('use_dropout=False is not supported (the reference graph itself raises on that branch)')
         self.flags = _lib.flags_of(o)
         # keep the projected context blocks of a batch resident in L2 across the decode steps: the
         # attention kernel copies them with evict_last priority, which only outlives the weight
@@ -77,9 +98,12 @@ class Engine(object):
         return StatDims(B=B, T=T, R=R, Dg=o['ctxg_dim'], Dm=o['ctxm_dim'], Dr=o['ctxl_dim'], H=o['dim'],
                         E=o['dim_word'], V=o['n_words'], flags=self.flags)
 
-    def workspace(self, B, T, R, rows=None):
+    @_on_device
+    def workspace(self, B, T, R, rows=None, tag=None):
+        """`tag`: callers that keep results cached in a workspace across calls (build_sampler's per-clip
+        context) pass a private tag so that no other user of the same shape overwrites it."""
         rows = B if rows is None else rows
-        key = (B, T, R, rows)
+        key = (B, T, R, rows) if tag is None else (B, T, R, rows, tag)
         ws = self._ws.get(key)
         if ws is None:
             d = self.dims(B, T, R)
@@ -119,6 +143,7 @@ class Engine(object):
         return t.to(self.device, non_blocking=True)
 
     # ---- parameters --------------------------------------------------------
+    @_on_device
     def set_params(self, params):
         """params: mapping name -> numpy / torch array in the reference's layout
         (init_params, model_attention.py:518-581)."""
@@ -146,18 +171,20 @@ class Engine(object):
             raise _lib.StatError('set_params() has not been called')
 
     # ---- K0 ----------------------------------------------------------------
-    def precompute(self, ctxg, mask_ctxg, ctxl, ctxm, rows=None):
+    @_on_device
+    def precompute(self, ctxg, mask_ctxg, ctxl, ctxm, rows=None, ws_tag=None):
         """ctxg (B,T,Dg) mask (B,T) ctxl (B,T,R,Dr) ctxm (B,T,Dm), device fp32 tensors."""
         self._need_params()
         B, T = ctxg.shape[0], ctxg.shape[1]
         R = ctxl.shape[2]
-        ws = self.workspace(B, T, R, rows)
+        ws = self.workspace(B, T, R, rows, tag=ws_tag)
         d = self.dims(B, T, R)
         check(self.lib.stat_precompute(C.byref(d), _ptr(self.prepared), _ptr(ctxg), _ptr(mask_ctxg), _ptr(ctxl),
                                        _ptr(ctxm), _ptr(ws), _stream()))
         return ws, d
 
     # ---- f_init ----------------------------------------------------------------
+    @_on_device
     def init_state(self, ctxg, mask_ctxg):
         self._need_params()
         B, T = ctxg.shape[0], ctxg.shape[1]
@@ -170,6 +197,7 @@ class Engine(object):
         return h0, c0
 
     # ---- f_log_probs ---------------------------------------------------------
+    @_on_device
     def forward_teacher(self, ws, d, x, mask, dp_gates=None, dp_h=None, dp_z=None, want_alphas=False,
                         want_h=False):
         L, B = x.shape
@@ -189,6 +217,7 @@ class Engine(object):
         return out, (al, ag, am, alt), hh
 
     # ---- f_grad_shared (gradients only; clipping / update live in optim.py) ----------
+    @_on_device
     def grad_shared(self, ws, d, batch_dev, alphas, h_all, grad_views, inv_batch, alpha_c=0., decay_c=0.,
                     dp_gates=None, dp_h=None, dp_z=None):
         """Gradients of the training cost (model_attention.py:1129-1147, :1193) for the batch whose forward
@@ -223,6 +252,7 @@ class Engine(object):
                                         _stream()))
 
     # ---- greedy ----------------------------------------------------------------
+    @_on_device
     def decode_greedy(self, ws, d, maxlen, out=None):
         B = d.B
         if out is None:
@@ -235,6 +265,7 @@ class Engine(object):
         return tokens, lengths, scores
 
     # ---- beam search ---------------------------------------------------------
+    @_on_device
     def decode_beam(self, ws, d, k, maxlen):
         """ws: precompute(..., rows=B*k).  -> tokens (B,k,maxlen) i64, lengths (B,k) i32,
         scores (B,k) f32, count (B,) i32, device tensors in the reference's hypothesis order."""
@@ -249,6 +280,7 @@ class Engine(object):
                                         _ptr(lengths), _ptr(scores), _ptr(count), _stream()))
         return tokens, lengths, scores, count
 
+    @_on_device
     def beam_captions(self, ctxg, mask_ctxg, ctxl, ctxm, k, maxlen, use_graph=False):
         """Features on the device -> decode_beam outputs (K0 + maxlen beam steps).  With use_graph the
         launch sequence is captured once per shape and replayed (outputs are then reused buffers)."""
@@ -287,6 +319,7 @@ class Engine(object):
         return out
 
     # ---- f_next ----------------------------------------------------------------
+    @_on_device
     def step(self, ws, d, x, h, c, row_clip=None):
         rows = x.shape[0]
         if self.lib.stat_workspace_bytes(C.byref(d), rows) > ws.numel() * 4:
@@ -299,6 +332,7 @@ class Engine(object):
         return probs, h2, c2
 
     # ---- whole-batch greedy captioning, optionally replayed from a CUDA graph ------
+    @_on_device
     def greedy_captions(self, ctxg, mask_ctxg, ctxl, ctxm, maxlen, use_graph=True):
         """Features already on the device -> (tokens (B,maxlen) i64, lengths (B,) i32,
         scores (B,) f32), all device tensors.  Runs K0 + the maxlen-step decode; with
@@ -353,6 +387,8 @@ class Engine(object):
         (tokens (B,maxlen) int64, lengths (B,) int32, scores (B,) float32) numpy arrays, in
         order, each as soon as its batch has finished."""
         self._need_params()
+        if torch.cuda.current_device() != self.device.index:
+            raise _lib.StatError('caption_stream: make %s the current device first (torch.cuda.set_device)' % self.device)
         compute = torch.cuda.current_stream()
         copy = self._copy_stream = getattr(self, '_copy_stream', None) or torch.cuda.Stream(device=self.device)
         slots = None
@@ -405,11 +441,13 @@ class Engine(object):
         return None if g is None else g[1]
 
     # ---- the attention fragment alone (timing) ------------------------------------
+    @_on_device
     def attention(self, ws, d, rows=None, row_clip=None):
         check(self.lib.stat_attention(C.byref(d), _ptr(self.prepared), _ptr(ws), d.B if rows is None else rows,
                                       _ptr(row_clip), _stream()))
 
     # ---- in-situ phase timing ------------------------------------------------------
+    @_on_device
     def profile(self, fn):
         """Run fn() with the library's per-phase CUDA-event timing on; returns
         {phase: (total_ms, launches_groups)}.  Not for use under graph capture."""
@@ -428,6 +466,7 @@ class Engine(object):
         return int(self.lib.stat_launch_count())
 
     # ---- the dense primitive (tests) ---------------------------------------------
+    @_on_device
     def gemm(self, A, Bt, bias=None, alpha=1.0, post=1.0, act=0, swap=False):
         M, K = A.shape
         N = Bt.shape[0]

@@ -151,6 +151,10 @@ def draw_tokens(p, rng):
 def validate_options(options):
     if options.get('ctx2out') and not options.get('ctxglm_dim', options['dim']) == options['dim']:
         raise ValueError('ctxglm_dim must equal dim (fusion is a sum, model_attention.py:430)')
+    if not options.get('use_dropout', True):
+        raise ValueError('use_dropout=False is not supported: the kernels implement the dropout graph, and the '
+                         "reference's own no-dropout branch calls _step with a stale signature "
+                         '(model_attention.py:480-488)')
     if options['dim_word'] > options['dim']:
         # model_attention.py:38-39
         print('WARNING: dim_word should only be as large as dim.')
@@ -199,8 +203,10 @@ class Attention(object):
             raise ValueError('the reference graph needs ctxg_dim == dim (SURVEY F3); '
                              'set global_proj=True to enable the ff_global layer')
         if o.get('encoder', 'none') != 'none' or o.get('n_layers_init', 0) > 0 or o.get('n_layers_out', 1) != 1:
-            raise NotImplementedError('encoder / n_layers_init / n_layers_out>1 are dead code in the '
-                                      'reference (SURVEY §2) and outside the hot path')
+            raise NotImplementedError('encoder != none, n_layers_init > 0 and n_layers_out > 1 are not supported: the '
+                                      'encoder branches are dead in the reference; the extra ReLU readout layers '
+                                      '(model_attention.py:697-702) are live code there but switched off by the '
+                                      'shipped config (n_layers_out=1, config.py) and outside SURVEY 8a')
         params = OrderedDict()
         params['Wemb'] = common.norm_weight(o['n_words'], o['dim_word'])
         self.param_init_fflayer(o, params, 'ff_state', o['ctxg_dim'], o['dim'])
@@ -251,6 +257,9 @@ class Attention(object):
         model = trng if isinstance(trng, _Model) else _Model(tparams, dict(options), use_noise, common.rng_seed)
         f32 = torch.float32
         cache = {}
+        # the clip's context blocks stay cached in a workspace between f_next calls: a workspace of this
+        # sampler alone (no other user of the engine with the same shape may rewrite it)
+        tag = ('sampler', id(cache))
 
         def fingerprint(*arrs):
             fp = []
@@ -270,7 +279,7 @@ class Attention(object):
                 ld = eng.to_device(numpy.asarray(ctxl, 'float32')[None], f32)
                 md = eng.to_device(numpy.asarray(ctxm, 'float32')[None], f32)
                 cache['max_rows'] = 16
-                ws, d = eng.precompute(gd, gm, ld, md, rows=cache['max_rows'])
+                ws, d = eng.precompute(gd, gm, ld, md, rows=cache['max_rows'], ws_tag=tag)
                 cache.update(key=key, version=model.tparams.version, ws=ws, d=d, feats=(gd, gm, ld, md))
             return eng, cache
 
@@ -286,7 +295,7 @@ class Attention(object):
             k = int(numpy.asarray(x).shape[0])
             if k > cc['max_rows']:
                 cc['max_rows'] = k
-                cc['ws'], cc['d'] = eng.precompute(*cc['feats'], rows=k)
+                cc['ws'], cc['d'] = eng.precompute(*cc['feats'], rows=k, ws_tag=tag)
             xd = eng.to_device(numpy.asarray(x, 'int64'), torch.int64)
             hd = eng.to_device(numpy.asarray(h, 'float32').reshape(k, -1), f32)
             cd = eng.to_device(numpy.asarray(c, 'float32').reshape(k, -1), f32)
@@ -381,11 +390,16 @@ class Attention(object):
     # ---- evaluation loop (model_attention.py:996-1032) -------------------------------
     def pred_probs(self, whichset, f_log_probs, verbose=True, prepare_data=None):
         """Mean NLL and perplexity over a split of ``self.engine`` (the data engine).
-        ``prepare_data(engine, tags)`` defaults to the engine's own method."""
+        ``prepare_data(engine, tags)`` defaults to the engine's own method when it has one (MemoryEngine) and to
+        the module function ``data_engine.prepare_data`` otherwise -- the reference's Movie2Caption engine has
+        no such method, prepare_data is a module function there (data_engine.py:258)."""
         eng = self.engine
         tags = getattr(eng, whichset)
         iterator = getattr(eng, 'kf_' + whichset)
-        prep = prepare_data or eng.prepare_data
+        prep = prepare_data or getattr(eng, 'prepare_data', None)
+        if prep is None:
+            from . import data_engine as _de
+            prep = _de.prepare_data
         probs, nll, lens = [], [], []
         n_done, n_samples = 0, sum(len(i) for i in iterator)
         for index in iterator:

@@ -30,7 +30,7 @@ __all__ = ['Trainer']
 
 class Trainer(object):
     def __init__(self, params, options, optimizer='adam', alpha_c=0., decay_c=0., clip_c=0., device=None,
-                 group=None, use_noise=True, seed=1234):
+                 group=None, use_noise=True, seed=1234, sync_cost=True):
         self.options = dict(options)
         self.engine = Engine(self.options, device)
         self.flat = optim.FlatParams(params, self.engine.device)
@@ -43,8 +43,12 @@ class Trainer(object):
         self.alpha_c, self.decay_c, self.clip_c = float(alpha_c), float(decay_c), float(clip_c)
         self.group = group
         self.use_noise = bool(use_noise)
+        # data-parallel ranks must not draw identical dropout masks for their shards: seed + rank
         self.gen = torch.Generator(device=self.engine.device)
-        self.gen.manual_seed(seed)
+        self.gen.manual_seed(seed + self._world()[0])
+        # sync_cost=False: f_grad_shared returns the cost as a 0-d device tensor instead of a python float, which
+        # removes the one host synchronisation of the step (the reference's numpy return forces it, :1259-1262)
+        self.sync_cost = bool(sync_cost)
         self._dirty = True
         self.grad_views = OrderedDict()
         for k, shp in self.flat.shapes.items():
@@ -66,8 +70,11 @@ class Trainer(object):
             return None, None, None
         H, E = self.options['dim'], self.options['dim_word']
         dev = self.engine.device
-        draw = lambda *s: (torch.rand(*s, device=dev, generator=self.gen) < 0.5).float()
-        return draw(L, B, 3 * H), draw(L, B, H), draw(L, B, E)
+        # one draw for the three masks (contiguous chunks of one buffer): 2 launches instead of 6
+        n = L * B
+        u = (torch.rand(n * (4 * H + E), device=dev, generator=self.gen) < 0.5).float()
+        return (u[:n * 3 * H].view(L, B, 3 * H), u[n * 3 * H:n * 4 * H].view(L, B, H),
+                u[n * 4 * H:].view(L, B, E))
 
     # ---- f_grad_shared -------------------------------------------------------------------------
     def f_grad_shared(self, x, mask, ctxg, mask_ctxg, ctxl, mask_ctxl, ctxm, mask_ctxm, dropout=None,
@@ -125,7 +132,7 @@ class Trainer(object):
         if self.decay_c > 0.:
             cost = cost + self.decay_c * self.flat.flat.double().square().sum()
         self.last = dict(logp=lp, g2=g2, tokens=md.sum())
-        out = [float(cost), None] + list(alphas)
+        out = [float(cost) if self.sync_cost else cost, None] + list(alphas)
         if return_grads:
             out += list(self.grads().values())
         return out
@@ -137,6 +144,13 @@ class Trainer(object):
         self.opt.f_update(lr)
         self._dirty = True
         return []
+
+    def grad_norm2(self):
+        """Squared global norm of the last all-reduced gradient, before clipping (the first stage of the clip,
+        model_attention.py:1194-1197) -- what train() checks for NaN / inf (the reference's grad_nan_report,
+        :1263-1269).  None when clipping is off."""
+        g2 = self.last.get('g2')
+        return None if g2 is None else float(g2[0])
 
     def grads(self):
         """host copies of the current (clipped, all-reduced) gradients, init_params order"""

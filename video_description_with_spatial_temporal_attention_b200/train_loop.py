@@ -57,11 +57,14 @@ def _zero_scores():
 def train(model, data_engine_module, f_grad_shared, f_update, f_log_probs, f_alphas, get_params, set_params,
           model_options, save_model_dir, use_noise=None, lrate=0.01, patience=10, max_epochs=5000, dispFreq=100,
           validFreq=10, sampleFreq=10, debug=False, verbose=False, score_fn=None, on_sample=None,
-          history_errs=None, log=print):
+          history_errs=None, log=print, grad_norm2=None):
     """Runs the loop; returns (train_err, valid_err, test_err) like the reference (:1558).
     `model` is the Attention host mirror (its `.engine` is the data engine; `pred_probs` is called on it),
     `data_engine_module.prepare_data(engine, tags)` builds the batches (data_engine.py:258-337)."""
     eng = model.engine
+    # pred_probs is called with the reference's own 3-argument signature (:996); the host mirror falls back to
+    # the module-level prepare_data (data_engine.py:258) when the data engine has no such method, as the
+    # reference's Movie2Caption has not
     path = lambda name: os.path.join(save_model_dir, name)
     history_errs = [list(r) for r in history_errs] if history_errs is not None else []     # reload (:1215-1218)
     ratios = OrderedDict((k, []) for k in ('alphal', 'alphag', 'alpham', 'alphalt'))
@@ -95,6 +98,11 @@ def train(model, data_engine_module, f_grad_shared, f_update, f_log_probs, f_alp
             cost = rvals[0]
             if numpy.isnan(cost) or numpy.isinf(cost):                                      # :1273-1275
                 raise FloatingPointError('NaN / inf detected in cost at update %d' % uidx)
+            # the reference's grad_nan_report over rvals[6:] (:1263-1269): the squared global gradient norm is
+            # already on the device (the clip's first stage); a NaN / inf there must stop the update
+            g2 = grad_norm2() if grad_norm2 is not None else None
+            if g2 is not None and not numpy.isfinite(g2):
+                raise FloatingPointError('NaN / inf detected in the gradients at update %d' % uidx)
             f_update(lrate)
             train_error = cost if eidx == 0 else train_error * 0.95 + cost * 0.05          # :1280-1283
             train_costs.append(cost)
@@ -197,5 +205,6 @@ def fit(model, tparams, model_options, trainer, f_log_probs, f_alphas, save_mode
                                          whichset='both', on_cpu=False, one_time=True, model=model,
                                          scorer=caption_scorer, tparams=tparams)
         kw['score_fn'] = score_fn
+    kw.setdefault('grad_norm2', getattr(trainer, 'grad_norm2', None))
     return train(model, data_engine_module, trainer.f_grad_shared, trainer.f_update, f_log_probs, f_alphas,
                  get_params, set_params, model_options, save_model_dir, use_noise=use_noise, **kw)
