@@ -178,6 +178,63 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def run_train_dp(o, dev, rank, world, steps=6, warmup=2, Bt=64):
+    """tokens/s of the data-parallel training step (config 4): per rank B=64 clips, L=20, T=26, R=8, BASELINE widths,
+    dropout on, alpha_c / decay_c / clip_c of the shipped config, adam.  Device time (CUDA events), max over
+    ranks; the all-reduce share from events around the collective."""
+    import torch
+    import torch.distributed as dist
+    from video_description_with_spatial_temporal_attention_b200 import model_attention as ma
+    from video_description_with_spatial_temporal_attention_b200.train import Trainer
+    params = ma.Attention().init_params(o)
+    tr = Trainer(params, o, optimizer='adam', alpha_c=0.70602, decay_c=1e-4, clip_c=10., use_noise=True, seed=1234,
+                 device=dev, sync_cost=False)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    L = MAXLEN
+    ctxg = torch.randn(Bt, T, o['ctxg_dim'], device=dev, generator=g) * 0.5
+    ctxl = torch.randn(Bt, T, R, o['ctxl_dim'], device=dev, generator=g) * 0.5
+    ctxm = torch.randn(Bt, T, o['ctxm_dim'], device=dev, generator=g) * 0.5
+    mg = torch.ones(Bt, T, device=dev)
+    x = torch.randint(2, o['n_words'], (L, Bt), device=dev, generator=g)
+    x[L - 1] = 0
+    mask = torch.ones(L, Bt, device=dev)
+    batch = (x, mask, ctxg, mg, ctxl, None, ctxm, None)
+    for _ in range(warmup):
+        tr.f_grad_shared(*batch)
+        tr.f_update(0.01)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tr.time_allreduce = True
+    tr.allreduce_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = tr.engine.launch_count()
+    e0.record()
+    for _ in range(steps):
+        cost = tr.f_grad_shared(*batch)[0]
+        tr.f_update(0.01)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ms_ar = float(np.mean([a.elapsed_time(b) for a, b in tr.allreduce_events])) if tr.allreduce_events else 0.0
+    t = torch.tensor([ms, ms_ar], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_ar = float(t[0]), float(t[1])
+    tokens = float(mask.sum()) * world
+    return {'workload': 'configs[3]: data-parallel training step (fwd + bwd + all-reduce + clip + adam), B=%d clips per '
+                        'GPU, L=%d, T=%d, R=%d, BASELINE widths, dropout on' % (Bt, L, T, R),
+            'tokens_per_s': tokens / (ms * 1e-3), 'ms_per_step': ms, 'ms_allreduce': ms_ar,
+            'allreduce_bytes': int(tr.flat.n) * 4, 'allreduce_GBps_bus': (2.0 * (world - 1) / world) * tr.flat.n * 4 /
+            (ms_ar * 1e-3) / 1e9 if ms_ar > 0 and world > 1 else None,
+            'n_gpus': world, 'steps': steps, 'warmup': warmup, 'cost': float(cost),
+            'launches_per_step': int(tr.engine.launch_count() - n0) // steps,
+            'timing': 'CUDA events, max over ranks; collective = torch.distributed all_reduce(SUM) over NCCL on the '
+                      'flat fp32 gradient buffer, not overlapped with the backward pass'}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -331,6 +388,19 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- secondary (BASELINE configs[3]): data-parallel training, B=64 clips per GPU, one NCCL all-reduce of the
+    # flat gradient per step, clip after the reduce, identical adam update on every rank.  Runs at every N (N=1 is
+    # the efficiency denominator), under the process group of this bench.
+    train_dp = None
+    if os.environ.get('STAT_BENCH_TRAIN', '1') != '0':
+        try:
+            eng._graphs.clear()
+            eng._ws.clear()
+            torch.cuda.empty_cache()
+            train_dp = run_train_dp(o, dev, rank, world)
+        except Exception as e:                                   # secondary: never fail the headline line
+            train_dp = {'error': str(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -362,6 +432,7 @@ def run_ours(args, rank, world, local_rank):
                 'isolated_back_to_back_us': att_warm_us,
                 'isolated_back_to_back_GBps': ctx_step_bytes / att_warm_us / 1e3}
     cpu = None
+    parity = None
     if world == 1:
         rate1, dt1 = cpu_reference_rate(o, params, feats, 1)            # warm-up + calibration
         n = int(max(2, min(64, 12.0 / max(dt1, 1e-3))))
@@ -376,8 +447,18 @@ def run_ours(args, rank, world, local_rank):
         all_host_threads()
         so.greedy_decode_batch(params, o, *feats, MAXLEN)
         t0 = time.perf_counter()
-        so.greedy_decode_batch(params, o, *feats, MAXLEN)
+        wt, wl, wsc = so.greedy_decode_batch(params, o, *feats, MAXLEN)
         dth = time.perf_counter() - t0
+        # the timed graph's own output against the oracle (the checker, outside every timed region): token ids
+        # of all 64 captions and their cumulative scores.  A kernel whose captions differ has no number.
+        glen, gsc = out[1].cpu().numpy(), out[2].cpu().numpy()
+        same = [bool(glen[b] == wl[b] and (tokens[b, :wl[b]] == wt[b, :wl[b]]).all()) for b in range(B)]
+        serr = float(max([abs(float(gsc[b]) - float(wsc[b])) for b in range(B) if same[b]] or [0.0]))
+        parity = {'checker': 'oracle/stat_oracle.greedy_decode_batch (fp32, hoisted), same features and parameters',
+                  'captions_identical': int(sum(same)), 'captions': B, 'max_abs_score_err': serr,
+                  'tokens_checksum_oracle': int(np.where(wt >= 0, wt, -1).astype(np.int64).sum())}
+        # an fp32-vs-fp32 argmax near-tie may legitimately flip a caption; anything more is a wrong kernel
+        assert sum(same) >= B - 2 and serr < 1e-3, ('greedy captions differ from the oracle', parity)
         cpu['hoisted_batched'] = {'value': B / dth, 'unit': 'captions/s',
                                   'sample': 'one B=64 batch (%.1f s): projections computed once per batch, all clips '
                                             'stepped together; numpy fp32 BLAS on all host cores' % dth}
@@ -433,7 +514,7 @@ def run_ours(args, rank, world, local_rank):
                            'achieved_GBps': total_bytes / (ms / args.steps * 1e-3) / 1e9,
                            'frac_of_hbm_peak': total_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
             'beam5': beam, 'train_step': train, 'train_step_fast': train_fast, 'l2_persist_bytes': eng.l2_persist_bytes,
-            'tokens_checksum': int(tokens.astype(np.int64).sum())}
+            'tokens_checksum': int(tokens.astype(np.int64).sum()), 'parity': parity, 'train_dp': train_dp}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

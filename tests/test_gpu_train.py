@@ -109,6 +109,51 @@ def test_grad_shared_wide_vs_oracle(torch_cuda):
     assert all(np.array_equal(g1[k], g2[k]) for k in g1)
 
 
+def test_grad_shared_config3_width_vs_oracle(torch_cuda):
+    """BASELINE config 3 at its own size: B = 128 clips, H = E = 512, V = 12594, Dg = 2048, Dm = Dr = 4096, T = 26,
+    R = 8, L = 20, ragged captions, against the fp64 autograd oracle (about 10 GB of host memory and a few seconds
+    on the host cores; B = 32 when the box has less than 24 GB free)."""
+    import psutil
+    from video_description_with_spatial_temporal_attention_b200.train import Trainer
+    B = 128 if psutil.virtual_memory().available > 24 * 2 ** 30 else 32
+    o = stat.baseline_options()
+    params = so.trained_like_params(o, seed=11)
+    batch = synthetic.make_batch(o, B=B, T=26, R=8, L=20, seed=11, zero_tail=True)
+    kw = dict(alpha_c=0.70602, decay_c=1e-4)
+    tr = Trainer(params, o, use_noise=False, **kw)
+    cost = tr.f_grad_shared(*batch)[0]
+    want_cost, want, _ = go.cost_and_grads(params, o, batch, **kw)
+    assert abs(cost - want_cost) < 1e-4 * max(1.0, abs(want_cost))
+    worst = _compare(tr.grads(), want, rtol=5e-4)
+    print('config 3 (B=%d): worst relative gradient error' % B, worst)
+
+
+def test_grad_shared_config3_b128_properties(torch_cuda):
+    """B = 128 at BASELINE widths: finite, bit-reproducible, and the gradient of the batch equals the sum of the
+    gradients of its two halves computed with the same 1/B_global (the data-parallel identity of SURVEY 8e)."""
+    from video_description_with_spatial_temporal_attention_b200.train import Trainer
+    o = stat.baseline_options()
+    params = so.trained_like_params(o, seed=12)
+    batch = synthetic.make_batch(o, B=128, T=26, R=8, L=20, seed=12, zero_tail=True)
+    kw = dict(alpha_c=0.70602, decay_c=0.0)
+    tr = Trainer(params, o, use_noise=False, **kw)
+    tr.f_grad_shared(*batch)
+    g = {k: v.copy() for k, v in tr.grads().items()}
+    assert all(np.isfinite(v).all() for v in g.values())
+    tr.f_grad_shared(*batch)
+    g2 = tr.grads()
+    assert all(np.array_equal(g[k], g2[k]) for k in g)
+    halves = []
+    for sl in (slice(0, 64), slice(64, 128)):
+        hb = tuple(a[:, sl] if i < 2 else a[sl] for i, a in enumerate(batch))
+        tr.f_grad_shared(*hb, global_batch=128)
+        halves.append({k: v.astype('float64') for k, v in tr.grads().items()})
+    for k in g:
+        s_ = halves[0][k] + halves[1][k]
+        scale = max(float(np.abs(s_).max()), 1e-6)
+        assert float(np.abs(g[k] - s_).max()) <= 2e-5 * scale + 1e-7, k
+
+
 @pytest.mark.parametrize('optimizer', ['adam', 'adadelta'])
 def test_training_steps_follow_the_reference_update(torch_cuda, optimizer):
     """Three full steps (gradients -> global-norm clip -> update).  Per step: the clipped device gradients equal

@@ -49,6 +49,9 @@ class Trainer(object):
         # sync_cost=False: f_grad_shared returns the cost as a 0-d device tensor instead of a python float, which
         # removes the one host synchronisation of the step (the reference's numpy return forces it, :1259-1262)
         self.sync_cost = bool(sync_cost)
+        # measurement hook: CUDA events around the gradient all-reduce of every step (bench.py train_dp)
+        self.time_allreduce = False
+        self.allreduce_events = []
         self._dirty = True
         self.grad_views = OrderedDict()
         for k, shp in self.flat.shapes.items():
@@ -109,7 +112,14 @@ class Trainer(object):
         eng.grad_shared(ws, d, (xd, md, gd, gmd, ld, mmd), alphas, h_all, self.grad_views, inv_batch,
                         alpha_c=self.alpha_c, decay_c=self.decay_c if rank == 0 else 0.,
                         dp_gates=dpg, dp_h=dph, dp_z=dpz)
-        optim.allreduce_grads(self.opt.grads, self.group)
+        if self.time_allreduce:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            optim.allreduce_grads(self.opt.grads, self.group)
+            e1.record()
+            self.allreduce_events.append((e0, e1))
+        else:
+            optim.allreduce_grads(self.opt.grads, self.group)
         g2 = self.opt.clip(self.clip_c) if self.clip_c > 0. else None
         if isinstance(self.opt, optim.Adadelta):
             self.opt.grad_shared()
