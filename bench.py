@@ -473,7 +473,7 @@ def run_ours(args, rank, world, local_rank):
             cpu['train_step'] = {'error': str(e)[:200]}
     # secondary (BASELINE config 3): one training step -- forward, backward, clip, adam -- at B=128, timed by
     # tools/train_bench.py in its own process so that nothing it does can cost the headline line
-    train = train_fast = None
+    train = None
     if world == 1 and os.environ.get('STAT_BENCH_TRAIN', '1') != '0':
         def train_line(extra_env):
             try:
@@ -490,9 +490,7 @@ def run_ours(args, rank, world, local_rank):
                 return out
             except Exception as e:
                 return {'error': str(e)[:200]}
-        train = train_line({'STAT_BW_FAST': '0'})
-        # the same step with the optimised backward variants (parity-checked on the GPU, not yet the default)
-        train_fast = train_line({'STAT_BW_FAST': '1'}) if 'error' not in train else None
+        train = train_line({})
     total_bytes = B * 4 * T * (o['ctxg_dim'] + o['ctxm_dim'] + R * o['ctxl_dim']) + MAXLEN * (
         ctx_step_bytes + 41571528) + 8 * B * MAXLEN
     line = {'metric': METRIC, 'value': world * B * args.steps / (ms * 1e-3), 'unit': 'captions/s',
@@ -513,7 +511,7 @@ def run_ours(args, rank, world, local_rank):
             'whole_path': {'algorithmic_bytes_per_step': total_bytes,
                            'achieved_GBps': total_bytes / (ms / args.steps * 1e-3) / 1e9,
                            'frac_of_hbm_peak': total_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
-            'beam5': beam, 'train_step': train, 'train_step_fast': train_fast, 'l2_persist_bytes': eng.l2_persist_bytes,
+            'beam5': beam, 'train_step': train, 'l2_persist_bytes': eng.l2_persist_bytes,
             'tokens_checksum': int(tokens.astype(np.int64).sum()), 'parity': parity, 'train_dp': train_dp}
     print(json.dumps(line))
     if world > 1:

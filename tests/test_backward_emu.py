@@ -126,8 +126,7 @@ def test_grads_match_oracle(emu, global_proj):
 
 @pytest.mark.parametrize('fast', [False, True])
 def test_grads_without_regularisers_and_options_off(emu, fast, monkeypatch):
-    if fast:
-        monkeypatch.setenv('STAT_BW_FAST', '1')
+    monkeypatch.setenv('STAT_BW_FAST', '1' if fast else '0')
     o, params, batch = _case(False, selector=False, ctx2out=False, prev2out=False)
     grads = run_emu(emu, o, params, batch, 0., 0., flat=fast)
     _, want, _ = go.cost_and_grads(params, o, batch)
@@ -136,8 +135,7 @@ def test_grads_without_regularisers_and_options_off(emu, fast, monkeypatch):
 
 @pytest.mark.parametrize('fast', [False, True])
 def test_grads_with_dropout_factors(emu, fast, monkeypatch):
-    if fast:
-        monkeypatch.setenv('STAT_BW_FAST', '1')
+    monkeypatch.setenv('STAT_BW_FAST', '1' if fast else '0')
     o, params, batch = _case(True)
     L, B = batch[0].shape
     H, E = o['dim'], o['dim_word']
@@ -152,7 +150,7 @@ def test_grads_with_dropout_factors(emu, fast, monkeypatch):
 
 @pytest.mark.parametrize('fast', [False, True])
 def test_grads_wider_than_a_block(emu, fast, monkeypatch):
-    """(fast: the STAT_BW_FAST=1 variants -- k-split products summed from planes, row-wise embedding scatter, aligned
+    """(fast: the default variants -- k-split products summed from planes, owner-block embedding scatter, aligned
     copies of the weights that sit 4-byte aligned in a flat parameter buffer.)
     H = 160 > the 128 threads of the per-frame blocks (strided column loops, two columns per thread for some
     threads only), R = 3, a vocabulary that is not a multiple of 4, a single-frame tail."""
@@ -160,8 +158,7 @@ def test_grads_wider_than_a_block(emu, fast, monkeypatch):
     o = stat.default_options(ctxg_dim=24, global_proj=True, **kw)
     params = so.trained_like_params(o, seed=9)
     batch = synthetic.make_batch(o, B=2, T=5, R=3, L=3, seed=9, zero_tail=True)
-    if fast:
-        monkeypatch.setenv('STAT_BW_FAST', '1')
+    monkeypatch.setenv('STAT_BW_FAST', '1' if fast else '0')
     grads = run_emu(emu, o, params, batch, 0.70602, 1e-4, flat=fast)
     _, want, _ = go.cost_and_grads(params, o, batch, alpha_c=0.70602, decay_c=1e-4)
     _compare(grads, want)
