@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     om[q] = mx;
     os[q] = den;
   }
-  float *ctx = a.ctx + static_cast<size_t>(row) * H;
+  float *ctx = a.ctx + static_cast<size_t>(row) * (a.ldctx ? a.ldctx : H);
   if (cs == 1) {
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) {

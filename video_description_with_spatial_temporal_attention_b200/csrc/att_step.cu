@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(512, 1) att_step_kernel(const AttArgs a) {
       alt = fmaf(s_e[2 * a.Tc + f], s_cL[f * H + col], alt);
     }
     if (single) {
-      a.ctx[static_cast<size_t>(row) * H + col] = beta * (ag / s_ms[1] + am / s_ms[3] + alt / s_ms[5]);
+      a.ctx[static_cast<size_t>(row) * (a.ldctx ? a.ldctx : H) + col] = beta * (ag / s_ms[1] + am / s_ms[3] + alt / s_ms[5]);
     } else {
       rv[0 * H + col] = ag;
       rv[1 * H + col] = am;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(512, 1) att_step_kernel(const AttArgs a) {
                    __ldcg(rv_all + (static_cast<size_t>(s) * 3 + k) * H + col), num);
       out += num / s_ms[2 * k + 1];
     }
-    a.ctx[static_cast<size_t>(row) * H + col] = beta * out;
+    a.ctx[static_cast<size_t>(row) * (a.ldctx ? a.ldctx : H) + col] = beta * out;
   }
   if (threadIdx.x == 0) a.counters[row] = 0u;
 }

@@ -1,0 +1,358 @@
+// Tile engine of the fused decode-step products (sm_100a): one 128 x BQ output tile of
+//     D = P . Q^T          P (lane operand, 128 rows) and Q (column operand, BQ rows), both K-major fp32
+// with fp32-faithful 3xTF32 accuracy on tcgen05 (the scheme of gemm_tf32x3.cu: the lane operand is split
+// into hi / lo in registers and stored to tensor memory, the column operand is split in shared memory;
+// lo.hi + hi.lo + hi.hi accumulate in fp32 TMEM), and the epilogues that replace the separate
+// gates / readout-activation / vocabulary-reduction kernels of a decode step:
+//   FE_STORE  out = acc + bias                                     attention queries, selector logit
+//   FE_GATES  S10-S13 of SURVEY App. A on gate-interleaved rows    (model_attention.py:437-457)
+//   FE_ZC     readout addend  bz + ctx.Wctx (+ Wemb[tok])           (:689-693)
+//   FE_Z      z = post * tanh(alpha * h.Wl + zadd)                  (:684-696)
+//   FE_PICK   per-row partial (max, sum exp, arg-max) of the logits (:704-709), target logit
+// "swap" tiles put the weights on the 128-lane axis (skinny activations: 32 decode rows per tile),
+// "normal" tiles the decode rows (vocabulary product: 128 vocabulary columns per tile).
+// The engine is a set of device functions over a per-CTA pipeline (STAGES-deep shared-memory ring, three
+// mbarrier arrays, tensor memory) so that the per-phase kernels (one tile per CTA) and the persistent
+// decode kernel (a static list of tiles per step and CTA) share it.
+#pragma once
+
+#include "kernels.cuh"
+#include "stat_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace stat {
+namespace fused {
+
+using namespace tcx;
+
+constexpr int BP = 128;                    // tile rows (TMEM lanes)
+constexpr int BK = 32;                     // fp32 per k-atom row = 128 B = one swizzle row
+constexpr int UMMA_K = 8;                  // tf32 MMA K
+constexpr int NSPLIT = 256;                // splitter / epilogue threads (warps 2..9)
+constexpr int NROLE = 64 + NSPLIT;         // + TMA producer warp (0) + MMA issuer warp (1)
+constexpr int STAGES = 4;
+constexpr int P_BYTES = BP * BK * 4;       // 16 KB
+constexpr int QMAX = 128;
+constexpr int Q_BYTES_MAX = QMAX * BK * 4; // 16 KB
+constexpr int STAGE_BYTES = P_BYTES + 2 * Q_BYTES_MAX;      // raw P | Q hi | Q lo
+constexpr int RING_BYTES = STAGES * STAGE_BYTES;            // 192 KB
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + BAR_BYTES;
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_A_BASE = 256;           // A-operand stage s: hi at 256 + 64 s (32 cols), lo 32 cols further
+
+using EpiParams = FusedEpi;
+
+struct Cta {
+  uint8_t *ring;            // 1024-byte aligned
+  uint32_t bar_full, bar_split, bar_empty, bar_acc;
+  uint32_t tmem;
+};
+
+struct Ring {
+  int s;
+  uint32_t ph;
+  __device__ __forceinline__ void next() {
+    if (++s == STAGES) { s = 0; ph ^= 1; }
+  }
+};
+
+// ---- set-up / tear-down (all threads of the CTA) ------------------------------------------------------
+__device__ __forceinline__ void cta_setup(Cta &c, uint8_t *smem_raw, uint32_t *tmem_slot) {
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  c.ring = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING_BYTES);
+  c.bar_full = smem_u32(bars);
+  c.bar_split = c.bar_full + 8 * STAGES;
+  c.bar_empty = c.bar_split + 8 * STAGES;
+  c.bar_acc = c.bar_empty + 8 * STAGES;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(c.bar_full + 8 * s, 1);
+      mbar_init(c.bar_split + 8 * s, NSPLIT);
+      mbar_init(c.bar_empty + 8 * s, 1);
+    }
+    mbar_init(c.bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if ((threadIdx.x >> 5) == 1) tc_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem = *tmem_slot;
+}
+__device__ __forceinline__ void cta_teardown(const Cta &c) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) {
+    tc_fence_after();
+    tc_dealloc(c.tmem, TMEM_COLS);
+  }
+}
+
+// ---- the three mainloop roles ------------------------------------------------------------------------
+// producer: one thread.  k-atoms [kb0, kb1) of the P rows [prow, prow+128) and the Q rows [qrow, qrow+bq)
+__device__ __forceinline__ void produce(const Cta &c, Ring &r, const CUtensorMap *tmP, int prow, const CUtensorMap *tmQ,
+                                        int qrow, int kb0, int kb1, int bq, unsigned long long pol_p,
+                                        unsigned long long pol_q) {
+  for (int kb = kb0; kb < kb1; ++kb) {
+    mbar_wait(c.bar_empty + 8 * r.s, r.ph ^ 1);
+    const uint32_t stage = smem_u32(c.ring + r.s * STAGE_BYTES);
+    mbar_expect_tx(c.bar_full + 8 * r.s, static_cast<uint32_t>(P_BYTES + bq * BK * 4));
+    tma_load_2d(stage, tmP, kb * BK, prow, c.bar_full + 8 * r.s, pol_p);
+    tma_load_2d(stage + P_BYTES, tmQ, kb * BK, qrow, c.bar_full + 8 * r.s, pol_q);
+    r.next();
+  }
+}
+
+// MMA issuer: the whole warp 1 calls this (lane 0 issues).  `fresh`: the first MMA overwrites the accumulator;
+// `last`: the accumulator is complete after these k-atoms (commit to bar_acc).
+__device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, bool fresh, bool last, int lane) {
+  const uint32_t idesc = make_idesc_tf32(BP, bq);
+  for (int kb = 0; kb < nk; ++kb) {
+    mbar_wait(c.bar_split + 8 * r.s, r.ph);
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t stage = smem_u32(c.ring + r.s * STAGE_BYTES);
+      const uint64_t dQh = make_desc(stage + P_BYTES);
+      const uint64_t dQl = make_desc(stage + P_BYTES + Q_BYTES_MAX);
+      const uint32_t a_hi = c.tmem + TMEM_A_BASE + 64 * r.s, a_lo = a_hi + 32;
+#pragma unroll
+      for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+        const uint64_t adv = static_cast<uint64_t>((ks * UMMA_K * 4) >> 4);   // 32 B per k-step
+        tc_mma_tf32_ts(c.tmem, a_lo + ks * UMMA_K, dQh + adv, idesc, (fresh && kb == 0 && ks == 0) ? 0u : 1u);
+        tc_mma_tf32_ts(c.tmem, a_hi + ks * UMMA_K, dQl + adv, idesc, 1u);
+        tc_mma_tf32_ts(c.tmem, a_hi + ks * UMMA_K, dQh + adv, idesc, 1u);
+      }
+      tc_commit(c.bar_empty + 8 * r.s);
+      if (last && kb == nk - 1) tc_commit(c.bar_acc);
+    }
+    __syncwarp();
+    r.next();
+  }
+}
+
+// splitter: warps 2..9 (t = threadIdx.x - 64).  P: this thread owns tile row prow (= its TMEM lane) and 16 of
+// the 32 k-columns; the TMA tile is SWIZZLE_128B (16-byte chunk c of row r sits at chunk c ^ (r & 7)).
+__device__ __forceinline__ void split(const Cta &c, Ring &r, int nk, int bq, int warp, int lane) {
+  const int t = threadIdx.x - 64;
+  const int prow = (warp & 3) * 32 + lane;
+  const int ch = (warp - 2) >> 2;
+  const int nq4 = bq * (BK / 4);                     // 16-byte chunks of the Q tile
+  for (int kb = 0; kb < nk; ++kb) {
+    mbar_wait(c.bar_full + 8 * r.s, r.ph);
+    uint8_t *stage = c.ring + r.s * STAGE_BYTES;
+    const uint8_t *rowp = stage + prow * 128;
+    float4 *Qh = reinterpret_cast<float4 *>(stage + P_BYTES);
+    float4 *Ql = reinterpret_cast<float4 *>(stage + P_BYTES + Q_BYTES_MAX);
+    float4 xp[4], xq[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xp[i] = *reinterpret_cast<const float4 *>(rowp + (((4 * ch + i) ^ (prow & 7)) << 4));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = t + i * NSPLIT;
+      xq[i] = idx < nq4 ? Qh[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float xs[4] = {xp[i].x, xp[i].y, xp[i].z, xp[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float h = rna_tf32(xs[e]);
+        hi[4 * i + e] = __float_as_uint(h);
+        lo[4 * i + e] = __float_as_uint(xs[e] - h);   // exact; the tensor core reads its top 19 bits
+      }
+    }
+    const uint32_t ta = c.tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + TMEM_A_BASE + 64 * r.s + 16 * ch;
+    tc_st16(ta, hi);
+    tc_st16(ta + 32, lo);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = t + i * NSPLIT;
+      if (idx < nq4) {
+        float4 h, l;
+        h.x = rna_tf32(xq[i].x); h.y = rna_tf32(xq[i].y); h.z = rna_tf32(xq[i].z); h.w = rna_tf32(xq[i].w);
+        l.x = xq[i].x - h.x; l.y = xq[i].y - h.y; l.z = xq[i].z - h.z; l.w = xq[i].w - h.w;
+        Qh[idx] = h;
+        Ql[idx] = l;
+      }
+    }
+    tc_wait_st();
+    tc_fence_before();
+    fence_proxy_async_smem();
+    mbar_arrive(c.bar_split + 8 * r.s);
+    r.next();
+  }
+}
+
+// ---- epilogues (warps 2..9, after bar_acc) --------------------------------------------------------------
+// swap tiles: lane = feature f0 + wq*32 + lane of the segment, TMEM column = decode row q0 + col; the two warps
+// of a lane quadrant take half of the bq columns each.
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// one chunk of up to 16 decode rows [r0, r0 + 16) for feature j (index inside the segment)
+__device__ __forceinline__ void epi_store16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0) {
+  const float b = (jok && e.bias) ? __ldg(e.bias + j) : 0.f;
+  if (!jok) return;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = r0 + i;
+    if (r < e.rows) e.out[static_cast<size_t>(r) * e.ldo + j] = __uint_as_float(v[i]) + b;
+  }
+}
+
+__device__ __forceinline__ void epi_zc16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0) {
+  if (!jok) return;
+  const float b = __ldg(e.bz + j);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = r0 + i;
+    if (r < e.rows) {
+      float z = __uint_as_float(v[i]) + b;
+      if (e.prev2out && e.tok_prev) {
+        const long long tok = e.tok_prev[r];
+        if (tok >= 0) z += __ldg(e.Wemb + static_cast<size_t>(tok) * e.E + j);
+      }
+      e.zadd[static_cast<size_t>(r) * e.E + j] = z;
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_z16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0) {
+  if (!jok) return;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = r0 + i;
+    if (r < e.rows) {
+      const size_t at = static_cast<size_t>(r) * e.E + j;
+      const float x = tanhf(fmaf(e.z_alpha, __uint_as_float(v[i]), e.zadd[at]));
+      e.z[at] = x * (e.dp_z ? e.dp_z[at] : 0.5f);
+    }
+  }
+}
+
+// FE_GATES: feature j = 4*u + g (g: 0 input, 1 forget, 2 output, 3 candidate), i.e. the four gates of a hidden
+// unit sit in four adjacent lanes; lane g == 0 gathers them and updates (c, h) of (row, u).
+// creg != null: the cell state of this thread's 16 (row, unit) pairs lives in registers across decode steps
+// (persistent kernel) instead of c_in / c_out.
+__device__ __forceinline__ void epi_gates16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0,
+                                            float *creg, bool creg_load) {
+  const int H = e.H;
+  const int u = j >> 2, g = j & 3;
+  const float *ew[16];
+  float xw[16], cprev[16];
+  // every load of the chunk first
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = r0 + i;
+    const bool ok = jok && r < e.rows;
+    long long tok = -1;
+    if (ok && e.tok_prev) tok = e.tok_prev[r];
+    ew[i] = e.EWi + static_cast<size_t>(tok >= 0 ? tok : e.V) * 4 * H + j;
+    xw[i] = ok ? __ldg(ew[i]) : 0.f;
+    cprev[i] = 0.f;
+    if (ok && g == 0) {
+      if (creg && !creg_load) cprev[i] = creg[i];
+      else cprev[i] = e.c_in[static_cast<size_t>(r) * H + u];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = r0 + i;
+    const bool ok = jok && r < e.rows;
+    const float pre = __uint_as_float(v[i]) + xw[i];
+    float dp = 0.5f;
+    if (ok && g < 3 && e.dp_gates) dp = e.dp_gates[static_cast<size_t>(r) * 3 * H + g * H + u];
+    const float a = (g == 3) ? tanhf(pre) : sigmoid_f(pre * dp);
+    const float af = __shfl_down_sync(0xffffffffu, a, 1);
+    const float ao = __shfl_down_sync(0xffffffffu, a, 2);
+    const float ag = __shfl_down_sync(0xffffffffu, a, 3);
+    if (ok && g == 0) {
+      const float m = e.mask ? e.mask[r] : 1.0f;
+      const float c_ = cprev[i];
+      float c = af * c_ + a * ag;
+      c = m * c + (1.0f - m) * c_;
+      float h = ao * tanhf(c);
+      if (e.mask) {
+        const float h_ = e.h_in[static_cast<size_t>(r) * e.ld_hin + u];
+        h = m * h + (1.0f - m) * h_;
+      }
+      if (creg) creg[i] = c;
+      if (e.c_out) e.c_out[static_cast<size_t>(r) * H + u] = c;
+      e.h_out[static_cast<size_t>(r) * e.ld_hout + u] = h;
+      if (e.h_copy) e.h_copy[static_cast<size_t>(r) * H + u] = h;
+      if (e.h_all) e.h_all[static_cast<size_t>(r) * H + u] = h;
+      if (e.dp_h) e.hd_out[static_cast<size_t>(r) * H + u] = h * e.dp_h[static_cast<size_t>(r) * H + u];
+    }
+  }
+}
+
+// normal tiles (FE_PICK): lane = decode row, TMEM column = vocabulary word q0 + col.  Each thread folds its
+// columns [c0, c1) into a (max, sum exp, arg-max) partial; the first maximum wins ties (ascending words).
+struct PickAcc {
+  float m, s;
+  int bi;
+  float tv;        // target logit when it falls into this thread's columns
+  int thit;
+};
+__device__ __forceinline__ void pick_fold16(const EpiParams &e, const uint32_t (&v)[16], int w0, int V, long long tgt_word,
+                                            PickAcc &a) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int w = w0 + i;
+    if (w < V) {
+      const float x = __uint_as_float(v[i]) + __ldg(e.bv + w);
+      if (w == tgt_word) { a.tv = x; a.thit = 1; }
+      if (x > a.m) {
+        a.s = a.s * expf(a.m - x) + 1.0f;     // exp(-inf) = 0 on the first word
+        a.m = x;
+        a.bi = w;
+      } else {
+        a.s += expf(x - a.m);
+      }
+    }
+  }
+}
+
+// Whole-tile epilogue.  kind / geometry are uniform over the CTA.
+//   swap tiles:   f0 = first feature of the tile inside its segment, nfeat = features of the segment, q0 = first row
+//   normal tiles: q0 = first vocabulary word of the tile, part = partial slot of this tile's first half
+__device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int kind, int bq, int f0, int nfeat, int q0,
+                                         int warp, int lane, float *creg, bool creg_load) {
+  const int wq = warp & 3;
+  const int chalf = (warp - 2) >> 2;
+  const int ch = bq >> 1;                               // columns per warp
+  const uint32_t trow = c.tmem + (static_cast<uint32_t>(wq * 32) << 16);
+  if (kind == FE_PICK) {
+    const int r = wq * 32 + lane;                       // decode row (single row tile: rows <= 128)
+    PickAcc a;
+    a.m = -INFINITY; a.s = 0.f; a.bi = 0x7fffffff; a.tv = 0.f; a.thit = 0;
+    const long long tgt_word = (e.x_t && r < e.rows) ? e.x_t[r] : -1;
+    for (int cc = chalf * ch; cc < (chalf + 1) * ch; cc += 16) {
+      uint32_t v[16];
+      tc_ld16(trow + cc, v);
+      pick_fold16(e, v, q0 + cc, e.V, tgt_word, a);
+    }
+    if (r < e.rows) {
+      float4 *dst = reinterpret_cast<float4 *>(e.part) + static_cast<size_t>(r) * e.npart + e.part0 + chalf;
+      *dst = make_float4(a.m, a.s, __int_as_float(a.bi), 0.f);
+      if (a.thit) e.tgt[r] = a.tv;
+    }
+    return;
+  }
+  const int j = f0 + wq * 32 + lane;
+  const bool jok = j < nfeat;
+  for (int cc = chalf * ch; cc < (chalf + 1) * ch; cc += 16) {
+    uint32_t v[16];
+    tc_ld16(trow + cc, v);
+    const int r0 = q0 + cc;
+    if (kind == FE_STORE) epi_store16(e, v, j, jok, r0);
+    else if (kind == FE_GATES) epi_gates16(e, v, j, jok, r0, creg, creg_load);
+    else if (kind == FE_ZC) epi_zc16(e, v, j, jok, r0);
+    else epi_z16(e, v, j, jok, r0);
+  }
+}
+
+}  // namespace fused
+}  // namespace stat

@@ -633,7 +633,9 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_map(CUtensorMap *tm, const float *base, int rows, int K, int ld, int box_rows) {
+}  // namespace
+
+int make_tensor_map(CUtensorMap *tm, const float *base, int rows, int K, int ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
   STAT_REQUIRE(enc != nullptr, STAT_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
@@ -648,11 +650,13 @@ int make_map(CUtensorMap *tm, const float *base, int rows, int K, int ld, int bo
   return STAT_OK;
 }
 
+namespace {
+
 template <int BQ, bool TS>
 int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   CUtensorMap tmP, tmQ;
-  STAT_TRY(make_map(&tmP, a.P, a.NP, a.K, a.ldp, BP));
-  STAT_TRY(make_map(&tmQ, a.Q, a.NQ, a.K, a.ldq, BQ));
+  STAT_TRY(make_tensor_map(&tmP, a.P, a.NP, a.K, a.ldp, BP));
+  STAT_TRY(make_tensor_map(&tmQ, a.Q, a.NQ, a.K, a.ldq, BQ));
   static size_t smem_set[STAT_MAX_DEV] = {};
   STAT_TRY(ensure_dyn_smem(gemm_tf32x3_kernel<BQ, TS>, Cfg<BQ>::smem_bytes(Cfg<BQ>::MAX_STAGES), smem_set));
   DevArgs db = da;

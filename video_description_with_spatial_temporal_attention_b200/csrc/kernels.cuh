@@ -21,7 +21,8 @@ struct AttArgs {
   int rows, T, R, H;
   int S, Tc;                                     // segments per row, frames per segment
   int selector;
-  float *ctx;                                    // (rows,H) out: fused, gated context
+  float *ctx;                                    // (rows,ldctx) out: fused, gated context
+  int ldctx;                                     // row pitch of ctx (0 = H)
   float *rec_vec;                                // (rows,S,3,H) partial weighted sums
   float *rec_ms;                                 // (rows,S,3,2) partial (max,sum)
   unsigned int *counters;                        // (rows) tickets, zero between launches
@@ -49,7 +50,7 @@ struct GateArgs {
   int ldhp, off_u;
   int hp_parts;
   size_t hp_plane;
-  const float *EW;         // (V+1,4H) token -> emb.W + b
+  const float *EW;         // (V+1,4H) token -> emb.W + b, gate-interleaved columns 4*unit + gate
   const float *Wemb;       // (V,E)
   const int64_t *tok_prev; // (rows) or null = no previous word
   const float *mask;       // (rows) or null = 1
@@ -133,6 +134,54 @@ int beam_init_launch(const BeamArgs &a, const float *h0c0, float *h, float *c, i
 int gather_state_launch(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h, float *dst_c,
                         int rows, int H, cudaStream_t stream);
 
+// ---- step_fused.cu: the fused products of a decode step (fused_tile.cuh) ----------------------------------
+enum { FE_STORE = 0, FE_GATES = 1, FE_ZC = 2, FE_Z = 3, FE_PICK = 4 };
+// epilogue parameters (the union of all kinds; a launch reads what its kinds need)
+struct FusedEpi {
+  int rows;
+  // FE_STORE: out[r*ldo + j] = acc + bias[j]
+  float *out; int ldo; const float *bias;
+  // FE_GATES (model_attention.py:437-457) on gate-interleaved features j = 4*unit + gate
+  int H, V;
+  const float *EWi;                  // (V+1, 4H) gate-interleaved token table (row V = bias alone)
+  const int64_t *tok_prev;           // (rows) or null = no previous word
+  const float *mask;                 // (rows) or null
+  const float *dp_gates;             // (rows, 3H) or null = 0.5
+  const float *c_in; float *c_out;   // (rows, H)
+  const float *h_in; int ld_hin;     // previous hidden state (masked bypass)
+  float *h_out; int ld_hout;         // new hidden state -> activation buffer of the next products
+  float *h_copy;                     // (rows, H) dense copy or null
+  float *h_all;                      // (rows, H) or null
+  float *hd_out; const float *dp_h;  // h * dp_h (explicit dropout) or null
+  // FE_ZC (:689-693): zadd = acc + bz (+ Wemb[tok])
+  float *zadd; int E; const float *bz; const float *Wemb; int prev2out;
+  // FE_Z (:684-696): z = post * tanh(z_alpha * acc + zadd), post = dp_z or 0.5
+  float *z; float z_alpha; const float *dp_z;
+  // FE_PICK (:704-709): per (row, half tile) partial (max, sum exp, arg-max) of acc + bv; target logit
+  const float *bv; float *part; int npart; int part0;
+  const int64_t *x_t; float *tgt;
+};
+struct FusedSegment {
+  int kind;      // FE_*
+  int wrow0;     // first weight row of the segment in W
+  int nfeat;     // features
+  int K;         // reduction length (floats)
+  int xsel;      // activation operand 0 / 1
+};
+struct FusedPhase {
+  int swap;                          // 1: weights on the 128-lane axis, 32 decode rows per tile; 0: rows on lanes
+  const float *W; int wrows, wK, ldw;          // packed K-major weights
+  const float *X[2]; int xK[2], ldx[2];        // K-major activations (rows, xK)
+  int rows;
+  int nseg;
+  FusedSegment seg[2];
+  FusedEpi e;
+};
+bool fused_supported(int H, int E);
+int fused_phase_launch(const FusedPhase &p, cudaStream_t stream);
+// combine of the FE_PICK partials of one step + greedy / teacher-forcing bookkeeping (PickArgs as pick_launch)
+int pick_combine_launch(const PickArgs &a, const float *part, int npart, const float *tgt, cudaStream_t stream);
+
 // ---- optim.cu: gradient clipping and the reference's optimizers over one flat parameter buffer ----
 size_t clip_scratch_bytes();
 int grad_clip_launch(float *grads, size_t n, float clip_c, void *scratch, cudaStream_t stream);
@@ -144,6 +193,9 @@ int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, in
                     cudaStream_t stream);
 // dst (rows_out, ld_dst) [r0 + n][k] = src (K, N) [k][n]   (weights -> K-major)
 int transpose_launch(const float *src, int K, int N, float *dst, int ld_dst, int r0, cudaStream_t stream);
+// gate-interleaving variants (rows 4*unit + gate): weights (K, 4H) -> K-major rows at column offset c0; vectors (4H)
+int transpose_il_launch(const float *src, int K, int H, float *dst, int ld_dst, int c0, cudaStream_t stream);
+int interleave4_launch(const float *src, float *dst, int H, cudaStream_t stream);
 int softmax_rows_launch(const float *scores, float *out, int nrows, int n, cudaStream_t stream);
 int scale_launch(float *x, const float *f, size_t n, cudaStream_t stream);
 int init_rows_launch(int rows, int64_t *tok_prev, int32_t *alive, int32_t *lengths, float *scores,

@@ -42,10 +42,12 @@ __global__ void __launch_bounds__(128) gates_kernel(const GateArgs a) {
       df = dp[H + j];
       dO = dp[2 * H + j];
     }
-    const float pi = (su[0] + __ldg(ew + j)) + sc[0];
-    const float pf = (su[1] + __ldg(ew + H + j)) + sc[1];
-    const float po = (su[2] + __ldg(ew + 2 * H + j)) + sc[2];
-    const float pg = (su[3] + __ldg(ew + 3 * H + j)) + sc[3];
+    // the token table is gate-interleaved: the four gate inputs of unit j are adjacent
+    const float4 e4 = __ldg(reinterpret_cast<const float4 *>(ew) + j);
+    const float pi = (su[0] + e4.x) + sc[0];
+    const float pf = (su[1] + e4.y) + sc[1];
+    const float po = (su[2] + e4.z) + sc[2];
+    const float pg = (su[3] + e4.w) + sc[3];
     const float ig = sigmoid_acc(pi * di);
     const float fg = sigmoid_acc(pf * df);
     const float og = sigmoid_acc(po * dO);
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(128) gates2_kernel(const GateArgs a) {
   if (j < H) {
     const float *pc = a.pre_c + static_cast<size_t>(row) * a.ldpc + j;
     const float *u = a.hp + static_cast<size_t>(row) * a.ldhp + a.off_u + j;
-    const float *ew = a.EW + static_cast<size_t>(tok >= 0 ? tok : a.V) * 4 * H + j;
+    const float *ew = a.EW + static_cast<size_t>(tok >= 0 ? tok : a.V) * 4 * H + 4 * j;
     float2 xu[4][4], xc[4][4], xe[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -112,8 +114,12 @@ __global__ void __launch_bounds__(128) gates2_kernel(const GateArgs a) {
         xc[q][gi] = (q < a.pc_parts) ? *reinterpret_cast<const float2 *>(pc + q * a.pc_plane + gi * H)
                                      : make_float2(0.f, 0.f);
       }
-#pragma unroll
-    for (int gi = 0; gi < 4; ++gi) xe[gi] = __ldg(reinterpret_cast<const float2 *>(ew + gi * H));
+    {
+      // gate-interleaved token table: units j, j+1 = 8 adjacent floats
+      const float4 ea = __ldg(reinterpret_cast<const float4 *>(ew)), eb = __ldg(reinterpret_cast<const float4 *>(ew) + 1);
+      xe[0] = make_float2(ea.x, eb.x); xe[1] = make_float2(ea.y, eb.y);
+      xe[2] = make_float2(ea.z, eb.z); xe[3] = make_float2(ea.w, eb.w);
+    }
     const size_t idx = static_cast<size_t>(row) * H + j;
     const float2 c_ = *reinterpret_cast<const float2 *>(a.c_in + idx);
     const float2 h_ = *reinterpret_cast<const float2 *>(a.h_in + idx);
@@ -537,6 +543,29 @@ __global__ void transpose_kernel(const float *__restrict__ src, int K, int N, fl
   }
 }
 
+// dst[(4*(n % H) + n / H) * ld_dst + c0 + k] = src[k * N + n], N = 4H: a (K, 4H) gate-major weight becomes K-major
+// rows in gate-interleaved order (the four gates of a hidden unit adjacent), written at column offset c0
+__global__ void transpose_il_kernel(const float *__restrict__ src, int K, int N, float *__restrict__ dst, int ld_dst,
+                                    int c0, int H) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? src[static_cast<size_t>(k) * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N && k < K) dst[static_cast<size_t>(4 * (n % H) + n / H) * ld_dst + c0 + k] = tile[threadIdx.x][i];
+  }
+}
+
+// dst[4*u + g] = src[g*H + u]
+__global__ void interleave4_kernel(const float *__restrict__ src, float *__restrict__ dst, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4 * H) dst[4 * (i % H) + i / H] = src[i];
+}
+
 __global__ void softmax_rows_kernel(const float *__restrict__ sc, float *__restrict__ out, int nrows, int n) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -624,6 +653,21 @@ int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, in
 int transpose_launch(const float *src, int K, int N, float *dst, int ld_dst, int r0, cudaStream_t stream) {
   dim3 grid((N + 31) / 32, (K + 31) / 32);
   transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, K, N, dst, ld_dst, r0);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int transpose_il_launch(const float *src, int K, int H, float *dst, int ld_dst, int c0, cudaStream_t stream) {
+  dim3 grid((4 * H + 31) / 32, (K + 31) / 32);
+  transpose_il_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, K, 4 * H, dst, ld_dst, c0, H);
+  note_launch();
+  STAT_CUDA_CHECK(cudaGetLastError());
+  return STAT_OK;
+}
+
+int interleave4_launch(const float *src, float *dst, int H, cudaStream_t stream) {
+  interleave4_kernel<<<(4 * H + 255) / 256, 256, 0, stream>>>(src, dst, H);
   note_launch();
   STAT_CUDA_CHECK(cudaGetLastError());
   return STAT_OK;

@@ -23,10 +23,12 @@ namespace {
 // stream is being captured.
 // ---------------------------------------------------------------------------
 enum Phase { PH_INIT = 0, PH_K0_GLOBAL, PH_K0_MOTION, PH_K0_LOCAL, PH_K0_PROJ, PH_HPROJ, PH_ATT, PH_CTXPROJ,
-             PH_GATES, PH_READOUT, PH_LOGITS, PH_PICK, PH_COUNT };
+             PH_GATES, PH_READOUT, PH_LOGITS, PH_PICK, PH_FUSED_B, PH_FUSED_C, PH_FUSED_LOGITS, PH_COMBINE, PH_COUNT };
 const char *const kPhaseNames[PH_COUNT] = {"init_state", "k0_ff_global", "k0_ff_motion", "k0_ff_local",
                                            "k0_ctx_proj", "step_h_proj", "step_attention", "step_ctx_proj",
-                                           "step_gates", "step_readout", "step_logits", "step_pick"};
+                                           "step_gates", "step_readout", "step_logits", "step_pick",
+                                           "step_gates_fused", "step_queries_readout_fused", "step_logits_fused",
+                                           "step_pick_combine"};
 struct ProfRec { int phase; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
@@ -94,6 +96,12 @@ struct Prep {
   size_t U4;     // Ul | Ug | Um | Ult (4 x H) then cl, cg, cm, clt (4 scalars)
   size_t EW;     // (V+1, 4H): token -> emb.W + b ; row V = b
   size_t Wemb;   // (V, E) copy (prev2out add)
+  // fused step (step_fused.cu)
+  size_t WgT;    // (4H+E, 2H): rows 4u+g = [Wc[:, gH+u] | U[:, gH+u]] (gate-interleaved, K = [ctx | h_]);
+                 //             rows 4H.. = [ff_logit_ctxglm_W[:, e] | 0]
+  size_t WqT;    // (4H+1+E, H): Wdl | Wdg | Wdm | Wdlt | W_sel | ff_logit_lstm_W
+  size_t bq;     // (4H+1)    : 0 | 0 | 0 | blt | b_sel
+  size_t bdi;    // (4H)      : decoder_b, gate-interleaved
   size_t total;  // floats
   int NH, NC;
 };
@@ -136,6 +144,10 @@ Prep prep_layout(const StatDims &d) {
   p.U4 = take(4 * H + 4);
   p.EW = take((V + 1) * 4 * H);
   p.Wemb = take(V * E);
+  p.WgT = take((4 * H + E) * 2 * H);
+  p.WqT = take((4 * H + 1 + E) * H);
+  p.bq = take(4 * H + 1);
+  p.bdi = take(4 * H);
   p.total = o;
   return p;
 }
@@ -152,6 +164,8 @@ struct Ws {
   size_t rec_vec, rec_ms, att_scores, alpha_l;
   size_t counters, tok_prev, alive;  // byte-typed regions (still float offsets)
   size_t hb, cb, cand_cost, cand_word, hist, hist_len, bscore, src_row, row_clip, dead_k, bdone;   // beam search
+  size_t xh[2], hq, part, tgt;       // fused step: [ctx | h] activation rows (double-buffered), queries, vocabulary partials
+  int ldq2, npart;
   size_t total;                      // floats
   int ldhp, ldpc, ldl, S, Tc;
   int att_impl;      // 2 = att_group_kernel (bulk-copy streaming), 0 = the generic att_step_kernel
@@ -252,6 +266,13 @@ Ws ws_layout(const StatDims &d, int rows) {
   w.row_clip = take(n);
   w.dead_k = take(n);
   w.bdone = take(n);
+  w.ldq2 = static_cast<int>(up(4 * H + 1, 4));
+  w.npart = 2 * static_cast<int>((V + 127) / 128);
+  w.xh[0] = take(n * 2 * H);
+  w.xh[1] = take(n * 2 * H);
+  w.hq = take(n * w.ldq2);
+  w.part = take(n * w.npart * 4);
+  w.tgt = take(n);
   w.total = o;
   return w;
 }
@@ -508,6 +529,120 @@ int step_out(const StatDims &d, const Prep &p, const float *P, const Ws &w, floa
   return dense(W + w.z, E, rows, P + p.WvT, E, V, P + p.bv, W + w.logits, w.ldl, 0, 1.f, 1.f, nullptr, 0, st);
 }
 
+
+// ---------------------------------------------------------------------------
+// fused decode step (step_fused.cu): attention -> B (gates fused) -> C (queries + readout activation) on the
+// caller's stream, logits (partial vocabulary reduction fused) -> combine beside the next attention.
+// Activations live in two [ctx | h] row buffers: step t reads xh[t & 1] = [ctx_t | h_{t-1}] and writes h_t into
+// xh[(t+1) & 1] (the gate tiles of one launch read every h_{t-1} column while others already write h_t).
+// ---------------------------------------------------------------------------
+bool fused_enabled(const StatDims &d, int rows) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STAT_FUSED");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on && fused_supported(d.H, d.E) && rows <= 128;
+}
+
+AttArgs att_args_fused(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, int rows,
+                       const int32_t *row_clip, float *att_scores, float *alpha_l, int t) {
+  AttArgs a = att_args(d, p, P, w, W, rows, row_clip, att_scores, alpha_l);
+  const int H = d.H;
+  a.hp = W + w.hq; a.ldhp = w.ldq2; a.hp_parts = 1; a.hp_plane = 0;
+  a.off_sl = 0; a.off_sg = H; a.off_sm = 2 * H; a.off_slt = 3 * H; a.off_sel = 4 * H;
+  a.ctx = W + w.xh[t & 1];
+  a.ldctx = 2 * H;
+  return a;
+}
+
+// B: gates (S10-S13) from [ctx_t | h_{t-1}] and the readout addend; new state -> xh[(t+1)&1], c in place
+int fstep_gates(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io, int t,
+                cudaStream_t st) {
+  const int H = d.H, E = d.E;
+  FusedPhase f;
+  memset(&f, 0, sizeof(f));
+  f.swap = 1;
+  f.W = P + p.WgT; f.wrows = 4 * H + E; f.wK = 2 * H; f.ldw = 2 * H;
+  f.X[0] = W + w.xh[t & 1]; f.xK[0] = 2 * H; f.ldx[0] = 2 * H;
+  f.rows = io.rows;
+  f.nseg = 2;
+  f.seg[0] = FusedSegment{FE_GATES, 0, 4 * H, 2 * H, 0};
+  f.seg[1] = FusedSegment{FE_ZC, 4 * H, E, H, 0};
+  FusedEpi &e = f.e;
+  e.H = H; e.V = d.V; e.E = E;
+  e.EWi = P + p.EW;
+  e.tok_prev = io.tok_prev; e.mask = io.mask; e.dp_gates = io.dp_gates;
+  e.c_in = W + w.c; e.c_out = W + w.c;
+  e.h_in = W + w.xh[t & 1] + H; e.ld_hin = 2 * H;
+  e.h_out = W + w.xh[(t + 1) & 1] + H; e.ld_hout = 2 * H;
+  e.h_copy = nullptr;
+  e.h_all = io.h_all;
+  e.hd_out = io.dp_h ? W + w.hd : nullptr; e.dp_h = io.dp_h;
+  e.zadd = W + w.zadd; e.bz = P + p.bz; e.Wemb = P + p.Wemb; e.prev2out = (d.flags & STAT_PREV2OUT) ? 1 : 0;
+  ProfScope ps(PH_FUSED_B, st);
+  return fused_phase_launch(f, st);
+}
+
+// C: what multiplies h (held in xh[buf]): the attention queries / selector logit of the next cell (want_q) and the
+// readout activation z of this step (want_z; with explicit dropout on h the readout reads h * dp_h instead)
+int fstep_hidden(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io, int buf,
+                 bool want_q, bool want_z, cudaStream_t st) {
+  const int H = d.H, E = d.E;
+  const int nq = 4 * H + ((d.flags & STAT_SELECTOR) ? 1 : 0);
+  FusedPhase f;
+  memset(&f, 0, sizeof(f));
+  f.swap = 1;
+  f.W = P + p.WqT; f.wrows = 4 * H + 1 + E; f.wK = H; f.ldw = H;
+  f.X[0] = W + w.xh[buf] + H; f.xK[0] = H; f.ldx[0] = 2 * H;
+  if (io.dp_h) { f.X[1] = W + w.hd; f.xK[1] = H; f.ldx[1] = H; }
+  f.rows = io.rows;
+  int n = 0;
+  if (want_q) f.seg[n++] = FusedSegment{FE_STORE, 0, nq, H, 0};
+  if (want_z) f.seg[n++] = FusedSegment{FE_Z, 4 * H + 1, E, H, io.dp_h ? 1 : 0};
+  f.nseg = n;
+  FusedEpi &e = f.e;
+  e.E = E;
+  e.out = W + w.hq; e.ldo = w.ldq2; e.bias = P + p.bq;
+  e.z = W + w.z; e.zadd = W + w.zadd; e.z_alpha = io.dp_h ? 1.0f : 0.5f; e.dp_z = io.dp_z;
+  ProfScope ps(PH_FUSED_C, st);
+  return fused_phase_launch(f, st);
+}
+
+// logits tiles with the per-tile vocabulary reduction, then the combine + bookkeeping of PickArgs k
+int fstep_vocab(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, int rows, const PickArgs &k,
+                cudaStream_t st) {
+  FusedPhase f;
+  memset(&f, 0, sizeof(f));
+  f.swap = 0;
+  f.W = P + p.WvT; f.wrows = d.V; f.wK = d.E; f.ldw = d.E;
+  f.X[0] = W + w.z; f.xK[0] = d.E; f.ldx[0] = d.E;
+  f.rows = rows;
+  f.nseg = 1;
+  f.seg[0] = FusedSegment{FE_PICK, 0, d.V, d.E, 0};
+  FusedEpi &e = f.e;
+  e.V = d.V; e.bv = P + p.bv; e.part = W + w.part; e.npart = w.npart; e.x_t = k.x_t; e.tgt = W + w.tgt;
+  {
+    ProfScope ps(PH_FUSED_LOGITS, st);
+    STAT_TRY(fused_phase_launch(f, st));
+  }
+  ProfScope ps(PH_COMBINE, st);
+  return pick_combine_launch(k, W + w.part, w.npart, W + w.tgt, st);
+}
+
+// initial state of the B rows -> xh[0] h part and c; queries of the first cell
+int fused_begin(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, int rows, cudaStream_t st) {
+  const int H = d.H;
+  STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.xh[0] + H, sizeof(float) * 2 * H, W + w.h0c0, sizeof(float) * 2 * H,
+                                    sizeof(float) * H, rows, cudaMemcpyDeviceToDevice, st));
+  STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
+                                    sizeof(float) * H, rows, cudaMemcpyDeviceToDevice, st));
+  StepIO io;
+  memset(&io, 0, sizeof(io));
+  io.rows = rows;
+  return fstep_hidden(d, p, P, w, W, io, 0, true, false, st);
+}
+
 // The readout chain of step t (step_out + the vocabulary reduction) on a side stream, next to the
 // attention of step t+1 on the caller's stream; the two meet again at the gates of step t+1, which
 // need the token picked in step t.  Event based, so it also works under stream capture.
@@ -754,11 +889,26 @@ int stat_prepare_params(const StatDims *d, const StatParams *sp, void *prepared,
   STAT_CUDA_CHECK(cp(p.U4 + 4 * H + 2, sp->decoder_cm_att, 1));
   STAT_CUDA_CHECK(cp(p.U4 + 4 * H + 3, sp->decoder_clt_att, 1));
   // token -> gate input table: EW[x] = Wemb[x].W + b ; EW[V] = b (no previous word)
+  // (columns gate-interleaved, 4*unit + gate: the four gate inputs of a hidden unit are adjacent)
   STAT_CUDA_CHECK(cp(p.Wemb, sp->Wemb, static_cast<size_t>(V) * E));
-  STAT_TRY(transpose_launch(sp->decoder_W, E, 4 * H, P + p.WdT, E, 0, st));
-  STAT_TRY(dense(P + p.Wemb, E, V, P + p.WdT, E, 4 * H, sp->decoder_b, P + p.EW, 4 * H, 0, 1.f, 1.f, nullptr, 0,
+  STAT_TRY(transpose_il_launch(sp->decoder_W, E, H, P + p.WdT, E, 0, st));
+  STAT_TRY(interleave4_launch(sp->decoder_b, P + p.bdi, H, st));
+  STAT_TRY(dense(P + p.Wemb, E, V, P + p.WdT, E, 4 * H, P + p.bdi, P + p.EW, 4 * H, 0, 1.f, 1.f, nullptr, 0,
                  st));
-  STAT_CUDA_CHECK(cp(p.EW + static_cast<size_t>(V) * 4 * H, sp->decoder_b, 4 * H));
+  STAT_CUDA_CHECK(cp(p.EW + static_cast<size_t>(V) * 4 * H, P + p.bdi, 4 * H));
+  // fused step: [ctx | h_] . [Wc ; U] on gate-interleaved rows, the ctx -> readout rows behind them
+  STAT_TRY(transpose_il_launch(sp->decoder_Wc, H, H, P + p.WgT, 2 * H, 0, st));
+  STAT_TRY(transpose_il_launch(sp->decoder_U, H, H, P + p.WgT, 2 * H, H, st));
+  if (c2o) STAT_TRY(transpose_launch(sp->ff_logit_ctxglm_W, H, E, P + p.WgT, 2 * H, 4 * H, st));
+  // everything that multiplies the new hidden state: next step's attention queries, selector logit, readout
+  STAT_TRY(transpose_launch(sp->decoder_Wdl_att, H, H, P + p.WqT, H, 0, st));
+  STAT_TRY(transpose_launch(sp->decoder_Wdg_att, H, H, P + p.WqT, H, H, st));
+  STAT_TRY(transpose_launch(sp->decoder_Wdm_att, H, H, P + p.WqT, H, 2 * H, st));
+  STAT_TRY(transpose_launch(sp->decoder_Wdlt_att, H, H, P + p.WqT, H, 3 * H, st));
+  if (sel) STAT_CUDA_CHECK(cp(p.WqT + static_cast<size_t>(4) * H * H, sp->decoder_W_sel, H));
+  STAT_TRY(transpose_launch(sp->ff_logit_lstm_W, H, E, P + p.WqT, H, 4 * H + 1, st));
+  STAT_CUDA_CHECK(cp(p.bq + 3 * H, sp->decoder_blt_att, H));
+  if (sel) STAT_CUDA_CHECK(cp(p.bq + 4 * H, sp->decoder_b_sel, 1));
   return STAT_OK;
 }
 
@@ -890,12 +1040,53 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
   const bool want_t = out_alpha_g || out_alpha_m || out_alpha_lt;
   STAT_CUDA_CHECK(cudaMemsetAsync(out_logprob, 0, sizeof(float) * B, st));
   STAT_CUDA_CHECK(cudaMemsetAsync(W + w.counters, 0, sizeof(float) * B, st));
+  Overlap ov;
+  if (fused_enabled(*d, B)) {
+    STAT_TRY(fused_begin(*d, p, P, w, W, B, st));
+    STAT_TRY(ov.open(st, overlap_enabled()));
+    for (int t = 0; t < L; ++t) {
+      StepIO io;
+      memset(&io, 0, sizeof(io));
+      io.rows = B;
+      io.tok_prev = t > 0 ? x + static_cast<size_t>(t - 1) * B : nullptr;   // emb shifted by one step (:613-617)
+      io.mask = mask + static_cast<size_t>(t) * B;
+      io.dp_gates = dp_gates ? dp_gates + static_cast<size_t>(t) * B * 3 * H : nullptr;
+      io.dp_h = dp_h ? dp_h + static_cast<size_t>(t) * B * H : nullptr;
+      io.dp_z = dp_z ? dp_z + static_cast<size_t>(t) * B * E : nullptr;
+      io.h_all = out_h ? out_h + static_cast<size_t>(t) * B * H : nullptr;
+      io.alpha_l = out_alpha_l ? out_alpha_l + static_cast<size_t>(t) * B * T * R : nullptr;
+      io.att_scores = want_t ? W + w.att_scores : nullptr;
+      {
+        AttArgs a = att_args_fused(*d, p, P, w, W, B, nullptr, io.att_scores, io.alpha_l, t);
+        ProfScope ps(PH_ATT, st);
+        STAT_TRY(att_launch(w, a, st));
+      }
+      if (want_t) {
+        const size_t n = static_cast<size_t>(B) * T;
+        if (out_alpha_g) STAT_TRY(softmax_rows_launch(W + w.att_scores, out_alpha_g + t * n, B, T, st));
+        if (out_alpha_m) STAT_TRY(softmax_rows_launch(W + w.att_scores + n, out_alpha_m + t * n, B, T, st));
+        if (out_alpha_lt) STAT_TRY(softmax_rows_launch(W + w.att_scores + 2 * n, out_alpha_lt + t * n, B, T, st));
+      }
+      STAT_TRY(ov.join());                  // zadd / z / partial buffers of the previous step's readout are free
+      STAT_TRY(fstep_gates(*d, p, P, w, W, io, t, st));
+      STAT_TRY(fstep_hidden(*d, p, P, w, W, io, (t + 1) & 1, t + 1 < L, true, st));
+      STAT_TRY(ov.state_ready());
+      PickArgs k;
+      memset(&k, 0, sizeof(k));
+      k.rows = B; k.V = d->V;
+      k.x_t = x + static_cast<size_t>(t) * B;
+      k.mask_t = mask + static_cast<size_t>(t) * B;
+      k.logprob = out_logprob;
+      STAT_TRY(fstep_vocab(*d, p, P, w, W, B, k, ov.side()));
+      STAT_TRY(ov.side_enqueued());
+    }
+    return ov.join();
+  }
   STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.h, sizeof(float) * H, W + w.h0c0, sizeof(float) * 2 * H,
                                     sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
   STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
                                     sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
   STAT_TRY(h_proj(*d, p, P, w, W, W + w.h, B, 1, st));
-  Overlap ov;
   STAT_TRY(ov.open(st, overlap_enabled()));
   for (int t = 0; t < L; ++t) {
     StepIO io;
@@ -952,12 +1143,39 @@ int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws, int ma
   int32_t *alive = reinterpret_cast<int32_t *>(W + w.alive);
   STAT_CUDA_CHECK(cudaMemsetAsync(W + w.counters, 0, sizeof(float) * B, st));
   STAT_TRY(init_rows_launch(B, tok_prev, alive, out_lengths, out_scores, out_tokens, maxlen, st));
+  Overlap ov;
+  if (fused_enabled(*d, B)) {
+    STAT_TRY(fused_begin(*d, p, P, w, W, B, st));
+    STAT_TRY(ov.open(st, overlap_enabled()));
+    for (int t = 0; t < maxlen; ++t) {
+      StepIO io;
+      memset(&io, 0, sizeof(io));
+      io.rows = B;
+      io.tok_prev = tok_prev;   // -1 on the first step: no previous word (:893, :803-804)
+      {
+        AttArgs a = att_args_fused(*d, p, P, w, W, B, nullptr, nullptr, nullptr, t);
+        ProfScope ps(PH_ATT, st);
+        STAT_TRY(att_launch(w, a, st));
+      }
+      STAT_TRY(ov.join());                  // the gates need the word picked in the previous step
+      STAT_TRY(fstep_gates(*d, p, P, w, W, io, t, st));
+      STAT_TRY(fstep_hidden(*d, p, P, w, W, io, (t + 1) & 1, t + 1 < maxlen, true, st));
+      STAT_TRY(ov.state_ready());
+      PickArgs k;
+      memset(&k, 0, sizeof(k));
+      k.rows = B; k.V = d->V;
+      k.tokens = out_tokens; k.maxlen = maxlen; k.t = t;
+      k.lengths = out_lengths; k.scores = out_scores; k.alive = alive; k.tok_prev = tok_prev;
+      STAT_TRY(fstep_vocab(*d, p, P, w, W, B, k, ov.side()));
+      STAT_TRY(ov.side_enqueued());
+    }
+    return ov.join();
+  }
   STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.h, sizeof(float) * H, W + w.h0c0, sizeof(float) * 2 * H,
                                     sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
   STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
                                     sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
   STAT_TRY(h_proj(*d, p, P, w, W, W + w.h, B, 1, st));
-  Overlap ov;
   STAT_TRY(ov.open(st, overlap_enabled()));
   for (int t = 0; t < maxlen; ++t) {
     StepIO io;

@@ -1,6 +1,7 @@
 // Shared device helpers for the STAT decoder kernels (sm_100a only).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -158,6 +159,9 @@ struct GemmArgs {
 };
 
 int gemm_launch(const GemmArgs &a, cudaStream_t stream);
+// 2-D tensor map of a K-major fp32 operand (rows, K), row pitch ld floats (multiple of 4, base 16-byte aligned):
+// box = box_rows x 32 floats (one 128-byte swizzle row), SWIZZLE_128B, out-of-range elements read as 0
+int make_tensor_map(CUtensorMap *tm, const float *base, int rows, int K, int ld, int box_rows);
 void gemm_set_trace(long long *p);
 void gemm_set_impl(int impl);
 int gemm_get_impl();

@@ -1,0 +1,198 @@
+// Per-phase kernels of the fused decode step (one tile of fused_tile.cuh per CTA) and the small vocabulary
+// combine that follows the logits tiles.  A decode step on this path is
+//     attention -> B (gates fused) -> C (queries + readout activation)        dependent chain: 3 launches
+//     logits (partial arg-max / log-sum-exp fused) -> combine                  beside the next attention
+// instead of attention -> ctx_proj -> gates -> h_proj and readout -> logits -> pick (7 launches, 4 dependent).
+//   B:  [ctx | h_].[Wc ; U] on gate-interleaved rows (one product instead of two k-split ones, :437-439), epilogue
+//       = S10-S13 (the gates kernel is gone); the ctx.ff_logit_ctxglm_W rows ride in the same launch (:691-693)
+//   C:  h.[Wdl | Wdg | Wdm | Wdlt | W_sel] (next step's attention queries, :371,389,402,415,433) and
+//       z = 0.5 tanh(0.5 h.ff_logit_lstm_W + zadd) (:684-696) in one launch
+#include <string.h>
+
+#include "fused_tile.cuh"
+
+namespace stat {
+namespace fused {
+
+struct SegDev {
+  int kind;       // FE_*
+  int prow0;      // swap: first weight row of the segment in W
+  int nfeat;      // features of the segment
+  int nk;         // k-atoms
+  int xsel;       // which activation map
+};
+
+struct PhaseDev {
+  int swap, bq, nseg, qtiles, ntile0;
+  SegDev seg[2];
+  unsigned long long pol_w, pol_x;
+  EpiParams e;
+};
+
+__global__ void __launch_bounds__(NROLE, 1)
+    fused_phase_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX0,
+                       const __grid_constant__ CUtensorMap tmX1, const PhaseDev a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint32_t tmem_slot;
+  Cta c;
+  cta_setup(c, smem_raw, &tmem_slot);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x;
+  const int si = (a.nseg > 1 && idx >= a.ntile0) ? 1 : 0;
+  const int local = idx - (si ? a.ntile0 : 0);
+  const int kind = si ? a.seg[1].kind : a.seg[0].kind;
+  const int prow0 = si ? a.seg[1].prow0 : a.seg[0].prow0;
+  const int nfeat = si ? a.seg[1].nfeat : a.seg[0].nfeat;
+  const int nk = si ? a.seg[1].nk : a.seg[0].nk;
+  const int xsel = si ? a.seg[1].xsel : a.seg[0].xsel;
+  const CUtensorMap *tmX = xsel ? &tmX1 : &tmX0;
+  int f0, q0, prow, qrow;
+  const CUtensorMap *tmP, *tmQ;
+  unsigned long long pol_p, pol_q;
+  if (a.swap) {
+    const int pt = local / a.qtiles, qt = local - pt * a.qtiles;
+    f0 = pt * BP; q0 = qt * a.bq;
+    prow = prow0 + f0; qrow = q0;
+    tmP = &tmW; tmQ = tmX; pol_p = a.pol_w; pol_q = a.pol_x;
+  } else {
+    f0 = 0; q0 = local * a.bq;
+    prow = 0; qrow = q0;
+    tmP = tmX; tmQ = &tmW; pol_p = a.pol_x; pol_q = a.pol_w;
+  }
+  // everything above overlaps the previous kernel's tail; its results are read from here on
+  pdl_wait();
+  pdl_trigger();
+  Ring r = {0, 0};
+  if (warp == 0) {
+    if (lane == 0) produce(c, r, tmP, prow, tmQ, qrow, 0, nk, a.bq, pol_p, pol_q);
+    __syncwarp();
+  } else if (warp == 1) {
+    issue(c, r, nk, a.bq, true, true, lane);
+  } else {
+    split(c, r, nk, a.bq, warp, lane);
+    mbar_wait(c.bar_acc, 0);
+    tc_fence_after();
+    EpiParams e = a.e;
+    if (kind == FE_PICK) e.part0 = 2 * local;
+    epilogue(c, e, kind, a.bq, f0, nfeat, q0, warp, lane, nullptr, false);
+  }
+  cta_teardown(c);
+}
+
+// ---- combine of the per-tile vocabulary partials of one step: one warp per decode row -----------------------
+// (max, sum exp, arg-max) partials in ascending word order -> row maximum, lowest arg-max among equal maxima,
+// sum exp; then the greedy bookkeeping (model_attention.py:905-973 with k = 1) or the teacher-forced term
+// mask * log(p[x] + 1e-8) (:712-715), exactly as pick_kernel does it.
+__device__ __forceinline__ void combine_row(const PickArgs &a, const float4 *part, int npart, const float *tgt, int row,
+                                            int lane) {
+  float m = -INFINITY, s = 0.f;
+  int bi = 0x7fffffff;
+  for (int p = lane; p < npart; p += 32) {
+    const float4 v = part[static_cast<size_t>(row) * npart + p];
+    const int vi = __float_as_int(v.z);
+    if (v.x > m) {
+      s = s * expf(m - v.x) + v.y;
+      m = v.x;
+      bi = vi;
+    } else if (v.x > -INFINITY) {
+      s += v.y * expf(v.x - m);
+      if (v.x == m && vi < bi) bi = vi;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    const float os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, om);
+    const float w1 = (m == -INFINITY) ? 0.f : expf(m - mn);
+    const float w2 = (om == -INFINITY) ? 0.f : expf(om - mn);
+    s = s * w1 + os * w2;
+    if (om > m || (om == m && oi < bi)) bi = oi;
+    m = mn;
+  }
+  if (lane == 0) {
+    const int tok = bi;
+    if (a.tokens) {
+      const bool live = a.alive[row] != 0;
+      a.tokens[static_cast<size_t>(row) * a.maxlen + a.t] = live ? tok : -1;
+      if (live) {
+        a.scores[row] += logf(s);                  // -log p(argmax) = log sum exp(l - max)
+        a.lengths[row] = a.t + 1;
+        a.alive[row] = tok != 0;
+        a.tok_prev[row] = tok;
+      }
+    }
+    if (a.x_t) {
+      const float p = expf(tgt[row] - m) / s;
+      a.logprob[row] += a.mask_t[row] * logf(p + 1e-8f);       // model_attention.py:712-715
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pick_combine_kernel(const PickArgs a, const float4 *part, int npart,
+                                                           const float *tgt) {
+  pdl_wait();
+  pdl_trigger();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row < a.rows) combine_row(a, part, npart, tgt, row, threadIdx.x & 31);
+}
+
+}  // namespace fused
+
+int pick_combine_launch(const PickArgs &a, const float *part, int npart, const float *tgt, cudaStream_t stream) {
+  return launch_pdl(fused::pick_combine_kernel, dim3((a.rows + 7) / 8), dim3(256), 0, stream, a,
+                    reinterpret_cast<const float4 *>(part), npart, tgt);
+}
+
+int fused_phase_launch(const FusedPhase &p, cudaStream_t stream) {
+  using namespace fused;
+  STAT_REQUIRE(p.nseg == 1 || p.nseg == 2, STAT_EINVAL, "fused phase: nseg must be 1 or 2");
+  STAT_REQUIRE(p.rows >= 1 && (p.swap || p.rows <= BP), STAT_EINVAL, "fused phase: bad row count %d", p.rows);
+  PhaseDev d;
+  memset(&d, 0, sizeof(d));
+  d.swap = p.swap;
+  d.bq = p.swap ? 32 : 128;
+  d.nseg = p.nseg;
+  d.qtiles = p.swap ? (p.rows + d.bq - 1) / d.bq : 1;
+  int tiles[2] = {0, 0};
+  for (int i = 0; i < p.nseg; ++i) {
+    const FusedSegment &s = p.seg[i];
+    STAT_REQUIRE(s.nfeat >= 1 && s.K >= 1, STAT_EINVAL, "fused phase: empty segment");
+    d.seg[i].kind = s.kind;
+    d.seg[i].prow0 = s.wrow0;
+    d.seg[i].nfeat = s.nfeat;
+    d.seg[i].nk = (s.K + BK - 1) / BK;
+    d.seg[i].xsel = s.xsel;
+    tiles[i] = p.swap ? ((s.nfeat + BP - 1) / BP) * d.qtiles : (s.nfeat + d.bq - 1) / d.bq;
+  }
+  d.ntile0 = tiles[0];
+  // the step's weights are re-read by every decode step: keep them in L2 ahead of the streamed context blocks
+  d.pol_w = L2_EVICT_LAST;
+  d.pol_x = L2_EVICT_NORMAL;
+  d.e = p.e;
+  d.e.rows = p.rows;
+  CUtensorMap tmW, tmX0, tmX1;
+  STAT_TRY(make_tensor_map(&tmW, p.W, p.wrows, p.wK, p.ldw, BP));
+  const int xbox = p.swap ? d.bq : BP;
+  STAT_TRY(make_tensor_map(&tmX0, p.X[0], p.rows, p.xK[0], p.ldx[0], xbox));
+  if (p.X[1]) STAT_TRY(make_tensor_map(&tmX1, p.X[1], p.rows, p.xK[1], p.ldx[1], xbox));
+  else tmX1 = tmX0;
+  static size_t smem_set[STAT_MAX_DEV] = {};
+  STAT_TRY(ensure_dyn_smem(fused_phase_kernel, SMEM_BYTES, smem_set));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles[0] + tiles[1]);
+  cfg.blockDim = dim3(NROLE);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr(attr);
+  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_phase_kernel, tmW, tmX0, tmX1, d));
+  note_launch();
+  return STAT_OK;
+}
+
+bool fused_supported(int H, int E) { return (H % 4) == 0 && (E % 4) == 0; }
+
+}  // namespace stat
