@@ -97,7 +97,7 @@ struct Prep {
   size_t EW;     // (V+1, 4H): token -> emb.W + b ; row V = b
   size_t Wemb;   // (V, E) copy (prev2out add)
   // fused step (step_fused.cu)
-  size_t WgT;    // (4H+E, 2H): rows 4u+g = [Wc[:, gH+u] | U[:, gH+u]] (gate-interleaved, K = [ctx | h_]);
+  size_t WxhT;   // (4H+E, 2H): rows 4u+g = [Wc[:, gH+u] | U[:, gH+u]] (gate-interleaved, K = [ctx | h_]);
                  //             rows 4H.. = [ff_logit_ctxglm_W[:, e] | 0]
   size_t WqT;    // (4H+1+E, H): Wdl | Wdg | Wdm | Wdlt | W_sel | ff_logit_lstm_W
   size_t bq;     // (4H+1)    : 0 | 0 | 0 | blt | b_sel
@@ -144,7 +144,7 @@ Prep prep_layout(const StatDims &d) {
   p.U4 = take(4 * H + 4);
   p.EW = take((V + 1) * 4 * H);
   p.Wemb = take(V * E);
-  p.WgT = take((4 * H + E) * 2 * H);
+  p.WxhT = take((4 * H + E) * 2 * H);
   p.WqT = take((4 * H + 1 + E) * H);
   p.bq = take(4 * H + 1);
   p.bdi = take(4 * H);
@@ -563,7 +563,7 @@ int fstep_gates(const StatDims &d, const Prep &p, const float *P, const Ws &w, f
   FusedPhase f;
   memset(&f, 0, sizeof(f));
   f.swap = 1;
-  f.W = P + p.WgT; f.wrows = 4 * H + E; f.wK = 2 * H; f.ldw = 2 * H;
+  f.W = P + p.WxhT; f.wrows = 4 * H + E; f.wK = 2 * H; f.ldw = 2 * H;
   f.X[0] = W + w.xh[t & 1]; f.xK[0] = 2 * H; f.ldx[0] = 2 * H;
   f.rows = io.rows;
   f.nseg = 2;
@@ -897,9 +897,9 @@ int stat_prepare_params(const StatDims *d, const StatParams *sp, void *prepared,
                  st));
   STAT_CUDA_CHECK(cp(p.EW + static_cast<size_t>(V) * 4 * H, P + p.bdi, 4 * H));
   // fused step: [ctx | h_] . [Wc ; U] on gate-interleaved rows, the ctx -> readout rows behind them
-  STAT_TRY(transpose_il_launch(sp->decoder_Wc, H, H, P + p.WgT, 2 * H, 0, st));
-  STAT_TRY(transpose_il_launch(sp->decoder_U, H, H, P + p.WgT, 2 * H, H, st));
-  if (c2o) STAT_TRY(transpose_launch(sp->ff_logit_ctxglm_W, H, E, P + p.WgT, 2 * H, 4 * H, st));
+  STAT_TRY(transpose_il_launch(sp->decoder_Wc, H, H, P + p.WxhT, 2 * H, 0, st));
+  STAT_TRY(transpose_il_launch(sp->decoder_U, H, H, P + p.WxhT, 2 * H, H, st));
+  if (c2o) STAT_TRY(transpose_launch(sp->ff_logit_ctxglm_W, H, E, P + p.WxhT, 2 * H, 4 * H, st));
   // everything that multiplies the new hidden state: next step's attention queries, selector logit, readout
   STAT_TRY(transpose_launch(sp->decoder_Wdl_att, H, H, P + p.WqT, H, 0, st));
   STAT_TRY(transpose_launch(sp->decoder_Wdg_att, H, H, P + p.WqT, H, H, st));
