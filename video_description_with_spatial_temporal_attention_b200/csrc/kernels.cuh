@@ -94,6 +94,7 @@ struct PickArgs {
   const int64_t *x_t;        // (rows) target tokens of this step or null
   const float *mask_t;       // (rows)
   float *logprob;            // (rows) accumulated
+  float *logprob_comp;       // (rows) Kahan compensation of the accumulation (zero at the first step) or null
   // f_next
   float *probs;              // (rows,V) or null
   // beam search: the beam_k most probable words of every live row and their cumulative costs

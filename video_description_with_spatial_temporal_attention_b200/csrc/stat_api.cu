@@ -164,6 +164,7 @@ struct Ws {
   size_t rec_vec, rec_ms, att_scores, alpha_l;
   size_t counters, tok_prev, alive;  // byte-typed regions (still float offsets)
   size_t hb, cb, cand_cost, cand_word, hist, hist_len, bscore, src_row, row_clip, dead_k, bdone;   // beam search
+  size_t lpc;                        // Kahan compensation of the teacher-forced log-prob accumulation
   size_t xh[2], hq, part, tgt;       // fused step: [ctx | h] activation rows (double-buffered), queries, vocabulary partials
   int ldq2, npart;
   size_t total;                      // floats
@@ -273,6 +274,7 @@ Ws ws_layout(const StatDims &d, int rows) {
   w.hq = take(n * w.ldq2);
   w.part = take(n * w.npart * 4);
   w.tgt = take(n);
+  w.lpc = take(n);
   w.total = o;
   return w;
 }
@@ -1039,6 +1041,7 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
   const int B = d->B, T = d->T, R = d->R, H = d->H, E = d->E;
   const bool want_t = out_alpha_g || out_alpha_m || out_alpha_lt;
   STAT_CUDA_CHECK(cudaMemsetAsync(out_logprob, 0, sizeof(float) * B, st));
+  STAT_CUDA_CHECK(cudaMemsetAsync(W + w.lpc, 0, sizeof(float) * B, st));
   STAT_CUDA_CHECK(cudaMemsetAsync(W + w.counters, 0, sizeof(float) * B, st));
   Overlap ov;
   if (fused_enabled(*d, B)) {
@@ -1076,7 +1079,7 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
       k.rows = B; k.V = d->V;
       k.x_t = x + static_cast<size_t>(t) * B;
       k.mask_t = mask + static_cast<size_t>(t) * B;
-      k.logprob = out_logprob;
+      k.logprob = out_logprob; k.logprob_comp = W + w.lpc;
       STAT_TRY(fstep_vocab(*d, p, P, w, W, B, k, ov.side()));
       STAT_TRY(ov.side_enqueued());
     }
@@ -1117,7 +1120,7 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
     k.rows = B; k.V = d->V; k.ldl = w.ldl; k.logits = W + w.logits;
     k.x_t = x + static_cast<size_t>(t) * B;
     k.mask_t = mask + static_cast<size_t>(t) * B;
-    k.logprob = out_logprob;
+    k.logprob = out_logprob; k.logprob_comp = W + w.lpc;
     {
       ProfScope ps(PH_PICK, ov.side());
       STAT_TRY(pick_launch(k, ov.side()));

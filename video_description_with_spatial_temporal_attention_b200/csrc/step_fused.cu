@@ -125,7 +125,19 @@ __device__ __forceinline__ void combine_row(const PickArgs &a, const float4 *par
     }
     if (a.x_t) {
       const float p = expf(tgt[row] - m) / s;
-      a.logprob[row] += a.mask_t[row] * logf(p + 1e-8f);       // model_attention.py:712-715
+      {
+        // compensated accumulation: the sum of L terms of magnitude ~10 would otherwise lose ~L/2 ulp of the sum
+        const float term = a.mask_t[row] * logf(p + 1e-8f);      // model_attention.py:712-715
+        if (a.logprob_comp) {
+          const float y = term - a.logprob_comp[row];
+          const float sum = a.logprob[row];
+          const float tt = sum + y;
+          a.logprob_comp[row] = (tt - sum) - y;
+          a.logprob[row] = tt;
+        } else {
+          a.logprob[row] += term;
+        }
+      }
     }
   }
 }
