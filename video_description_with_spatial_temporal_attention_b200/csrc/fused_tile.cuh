@@ -69,7 +69,7 @@ __device__ __forceinline__ void cta_setup(Cta &c, uint8_t *smem_raw, uint32_t *t
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(c.bar_full + 8 * s, 1);
-      mbar_init(c.bar_split + 8 * s, NSPLIT);
+      mbar_init(c.bar_split + 8 * s, 4);          // one arrival per warp of the splitter group that owns the k-atom
       mbar_init(c.bar_empty + 8 * s, 1);
     }
     mbar_init(c.bar_acc, 1);
@@ -91,27 +91,36 @@ __device__ __forceinline__ void cta_teardown(const Cta &c) {
 }
 
 // ---- the three mainloop roles ------------------------------------------------------------------------
-// producer: one thread.  k-atoms [kb0, kb1) of the P rows [prow, prow+128) and the Q rows [qrow, qrow+bq)
+// producer: one thread.  k-atoms [kb0, kb1) of the P rows [prow, prow+mp) and the Q rows [qrow, qrow+bq)
+// (mp = rows of the P box: 128, or 64 / 32 for half / quarter tiles -- the remaining lanes then hold garbage)
 __device__ __forceinline__ void produce(const Cta &c, Ring &r, const CUtensorMap *tmP, int prow, const CUtensorMap *tmQ,
-                                        int qrow, int kb0, int kb1, int bq, unsigned long long pol_p,
-                                        unsigned long long pol_q) {
+                                        int qrow, int kb0, int kb1, int mp, int bq, unsigned long long pol_p,
+                                        unsigned long long pol_q, long long *trace = nullptr) {
   for (int kb = kb0; kb < kb1; ++kb) {
     mbar_wait(c.bar_empty + 8 * r.s, r.ph ^ 1);
+    if (trace && kb - kb0 < 32) trace[100 + kb - kb0] = clock64();
     const uint32_t stage = smem_u32(c.ring + r.s * STAGE_BYTES);
-    mbar_expect_tx(c.bar_full + 8 * r.s, static_cast<uint32_t>(P_BYTES + bq * BK * 4));
+    mbar_expect_tx(c.bar_full + 8 * r.s, static_cast<uint32_t>((mp + bq) * BK * 4));
     tma_load_2d(stage, tmP, kb * BK, prow, c.bar_full + 8 * r.s, pol_p);
     tma_load_2d(stage + P_BYTES, tmQ, kb * BK, qrow, c.bar_full + 8 * r.s, pol_q);
     r.next();
   }
 }
 
-// MMA issuer: the whole warp 1 calls this (lane 0 issues).  `fresh`: the first MMA overwrites the accumulator;
-// `last`: the accumulator is complete after these k-atoms (commit to bar_acc).
-__device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, bool fresh, bool last, int lane) {
+// MMA issuer: the whole warp 1 calls this (lane 0 issues).  Back-to-back tcgen05.mma that accumulate into the SAME
+// tensor-memory tile serialise on its ~110-cycle pipeline latency (measured: 12 dependent MMAs per k-atom cost
+// 1300-1400 cycles whether N is 32 or 128), so the 12 products of a k-atom (4 k-steps x lo.hi, hi.lo, hi.hi)
+// rotate over nacc = 256 / bq accumulators in columns [0, 256): MMA number n goes to accumulator n % nacc, the
+// epilogue adds the accumulators in order.  `n` = products issued so far for this tile (0 for a fresh tile);
+// `last`: the accumulators are complete after these k-atoms (commit to bar_acc).
+__device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, uint32_t &n, bool last, int lane,
+                                      long long *trace = nullptr) {
   const uint32_t idesc = make_idesc_tf32(BP, bq);
+  const uint32_t nacc = 256u / static_cast<uint32_t>(bq);
   for (int kb = 0; kb < nk; ++kb) {
     mbar_wait(c.bar_split + 8 * r.s, r.ph);
     tc_fence_after();
+    if (trace && lane == 0 && kb < 32) trace[180 + kb] = clock64();
     if (lane == 0) {
       const uint32_t stage = smem_u32(c.ring + r.s * STAGE_BYTES);
       const uint64_t dQh = make_desc(stage + P_BYTES);
@@ -120,9 +129,12 @@ __device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, boo
 #pragma unroll
       for (int ks = 0; ks < BK / UMMA_K; ++ks) {
         const uint64_t adv = static_cast<uint64_t>((ks * UMMA_K * 4) >> 4);   // 32 B per k-step
-        tc_mma_tf32_ts(c.tmem, a_lo + ks * UMMA_K, dQh + adv, idesc, (fresh && kb == 0 && ks == 0) ? 0u : 1u);
-        tc_mma_tf32_ts(c.tmem, a_hi + ks * UMMA_K, dQl + adv, idesc, 1u);
-        tc_mma_tf32_ts(c.tmem, a_hi + ks * UMMA_K, dQh + adv, idesc, 1u);
+        tc_mma_tf32_ts(c.tmem + (n % nacc) * bq, a_lo + ks * UMMA_K, dQh + adv, idesc, n >= nacc ? 1u : 0u);
+        ++n;
+        tc_mma_tf32_ts(c.tmem + (n % nacc) * bq, a_hi + ks * UMMA_K, dQl + adv, idesc, n >= nacc ? 1u : 0u);
+        ++n;
+        tc_mma_tf32_ts(c.tmem + (n % nacc) * bq, a_hi + ks * UMMA_K, dQh + adv, idesc, n >= nacc ? 1u : 0u);
+        ++n;
       }
       tc_commit(c.bar_empty + 8 * r.s);
       if (last && kb == nk - 1) tc_commit(c.bar_acc);
@@ -130,58 +142,66 @@ __device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, boo
     __syncwarp();
     r.next();
   }
+  n = __shfl_sync(0xffffffffu, n, 0);
 }
 
-// splitter: warps 2..9 (t = threadIdx.x - 64).  P: this thread owns tile row prow (= its TMEM lane) and 16 of
-// the 32 k-columns; the TMA tile is SWIZZLE_128B (16-byte chunk c of row r sits at chunk c ^ (r & 7)).
-__device__ __forceinline__ void split(const Cta &c, Ring &r, int nk, int bq, int warp, int lane) {
-  const int t = threadIdx.x - 64;
+// splitter: warps 2..9 in two groups of four warps (one warp per TMEM lane quadrant) that take alternate k-atoms,
+// so that the latencies of one k-atom's split (shared-memory loads, tensor-memory stores and their wait, the proxy
+// fence) overlap the other group's.  `kc` = k-atoms this CTA has split so far (both groups count all of them).
+// P: a thread owns tile row prow (= its TMEM lane) and all 32 k-columns, in two halves of 16; the TMA tile is
+// SWIZZLE_128B (16-byte chunk c of row r sits at chunk c ^ (r & 7)).  Q: hi in place, lo beside it.
+__device__ __forceinline__ void split(const Cta &c, Ring &r, int nk, int mp, int bq, uint32_t &kc, int warp, int lane,
+                                      long long *trace = nullptr) {
+  const int grp = (warp - 2) >> 2;
+  const int tg = ((warp - 2) & 3) * 32 + lane;       // 0..127 inside the group
   const int prow = (warp & 3) * 32 + lane;
-  const int ch = (warp - 2) >> 2;
   const int nq4 = bq * (BK / 4);                     // 16-byte chunks of the Q tile
-  for (int kb = 0; kb < nk; ++kb) {
-    mbar_wait(c.bar_full + 8 * r.s, r.ph);
-    uint8_t *stage = c.ring + r.s * STAGE_BYTES;
-    const uint8_t *rowp = stage + prow * 128;
-    float4 *Qh = reinterpret_cast<float4 *>(stage + P_BYTES);
-    float4 *Ql = reinterpret_cast<float4 *>(stage + P_BYTES + Q_BYTES_MAX);
-    float4 xp[4], xq[4];
+  for (int kb = 0; kb < nk; ++kb, ++kc) {
+    if ((kc & 1u) == static_cast<uint32_t>(grp)) {
+      mbar_wait(c.bar_full + 8 * r.s, r.ph);
+      if (trace && tg == 0 && kb < 32) trace[2 + kb] = clock64();
+      uint8_t *stage = c.ring + r.s * STAGE_BYTES;
+      const uint8_t *rowp = stage + prow * 128;
+      float4 *Qh = reinterpret_cast<float4 *>(stage + P_BYTES);
+      float4 *Ql = reinterpret_cast<float4 *>(stage + P_BYTES + Q_BYTES_MAX);
+      if ((warp & 3) * 32 < mp) {
+        const uint32_t ta = c.tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + TMEM_A_BASE + 64 * r.s;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) xp[i] = *reinterpret_cast<const float4 *>(rowp + (((4 * ch + i) ^ (prow & 7)) << 4));
+        for (int half = 0; half < 2; ++half) {
+          float4 xp[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = t + i * NSPLIT;
-      xq[i] = idx < nq4 ? Qh[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    uint32_t hi[16], lo[16];
+          for (int i = 0; i < 4; ++i)
+            xp[i] = *reinterpret_cast<const float4 *>(rowp + (((4 * half + i) ^ (prow & 7)) << 4));
+          uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float xs[4] = {xp[i].x, xp[i].y, xp[i].z, xp[i].w};
+          for (int i = 0; i < 4; ++i) {
+            const float xs[4] = {xp[i].x, xp[i].y, xp[i].z, xp[i].w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float h = rna_tf32(xs[e]);
-        hi[4 * i + e] = __float_as_uint(h);
-        lo[4 * i + e] = __float_as_uint(xs[e] - h);   // exact; the tensor core reads its top 19 bits
+            for (int e = 0; e < 4; ++e) {
+              const float h = rna_tf32(xs[e]);
+              hi[4 * i + e] = __float_as_uint(h);
+              lo[4 * i + e] = __float_as_uint(xs[e] - h);   // exact; the tensor core reads its top 19 bits
+            }
+          }
+          tc_st16(ta + 16 * half, hi);
+          tc_st16(ta + 32 + 16 * half, lo);
+        }
       }
-    }
-    const uint32_t ta = c.tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + TMEM_A_BASE + 64 * r.s + 16 * ch;
-    tc_st16(ta, hi);
-    tc_st16(ta + 32, lo);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = t + i * NSPLIT;
-      if (idx < nq4) {
+      for (int idx = tg; idx < nq4; idx += 128) {
+        const float4 x = Qh[idx];
         float4 h, l;
-        h.x = rna_tf32(xq[i].x); h.y = rna_tf32(xq[i].y); h.z = rna_tf32(xq[i].z); h.w = rna_tf32(xq[i].w);
-        l.x = xq[i].x - h.x; l.y = xq[i].y - h.y; l.z = xq[i].z - h.z; l.w = xq[i].w - h.w;
+        h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+        l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
         Qh[idx] = h;
         Ql[idx] = l;
       }
+      tc_wait_st();
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(c.bar_split + 8 * r.s);
+      if (trace && tg == 0 && kb < 32) trace[36 + kb] = clock64();
     }
-    tc_wait_st();
-    tc_fence_before();
-    fence_proxy_async_smem();
-    mbar_arrive(c.bar_split + 8 * r.s);
     r.next();
   }
 }
@@ -318,9 +338,21 @@ __device__ __forceinline__ void pick_fold16(const EpiParams &e, const uint32_t (
 // Whole-tile epilogue.  kind / geometry are uniform over the CTA.
 //   swap tiles:   f0 = first feature of the tile inside its segment, nfeat = features of the segment, q0 = first row
 //   normal tiles: q0 = first vocabulary word of the tile, part = partial slot of this tile's first half
-__device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int kind, int bq, int f0, int nfeat, int q0,
-                                         int warp, int lane, float *creg, bool creg_load) {
+// v[i] = sum over the rotating accumulators (in order) of columns [col, col + 16)
+__device__ __forceinline__ void acc_ld16(uint32_t trow, int col, int bq, uint32_t (&v)[16]) {
+  tc_ld16(trow + col, v);
+  for (int a = bq; a < 256; a += bq) {
+    uint32_t w[16];
+    tc_ld16(trow + a + col, w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+  }
+}
+
+__device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int kind, int mp, int bq, int f0, int nfeat,
+                                         int q0, int warp, int lane, float *creg, bool creg_load) {
   const int wq = warp & 3;
+  if (wq * 32 >= mp) return;                             // lanes beyond the tile height hold nothing
   const int chalf = (warp - 2) >> 2;
   const int ch = bq >> 1;                               // columns per warp
   const uint32_t trow = c.tmem + (static_cast<uint32_t>(wq * 32) << 16);
@@ -331,7 +363,7 @@ __device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int k
     const long long tgt_word = (e.x_t && r < e.rows) ? e.x_t[r] : -1;
     for (int cc = chalf * ch; cc < (chalf + 1) * ch; cc += 16) {
       uint32_t v[16];
-      tc_ld16(trow + cc, v);
+      acc_ld16(trow, cc, bq, v);
       pick_fold16(e, v, q0 + cc, e.V, tgt_word, a);
     }
     if (r < e.rows) {
@@ -345,7 +377,7 @@ __device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int k
   const bool jok = j < nfeat;
   for (int cc = chalf * ch; cc < (chalf + 1) * ch; cc += 16) {
     uint32_t v[16];
-    tc_ld16(trow + cc, v);
+    acc_ld16(trow, cc, bq, v);
     const int r0 = q0 + cc;
     if (kind == FE_STORE) epi_store16(e, v, j, jok, r0);
     else if (kind == FE_GATES) epi_gates16(e, v, j, jok, r0, creg, creg_load);

@@ -62,6 +62,7 @@ unsigned long long launch_count() { return g_launches; }
 
 static long long *g_trace = nullptr;
 void gemm_set_trace(long long *p) { g_trace = p; }
+long long *gemm_get_trace() { return g_trace; }
 
 static int g_gemm_impl = 0;
 void gemm_set_impl(int impl) { g_gemm_impl = impl; }

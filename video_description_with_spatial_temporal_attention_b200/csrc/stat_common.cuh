@@ -163,6 +163,7 @@ int gemm_launch(const GemmArgs &a, cudaStream_t stream);
 // box = box_rows x 32 floats (one 128-byte swizzle row), SWIZZLE_128B, out-of-range elements read as 0
 int make_tensor_map(CUtensorMap *tm, const float *base, int rows, int K, int ld, int box_rows);
 void gemm_set_trace(long long *p);
+long long *gemm_get_trace();
 void gemm_set_impl(int impl);
 int gemm_get_impl();
 

@@ -7,6 +7,7 @@
 //       = S10-S13 (the gates kernel is gone); the ctx.ff_logit_ctxglm_W rows ride in the same launch (:691-693)
 //   C:  h.[Wdl | Wdg | Wdm | Wdlt | W_sel] (next step's attention queries, :371,389,402,415,433) and
 //       z = 0.5 tanh(0.5 h.ff_logit_lstm_W + zadd) (:684-696) in one launch
+#include <stdlib.h>
 #include <string.h>
 
 #include "fused_tile.cuh"
@@ -23,9 +24,10 @@ struct SegDev {
 };
 
 struct PhaseDev {
-  int swap, bq, nseg, qtiles, ntile0;
+  int swap, mp, bq, nseg, qtiles, ntile0;
   SegDev seg[2];
   unsigned long long pol_w, pol_x;
+  long long *trace;     // debug: clock64 stamps of CTA 0 (stat_debug_gemm_trace), or null
   EpiParams e;
 };
 
@@ -34,6 +36,7 @@ __global__ void __launch_bounds__(NROLE, 1)
                        const __grid_constant__ CUtensorMap tmX1, const PhaseDev a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint32_t tmem_slot;
+  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[0] = clock64();
   Cta c;
   cta_setup(c, smem_raw, &tmem_slot);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(NROLE, 1)
   unsigned long long pol_p, pol_q;
   if (a.swap) {
     const int pt = local / a.qtiles, qt = local - pt * a.qtiles;
-    f0 = pt * BP; q0 = qt * a.bq;
+    f0 = pt * a.mp; q0 = qt * a.bq;
     prow = prow0 + f0; qrow = q0;
     tmP = &tmW; tmQ = tmX; pol_p = a.pol_w; pol_q = a.pol_x;
   } else {
@@ -62,21 +65,28 @@ __global__ void __launch_bounds__(NROLE, 1)
   // everything above overlaps the previous kernel's tail; its results are read from here on
   pdl_wait();
   pdl_trigger();
+  long long *trace = (a.trace && blockIdx.x == 0) ? a.trace : nullptr;
+  if (trace && threadIdx.x == 0) trace[1] = clock64();
   Ring r = {0, 0};
   if (warp == 0) {
-    if (lane == 0) produce(c, r, tmP, prow, tmQ, qrow, 0, nk, a.bq, pol_p, pol_q);
+    if (lane == 0) produce(c, r, tmP, prow, tmQ, qrow, 0, nk, a.mp, a.bq, pol_p, pol_q, trace);
     __syncwarp();
   } else if (warp == 1) {
-    issue(c, r, nk, a.bq, true, true, lane);
+    uint32_t n = 0;
+    issue(c, r, nk, a.bq, n, true, lane, trace);
   } else {
-    split(c, r, nk, a.bq, warp, lane);
+    uint32_t kc = 0;
+    split(c, r, nk, a.mp, a.bq, kc, warp, lane, trace);
     mbar_wait(c.bar_acc, 0);
     tc_fence_after();
+    if (trace && threadIdx.x == 64) trace[140] = clock64();
     EpiParams e = a.e;
     if (kind == FE_PICK) e.part0 = 2 * local;
-    epilogue(c, e, kind, a.bq, f0, nfeat, q0, warp, lane, nullptr, false);
+    epilogue(c, e, kind, a.mp, a.bq, f0, nfeat, q0, warp, lane, nullptr, false);
+    if (trace && threadIdx.x == 64) trace[141] = clock64();
   }
   cta_teardown(c);
+  if (trace && threadIdx.x == 0) trace[142] = clock64();
 }
 
 // ---- combine of the per-tile vocabulary partials of one step: one warp per decode row -----------------------
@@ -164,6 +174,9 @@ int fused_phase_launch(const FusedPhase &p, cudaStream_t stream) {
   PhaseDev d;
   memset(&d, 0, sizeof(d));
   d.swap = p.swap;
+  // swap tiles: 64 features x 32 decode rows (half-height tiles: twice the CTAs, half the weight bytes per CTA -- the
+  // per-SM load rate, not the tensor pipe, bounds these products); normal tiles: all rows x 128 vocabulary words
+  d.mp = p.swap ? 64 : BP;
   d.bq = p.swap ? 32 : 128;
   d.nseg = p.nseg;
   d.qtiles = p.swap ? (p.rows + d.bq - 1) / d.bq : 1;
@@ -176,7 +189,7 @@ int fused_phase_launch(const FusedPhase &p, cudaStream_t stream) {
     d.seg[i].nfeat = s.nfeat;
     d.seg[i].nk = (s.K + BK - 1) / BK;
     d.seg[i].xsel = s.xsel;
-    tiles[i] = p.swap ? ((s.nfeat + BP - 1) / BP) * d.qtiles : (s.nfeat + d.bq - 1) / d.bq;
+    tiles[i] = p.swap ? ((s.nfeat + d.mp - 1) / d.mp) * d.qtiles : (s.nfeat + d.bq - 1) / d.bq;
   }
   d.ntile0 = tiles[0];
   // the step's weights are re-read by every decode step: keep them in L2 ahead of the streamed context blocks
@@ -184,8 +197,13 @@ int fused_phase_launch(const FusedPhase &p, cudaStream_t stream) {
   d.pol_x = L2_EVICT_NORMAL;
   d.e = p.e;
   d.e.rows = p.rows;
+  d.trace = gemm_get_trace();
+  if (d.trace) {   // debug: STAT_TRACE_KIND selects which launches stamp the trace buffer (FE_* of the first segment)
+    const char *tk = getenv("STAT_TRACE_KIND");
+    if (tk && atoi(tk) != p.seg[0].kind) d.trace = nullptr;
+  }
   CUtensorMap tmW, tmX0, tmX1;
-  STAT_TRY(make_tensor_map(&tmW, p.W, p.wrows, p.wK, p.ldw, BP));
+  STAT_TRY(make_tensor_map(&tmW, p.W, p.wrows, p.wK, p.ldw, p.swap ? d.mp : d.bq));
   const int xbox = p.swap ? d.bq : BP;
   STAT_TRY(make_tensor_map(&tmX0, p.X[0], p.rows, p.xK[0], p.ldx[0], xbox));
   if (p.X[1]) STAT_TRY(make_tensor_map(&tmX1, p.X[1], p.rows, p.xK[1], p.ldx[1], xbox));
