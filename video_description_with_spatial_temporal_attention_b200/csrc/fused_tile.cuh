@@ -107,42 +107,53 @@ __device__ __forceinline__ void produce(const Cta &c, Ring &r, const CUtensorMap
   }
 }
 
-// MMA issuer: the whole warp 1 calls this (lane 0 issues).  Back-to-back tcgen05.mma that accumulate into the SAME
-// tensor-memory tile serialise on its ~110-cycle pipeline latency (measured: 12 dependent MMAs per k-atom cost
-// 1300-1400 cycles whether N is 32 or 128), so the 12 products of a k-atom (4 k-steps x lo.hi, hi.lo, hi.hi)
-// rotate over nacc = 256 / bq accumulators in columns [0, 256): MMA number n goes to accumulator n % nacc, the
-// epilogue adds the accumulators in order.  `n` = products issued so far for this tile (0 for a fresh tile);
-// `last`: the accumulators are complete after these k-atoms (commit to bar_acc).
-__device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, uint32_t &n, bool last, int lane,
+// MMA issuer: the whole warp 1 calls this.  Every lane computes the (warp-uniform) descriptors and tensor-memory
+// addresses so that they live in uniform registers -- inside an `if (lane == 0)` block the compiler moves each
+// operand of each tcgen05.mma from a vector to a uniform register through an ELECT / R2UR / branch loop, which
+// costs more than the instruction itself (measured: 110-170 cycles per MMA, 1300-2000 per k-atom) -- and only the
+// MMA / commit instructions themselves are predicated on the elected lane.
+// The 12 products of a k-atom (4 k-steps x lo.hi, hi.lo, hi.hi) rotate over nacc (power of two, nacc * bq <= 256)
+// accumulators in columns [0, 256): product number n goes to accumulator n & (nacc - 1), the epilogue adds the
+// accumulators in order.  `n` = products issued so far for this tile (0 for a fresh tile); `last`: the
+// accumulators are complete after these k-atoms (commit to bar_acc).
+__device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, int nacc, uint32_t &n, bool last, int lane,
                                       long long *trace = nullptr) {
   const uint32_t idesc = make_idesc_tf32(BP, bq);
-  const uint32_t nacc = 256u / static_cast<uint32_t>(bq);
+  const uint32_t tmem = __shfl_sync(0xffffffffu, c.tmem, 0);
+  const uint32_t ring0 = __shfl_sync(0xffffffffu, smem_u32(c.ring), 0);
+  const uint32_t amask = static_cast<uint32_t>(nacc - 1), ubq = static_cast<uint32_t>(bq), unacc = static_cast<uint32_t>(nacc);
   for (int kb = 0; kb < nk; ++kb) {
     mbar_wait(c.bar_split + 8 * r.s, r.ph);
+    __syncwarp();
+    const bool leader = elect_one();
     tc_fence_after();
-    if (trace && lane == 0 && kb < 32) trace[180 + kb] = clock64();
-    if (lane == 0) {
-      const uint32_t stage = smem_u32(c.ring + r.s * STAGE_BYTES);
-      const uint64_t dQh = make_desc(stage + P_BYTES);
-      const uint64_t dQl = make_desc(stage + P_BYTES + Q_BYTES_MAX);
-      const uint32_t a_hi = c.tmem + TMEM_A_BASE + 64 * r.s, a_lo = a_hi + 32;
+    if (trace && leader && kb < 32) trace[180 + kb] = clock64();
+    const uint32_t stage = ring0 + static_cast<uint32_t>(r.s) * STAGE_BYTES;
+    const uint64_t dQh = make_desc(stage + P_BYTES);
+    const uint64_t dQl = make_desc(stage + P_BYTES + Q_BYTES_MAX);
+    const uint32_t a_hi = tmem + TMEM_A_BASE + 64 * r.s, a_lo = a_hi + 32;
+    if (nacc == 1) {
+      if (leader) tc_mma_tf32_katom(tmem, a_hi, dQh, dQl, idesc, n ? 1u : 0u);
+      n += 12;
+    } else
 #pragma unroll
-      for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-        const uint64_t adv = static_cast<uint64_t>((ks * UMMA_K * 4) >> 4);   // 32 B per k-step
-        tc_mma_tf32_ts(c.tmem + (n % nacc) * bq, a_lo + ks * UMMA_K, dQh + adv, idesc, n >= nacc ? 1u : 0u);
-        ++n;
-        tc_mma_tf32_ts(c.tmem + (n % nacc) * bq, a_hi + ks * UMMA_K, dQl + adv, idesc, n >= nacc ? 1u : 0u);
-        ++n;
-        tc_mma_tf32_ts(c.tmem + (n % nacc) * bq, a_hi + ks * UMMA_K, dQh + adv, idesc, n >= nacc ? 1u : 0u);
-        ++n;
+    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+      const uint64_t adv = static_cast<uint64_t>((ks * UMMA_K * 4) >> 4);   // 32 B per k-step
+      const uint32_t d0 = tmem + (n & amask) * ubq, d1 = tmem + ((n + 1) & amask) * ubq, d2 = tmem + ((n + 2) & amask) * ubq;
+      if (leader) {
+        tc_mma_tf32_ts(d0, a_lo + ks * UMMA_K, dQh + adv, idesc, n >= unacc ? 1u : 0u);
+        tc_mma_tf32_ts(d1, a_hi + ks * UMMA_K, dQl + adv, idesc, n + 1 >= unacc ? 1u : 0u);
+        tc_mma_tf32_ts(d2, a_hi + ks * UMMA_K, dQh + adv, idesc, n + 2 >= unacc ? 1u : 0u);
       }
+      n += 3;
+    }
+    if (leader) {
       tc_commit(c.bar_empty + 8 * r.s);
       if (last && kb == nk - 1) tc_commit(c.bar_acc);
     }
     __syncwarp();
     r.next();
   }
-  n = __shfl_sync(0xffffffffu, n, 0);
 }
 
 // splitter: warps 2..9 in two groups of four warps (one warp per TMEM lane quadrant) that take alternate k-atoms,
@@ -339,9 +350,9 @@ __device__ __forceinline__ void pick_fold16(const EpiParams &e, const uint32_t (
 //   swap tiles:   f0 = first feature of the tile inside its segment, nfeat = features of the segment, q0 = first row
 //   normal tiles: q0 = first vocabulary word of the tile, part = partial slot of this tile's first half
 // v[i] = sum over the rotating accumulators (in order) of columns [col, col + 16)
-__device__ __forceinline__ void acc_ld16(uint32_t trow, int col, int bq, uint32_t (&v)[16]) {
+__device__ __forceinline__ void acc_ld16(uint32_t trow, int col, int bq, int nacc, uint32_t (&v)[16]) {
   tc_ld16(trow + col, v);
-  for (int a = bq; a < 256; a += bq) {
+  for (int a = bq; a < nacc * bq; a += bq) {
     uint32_t w[16];
     tc_ld16(trow + a + col, w);
 #pragma unroll
@@ -349,8 +360,8 @@ __device__ __forceinline__ void acc_ld16(uint32_t trow, int col, int bq, uint32_
   }
 }
 
-__device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int kind, int mp, int bq, int f0, int nfeat,
-                                         int q0, int warp, int lane, float *creg, bool creg_load) {
+__device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int kind, int mp, int bq, int nacc, int f0,
+                                         int nfeat, int q0, int warp, int lane, float *creg, bool creg_load) {
   const int wq = warp & 3;
   if (wq * 32 >= mp) return;                             // lanes beyond the tile height hold nothing
   const int chalf = (warp - 2) >> 2;
@@ -363,7 +374,7 @@ __device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int k
     const long long tgt_word = (e.x_t && r < e.rows) ? e.x_t[r] : -1;
     for (int cc = chalf * ch; cc < (chalf + 1) * ch; cc += 16) {
       uint32_t v[16];
-      acc_ld16(trow, cc, bq, v);
+      acc_ld16(trow, cc, bq, nacc, v);
       pick_fold16(e, v, q0 + cc, e.V, tgt_word, a);
     }
     if (r < e.rows) {
@@ -377,7 +388,7 @@ __device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int k
   const bool jok = j < nfeat;
   for (int cc = chalf * ch; cc < (chalf + 1) * ch; cc += 16) {
     uint32_t v[16];
-    acc_ld16(trow, cc, bq, v);
+    acc_ld16(trow, cc, bq, nacc, v);
     const int r0 = q0 + cc;
     if (kind == FE_STORE) epi_store16(e, v, j, jok, r0);
     else if (kind == FE_GATES) epi_gates16(e, v, j, jok, r0, creg, creg_load);

@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include "stat_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace stat {
 
@@ -350,30 +351,36 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     // b=TF32 [10,13)=2, K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BQ >> 3) << 17) |
                            (static_cast<uint32_t>(BP >> 4) << 24);
+    // Every lane computes the (warp-uniform) descriptors; only the MMA / commit instructions run in the lane
+    // chosen by elect.sync.  With `if (lane == 0)` around per-MMA asm statements ptxas wraps every tcgen05.mma in
+    // an ELECT / R2UR / branch loop that costs 110-160 cycles per MMA -- more than the 64 cycles a 128x128x8
+    // tf32 MMA takes -- which is what held this kernel at ~0.57 of the 3xTF32 ceiling in round 1.
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t ring_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
     int s = 0;
     uint32_t ph = 0;
     for (int kb = 0; kb < nk; ++kb) {
       mbar_wait(bar_split + 8 * s, ph);
       tc_fence_after();
-      if (trace && lane == 0 && kb < 16) trace[40 + kb] = clock64();
-      if (lane == 0) {
-        const uint32_t stage = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint64_t dPh = make_desc(stage);
-        const uint64_t dPl = make_desc(stage + C::P_BYTES);
-        const uint64_t dQh = make_desc(stage + 2 * C::P_BYTES);
-        const uint64_t dQl = make_desc(stage + 2 * C::P_BYTES + C::Q_BYTES);
-        const uint32_t a_hi = tmem_base + C::TS_A_BASE + 64 * s, a_lo = a_hi + 32;
+      __syncwarp();
+      const bool leader = tcx::elect_one();
+      if (trace && leader && kb < 16) trace[40 + kb] = clock64();
+      const uint32_t stage = ring_u + static_cast<uint32_t>(s) * C::STAGE_BYTES;
+      const uint64_t dPh = make_desc(stage);
+      const uint64_t dPl = make_desc(stage + C::P_BYTES);
+      const uint64_t dQh = make_desc(stage + 2 * C::P_BYTES);
+      const uint64_t dQl = make_desc(stage + 2 * C::P_BYTES + C::Q_BYTES);
+      const uint32_t a_hi = tmem_u + C::TS_A_BASE + 64 * s;
+      if (leader) {
+        if constexpr (TS) {
+          tcx::tc_mma_tf32_katom(tmem_u, a_hi, dQh, dQl, idesc, kb ? 1u : 0u);
+        } else {
 #pragma unroll
-        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          const uint64_t adv = static_cast<uint64_t>((ks * UMMA_K * 4) >> 4);  // 32 B per k-step
-          if constexpr (TS) {
-            tc_mma_tf32_ts(tmem_base, a_lo + ks * UMMA_K, dQh + adv, idesc, (kb | ks) ? 1u : 0u);
-            tc_mma_tf32_ts(tmem_base, a_hi + ks * UMMA_K, dQl + adv, idesc, 1u);
-            tc_mma_tf32_ts(tmem_base, a_hi + ks * UMMA_K, dQh + adv, idesc, 1u);
-          } else {
-            tc_mma_tf32(tmem_base, dPl + adv, dQh + adv, idesc, (kb | ks) ? 1u : 0u);
-            tc_mma_tf32(tmem_base, dPh + adv, dQl + adv, idesc, 1u);
-            tc_mma_tf32(tmem_base, dPh + adv, dQh + adv, idesc, 1u);
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            const uint64_t adv = static_cast<uint64_t>((ks * UMMA_K * 4) >> 4);  // 32 B per k-step
+            tc_mma_tf32(tmem_u, dPl + adv, dQh + adv, idesc, (kb | ks) ? 1u : 0u);
+            tc_mma_tf32(tmem_u, dPh + adv, dQl + adv, idesc, 1u);
+            tc_mma_tf32(tmem_u, dPh + adv, dQh + adv, idesc, 1u);
           }
         }
         tc_commit(bar_empty + 8 * s);

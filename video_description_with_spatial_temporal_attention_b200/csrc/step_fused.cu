@@ -24,7 +24,7 @@ struct SegDev {
 };
 
 struct PhaseDev {
-  int swap, mp, bq, nseg, qtiles, ntile0;
+  int swap, mp, bq, nacc, nseg, qtiles, ntile0;
   SegDev seg[2];
   unsigned long long pol_w, pol_x;
   long long *trace;     // debug: clock64 stamps of CTA 0 (stat_debug_gemm_trace), or null
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(NROLE, 1)
     __syncwarp();
   } else if (warp == 1) {
     uint32_t n = 0;
-    issue(c, r, nk, a.bq, n, true, lane, trace);
+    issue(c, r, nk, a.bq, a.nacc, n, true, lane, trace);
   } else {
     uint32_t kc = 0;
     split(c, r, nk, a.mp, a.bq, kc, warp, lane, trace);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NROLE, 1)
     if (trace && threadIdx.x == 64) trace[140] = clock64();
     EpiParams e = a.e;
     if (kind == FE_PICK) e.part0 = 2 * local;
-    epilogue(c, e, kind, a.mp, a.bq, f0, nfeat, q0, warp, lane, nullptr, false);
+    epilogue(c, e, kind, a.mp, a.bq, a.nacc, f0, nfeat, q0, warp, lane, nullptr, false);
     if (trace && threadIdx.x == 64) trace[141] = clock64();
   }
   cta_teardown(c);
@@ -178,6 +178,16 @@ int fused_phase_launch(const FusedPhase &p, cudaStream_t stream) {
   // per-SM load rate, not the tensor pipe, bounds these products); normal tiles: all rows x 128 vocabulary words
   d.mp = p.swap ? 64 : BP;
   d.bq = p.swap ? 32 : 128;
+  {   // accumulators the products of a k-atom rotate over (debug knob STAT_FUSED_NACC: 1, 2, 4, 8)
+    static int nacc_env = -1;
+    if (nacc_env < 0) {
+      const char *e = getenv("STAT_FUSED_NACC");
+      nacc_env = e ? atoi(e) : 1;
+      if (nacc_env != 1 && nacc_env != 2 && nacc_env != 4 && nacc_env != 8) nacc_env = 1;
+    }
+    d.nacc = nacc_env;
+    while (d.nacc * d.bq > 256) d.nacc >>= 1;
+  }
   d.nseg = p.nseg;
   d.qtiles = p.swap ? (p.rows + d.bq - 1) / d.bq : 1;
   int tiles[2] = {0, 0};

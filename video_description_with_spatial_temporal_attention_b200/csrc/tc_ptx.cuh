@@ -59,6 +59,19 @@ constexpr unsigned long long L2_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr unsigned long long L2_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr unsigned long long L2_EVICT_LAST = 0x14F0000000000000ull;
 
+// one lane of the (converged) warp; ptxas knows that code predicated on an elect.sync result runs in a single
+// thread and issues tcgen05.mma / commit there without wrapping each one in an elect / branch loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -74,6 +87,48 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The 12 products of one k-atom (32 fp32 of K = 4 k-steps of 8; per k-step lo.hi, hi.lo, hi.hi) into ONE accumulator,
+// as a single asm block: the operands cross from vector to uniform registers once per k-atom instead of once per
+// MMA.  a_hi: tensor-memory address of the hi half of the A stage (lo half 32 columns further); dqh / dql: shared
+// memory descriptors of the hi / lo B tiles (k-step advance = 32 bytes = +2 in the descriptor's address field).
+__device__ __forceinline__ void tc_mma_tf32_katom(uint32_t tmem_d, uint32_t a_hi, uint64_t dqh, uint64_t dql,
+                                                  uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, pt;\n\t"
+      ".reg .b32 ah1, ah2, ah3, al0, al1, al2, al3;\n\t"
+      ".reg .b64 qh1, qh2, qh3, ql1, ql2, ql3;\n\t"
+      "setp.ne.b32 p0, %5, 0;\n\t"
+      "setp.eq.b32 pt, %5, %5;\n\t"
+      "add.u32 al0, %1, 32;\n\t"
+      "add.u32 ah1, %1, 8;\n\t"
+      "add.u32 al1, %1, 40;\n\t"
+      "add.u32 ah2, %1, 16;\n\t"
+      "add.u32 al2, %1, 48;\n\t"
+      "add.u32 ah3, %1, 24;\n\t"
+      "add.u32 al3, %1, 56;\n\t"
+      "add.s64 qh1, %2, 2;\n\t"
+      "add.s64 ql1, %3, 2;\n\t"
+      "add.s64 qh2, %2, 4;\n\t"
+      "add.s64 ql2, %3, 4;\n\t"
+      "add.s64 qh3, %2, 6;\n\t"
+      "add.s64 ql3, %3, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al0], %2, %4, p0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %3, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al1], qh1, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], ql1, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], qh1, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al2], qh2, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], ql2, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], qh2, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al3], qh3, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], ql3, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], qh3, %4, pt;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_hi), "l"(dqh), "l"(dql), "r"(idesc), "r"(accumulate_first)
       : "memory");
 }
 __device__ __forceinline__ void tc_alloc(uint32_t smem_dst, uint32_t cols) {
