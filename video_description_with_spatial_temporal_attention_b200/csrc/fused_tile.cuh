@@ -29,7 +29,8 @@ constexpr int BP = 128;                    // tile rows (TMEM lanes)
 constexpr int BK = 32;                     // fp32 per k-atom row = 128 B = one swizzle row
 constexpr int UMMA_K = 8;                  // tf32 MMA K
 constexpr int NSPLIT = 256;                // splitter / epilogue threads (warps 2..9)
-constexpr int NROLE = 64 + NSPLIT;         // + TMA producer warp (0) + MMA issuer warp (1)
+constexpr int NISSUE = 2;                  // MMA-issuing warps: warp 1 and warps 10 .. 10 + NISSUE - 2
+constexpr int NROLE = 64 + NSPLIT + 32 * (NISSUE - 1);   // + TMA producer warp (0) + MMA issuer warps
 constexpr int STAGES = 4;
 constexpr int P_BYTES = BP * BK * 4;       // 16 KB
 constexpr int QMAX = 128;
@@ -72,7 +73,7 @@ __device__ __forceinline__ void cta_setup(Cta &c, uint8_t *smem_raw, uint32_t *t
       mbar_init(c.bar_split + 8 * s, 4);          // one arrival per warp of the splitter group that owns the k-atom
       mbar_init(c.bar_empty + 8 * s, 1);
     }
-    mbar_init(c.bar_acc, 1);
+    mbar_init(c.bar_acc, NISSUE);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if ((threadIdx.x >> 5) == 1) tc_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -107,52 +108,47 @@ __device__ __forceinline__ void produce(const Cta &c, Ring &r, const CUtensorMap
   }
 }
 
-// MMA issuer: the whole warp 1 calls this.  Every lane computes the (warp-uniform) descriptors and tensor-memory
-// addresses so that they live in uniform registers -- inside an `if (lane == 0)` block the compiler moves each
-// operand of each tcgen05.mma from a vector to a uniform register through an ELECT / R2UR / branch loop, which
-// costs more than the instruction itself (measured: 110-170 cycles per MMA, 1300-2000 per k-atom) -- and only the
-// MMA / commit instructions themselves are predicated on the elected lane.
-// The 12 products of a k-atom (4 k-steps x lo.hi, hi.lo, hi.hi) rotate over nacc (power of two, nacc * bq <= 256)
-// accumulators in columns [0, 256): product number n goes to accumulator n & (nacc - 1), the epilogue adds the
-// accumulators in order.  `n` = products issued so far for this tile (0 for a fresh tile); `last`: the
-// accumulators are complete after these k-atoms (commit to bar_acc).
-__device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, int nacc, uint32_t &n, bool last, int lane,
-                                      long long *trace = nullptr) {
+// MMA issuers: NISSUE warps (warp 1 and warps 10..), issuer ii takes the k-atoms kt with kt % NISSUE == ii of a
+// tile (kt = k-atoms of the tile so far) and accumulates them in its own accumulator, columns [ii*bq, (ii+1)*bq);
+// the epilogue adds the accumulators in order.  One tcgen05.mma.kind::tf32 covers K = 8, so a k-atom is 12
+// instructions whatever N is, and a single thread issues them at ~58 cycles each (measured: 700 cycles per
+// k-atom at N = 32, 1030 at N = 128): with skinny tiles the issue rate of one thread, not the tensor pipe, bounds
+// the mainloop -- hence several issuing threads.
+// Every lane computes the (warp-uniform) descriptors so that they live in uniform registers, and the MMA / commit
+// instructions run in the lane chosen by elect.sync: inside an `if (lane == 0)` block ptxas wraps each
+// tcgen05.mma in an ELECT / R2UR / branch loop (measured 110-170 cycles per MMA).
+// `n` = products this issuer has issued for the tile (0 = its first one overwrites its accumulator); `last`: the
+// tile is complete after these k-atoms (every issuer commits to bar_acc, which expects NISSUE arrivals).
+__device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, int ii, uint32_t &kt, uint32_t &n,
+                                      bool last, long long *trace = nullptr) {
   const uint32_t idesc = make_idesc_tf32(BP, bq);
   const uint32_t tmem = __shfl_sync(0xffffffffu, c.tmem, 0);
   const uint32_t ring0 = __shfl_sync(0xffffffffu, smem_u32(c.ring), 0);
-  const uint32_t amask = static_cast<uint32_t>(nacc - 1), ubq = static_cast<uint32_t>(bq), unacc = static_cast<uint32_t>(nacc);
-  for (int kb = 0; kb < nk; ++kb) {
-    mbar_wait(c.bar_split + 8 * r.s, r.ph);
-    __syncwarp();
-    const bool leader = elect_one();
-    tc_fence_after();
-    if (trace && leader && kb < 32) trace[180 + kb] = clock64();
-    const uint32_t stage = ring0 + static_cast<uint32_t>(r.s) * STAGE_BYTES;
-    const uint64_t dQh = make_desc(stage + P_BYTES);
-    const uint64_t dQl = make_desc(stage + P_BYTES + Q_BYTES_MAX);
-    const uint32_t a_hi = tmem + TMEM_A_BASE + 64 * r.s, a_lo = a_hi + 32;
-    if (nacc == 1) {
-      if (leader) tc_mma_tf32_katom(tmem, a_hi, dQh, dQl, idesc, n ? 1u : 0u);
-      n += 12;
-    } else
-#pragma unroll
-    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-      const uint64_t adv = static_cast<uint64_t>((ks * UMMA_K * 4) >> 4);   // 32 B per k-step
-      const uint32_t d0 = tmem + (n & amask) * ubq, d1 = tmem + ((n + 1) & amask) * ubq, d2 = tmem + ((n + 2) & amask) * ubq;
+  const uint32_t acc = tmem + static_cast<uint32_t>(ii * bq);
+  for (int kb = 0; kb < nk; ++kb, ++kt) {
+    if (kt % NISSUE == static_cast<uint32_t>(ii)) {
+      mbar_wait(c.bar_split + 8 * r.s, r.ph);
+      tc_fence_after();
+      __syncwarp();
+      const bool leader = elect_one();
+      if (trace && leader && kb < 32) trace[180 + kb] = clock64();
+      const uint32_t stage = ring0 + static_cast<uint32_t>(r.s) * STAGE_BYTES;
+      const uint64_t dQh = make_desc(stage + P_BYTES);
+      const uint64_t dQl = make_desc(stage + P_BYTES + Q_BYTES_MAX);
+      const uint32_t a_hi = tmem + TMEM_A_BASE + 64 * r.s;
       if (leader) {
-        tc_mma_tf32_ts(d0, a_lo + ks * UMMA_K, dQh + adv, idesc, n >= unacc ? 1u : 0u);
-        tc_mma_tf32_ts(d1, a_hi + ks * UMMA_K, dQl + adv, idesc, n + 1 >= unacc ? 1u : 0u);
-        tc_mma_tf32_ts(d2, a_hi + ks * UMMA_K, dQh + adv, idesc, n + 2 >= unacc ? 1u : 0u);
+        tc_mma_tf32_katom(acc, a_hi, dQh, dQl, idesc, n ? 1u : 0u);
+        tc_commit(c.bar_empty + 8 * r.s);
       }
-      n += 3;
+      n += 12;
+      __syncwarp();
     }
-    if (leader) {
-      tc_commit(c.bar_empty + 8 * r.s);
-      if (last && kb == nk - 1) tc_commit(c.bar_acc);
-    }
-    __syncwarp();
     r.next();
+  }
+  if (last) {
+    __syncwarp();
+    if (elect_one()) tc_commit(c.bar_acc);
+    __syncwarp();
   }
 }
 
@@ -233,20 +229,29 @@ __device__ __forceinline__ void epi_store16(const EpiParams &e, const uint32_t (
   }
 }
 
-__device__ __forceinline__ void epi_zc16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0) {
+// previous word of the 16 decode rows [r0, r0 + 16): one load per lane (lanes 0..15), then broadcast -- a single
+// memory round trip for the whole chunk instead of one per row in front of the dependent table loads
+__device__ __forceinline__ void load_tokens16(const int64_t *tok_prev, int r0, int rows, int lane, long long (&tk)[16]) {
+  long long mine = -1;
+  if (tok_prev && lane < 16 && r0 + lane < rows) mine = tok_prev[r0 + lane];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tk[i] = __shfl_sync(0xffffffffu, mine, i);
+}
+
+__device__ __forceinline__ void epi_zc16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0, int lane) {
+  long long tk[16];
+  const bool emb = e.prev2out && e.tok_prev;
+  if (emb) load_tokens16(e.tok_prev, r0, e.rows, lane, tk);
   if (!jok) return;
   const float b = __ldg(e.bz + j);
+  float add[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    add[i] = (emb && r0 + i < e.rows && tk[i] >= 0) ? __ldg(e.Wemb + static_cast<size_t>(tk[i]) * e.E + j) : 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int r = r0 + i;
-    if (r < e.rows) {
-      float z = __uint_as_float(v[i]) + b;
-      if (e.prev2out && e.tok_prev) {
-        const long long tok = e.tok_prev[r];
-        if (tok >= 0) z += __ldg(e.Wemb + static_cast<size_t>(tok) * e.E + j);
-      }
-      e.zadd[static_cast<size_t>(r) * e.E + j] = z;
-    }
+    if (r < e.rows) e.zadd[static_cast<size_t>(r) * e.E + j] = (__uint_as_float(v[i]) + b) + add[i];
   }
 }
 
@@ -268,20 +273,22 @@ __device__ __forceinline__ void epi_z16(const EpiParams &e, const uint32_t (&v)[
 // creg != null: the cell state of this thread's 16 (row, unit) pairs lives in registers across decode steps
 // (persistent kernel) instead of c_in / c_out.
 __device__ __forceinline__ void epi_gates16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0,
-                                            float *creg, bool creg_load) {
+                                            int lane, float *creg, bool creg_load) {
   const int H = e.H;
   const int u = j >> 2, g = j & 3;
-  const float *ew[16];
+  long long tk[16];
+  load_tokens16(e.tok_prev, r0, e.rows, lane, tk);
   float xw[16], cprev[16];
-  // every load of the chunk first
+  // every table / state load of the chunk in flight together
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool ok = jok && r0 + i < e.rows;
+    xw[i] = ok ? __ldg(e.EWi + static_cast<size_t>(tk[i] >= 0 ? tk[i] : e.V) * 4 * H + j) : 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int r = r0 + i;
     const bool ok = jok && r < e.rows;
-    long long tok = -1;
-    if (ok && e.tok_prev) tok = e.tok_prev[r];
-    ew[i] = e.EWi + static_cast<size_t>(tok >= 0 ? tok : e.V) * 4 * H + j;
-    xw[i] = ok ? __ldg(ew[i]) : 0.f;
     cprev[i] = 0.f;
     if (ok && g == 0) {
       if (creg && !creg_load) cprev[i] = creg[i];
@@ -391,8 +398,8 @@ __device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int k
     acc_ld16(trow, cc, bq, nacc, v);
     const int r0 = q0 + cc;
     if (kind == FE_STORE) epi_store16(e, v, j, jok, r0);
-    else if (kind == FE_GATES) epi_gates16(e, v, j, jok, r0, creg, creg_load);
-    else if (kind == FE_ZC) epi_zc16(e, v, j, jok, r0);
+    else if (kind == FE_GATES) epi_gates16(e, v, j, jok, r0, lane, creg, creg_load);
+    else if (kind == FE_ZC) epi_zc16(e, v, j, jok, r0, lane);
     else epi_z16(e, v, j, jok, r0);
   }
 }

@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(NROLE, 1)
   if (warp == 0) {
     if (lane == 0) produce(c, r, tmP, prow, tmQ, qrow, 0, nk, a.mp, a.bq, pol_p, pol_q, trace);
     __syncwarp();
-  } else if (warp == 1) {
-    uint32_t n = 0;
-    issue(c, r, nk, a.bq, a.nacc, n, true, lane, trace);
+  } else if (warp == 1 || warp >= 10) {
+    uint32_t kt = 0, n = 0;
+    issue(c, r, nk, a.bq, warp == 1 ? 0 : warp - 9, kt, n, true, trace);
   } else {
     uint32_t kc = 0;
     split(c, r, nk, a.mp, a.bq, kc, warp, lane, trace);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NROLE, 1)
     if (trace && threadIdx.x == 64) trace[140] = clock64();
     EpiParams e = a.e;
     if (kind == FE_PICK) e.part0 = 2 * local;
-    epilogue(c, e, kind, a.mp, a.bq, a.nacc, f0, nfeat, q0, warp, lane, nullptr, false);
+    epilogue(c, e, kind, a.mp, a.bq, nk < NISSUE ? nk : NISSUE, f0, nfeat, q0, warp, lane, nullptr, false);
     if (trace && threadIdx.x == 64) trace[141] = clock64();
   }
   cta_teardown(c);
