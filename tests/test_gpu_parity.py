@@ -344,7 +344,8 @@ def test_beam_k1_equals_greedy_and_limits(torch_cuda):
         assert all(np.array_equal(np.asarray(a[1]), np.asarray(b[1])) for a, b in zip(got3, want3))
     for b in range(4):
         assert got[b][0] == [[int(t) for t in toks[b, :lens[b]]]]
-        np.testing.assert_allclose(got[b][1][0], scores[b], atol=1e-5)
+        # greedy runs the fused step kernels, the beam search the separate ones: same math, different fp32 summation order
+        np.testing.assert_allclose(got[b][1][0], scores[b], atol=TOL_LP, rtol=4e-6)
     from video_description_with_spatial_temporal_attention_b200 import _lib
     with pytest.raises(_lib.StatError):
         model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=17, maxlen=8)

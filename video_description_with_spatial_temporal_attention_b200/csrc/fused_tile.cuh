@@ -29,18 +29,38 @@ constexpr int BP = 128;                    // tile rows (TMEM lanes)
 constexpr int BK = 32;                     // fp32 per k-atom row = 128 B = one swizzle row
 constexpr int UMMA_K = 8;                  // tf32 MMA K
 constexpr int NSPLIT = 256;                // splitter / epilogue threads (warps 2..9)
-constexpr int NISSUE = 2;                  // MMA-issuing warps: warp 1 and warps 10 .. 10 + NISSUE - 2
+constexpr int NISSUE = 1;                  // MMA-issuing warps: warp 1 and warps 10 .. 10 + NISSUE - 2 (a second issuer
+                                           // was measured: no gain, the mainloop is bound by the latency of a stage round)
 constexpr int NROLE = 64 + NSPLIT + 32 * (NISSUE - 1);   // + TMA producer warp (0) + MMA issuer warps
-constexpr int STAGES = 4;
-constexpr int P_BYTES = BP * BK * 4;       // 16 KB
-constexpr int QMAX = 128;
-constexpr int Q_BYTES_MAX = QMAX * BK * 4; // 16 KB
-constexpr int STAGE_BYTES = P_BYTES + 2 * Q_BYTES_MAX;      // raw P | Q hi | Q lo
-constexpr int RING_BYTES = STAGES * STAGE_BYTES;            // 192 KB
+constexpr int MAX_STAGES = 8;
+constexpr int RING_BYTES = 192 * 1024;
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + BAR_BYTES;
 constexpr int TMEM_COLS = 512;
-constexpr int TMEM_A_BASE = 256;           // A-operand stage s: hi at 256 + 64 s (32 cols), lo 32 cols further
+
+// Ring geometry of a tile shape.  A stage = raw P tile (mp x 128 B) | Q hi (bq x 128 B) | Q lo; its A operand
+// (hi 32 columns | lo 32 columns) sits in tensor-memory columns a_base + 64 s, behind the accumulators.  One stage
+// round (TMA issue -> arrival -> split -> MMA -> commit -> refill) takes ~2800 cycles (measured), so the mainloop
+// runs at nst / 2800 k-atoms per cycle: as many stages as tensor memory (64 columns each) and shared memory allow.
+struct Geo {
+  int nst;            // stages
+  int stage_bytes;
+  int q_off;          // Q hi from the stage start
+  int qlo_off;        // Q lo from Q hi
+  int a_base;         // first tensor-memory column of the A stages
+};
+__host__ __device__ inline Geo make_geo(int mp, int bq) {
+  Geo g;
+  g.q_off = mp * BK * 4;
+  g.qlo_off = bq * BK * 4;
+  g.stage_bytes = g.q_off + 2 * g.qlo_off;
+  g.a_base = (NISSUE * bq <= 128) ? 128 : 256;
+  int n = (TMEM_COLS - g.a_base) / 64;
+  if (n > RING_BYTES / g.stage_bytes) n = RING_BYTES / g.stage_bytes;
+  if (n > MAX_STAGES) n = MAX_STAGES;
+  g.nst = n;
+  return g;
+}
 
 using EpiParams = FusedEpi;
 
@@ -50,11 +70,15 @@ struct Cta {
   uint32_t tmem;
 };
 
+// ring position of one role: stage index and, per stage, the parity of the phase it is in (a bit per stage, so
+// that tiles with different stage counts can follow each other on the same barriers)
 struct Ring {
   int s;
-  uint32_t ph;
-  __device__ __forceinline__ void next() {
-    if (++s == STAGES) { s = 0; ph ^= 1; }
+  uint32_t bits;
+  __device__ __forceinline__ uint32_t ph() const { return (bits >> s) & 1u; }
+  __device__ __forceinline__ void next(int nst) {
+    bits ^= 1u << s;
+    if (++s == nst) s = 0;
   }
 };
 
@@ -64,11 +88,11 @@ __device__ __forceinline__ void cta_setup(Cta &c, uint8_t *smem_raw, uint32_t *t
   c.ring = smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING_BYTES);
   c.bar_full = smem_u32(bars);
-  c.bar_split = c.bar_full + 8 * STAGES;
-  c.bar_empty = c.bar_split + 8 * STAGES;
-  c.bar_acc = c.bar_empty + 8 * STAGES;
+  c.bar_split = c.bar_full + 8 * MAX_STAGES;
+  c.bar_empty = c.bar_split + 8 * MAX_STAGES;
+  c.bar_acc = c.bar_empty + 8 * MAX_STAGES;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(c.bar_full + 8 * s, 1);
       mbar_init(c.bar_split + 8 * s, 4);          // one arrival per warp of the splitter group that owns the k-atom
       mbar_init(c.bar_empty + 8 * s, 1);
@@ -95,16 +119,16 @@ __device__ __forceinline__ void cta_teardown(const Cta &c) {
 // producer: one thread.  k-atoms [kb0, kb1) of the P rows [prow, prow+mp) and the Q rows [qrow, qrow+bq)
 // (mp = rows of the P box: 128, or 64 / 32 for half / quarter tiles -- the remaining lanes then hold garbage)
 __device__ __forceinline__ void produce(const Cta &c, Ring &r, const CUtensorMap *tmP, int prow, const CUtensorMap *tmQ,
-                                        int qrow, int kb0, int kb1, int mp, int bq, unsigned long long pol_p,
+                                        int qrow, int kb0, int kb1, const Geo &g, unsigned long long pol_p,
                                         unsigned long long pol_q, long long *trace = nullptr) {
   for (int kb = kb0; kb < kb1; ++kb) {
-    mbar_wait(c.bar_empty + 8 * r.s, r.ph ^ 1);
+    mbar_wait(c.bar_empty + 8 * r.s, r.ph() ^ 1u);
     if (trace && kb - kb0 < 32) trace[100 + kb - kb0] = clock64();
-    const uint32_t stage = smem_u32(c.ring + r.s * STAGE_BYTES);
-    mbar_expect_tx(c.bar_full + 8 * r.s, static_cast<uint32_t>((mp + bq) * BK * 4));
+    const uint32_t stage = smem_u32(c.ring + r.s * g.stage_bytes);
+    mbar_expect_tx(c.bar_full + 8 * r.s, static_cast<uint32_t>(g.q_off + g.qlo_off));
     tma_load_2d(stage, tmP, kb * BK, prow, c.bar_full + 8 * r.s, pol_p);
-    tma_load_2d(stage + P_BYTES, tmQ, kb * BK, qrow, c.bar_full + 8 * r.s, pol_q);
-    r.next();
+    tma_load_2d(stage + g.q_off, tmQ, kb * BK, qrow, c.bar_full + 8 * r.s, pol_q);
+    r.next(g.nst);
   }
 }
 
@@ -119,23 +143,23 @@ __device__ __forceinline__ void produce(const Cta &c, Ring &r, const CUtensorMap
 // tcgen05.mma in an ELECT / R2UR / branch loop (measured 110-170 cycles per MMA).
 // `n` = products this issuer has issued for the tile (0 = its first one overwrites its accumulator); `last`: the
 // tile is complete after these k-atoms (every issuer commits to bar_acc, which expects NISSUE arrivals).
-__device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, int ii, uint32_t &kt, uint32_t &n,
-                                      bool last, long long *trace = nullptr) {
+__device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, const Geo &g, int ii, uint32_t &kt,
+                                      uint32_t &n, bool last, long long *trace = nullptr) {
   const uint32_t idesc = make_idesc_tf32(BP, bq);
   const uint32_t tmem = __shfl_sync(0xffffffffu, c.tmem, 0);
   const uint32_t ring0 = __shfl_sync(0xffffffffu, smem_u32(c.ring), 0);
   const uint32_t acc = tmem + static_cast<uint32_t>(ii * bq);
   for (int kb = 0; kb < nk; ++kb, ++kt) {
     if (kt % NISSUE == static_cast<uint32_t>(ii)) {
-      mbar_wait(c.bar_split + 8 * r.s, r.ph);
+      mbar_wait(c.bar_split + 8 * r.s, r.ph());
       tc_fence_after();
       __syncwarp();
       const bool leader = elect_one();
       if (trace && leader && kb < 32) trace[180 + kb] = clock64();
-      const uint32_t stage = ring0 + static_cast<uint32_t>(r.s) * STAGE_BYTES;
-      const uint64_t dQh = make_desc(stage + P_BYTES);
-      const uint64_t dQl = make_desc(stage + P_BYTES + Q_BYTES_MAX);
-      const uint32_t a_hi = tmem + TMEM_A_BASE + 64 * r.s;
+      const uint32_t stage = ring0 + static_cast<uint32_t>(r.s * g.stage_bytes);
+      const uint64_t dQh = make_desc(stage + g.q_off);
+      const uint64_t dQl = make_desc(stage + g.q_off + g.qlo_off);
+      const uint32_t a_hi = tmem + g.a_base + 64 * r.s;
       if (leader) {
         tc_mma_tf32_katom(acc, a_hi, dQh, dQl, idesc, n ? 1u : 0u);
         tc_commit(c.bar_empty + 8 * r.s);
@@ -143,7 +167,7 @@ __device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, int
       n += 12;
       __syncwarp();
     }
-    r.next();
+    r.next(g.nst);
   }
   if (last) {
     __syncwarp();
@@ -157,22 +181,22 @@ __device__ __forceinline__ void issue(const Cta &c, Ring &r, int nk, int bq, int
 // fence) overlap the other group's.  `kc` = k-atoms this CTA has split so far (both groups count all of them).
 // P: a thread owns tile row prow (= its TMEM lane) and all 32 k-columns, in two halves of 16; the TMA tile is
 // SWIZZLE_128B (16-byte chunk c of row r sits at chunk c ^ (r & 7)).  Q: hi in place, lo beside it.
-__device__ __forceinline__ void split(const Cta &c, Ring &r, int nk, int mp, int bq, uint32_t &kc, int warp, int lane,
-                                      long long *trace = nullptr) {
+__device__ __forceinline__ void split(const Cta &c, Ring &r, int nk, int mp, int bq, const Geo &g, uint32_t &kc,
+                                      int warp, int lane, long long *trace = nullptr) {
   const int grp = (warp - 2) >> 2;
   const int tg = ((warp - 2) & 3) * 32 + lane;       // 0..127 inside the group
   const int prow = (warp & 3) * 32 + lane;
   const int nq4 = bq * (BK / 4);                     // 16-byte chunks of the Q tile
   for (int kb = 0; kb < nk; ++kb, ++kc) {
     if ((kc & 1u) == static_cast<uint32_t>(grp)) {
-      mbar_wait(c.bar_full + 8 * r.s, r.ph);
+      mbar_wait(c.bar_full + 8 * r.s, r.ph());
       if (trace && tg == 0 && kb < 32) trace[2 + kb] = clock64();
-      uint8_t *stage = c.ring + r.s * STAGE_BYTES;
+      uint8_t *stage = c.ring + r.s * g.stage_bytes;
       const uint8_t *rowp = stage + prow * 128;
-      float4 *Qh = reinterpret_cast<float4 *>(stage + P_BYTES);
-      float4 *Ql = reinterpret_cast<float4 *>(stage + P_BYTES + Q_BYTES_MAX);
+      float4 *Qh = reinterpret_cast<float4 *>(stage + g.q_off);
+      float4 *Ql = reinterpret_cast<float4 *>(stage + g.q_off + g.qlo_off);
       if ((warp & 3) * 32 < mp) {
-        const uint32_t ta = c.tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + TMEM_A_BASE + 64 * r.s;
+        const uint32_t ta = c.tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g.a_base + 64 * r.s;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float4 xp[4];
@@ -209,7 +233,7 @@ __device__ __forceinline__ void split(const Cta &c, Ring &r, int nk, int mp, int
       if (lane == 0) mbar_arrive(c.bar_split + 8 * r.s);
       if (trace && tg == 0 && kb < 32) trace[36 + kb] = clock64();
     }
-    r.next();
+    r.next(g.nst);
   }
 }
 

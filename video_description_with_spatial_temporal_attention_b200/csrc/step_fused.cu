@@ -68,15 +68,16 @@ __global__ void __launch_bounds__(NROLE, 1)
   long long *trace = (a.trace && blockIdx.x == 0) ? a.trace : nullptr;
   if (trace && threadIdx.x == 0) trace[1] = clock64();
   Ring r = {0, 0};
+  const Geo g = make_geo(a.mp, a.bq);
   if (warp == 0) {
-    if (lane == 0) produce(c, r, tmP, prow, tmQ, qrow, 0, nk, a.mp, a.bq, pol_p, pol_q, trace);
+    if (lane == 0) produce(c, r, tmP, prow, tmQ, qrow, 0, nk, g, pol_p, pol_q, trace);
     __syncwarp();
   } else if (warp == 1 || warp >= 10) {
     uint32_t kt = 0, n = 0;
-    issue(c, r, nk, a.bq, warp == 1 ? 0 : warp - 9, kt, n, true, trace);
+    issue(c, r, nk, a.bq, g, warp == 1 ? 0 : warp - 9, kt, n, true, trace);
   } else {
     uint32_t kc = 0;
-    split(c, r, nk, a.mp, a.bq, kc, warp, lane, trace);
+    split(c, r, nk, a.mp, a.bq, g, kc, warp, lane, trace);
     mbar_wait(c.bar_acc, 0);
     tc_fence_after();
     if (trace && threadIdx.x == 64) trace[140] = clock64();
