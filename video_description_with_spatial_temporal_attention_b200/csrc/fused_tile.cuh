@@ -309,6 +309,13 @@ __device__ __forceinline__ void epi_gates16(const EpiParams &e, const uint32_t (
     const bool ok = jok && r0 + i < e.rows;
     xw[i] = ok ? __ldg(e.EWi + static_cast<size_t>(tk[i] >= 0 ? tk[i] : e.V) * 4 * H + j) : 0.f;
   }
+  if (e.hu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const bool ok = jok && r0 + i < e.rows;
+      if (ok) xw[i] += e.hu[static_cast<size_t>(r0 + i) * e.ld_hu + j];     // h_{t-1}.U (the previous step's C launch)
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int r = r0 + i;

@@ -145,6 +145,7 @@ struct FusedEpi {
   // FE_GATES (model_attention.py:437-457) on gate-interleaved features j = 4*unit + gate
   int H, V;
   const float *EWi;                  // (V+1, 4H) gate-interleaved token table (row V = bias alone)
+  const float *hu; int ld_hu;        // (rows, ld_hu) h_{t-1}.U, gate-interleaved, or null
   const int64_t *tok_prev;           // (rows) or null = no previous word
   const float *mask;                 // (rows) or null
   const float *dp_gates;             // (rows, 3H) or null = 0.5

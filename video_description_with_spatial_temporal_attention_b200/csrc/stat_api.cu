@@ -97,10 +97,11 @@ struct Prep {
   size_t EW;     // (V+1, 4H): token -> emb.W + b ; row V = b
   size_t Wemb;   // (V, E) copy (prev2out add)
   // fused step (step_fused.cu)
-  size_t WxhT;   // (4H+E, 2H): rows 4u+g = [Wc[:, gH+u] | U[:, gH+u]] (gate-interleaved, K = [ctx | h_]);
-                 //             rows 4H.. = [ff_logit_ctxglm_W[:, e] | 0]
-  size_t WqT;    // (4H+1+E, H): Wdl | Wdg | Wdm | Wdlt | W_sel | ff_logit_lstm_W
-  size_t bq;     // (4H+1)    : 0 | 0 | 0 | blt | b_sel
+  size_t WcI;    // (4H+E, H): rows 4u+g = Wc[:, gH+u] (gate-interleaved: the four gates of a unit adjacent);
+                 //            rows 4H.. = ff_logit_ctxglm_W[:, e]                          -- multiplies ctx
+  size_t WqT;    // (8H+1+E, H): Wdl | Wdg | Wdm | Wdlt | W_sel | U (gate-interleaved rows) | ff_logit_lstm_W
+                 //                                                                          -- multiplies h
+  size_t bq;     // (8H+1)    : 0 | 0 | 0 | blt | b_sel | 0 (4H)
   size_t bdi;    // (4H)      : decoder_b, gate-interleaved
   size_t total;  // floats
   int NH, NC;
@@ -144,9 +145,9 @@ Prep prep_layout(const StatDims &d) {
   p.U4 = take(4 * H + 4);
   p.EW = take((V + 1) * 4 * H);
   p.Wemb = take(V * E);
-  p.WxhT = take((4 * H + E) * 2 * H);
-  p.WqT = take((4 * H + 1 + E) * H);
-  p.bq = take(4 * H + 1);
+  p.WcI = take((4 * H + E) * H);
+  p.WqT = take((8 * H + 1 + E) * H);
+  p.bq = take(8 * H + 1);
   p.bdi = take(4 * H);
   p.total = o;
   return p;
@@ -165,7 +166,7 @@ struct Ws {
   size_t counters, tok_prev, alive;  // byte-typed regions (still float offsets)
   size_t hb, cb, cand_cost, cand_word, hist, hist_len, bscore, src_row, row_clip, dead_k, bdone;   // beam search
   size_t lpc;                        // Kahan compensation of the teacher-forced log-prob accumulation
-  size_t xh[2], hq, part, tgt;       // fused step: [ctx | h] activation rows (double-buffered), queries, vocabulary partials
+  size_t hq, part, tgt;              // fused step: [queries | selector logit | h.U] rows, vocabulary partials
   int ldq2, npart;
   size_t total;                      // floats
   int ldhp, ldpc, ldl, S, Tc;
@@ -267,10 +268,8 @@ Ws ws_layout(const StatDims &d, int rows) {
   w.row_clip = take(n);
   w.dead_k = take(n);
   w.bdone = take(n);
-  w.ldq2 = static_cast<int>(up(4 * H + 1, 4));
+  w.ldq2 = static_cast<int>(up(8 * H + 1, 4));
   w.npart = 2 * static_cast<int>((V + 127) / 128);
-  w.xh[0] = take(n * 2 * H);
-  w.xh[1] = take(n * 2 * H);
   w.hq = take(n * w.ldq2);
   w.part = take(n * w.npart * 4);
   w.tgt = take(n);
@@ -533,10 +532,9 @@ int step_out(const StatDims &d, const Prep &p, const float *P, const Ws &w, floa
 
 
 // ---------------------------------------------------------------------------
-// fused decode step (step_fused.cu): attention -> B (gates fused) -> C (queries + readout activation) on the
-// caller's stream, logits (partial vocabulary reduction fused) -> combine beside the next attention.
-// Activations live in two [ctx | h] row buffers: step t reads xh[t & 1] = [ctx_t | h_{t-1}] and writes h_t into
-// xh[(t+1) & 1] (the gate tiles of one launch read every h_{t-1} column while others already write h_t).
+// fused decode step (step_fused.cu): attention -> B (ctx.Wc, gates fused) -> C (everything that multiplies the new
+// h: next queries, selector logit, h.U of the next cell, readout activation) on the caller's stream, logits (partial
+// vocabulary reduction fused) -> combine beside the next attention.
 // ---------------------------------------------------------------------------
 bool fused_enabled(const StatDims &d, int rows) {
   static int on = -1;
@@ -548,36 +546,36 @@ bool fused_enabled(const StatDims &d, int rows) {
 }
 
 AttArgs att_args_fused(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, int rows,
-                       const int32_t *row_clip, float *att_scores, float *alpha_l, int t) {
+                       const int32_t *row_clip, float *att_scores, float *alpha_l) {
   AttArgs a = att_args(d, p, P, w, W, rows, row_clip, att_scores, alpha_l);
   const int H = d.H;
   a.hp = W + w.hq; a.ldhp = w.ldq2; a.hp_parts = 1; a.hp_plane = 0;
   a.off_sl = 0; a.off_sg = H; a.off_sm = 2 * H; a.off_slt = 3 * H; a.off_sel = 4 * H;
-  a.ctx = W + w.xh[t & 1];
-  a.ldctx = 2 * H;
   return a;
 }
 
-// B: gates (S10-S13) from [ctx_t | h_{t-1}] and the readout addend; new state -> xh[(t+1)&1], c in place
-int fstep_gates(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io, int t,
+// B: gate pre-activations ctx_t.Wc + h_{t-1}.U (from C of the previous step) + EW[word], S10-S13 in the epilogue;
+// the readout addend bz + ctx.Wctx (+ Wemb[word]) rides in the same launch.  h, c updated in place.
+int fstep_gates(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io,
                 cudaStream_t st) {
   const int H = d.H, E = d.E;
   FusedPhase f;
   memset(&f, 0, sizeof(f));
   f.swap = 1;
-  f.W = P + p.WxhT; f.wrows = 4 * H + E; f.wK = 2 * H; f.ldw = 2 * H;
-  f.X[0] = W + w.xh[t & 1]; f.xK[0] = 2 * H; f.ldx[0] = 2 * H;
+  f.W = P + p.WcI; f.wrows = 4 * H + E; f.wK = H; f.ldw = H;
+  f.X[0] = W + w.ctx; f.xK[0] = H; f.ldx[0] = H;
   f.rows = io.rows;
   f.nseg = 2;
-  f.seg[0] = FusedSegment{FE_GATES, 0, 4 * H, 2 * H, 0};
+  f.seg[0] = FusedSegment{FE_GATES, 0, 4 * H, H, 0};
   f.seg[1] = FusedSegment{FE_ZC, 4 * H, E, H, 0};
   FusedEpi &e = f.e;
   e.H = H; e.V = d.V; e.E = E;
   e.EWi = P + p.EW;
+  e.hu = W + w.hq + 4 * H + 1; e.ld_hu = w.ldq2;
   e.tok_prev = io.tok_prev; e.mask = io.mask; e.dp_gates = io.dp_gates;
   e.c_in = W + w.c; e.c_out = W + w.c;
-  e.h_in = W + w.xh[t & 1] + H; e.ld_hin = 2 * H;
-  e.h_out = W + w.xh[(t + 1) & 1] + H; e.ld_hout = 2 * H;
+  e.h_in = W + w.h; e.ld_hin = H;
+  e.h_out = W + w.h; e.ld_hout = H;
   e.h_copy = nullptr;
   e.h_all = io.h_all;
   e.hd_out = io.dp_h ? W + w.hd : nullptr; e.dp_h = io.dp_h;
@@ -586,22 +584,21 @@ int fstep_gates(const StatDims &d, const Prep &p, const float *P, const Ws &w, f
   return fused_phase_launch(f, st);
 }
 
-// C: what multiplies h (held in xh[buf]): the attention queries / selector logit of the next cell (want_q) and the
-// readout activation z of this step (want_z; with explicit dropout on h the readout reads h * dp_h instead)
-int fstep_hidden(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io, int buf,
+// C: what multiplies h: the attention queries / selector logit / h.U of the next cell (want_q) and the readout
+// activation z of this step (want_z; with explicit dropout on h the readout reads h * dp_h instead)
+int fstep_hidden(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io,
                  bool want_q, bool want_z, cudaStream_t st) {
   const int H = d.H, E = d.E;
-  const int nq = 4 * H + ((d.flags & STAT_SELECTOR) ? 1 : 0);
   FusedPhase f;
   memset(&f, 0, sizeof(f));
   f.swap = 1;
-  f.W = P + p.WqT; f.wrows = 4 * H + 1 + E; f.wK = H; f.ldw = H;
-  f.X[0] = W + w.xh[buf] + H; f.xK[0] = H; f.ldx[0] = 2 * H;
+  f.W = P + p.WqT; f.wrows = 8 * H + 1 + E; f.wK = H; f.ldw = H;
+  f.X[0] = W + w.h; f.xK[0] = H; f.ldx[0] = H;
   if (io.dp_h) { f.X[1] = W + w.hd; f.xK[1] = H; f.ldx[1] = H; }
   f.rows = io.rows;
   int n = 0;
-  if (want_q) f.seg[n++] = FusedSegment{FE_STORE, 0, nq, H, 0};
-  if (want_z) f.seg[n++] = FusedSegment{FE_Z, 4 * H + 1, E, H, io.dp_h ? 1 : 0};
+  if (want_q) f.seg[n++] = FusedSegment{FE_STORE, 0, 8 * H + 1, H, 0};
+  if (want_z) f.seg[n++] = FusedSegment{FE_Z, 8 * H + 1, E, H, io.dp_h ? 1 : 0};
   f.nseg = n;
   FusedEpi &e = f.e;
   e.E = E;
@@ -632,17 +629,17 @@ int fstep_vocab(const StatDims &d, const Prep &p, const float *P, const Ws &w, f
   return pick_combine_launch(k, W + w.part, w.npart, W + w.tgt, st);
 }
 
-// initial state of the B rows -> xh[0] h part and c; queries of the first cell
+// initial state of the rows -> h, c; queries / h.U of the first cell
 int fused_begin(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, int rows, cudaStream_t st) {
   const int H = d.H;
-  STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.xh[0] + H, sizeof(float) * 2 * H, W + w.h0c0, sizeof(float) * 2 * H,
+  STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.h, sizeof(float) * H, W + w.h0c0, sizeof(float) * 2 * H,
                                     sizeof(float) * H, rows, cudaMemcpyDeviceToDevice, st));
   STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
                                     sizeof(float) * H, rows, cudaMemcpyDeviceToDevice, st));
   StepIO io;
   memset(&io, 0, sizeof(io));
   io.rows = rows;
-  return fstep_hidden(d, p, P, w, W, io, 0, true, false, st);
+  return fstep_hidden(d, p, P, w, W, io, true, false, st);
 }
 
 // The readout chain of step t (step_out + the vocabulary reduction) on a side stream, next to the
@@ -898,17 +895,18 @@ int stat_prepare_params(const StatDims *d, const StatParams *sp, void *prepared,
   STAT_TRY(dense(P + p.Wemb, E, V, P + p.WdT, E, 4 * H, P + p.bdi, P + p.EW, 4 * H, 0, 1.f, 1.f, nullptr, 0,
                  st));
   STAT_CUDA_CHECK(cp(p.EW + static_cast<size_t>(V) * 4 * H, P + p.bdi, 4 * H));
-  // fused step: [ctx | h_] . [Wc ; U] on gate-interleaved rows, the ctx -> readout rows behind them
-  STAT_TRY(transpose_il_launch(sp->decoder_Wc, H, H, P + p.WxhT, 2 * H, 0, st));
-  STAT_TRY(transpose_il_launch(sp->decoder_U, H, H, P + p.WxhT, 2 * H, H, st));
-  if (c2o) STAT_TRY(transpose_launch(sp->ff_logit_ctxglm_W, H, E, P + p.WxhT, 2 * H, 4 * H, st));
-  // everything that multiplies the new hidden state: next step's attention queries, selector logit, readout
+  // fused step: ctx . Wc on gate-interleaved rows, the ctx -> readout rows behind them
+  STAT_TRY(transpose_il_launch(sp->decoder_Wc, H, H, P + p.WcI, H, 0, st));
+  if (c2o) STAT_TRY(transpose_launch(sp->ff_logit_ctxglm_W, H, E, P + p.WcI, H, 4 * H, st));
+  // everything that multiplies the new hidden state: next step's attention queries, selector logit, h.U of the
+  // next cell (gate-interleaved like ctx.Wc), readout
   STAT_TRY(transpose_launch(sp->decoder_Wdl_att, H, H, P + p.WqT, H, 0, st));
   STAT_TRY(transpose_launch(sp->decoder_Wdg_att, H, H, P + p.WqT, H, H, st));
   STAT_TRY(transpose_launch(sp->decoder_Wdm_att, H, H, P + p.WqT, H, 2 * H, st));
   STAT_TRY(transpose_launch(sp->decoder_Wdlt_att, H, H, P + p.WqT, H, 3 * H, st));
   if (sel) STAT_CUDA_CHECK(cp(p.WqT + static_cast<size_t>(4) * H * H, sp->decoder_W_sel, H));
-  STAT_TRY(transpose_launch(sp->ff_logit_lstm_W, H, E, P + p.WqT, H, 4 * H + 1, st));
+  STAT_TRY(transpose_il_launch(sp->decoder_U, H, H, P + p.WqT + static_cast<size_t>(4 * H + 1) * H, H, 0, st));
+  STAT_TRY(transpose_launch(sp->ff_logit_lstm_W, H, E, P + p.WqT, H, 8 * H + 1, st));
   STAT_CUDA_CHECK(cp(p.bq + 3 * H, sp->decoder_blt_att, H));
   if (sel) STAT_CUDA_CHECK(cp(p.bq + 4 * H, sp->decoder_b_sel, 1));
   return STAT_OK;
@@ -1060,7 +1058,7 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
       io.alpha_l = out_alpha_l ? out_alpha_l + static_cast<size_t>(t) * B * T * R : nullptr;
       io.att_scores = want_t ? W + w.att_scores : nullptr;
       {
-        AttArgs a = att_args_fused(*d, p, P, w, W, B, nullptr, io.att_scores, io.alpha_l, t);
+        AttArgs a = att_args_fused(*d, p, P, w, W, B, nullptr, io.att_scores, io.alpha_l);
         ProfScope ps(PH_ATT, st);
         STAT_TRY(att_launch(w, a, st));
       }
@@ -1071,8 +1069,8 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
         if (out_alpha_lt) STAT_TRY(softmax_rows_launch(W + w.att_scores + 2 * n, out_alpha_lt + t * n, B, T, st));
       }
       STAT_TRY(ov.join());                  // zadd / z / partial buffers of the previous step's readout are free
-      STAT_TRY(fstep_gates(*d, p, P, w, W, io, t, st));
-      STAT_TRY(fstep_hidden(*d, p, P, w, W, io, (t + 1) & 1, t + 1 < L, true, st));
+      STAT_TRY(fstep_gates(*d, p, P, w, W, io, st));
+      STAT_TRY(fstep_hidden(*d, p, P, w, W, io, t + 1 < L, true, st));
       STAT_TRY(ov.state_ready());
       PickArgs k;
       memset(&k, 0, sizeof(k));
@@ -1156,13 +1154,13 @@ int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws, int ma
       io.rows = B;
       io.tok_prev = tok_prev;   // -1 on the first step: no previous word (:893, :803-804)
       {
-        AttArgs a = att_args_fused(*d, p, P, w, W, B, nullptr, nullptr, nullptr, t);
+        AttArgs a = att_args_fused(*d, p, P, w, W, B, nullptr, nullptr, nullptr);
         ProfScope ps(PH_ATT, st);
         STAT_TRY(att_launch(w, a, st));
       }
       STAT_TRY(ov.join());                  // the gates need the word picked in the previous step
-      STAT_TRY(fstep_gates(*d, p, P, w, W, io, t, st));
-      STAT_TRY(fstep_hidden(*d, p, P, w, W, io, (t + 1) & 1, t + 1 < maxlen, true, st));
+      STAT_TRY(fstep_gates(*d, p, P, w, W, io, st));
+      STAT_TRY(fstep_hidden(*d, p, P, w, W, io, t + 1 < maxlen, true, st));
       STAT_TRY(ov.state_ready());
       PickArgs k;
       memset(&k, 0, sizeof(k));
