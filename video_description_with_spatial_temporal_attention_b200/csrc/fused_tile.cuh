@@ -240,7 +240,15 @@ __device__ __forceinline__ void split(const Cta &c, Ring &r, int nk, int mp, int
 // ---- epilogues (warps 2..9, after bar_acc) --------------------------------------------------------------
 // swap tiles: lane = feature f0 + wq*32 + lane of the segment, TMEM column = decode row q0 + col; the two warps
 // of a lane quadrant take half of the bq columns each.
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Branch-free activations for the epilogues (ex2.approx + rcp.approx, relative error ~3e-7): the library expf /
+// tanhf / IEEE division carry slow-path branches, and a branch per row keeps the compiler from interleaving the
+// 16 independent rows of a chunk -- the epilogue then runs at the latency of one dependent chain per row
+// (measured: 2400 cycles per row, 38 000 cycles per gate tile).
+__device__ __forceinline__ float sigmoid_f(float x) {
+  return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+}
+__device__ __forceinline__ float tanh_f(float x) { return tanh_fast(fminf(fmaxf(x, -15.0f), 15.0f)); }
+__device__ __forceinline__ float exp_f(float x) { return ex2_approx(1.4426950408889634f * x); }
 
 // one chunk of up to 16 decode rows [r0, r0 + 16) for feature j (index inside the segment)
 __device__ __forceinline__ void epi_store16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0) {
@@ -286,7 +294,7 @@ __device__ __forceinline__ void epi_z16(const EpiParams &e, const uint32_t (&v)[
     const int r = r0 + i;
     if (r < e.rows) {
       const size_t at = static_cast<size_t>(r) * e.E + j;
-      const float x = tanhf(fmaf(e.z_alpha, __uint_as_float(v[i]), e.zadd[at]));
+      const float x = tanh_f(fmaf(e.z_alpha, __uint_as_float(v[i]), e.zadd[at]));
       e.z[at] = x * (e.dp_z ? e.dp_z[at] : 0.5f);
     }
   }
@@ -297,11 +305,13 @@ __device__ __forceinline__ void epi_z16(const EpiParams &e, const uint32_t (&v)[
 // creg != null: the cell state of this thread's 16 (row, unit) pairs lives in registers across decode steps
 // (persistent kernel) instead of c_in / c_out.
 __device__ __forceinline__ void epi_gates16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0,
-                                            int lane, float *creg, bool creg_load) {
+                                            int lane, float *creg, bool creg_load, long long *trace = nullptr) {
   const int H = e.H;
   const int u = j >> 2, g = j & 3;
   long long tk[16];
+  if (trace) trace[150] = clock64();
   load_tokens16(e.tok_prev, r0, e.rows, lane, tk);
+  if (trace) trace[151] = clock64() + (tk[0] & 1);
   float xw[16], cprev[16];
   // every table / state load of the chunk in flight together
 #pragma unroll
@@ -316,6 +326,7 @@ __device__ __forceinline__ void epi_gates16(const EpiParams &e, const uint32_t (
       if (ok) xw[i] += e.hu[static_cast<size_t>(r0 + i) * e.ld_hu + j];     // h_{t-1}.U (the previous step's C launch)
     }
   }
+  if (trace) trace[152] = clock64() + (xw[0] > 1e30f ? 1 : 0);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int r = r0 + i;
@@ -326,6 +337,10 @@ __device__ __forceinline__ void epi_gates16(const EpiParams &e, const uint32_t (
       else cprev[i] = e.c_in[static_cast<size_t>(r) * H + u];
     }
   }
+  if (trace) trace[153] = clock64() + (cprev[0] > 1e30f ? 1 : 0);
+  // activations of all 16 rows (branch-free, independent: the compiler interleaves them)
+  float act[16];
+  const bool cand = g == 3;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int r = r0 + i;
@@ -333,28 +348,44 @@ __device__ __forceinline__ void epi_gates16(const EpiParams &e, const uint32_t (
     const float pre = __uint_as_float(v[i]) + xw[i];
     float dp = 0.5f;
     if (ok && g < 3 && e.dp_gates) dp = e.dp_gates[static_cast<size_t>(r) * 3 * H + g * H + u];
-    const float a = (g == 3) ? tanhf(pre) : sigmoid_f(pre * dp);
-    const float af = __shfl_down_sync(0xffffffffu, a, 1);
-    const float ao = __shfl_down_sync(0xffffffffu, a, 2);
-    const float ag = __shfl_down_sync(0xffffffffu, a, 3);
-    if (ok && g == 0) {
-      const float m = e.mask ? e.mask[r] : 1.0f;
-      const float c_ = cprev[i];
-      float c = af * c_ + a * ag;
-      c = m * c + (1.0f - m) * c_;
-      float h = ao * tanhf(c);
-      if (e.mask) {
-        const float h_ = e.h_in[static_cast<size_t>(r) * e.ld_hin + u];
-        h = m * h + (1.0f - m) * h_;
+    // tanh(x) = 2 sigmoid(2x) - 1: one exponential and one reciprocal per element for every gate
+    const float sg = sigmoid_f(cand ? 2.0f * fminf(fmaxf(pre, -15.0f), 15.0f) : pre * dp);
+    act[i] = cand ? fmaf(2.0f, sg, -1.0f) : sg;
+  }
+  // the four gates of a unit sit in four adjacent lanes: lane g == 0 gathers forget, output, candidate
+  const bool masked = e.mask != nullptr;
+  float mrow[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) mrow[i] = (masked && r0 + i < e.rows) ? e.mask[r0 + i] : 1.0f;
+  float cnew[16], hnew[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float af = __shfl_down_sync(0xffffffffu, act[i], 1);
+    const float ao = __shfl_down_sync(0xffffffffu, act[i], 2);
+    const float ag = __shfl_down_sync(0xffffffffu, act[i], 3);
+    float c = fmaf(af, cprev[i], act[i] * ag);
+    if (masked) c = mrow[i] * c + (1.0f - mrow[i]) * cprev[i];       // :454
+    cnew[i] = c;
+    hnew[i] = ao * tanh_f(c);                                        // :456 (the masked c)
+  }
+  if (jok && g == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = r0 + i;
+      if (r < e.rows) {
+        const float c = cnew[i];
+        float h = hnew[i];
+        if (masked) h = mrow[i] * h + (1.0f - mrow[i]) * e.h_in[static_cast<size_t>(r) * e.ld_hin + u];   // :457
+        if (creg) creg[i] = c;
+        if (e.c_out) e.c_out[static_cast<size_t>(r) * H + u] = c;
+        e.h_out[static_cast<size_t>(r) * e.ld_hout + u] = h;
+        if (e.h_copy) e.h_copy[static_cast<size_t>(r) * H + u] = h;
+        if (e.h_all) e.h_all[static_cast<size_t>(r) * H + u] = h;
+        if (e.dp_h) e.hd_out[static_cast<size_t>(r) * H + u] = h * e.dp_h[static_cast<size_t>(r) * H + u];
       }
-      if (creg) creg[i] = c;
-      if (e.c_out) e.c_out[static_cast<size_t>(r) * H + u] = c;
-      e.h_out[static_cast<size_t>(r) * e.ld_hout + u] = h;
-      if (e.h_copy) e.h_copy[static_cast<size_t>(r) * H + u] = h;
-      if (e.h_all) e.h_all[static_cast<size_t>(r) * H + u] = h;
-      if (e.dp_h) e.hd_out[static_cast<size_t>(r) * H + u] = h * e.dp_h[static_cast<size_t>(r) * H + u];
     }
   }
+  if (trace) trace[154] = clock64();
 }
 
 // normal tiles (FE_PICK): lane = decode row, TMEM column = vocabulary word q0 + col.  Each thread folds its
@@ -367,26 +398,31 @@ struct PickAcc {
 };
 __device__ __forceinline__ void pick_fold16(const EpiParams &e, const uint32_t (&v)[16], int w0, int V, long long tgt_word,
                                             PickAcc &a) {
+  // branch-free: chunk maximum first, one rescale of the running sum, then the 16 exponentials
+  float x[16];
+  float cm = -INFINITY;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int w = w0 + i;
-    if (w < V) {
-      const float x = __uint_as_float(v[i]) + __ldg(e.bv + w);
-      if (w == tgt_word) { a.tv = x; a.thit = 1; }
-      if (x > a.m) {
-        a.s = a.s * expf(a.m - x) + 1.0f;     // exp(-inf) = 0 on the first word
-        a.m = x;
-        a.bi = w;
-      } else {
-        a.s += expf(x - a.m);
-      }
-    }
+    x[i] = (w < V) ? __uint_as_float(v[i]) + __ldg(e.bv + w) : -INFINITY;
+    cm = fmaxf(cm, x[i]);
   }
+  if (cm == -INFINITY) return;                       // a chunk entirely beyond the vocabulary
+  int ci = 0x7fffffff;
+#pragma unroll
+  for (int i = 15; i >= 0; --i) ci = (x[i] == cm) ? w0 + i : ci;       // first word that attains the chunk maximum
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (static_cast<long long>(w0 + i) == tgt_word) { a.tv = x[i]; a.thit = 1; }
+  const float mn = fmaxf(a.m, cm);
+  float s = a.s * exp_f(a.m - mn);                   // exp(-inf) = 0 on the first chunk
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += exp_f(x[i] - mn);                  // words beyond V contribute exp(-inf) = 0
+  a.s = s;
+  if (cm > a.m) a.bi = ci;                           // strictly greater: the earlier chunk keeps ties
+  a.m = mn;
 }
 
-// Whole-tile epilogue.  kind / geometry are uniform over the CTA.
-//   swap tiles:   f0 = first feature of the tile inside its segment, nfeat = features of the segment, q0 = first row
-//   normal tiles: q0 = first vocabulary word of the tile, part = partial slot of this tile's first half
 // v[i] = sum over the rotating accumulators (in order) of columns [col, col + 16)
 __device__ __forceinline__ void acc_ld16(uint32_t trow, int col, int bq, int nacc, uint32_t (&v)[16]) {
   tc_ld16(trow + col, v);
@@ -399,7 +435,8 @@ __device__ __forceinline__ void acc_ld16(uint32_t trow, int col, int bq, int nac
 }
 
 __device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int kind, int mp, int bq, int nacc, int f0,
-                                         int nfeat, int q0, int warp, int lane, float *creg, bool creg_load) {
+                                         int nfeat, int q0, int warp, int lane, float *creg, bool creg_load,
+                                         long long *trace = nullptr) {
   const int wq = warp & 3;
   if (wq * 32 >= mp) return;                             // lanes beyond the tile height hold nothing
   const int chalf = (warp - 2) >> 2;
@@ -426,10 +463,12 @@ __device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int k
   const bool jok = j < nfeat;
   for (int cc = chalf * ch; cc < (chalf + 1) * ch; cc += 16) {
     uint32_t v[16];
+    if (trace && threadIdx.x == 128) trace[148] = clock64();
     acc_ld16(trow, cc, bq, nacc, v);
+    if (trace && threadIdx.x == 128) trace[149] = clock64() + (v[0] == 0x7fffffffu ? 1 : 0);
     const int r0 = q0 + cc;
     if (kind == FE_STORE) epi_store16(e, v, j, jok, r0);
-    else if (kind == FE_GATES) epi_gates16(e, v, j, jok, r0, lane, creg, creg_load);
+    else if (kind == FE_GATES) epi_gates16(e, v, j, jok, r0, lane, creg, creg_load, (trace && threadIdx.x == 128) ? trace : nullptr);
     else if (kind == FE_ZC) epi_zc16(e, v, j, jok, r0, lane);
     else epi_z16(e, v, j, jok, r0);
   }

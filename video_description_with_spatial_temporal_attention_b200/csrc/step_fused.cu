@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(NROLE, 1)
     if (trace && threadIdx.x == 64) trace[140] = clock64();
     EpiParams e = a.e;
     if (kind == FE_PICK) e.part0 = 2 * local;
-    epilogue(c, e, kind, a.mp, a.bq, nk < NISSUE ? nk : NISSUE, f0, nfeat, q0, warp, lane, nullptr, false);
+    epilogue(c, e, kind, a.mp, a.bq, nk < NISSUE ? nk : NISSUE, f0, nfeat, q0, warp, lane, nullptr, false, trace);
     if (trace && threadIdx.x == 64) trace[141] = clock64();
   }
   cta_teardown(c);
