@@ -38,7 +38,7 @@ for kind, label in ((1, 'B: gates tiles (swap, bq=32, 32 k-atoms)'), (0, 'C: que
     rel = lambda i: (t[i] - t0) if t[i] else None
     print(label)
     print('  setup', rel(1), 'acc_ready', rel(140), 'epi_done', rel(141), 'end', rel(142))
-    print('  epilogue (thread 128): acc_ld start/end', rel(148), rel(149), 'gates: start', rel(150), 'tokens', rel(151), 'table+hu', rel(152), 'c', rel(153), 'done', rel(154))
+    print('  epilogue: stage start', rel(148), 'staged', rel(149), 'done', rel(154))
     print('  tma_issue ', [rel(100 + k) for k in range(32)])
     print('  full      ', [rel(2 + k) for k in range(32)])
     print('  split_done', [rel(36 + k) for k in range(32)])

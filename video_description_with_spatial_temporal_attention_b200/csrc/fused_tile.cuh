@@ -238,158 +238,121 @@ __device__ __forceinline__ void split(const Cta &c, Ring &r, int nk, int mp, int
 }
 
 // ---- epilogues (warps 2..9, after bar_acc) --------------------------------------------------------------
-// swap tiles: lane = feature f0 + wq*32 + lane of the segment, TMEM column = decode row q0 + col; the two warps
-// of a lane quadrant take half of the bq columns each.
-// Branch-free activations for the epilogues (ex2.approx + rcp.approx, relative error ~3e-7): the library expf /
-// tanhf / IEEE division carry slow-path branches, and a branch per row keeps the compiler from interleaving the
-// 16 independent rows of a chunk -- the epilogue then runs at the latency of one dependent chain per row
-// (measured: 2400 cycles per row, 38 000 cycles per gate tile).
+// Branch-free activations (ex2.approx + rcp.approx, relative error ~3e-7; the attention kernel's tanh is the same).
 __device__ __forceinline__ float sigmoid_f(float x) {
   return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
 }
 __device__ __forceinline__ float tanh_f(float x) { return tanh_fast(fminf(fmaxf(x, -15.0f), 15.0f)); }
 __device__ __forceinline__ float exp_f(float x) { return ex2_approx(1.4426950408889634f * x); }
 
-// one chunk of up to 16 decode rows [r0, r0 + 16) for feature j (index inside the segment)
-__device__ __forceinline__ void epi_store16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0) {
-  const float b = (jok && e.bias) ? __ldg(e.bias + j) : 0.f;
-  if (!jok) return;
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// v[i] = sum over the accumulators (in order) of columns [col, col + 16) of this thread's lane
+__device__ __forceinline__ void acc_ld16(uint32_t trow, int col, int bq, int nacc, uint32_t (&v)[16]) {
+  tc_ld16(trow + col, v);
+  for (int a = bq; a < nacc * bq; a += bq) {
+    uint32_t w[16];
+    tc_ld16(trow + a + col, w);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int r = r0 + i;
-    if (r < e.rows) e.out[static_cast<size_t>(r) * e.ldo + j] = __uint_as_float(v[i]) + b;
+    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
   }
 }
 
-// previous word of the 16 decode rows [r0, r0 + 16): one load per lane (lanes 0..15), then broadcast -- a single
-// memory round trip for the whole chunk instead of one per row in front of the dependent table loads
-__device__ __forceinline__ void load_tokens16(const int64_t *tok_prev, int r0, int rows, int lane, long long (&tk)[16]) {
-  long long mine = -1;
-  if (tok_prev && lane < 16 && r0 + lane < rows) mine = tok_prev[r0 + lane];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) tk[i] = __shfl_sync(0xffffffffu, mine, i);
-}
+// Swap tiles.  The accumulator tile (lane = feature, column = decode row) is first transposed through shared memory
+// into S[row][feature] (the ring is free once bar_acc has completed), then all 256 epilogue threads walk (row,
+// feature group) items in SHORT ROLLED loops with coalesced global accesses.  A first version kept everything in
+// registers -- 16 rows per thread, fully unrolled -- and ran at the speed of cold instruction fetches: straight-line
+// code that every warp executes once per launch (ncu: `no_instructions` the top stall; 17 000 cycles for 32 stores).
+constexpr int SPAD = 4;     // S row pitch = mp + SPAD floats (16-byte aligned rows)
 
-__device__ __forceinline__ void epi_zc16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0, int lane) {
-  long long tk[16];
-  const bool emb = e.prev2out && e.tok_prev;
-  if (emb) load_tokens16(e.tok_prev, r0, e.rows, lane, tk);
-  if (!jok) return;
-  const float b = __ldg(e.bz + j);
-  float add[16];
+__device__ __forceinline__ void epi_stage(const Cta &c, float *S, int mp, int bq, int nacc, int warp, int lane) {
+  const int wq = warp & 3, chalf = (warp - 2) >> 2, ch = bq >> 1, SP = mp + SPAD;
+  if (wq * 32 < mp) {
+    const uint32_t trow = c.tmem + (static_cast<uint32_t>(wq * 32) << 16);
+#pragma unroll 1
+    for (int cc = chalf * ch; cc < (chalf + 1) * ch; cc += 16) {
+      uint32_t v[16];
+      acc_ld16(trow, cc, bq, nacc, v);
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    add[i] = (emb && r0 + i < e.rows && tk[i] >= 0) ? __ldg(e.Wemb + static_cast<size_t>(tk[i]) * e.E + j) : 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int r = r0 + i;
-    if (r < e.rows) e.zadd[static_cast<size_t>(r) * e.E + j] = (__uint_as_float(v[i]) + b) + add[i];
-  }
-}
-
-__device__ __forceinline__ void epi_z16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0) {
-  if (!jok) return;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int r = r0 + i;
-    if (r < e.rows) {
-      const size_t at = static_cast<size_t>(r) * e.E + j;
-      const float x = tanh_f(fmaf(e.z_alpha, __uint_as_float(v[i]), e.zadd[at]));
-      e.z[at] = x * (e.dp_z ? e.dp_z[at] : 0.5f);
+      for (int i = 0; i < 16; ++i) S[(cc + i) * SP + wq * 32 + lane] = __uint_as_float(v[i]);
     }
   }
+  epi_sync();
 }
 
-// FE_GATES: feature j = 4*u + g (g: 0 input, 1 forget, 2 output, 3 candidate), i.e. the four gates of a hidden
-// unit sit in four adjacent lanes; lane g == 0 gathers them and updates (c, h) of (row, u).
-// creg != null: the cell state of this thread's 16 (row, unit) pairs lives in registers across decode steps
-// (persistent kernel) instead of c_in / c_out.
-__device__ __forceinline__ void epi_gates16(const EpiParams &e, const uint32_t (&v)[16], int j, bool jok, int r0,
-                                            int lane, float *creg, bool creg_load, long long *trace = nullptr) {
-  const int H = e.H;
-  const int u = j >> 2, g = j & 3;
-  long long tk[16];
-  if (trace) trace[150] = clock64();
-  load_tokens16(e.tok_prev, r0, e.rows, lane, tk);
-  if (trace) trace[151] = clock64() + (tk[0] & 1);
-  float xw[16], cprev[16];
-  // every table / state load of the chunk in flight together
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const bool ok = jok && r0 + i < e.rows;
-    xw[i] = ok ? __ldg(e.EWi + static_cast<size_t>(tk[i] >= 0 ? tk[i] : e.V) * 4 * H + j) : 0.f;
-  }
-  if (e.hu) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const bool ok = jok && r0 + i < e.rows;
-      if (ok) xw[i] += e.hu[static_cast<size_t>(r0 + i) * e.ld_hu + j];     // h_{t-1}.U (the previous step's C launch)
+// FE_GATES: S10-S13 (model_attention.py:437-457).  Feature j = 4*unit + gate (0 input, 1 forget, 2 output,
+// 3 candidate): an item = (row, unit) reads its four pre-activations as one float4.  creg != null: the cell state
+// of this thread's items (item k of the thread -> creg[k]) lives in registers across decode steps.
+__device__ __forceinline__ void epi_gates(const EpiParams &e, const float *S, int mp, int bq, int f0, int nfeat, int q0,
+                                          int t, float *creg, bool creg_load) {
+  const int H = e.H, SP = mp + SPAD, nu = mp >> 2, u0 = f0 >> 2;
+  int k = 0;
+#pragma unroll 1
+  for (int it = t; it < bq * nu; it += NSPLIT, ++k) {
+    const int row = it / nu, ul = it - row * nu;
+    const int r = q0 + row, u = u0 + ul;
+    if (r >= e.rows || 4 * u >= nfeat) continue;
+    const float4 a = *reinterpret_cast<const float4 *>(S + row * SP + 4 * ul);
+    const long long tok = e.tok_prev ? e.tok_prev[r] : -1;
+    const float4 ew = __ldg(reinterpret_cast<const float4 *>(e.EWi + static_cast<size_t>(tok >= 0 ? tok : e.V) * 4 * H) + u);
+    float4 hu = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.hu) hu = *reinterpret_cast<const float4 *>(e.hu + static_cast<size_t>(r) * e.ld_hu + 4 * u);
+    const size_t at = static_cast<size_t>(r) * H + u;
+    const float c_ = (creg && !creg_load) ? creg[k] : e.c_in[at];
+    float di = 0.5f, df = 0.5f, dO = 0.5f;
+    if (e.dp_gates) {
+      const float *dp = e.dp_gates + static_cast<size_t>(r) * 3 * H + u;
+      di = dp[0]; df = dp[H]; dO = dp[2 * H];
     }
-  }
-  if (trace) trace[152] = clock64() + (xw[0] > 1e30f ? 1 : 0);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int r = r0 + i;
-    const bool ok = jok && r < e.rows;
-    cprev[i] = 0.f;
-    if (ok && g == 0) {
-      if (creg && !creg_load) cprev[i] = creg[i];
-      else cprev[i] = e.c_in[static_cast<size_t>(r) * H + u];
+    const float ig = sigmoid_f(((a.x + hu.x) + ew.x) * di);
+    const float fg = sigmoid_f(((a.y + hu.y) + ew.y) * df);
+    const float og = sigmoid_f(((a.z + hu.z) + ew.z) * dO);
+    const float gg = tanh_f((a.w + hu.w) + ew.w);
+    float c = fmaf(fg, c_, ig * gg);
+    float m = 1.0f;
+    if (e.mask) {
+      m = e.mask[r];
+      c = m * c + (1.0f - m) * c_;                                         // :454
     }
+    float h = og * tanh_f(c);                                              // :456 (the masked c)
+    if (e.mask) h = m * h + (1.0f - m) * e.h_in[static_cast<size_t>(r) * e.ld_hin + u];   // :457
+    if (creg) creg[k] = c;
+    if (e.c_out) e.c_out[at] = c;
+    e.h_out[static_cast<size_t>(r) * e.ld_hout + u] = h;
+    if (e.h_copy) e.h_copy[at] = h;
+    if (e.h_all) e.h_all[at] = h;
+    if (e.dp_h) e.hd_out[at] = h * e.dp_h[at];
   }
-  if (trace) trace[153] = clock64() + (cprev[0] > 1e30f ? 1 : 0);
-  // activations of all 16 rows (branch-free, independent: the compiler interleaves them)
-  float act[16];
-  const bool cand = g == 3;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int r = r0 + i;
-    const bool ok = jok && r < e.rows;
-    const float pre = __uint_as_float(v[i]) + xw[i];
-    float dp = 0.5f;
-    if (ok && g < 3 && e.dp_gates) dp = e.dp_gates[static_cast<size_t>(r) * 3 * H + g * H + u];
-    // tanh(x) = 2 sigmoid(2x) - 1: one exponential and one reciprocal per element for every gate
-    const float sg = sigmoid_f(cand ? 2.0f * fminf(fmaxf(pre, -15.0f), 15.0f) : pre * dp);
-    act[i] = cand ? fmaf(2.0f, sg, -1.0f) : sg;
-  }
-  // the four gates of a unit sit in four adjacent lanes: lane g == 0 gathers forget, output, candidate
-  const bool masked = e.mask != nullptr;
-  float mrow[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) mrow[i] = (masked && r0 + i < e.rows) ? e.mask[r0 + i] : 1.0f;
-  float cnew[16], hnew[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float af = __shfl_down_sync(0xffffffffu, act[i], 1);
-    const float ao = __shfl_down_sync(0xffffffffu, act[i], 2);
-    const float ag = __shfl_down_sync(0xffffffffu, act[i], 3);
-    float c = fmaf(af, cprev[i], act[i] * ag);
-    if (masked) c = mrow[i] * c + (1.0f - mrow[i]) * cprev[i];       // :454
-    cnew[i] = c;
-    hnew[i] = ao * tanh_f(c);                                        // :456 (the masked c)
-  }
-  if (jok && g == 0) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int r = r0 + i;
-      if (r < e.rows) {
-        const float c = cnew[i];
-        float h = hnew[i];
-        if (masked) h = mrow[i] * h + (1.0f - mrow[i]) * e.h_in[static_cast<size_t>(r) * e.ld_hin + u];   // :457
-        if (creg) creg[i] = c;
-        if (e.c_out) e.c_out[static_cast<size_t>(r) * H + u] = c;
-        e.h_out[static_cast<size_t>(r) * e.ld_hout + u] = h;
-        if (e.h_copy) e.h_copy[static_cast<size_t>(r) * H + u] = h;
-        if (e.h_all) e.h_all[static_cast<size_t>(r) * H + u] = h;
-        if (e.dp_h) e.hd_out[static_cast<size_t>(r) * H + u] = h * e.dp_h[static_cast<size_t>(r) * H + u];
+}
+
+// FE_STORE / FE_ZC / FE_Z: an item = (row, feature); consecutive threads take consecutive features of a row
+__device__ __forceinline__ void epi_rows(const EpiParams &e, int kind, const float *S, int mp, int bq, int f0, int nfeat,
+                                         int q0, int t) {
+  const int SP = mp + SPAD;
+#pragma unroll 1
+  for (int it = t; it < bq * mp; it += NSPLIT) {
+    const int row = it / mp, fl = it - row * mp;
+    const int r = q0 + row, j = f0 + fl;
+    if (r >= e.rows || j >= nfeat) continue;
+    const float acc = S[row * SP + fl];
+    if (kind == FE_STORE) {
+      e.out[static_cast<size_t>(r) * e.ldo + j] = acc + (e.bias ? __ldg(e.bias + j) : 0.f);
+    } else if (kind == FE_ZC) {
+      float z = acc + __ldg(e.bz + j);
+      if (e.prev2out && e.tok_prev) {
+        const long long tok = e.tok_prev[r];
+        if (tok >= 0) z += __ldg(e.Wemb + static_cast<size_t>(tok) * e.E + j);
       }
+      e.zadd[static_cast<size_t>(r) * e.E + j] = z;
+    } else {
+      const size_t at = static_cast<size_t>(r) * e.E + j;
+      e.z[at] = tanh_f(fmaf(e.z_alpha, acc, e.zadd[at])) * (e.dp_z ? e.dp_z[at] : 0.5f);
     }
   }
-  if (trace) trace[154] = clock64();
 }
 
 // normal tiles (FE_PICK): lane = decode row, TMEM column = vocabulary word q0 + col.  Each thread folds its
-// columns [c0, c1) into a (max, sum exp, arg-max) partial; the first maximum wins ties (ascending words).
+// columns into a (max, sum exp, arg-max) partial; the first maximum wins ties (ascending words).
 struct PickAcc {
   float m, s;
   int bi;
@@ -423,30 +386,20 @@ __device__ __forceinline__ void pick_fold16(const EpiParams &e, const uint32_t (
   a.m = mn;
 }
 
-// v[i] = sum over the rotating accumulators (in order) of columns [col, col + 16)
-__device__ __forceinline__ void acc_ld16(uint32_t trow, int col, int bq, int nacc, uint32_t (&v)[16]) {
-  tc_ld16(trow + col, v);
-  for (int a = bq; a < nacc * bq; a += bq) {
-    uint32_t w[16];
-    tc_ld16(trow + a + col, w);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
-  }
-}
-
+// Whole-tile epilogue.  kind / geometry are uniform over the CTA.
+//   swap tiles:   f0 = first feature of the tile inside its segment, nfeat = features of the segment, q0 = first row
+//   normal tiles: q0 = first vocabulary word of the tile, e.part0 = partial slot of this tile's first half
 __device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int kind, int mp, int bq, int nacc, int f0,
                                          int nfeat, int q0, int warp, int lane, float *creg, bool creg_load,
                                          long long *trace = nullptr) {
-  const int wq = warp & 3;
-  if (wq * 32 >= mp) return;                             // lanes beyond the tile height hold nothing
-  const int chalf = (warp - 2) >> 2;
-  const int ch = bq >> 1;                               // columns per warp
-  const uint32_t trow = c.tmem + (static_cast<uint32_t>(wq * 32) << 16);
   if (kind == FE_PICK) {
+    const int wq = warp & 3, chalf = (warp - 2) >> 2, ch = bq >> 1;
+    const uint32_t trow = c.tmem + (static_cast<uint32_t>(wq * 32) << 16);
     const int r = wq * 32 + lane;                       // decode row (single row tile: rows <= 128)
     PickAcc a;
     a.m = -INFINITY; a.s = 0.f; a.bi = 0x7fffffff; a.tv = 0.f; a.thit = 0;
     const long long tgt_word = (e.x_t && r < e.rows) ? e.x_t[r] : -1;
+#pragma unroll 1
     for (int cc = chalf * ch; cc < (chalf + 1) * ch; cc += 16) {
       uint32_t v[16];
       acc_ld16(trow, cc, bq, nacc, v);
@@ -459,19 +412,14 @@ __device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int k
     }
     return;
   }
-  const int j = f0 + wq * 32 + lane;
-  const bool jok = j < nfeat;
-  for (int cc = chalf * ch; cc < (chalf + 1) * ch; cc += 16) {
-    uint32_t v[16];
-    if (trace && threadIdx.x == 128) trace[148] = clock64();
-    acc_ld16(trow, cc, bq, nacc, v);
-    if (trace && threadIdx.x == 128) trace[149] = clock64() + (v[0] == 0x7fffffffu ? 1 : 0);
-    const int r0 = q0 + cc;
-    if (kind == FE_STORE) epi_store16(e, v, j, jok, r0);
-    else if (kind == FE_GATES) epi_gates16(e, v, j, jok, r0, lane, creg, creg_load, (trace && threadIdx.x == 128) ? trace : nullptr);
-    else if (kind == FE_ZC) epi_zc16(e, v, j, jok, r0, lane);
-    else epi_z16(e, v, j, jok, r0);
-  }
+  float *S = reinterpret_cast<float *>(c.ring);
+  const int t = threadIdx.x - 64;
+  if (trace && t == 0) trace[148] = clock64();
+  epi_stage(c, S, mp, bq, nacc, warp, lane);
+  if (trace && t == 0) trace[149] = clock64();
+  if (kind == FE_GATES) epi_gates(e, S, mp, bq, f0, nfeat, q0, t, creg, creg_load);
+  else epi_rows(e, kind, S, mp, bq, f0, nfeat, q0, t);
+  if (trace && t == 0) trace[154] = clock64();
 }
 
 }  // namespace fused

@@ -99,9 +99,9 @@ struct Prep {
   // fused step (step_fused.cu)
   size_t WcI;    // (4H+E, H): rows 4u+g = Wc[:, gH+u] (gate-interleaved: the four gates of a unit adjacent);
                  //            rows 4H.. = ff_logit_ctxglm_W[:, e]                          -- multiplies ctx
-  size_t WqT;    // (8H+1+E, H): Wdl | Wdg | Wdm | Wdlt | W_sel | U (gate-interleaved rows) | ff_logit_lstm_W
-                 //                                                                          -- multiplies h
-  size_t bq;     // (8H+1)    : 0 | 0 | 0 | blt | b_sel | 0 (4H)
+  size_t WqT;    // (8H+4+E, H): Wdl | Wdg | Wdm | Wdlt | W_sel | 3 zero rows | U (gate-interleaved rows) |
+                 //              ff_logit_lstm_W                                             -- multiplies h
+  size_t bq;     // (8H+4)    : 0 | 0 | 0 | blt | b_sel | 0 ...
   size_t bdi;    // (4H)      : decoder_b, gate-interleaved
   size_t total;  // floats
   int NH, NC;
@@ -146,8 +146,8 @@ Prep prep_layout(const StatDims &d) {
   p.EW = take((V + 1) * 4 * H);
   p.Wemb = take(V * E);
   p.WcI = take((4 * H + E) * H);
-  p.WqT = take((8 * H + 1 + E) * H);
-  p.bq = take(8 * H + 1);
+  p.WqT = take((8 * H + 4 + E) * H);
+  p.bq = take(8 * H + 4);
   p.bdi = take(4 * H);
   p.total = o;
   return p;
@@ -268,7 +268,7 @@ Ws ws_layout(const StatDims &d, int rows) {
   w.row_clip = take(n);
   w.dead_k = take(n);
   w.bdone = take(n);
-  w.ldq2 = static_cast<int>(up(8 * H + 1, 4));
+  w.ldq2 = static_cast<int>(8 * H + 4);
   w.npart = 2 * static_cast<int>((V + 127) / 128);
   w.hq = take(n * w.ldq2);
   w.part = take(n * w.npart * 4);
@@ -571,7 +571,7 @@ int fstep_gates(const StatDims &d, const Prep &p, const float *P, const Ws &w, f
   FusedEpi &e = f.e;
   e.H = H; e.V = d.V; e.E = E;
   e.EWi = P + p.EW;
-  e.hu = W + w.hq + 4 * H + 1; e.ld_hu = w.ldq2;
+  e.hu = W + w.hq + 4 * H + 4; e.ld_hu = w.ldq2;
   e.tok_prev = io.tok_prev; e.mask = io.mask; e.dp_gates = io.dp_gates;
   e.c_in = W + w.c; e.c_out = W + w.c;
   e.h_in = W + w.h; e.ld_hin = H;
@@ -592,13 +592,13 @@ int fstep_hidden(const StatDims &d, const Prep &p, const float *P, const Ws &w, 
   FusedPhase f;
   memset(&f, 0, sizeof(f));
   f.swap = 1;
-  f.W = P + p.WqT; f.wrows = 8 * H + 1 + E; f.wK = H; f.ldw = H;
+  f.W = P + p.WqT; f.wrows = 8 * H + 4 + E; f.wK = H; f.ldw = H;
   f.X[0] = W + w.h; f.xK[0] = H; f.ldx[0] = H;
   if (io.dp_h) { f.X[1] = W + w.hd; f.xK[1] = H; f.ldx[1] = H; }
   f.rows = io.rows;
   int n = 0;
-  if (want_q) f.seg[n++] = FusedSegment{FE_STORE, 0, 8 * H + 1, H, 0};
-  if (want_z) f.seg[n++] = FusedSegment{FE_Z, 8 * H + 1, E, H, io.dp_h ? 1 : 0};
+  if (want_q) f.seg[n++] = FusedSegment{FE_STORE, 0, 8 * H + 4, H, 0};
+  if (want_z) f.seg[n++] = FusedSegment{FE_Z, 8 * H + 4, E, H, io.dp_h ? 1 : 0};
   f.nseg = n;
   FusedEpi &e = f.e;
   e.E = E;
@@ -905,8 +905,8 @@ int stat_prepare_params(const StatDims *d, const StatParams *sp, void *prepared,
   STAT_TRY(transpose_launch(sp->decoder_Wdm_att, H, H, P + p.WqT, H, 2 * H, st));
   STAT_TRY(transpose_launch(sp->decoder_Wdlt_att, H, H, P + p.WqT, H, 3 * H, st));
   if (sel) STAT_CUDA_CHECK(cp(p.WqT + static_cast<size_t>(4) * H * H, sp->decoder_W_sel, H));
-  STAT_TRY(transpose_il_launch(sp->decoder_U, H, H, P + p.WqT + static_cast<size_t>(4 * H + 1) * H, H, 0, st));
-  STAT_TRY(transpose_launch(sp->ff_logit_lstm_W, H, E, P + p.WqT, H, 8 * H + 1, st));
+  STAT_TRY(transpose_il_launch(sp->decoder_U, H, H, P + p.WqT + static_cast<size_t>(4 * H + 4) * H, H, 0, st));
+  STAT_TRY(transpose_launch(sp->ff_logit_lstm_W, H, E, P + p.WqT, H, 8 * H + 4, st));
   STAT_CUDA_CHECK(cp(p.bq + 3 * H, sp->decoder_blt_att, H));
   if (sel) STAT_CUDA_CHECK(cp(p.bq + 4 * H, sp->decoder_b_sel, 1));
   return STAT_OK;
