@@ -283,16 +283,35 @@ __device__ __forceinline__ void epi_stage(const Cta &c, float *S, int mp, int bq
 // FE_GATES: S10-S13 (model_attention.py:437-457).  Feature j = 4*unit + gate (0 input, 1 forget, 2 output,
 // 3 candidate): an item = (row, unit) reads its four pre-activations as one float4.  creg != null: the cell state
 // of this thread's items (item k of the thread -> creg[k]) lives in registers across decode steps.
+// k-split tiles: the ks CTAs of a cluster each hold the partial tile of their K slice in their own S; an item is
+// summed over the ranks in rank order (deterministic) through distributed shared memory, and the items are dealt
+// out over the CTAs of the cluster (item it -> CTA (it / NSPLIT) % ks).
+__device__ __forceinline__ float4 s_sum4(const float *p, int ks) {
+  if (ks == 1) return *reinterpret_cast<const float4 *>(p);
+  float4 a = ld_dsmem4(dsmem_addr(p, 0));
+  for (int r = 1; r < ks; ++r) {
+    const float4 b = ld_dsmem4(dsmem_addr(p, r));
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  return a;
+}
+__device__ __forceinline__ float s_sum1(const float *p, int ks) {
+  if (ks == 1) return *p;
+  float a = ld_dsmem(dsmem_addr(p, 0));
+  for (int r = 1; r < ks; ++r) a += ld_dsmem(dsmem_addr(p, r));
+  return a;
+}
+
 __device__ __forceinline__ void epi_gates(const EpiParams &e, const float *S, int mp, int bq, int f0, int nfeat, int q0,
-                                          int t, float *creg, bool creg_load) {
+                                          int t, int ks, int rank, float *creg, bool creg_load) {
   const int H = e.H, SP = mp + SPAD, nu = mp >> 2, u0 = f0 >> 2;
   int k = 0;
 #pragma unroll 1
-  for (int it = t; it < bq * nu; it += NSPLIT, ++k) {
+  for (int it = t + NSPLIT * rank; it < bq * nu; it += NSPLIT * ks, ++k) {
     const int row = it / nu, ul = it - row * nu;
     const int r = q0 + row, u = u0 + ul;
     if (r >= e.rows || 4 * u >= nfeat) continue;
-    const float4 a = *reinterpret_cast<const float4 *>(S + row * SP + 4 * ul);
+    const float4 a = s_sum4(S + row * SP + 4 * ul, ks);
     const long long tok = e.tok_prev ? e.tok_prev[r] : -1;
     const float4 ew = __ldg(reinterpret_cast<const float4 *>(e.EWi + static_cast<size_t>(tok >= 0 ? tok : e.V) * 4 * H) + u);
     float4 hu = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -327,14 +346,14 @@ __device__ __forceinline__ void epi_gates(const EpiParams &e, const float *S, in
 
 // FE_STORE / FE_ZC / FE_Z: an item = (row, feature); consecutive threads take consecutive features of a row
 __device__ __forceinline__ void epi_rows(const EpiParams &e, int kind, const float *S, int mp, int bq, int f0, int nfeat,
-                                         int q0, int t) {
+                                         int q0, int t, int ks, int rank) {
   const int SP = mp + SPAD;
 #pragma unroll 1
-  for (int it = t; it < bq * mp; it += NSPLIT) {
+  for (int it = t + NSPLIT * rank; it < bq * mp; it += NSPLIT * ks) {
     const int row = it / mp, fl = it - row * mp;
     const int r = q0 + row, j = f0 + fl;
     if (r >= e.rows || j >= nfeat) continue;
-    const float acc = S[row * SP + fl];
+    const float acc = s_sum1(S + row * SP + fl, ks);
     if (kind == FE_STORE) {
       e.out[static_cast<size_t>(r) * e.ldo + j] = acc + (e.bias ? __ldg(e.bias + j) : 0.f);
     } else if (kind == FE_ZC) {
@@ -386,12 +405,13 @@ __device__ __forceinline__ void pick_fold16(const EpiParams &e, const uint32_t (
   a.m = mn;
 }
 
-// Whole-tile epilogue.  kind / geometry are uniform over the CTA.
-//   swap tiles:   f0 = first feature of the tile inside its segment, nfeat = features of the segment, q0 = first row
-//   normal tiles: q0 = first vocabulary word of the tile, e.part0 = partial slot of this tile's first half
-__device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int kind, int mp, int bq, int nacc, int f0,
-                                         int nfeat, int q0, int warp, int lane, float *creg, bool creg_load,
-                                         long long *trace = nullptr) {
+// Tile epilogue in two parts (kind / geometry are uniform over the CTA; warps 2..9):
+//   epilogue_stage: FE_PICK does everything here (normal tiles: q0 = first vocabulary word, e.part0 = partial slot);
+//                   swap tiles transpose their accumulators into S (f0 = first feature of the tile inside its
+//                   segment, nfeat = features of the segment, q0 = first decode row)
+//   epilogue_items: swap tiles only, after the cluster barrier when the tile is k-split over ks CTAs
+__device__ __forceinline__ void epilogue_stage(const Cta &c, const EpiParams &e, int kind, int mp, int bq, int nacc,
+                                               int q0, int warp, int lane) {
   if (kind == FE_PICK) {
     const int wq = warp & 3, chalf = (warp - 2) >> 2, ch = bq >> 1;
     const uint32_t trow = c.tmem + (static_cast<uint32_t>(wq * 32) << 16);
@@ -412,14 +432,16 @@ __device__ __forceinline__ void epilogue(const Cta &c, const EpiParams &e, int k
     }
     return;
   }
-  float *S = reinterpret_cast<float *>(c.ring);
+  epi_stage(c, reinterpret_cast<float *>(c.ring), mp, bq, nacc, warp, lane);
+}
+
+__device__ __forceinline__ void epilogue_items(const Cta &c, const EpiParams &e, int kind, int mp, int bq, int f0,
+                                               int nfeat, int q0, int ks, int rank, float *creg, bool creg_load) {
+  if (kind == FE_PICK) return;
+  const float *S = reinterpret_cast<const float *>(c.ring);
   const int t = threadIdx.x - 64;
-  if (trace && t == 0) trace[148] = clock64();
-  epi_stage(c, S, mp, bq, nacc, warp, lane);
-  if (trace && t == 0) trace[149] = clock64();
-  if (kind == FE_GATES) epi_gates(e, S, mp, bq, f0, nfeat, q0, t, creg, creg_load);
-  else epi_rows(e, kind, S, mp, bq, f0, nfeat, q0, t);
-  if (trace && t == 0) trace[154] = clock64();
+  if (kind == FE_GATES) epi_gates(e, S, mp, bq, f0, nfeat, q0, t, ks, rank, creg, creg_load);
+  else epi_rows(e, kind, S, mp, bq, f0, nfeat, q0, t, ks, rank);
 }
 
 }  // namespace fused

@@ -24,7 +24,7 @@ struct SegDev {
 };
 
 struct PhaseDev {
-  int swap, mp, bq, nacc, nseg, qtiles, ntile0;
+  int swap, mp, bq, nacc, nseg, qtiles, ntile0, ks;    // ks: k-slices = CTAs of a cluster that share a tile
   SegDev seg[2];
   unsigned long long pol_w, pol_x;
   long long *trace;     // debug: clock64 stamps of CTA 0 (stat_debug_gemm_trace), or null
@@ -40,14 +40,19 @@ __global__ void __launch_bounds__(NROLE, 1)
   Cta c;
   cta_setup(c, smem_raw, &tmem_slot);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x;
+  const int ks = a.ks;
+  const int rank = ks > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int idx = static_cast<int>(blockIdx.x) / ks;
   const int si = (a.nseg > 1 && idx >= a.ntile0) ? 1 : 0;
   const int local = idx - (si ? a.ntile0 : 0);
   const int kind = si ? a.seg[1].kind : a.seg[0].kind;
   const int prow0 = si ? a.seg[1].prow0 : a.seg[0].prow0;
   const int nfeat = si ? a.seg[1].nfeat : a.seg[0].nfeat;
-  const int nk = si ? a.seg[1].nk : a.seg[0].nk;
+  const int nk_all = si ? a.seg[1].nk : a.seg[0].nk;
   const int xsel = si ? a.seg[1].xsel : a.seg[0].xsel;
+  // this CTA's K slice
+  const int kb0 = (rank * nk_all) / ks, kb1 = ((rank + 1) * nk_all) / ks;
+  const int nk = kb1 - kb0;
   const CUtensorMap *tmX = xsel ? &tmX1 : &tmX0;
   int f0, q0, prow, qrow;
   const CUtensorMap *tmP, *tmQ;
@@ -69,8 +74,11 @@ __global__ void __launch_bounds__(NROLE, 1)
   if (trace && threadIdx.x == 0) trace[1] = clock64();
   Ring r = {0, 0};
   const Geo g = make_geo(a.mp, a.bq);
+  const int nacc = nk < NISSUE ? nk : NISSUE;
+  EpiParams e = a.e;
+  if (kind == FE_PICK) e.part0 = 2 * local;
   if (warp == 0) {
-    if (lane == 0) produce(c, r, tmP, prow, tmQ, qrow, 0, nk, g, pol_p, pol_q, trace);
+    if (lane == 0) produce(c, r, tmP, prow, tmQ, qrow, kb0, kb1, g, pol_p, pol_q, trace);
     __syncwarp();
   } else if (warp == 1 || warp >= 10) {
     uint32_t kt = 0, n = 0;
@@ -81,11 +89,20 @@ __global__ void __launch_bounds__(NROLE, 1)
     mbar_wait(c.bar_acc, 0);
     tc_fence_after();
     if (trace && threadIdx.x == 64) trace[140] = clock64();
-    EpiParams e = a.e;
-    if (kind == FE_PICK) e.part0 = 2 * local;
-    epilogue(c, e, kind, a.mp, a.bq, nk < NISSUE ? nk : NISSUE, f0, nfeat, q0, warp, lane, nullptr, false, trace);
-    if (trace && threadIdx.x == 64) trace[141] = clock64();
+    epilogue_stage(c, e, kind, a.mp, a.bq, nacc, q0, warp, lane);
+    if (trace && threadIdx.x == 64) trace[149] = clock64();
   }
+  if (ks > 1) {
+    // the partial tiles of all K slices are staged: every thread of the cluster passes the barrier, then the
+    // items are summed over the ranks through distributed shared memory
+    __syncthreads();
+    cluster_sync_all();
+  }
+  if (warp >= 2 && warp < 10) {
+    epilogue_items(c, e, kind, a.mp, a.bq, f0, nfeat, q0, ks, rank, nullptr, false);
+    if (trace && threadIdx.x == 64) trace[154] = clock64();
+  }
+  if (ks > 1) cluster_sync_all();      // nobody leaves while a partner still reads its shared memory
   cta_teardown(c);
   if (trace && threadIdx.x == 0) trace[142] = clock64();
 }
@@ -175,9 +192,9 @@ int fused_phase_launch(const FusedPhase &p, cudaStream_t stream) {
   PhaseDev d;
   memset(&d, 0, sizeof(d));
   d.swap = p.swap;
-  // swap tiles: 64 features x 32 decode rows (half-height tiles: twice the CTAs, half the weight bytes per CTA -- the
-  // per-SM load rate, not the tensor pipe, bounds these products); normal tiles: all rows x 128 vocabulary words
-  d.mp = p.swap ? 64 : BP;
+  // swap tiles: 128 features x 32 decode rows, K split over the CTAs of a cluster; normal tiles: all rows x 128
+  // vocabulary words
+  d.mp = BP;
   d.bq = p.swap ? 32 : 128;
   {   // accumulators the products of a k-atom rotate over (debug knob STAT_FUSED_NACC: 1, 2, 4, 8)
     static int nacc_env = -1;
@@ -203,6 +220,26 @@ int fused_phase_launch(const FusedPhase &p, cudaStream_t stream) {
     tiles[i] = p.swap ? ((s.nfeat + d.mp - 1) / d.mp) * d.qtiles : (s.nfeat + d.bq - 1) / d.bq;
   }
   d.ntile0 = tiles[0];
+  // k-split: one tcgen05.mma.kind::tf32 covers K = 8 and takes ~55-65 cycles whatever N <= 128 is, so a K = 512 tile
+  // costs ~5.5 us in one CTA: spread the K range of every tile over the CTAs of a cluster (as many as keep the grid
+  // inside one wave) and sum the partial tiles through distributed shared memory in the epilogue
+  d.ks = 1;
+  if (p.swap) {
+    int nk_min = d.seg[0].nk;
+    for (int i = 1; i < p.nseg; ++i) nk_min = d.seg[i].nk < nk_min ? d.seg[i].nk : nk_min;
+    static int ks_env = -1;
+    if (ks_env < 0) {
+      const char *e = getenv("STAT_FUSED_KSPLIT");     // 0 = automatic, n = at most n
+      ks_env = e ? atoi(e) : 0;
+    }
+    const int total = tiles[0] + tiles[1];
+    int ks = 148 / total;
+    if (ks > 8) ks = 8;
+    if (ks_env > 0 && ks > ks_env) ks = ks_env;
+    if (ks > nk_min) ks = nk_min;
+    if (ks < 1) ks = 1;
+    d.ks = ks;
+  }
   // the step's weights are re-read by every decode step: keep them in L2 ahead of the streamed context blocks
   d.pol_w = L2_EVICT_LAST;
   d.pol_x = L2_EVICT_NORMAL;
@@ -222,13 +259,22 @@ int fused_phase_launch(const FusedPhase &p, cudaStream_t stream) {
   static size_t smem_set[STAT_MAX_DEV] = {};
   STAT_TRY(ensure_dyn_smem(fused_phase_kernel, SMEM_BYTES, smem_set));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tiles[0] + tiles[1]);
+  cfg.gridDim = dim3((tiles[0] + tiles[1]) * d.ks);
   cfg.blockDim = dim3(NROLE);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_attr(attr);
+  int na = 0;
+  if (d.ks > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = d.ks;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  na += pdl_attr(attr + na);
+  cfg.numAttrs = na;
   STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_phase_kernel, tmW, tmX0, tmX1, d));
   note_launch();
   return STAT_OK;

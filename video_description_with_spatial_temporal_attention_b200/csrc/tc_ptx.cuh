@@ -180,6 +180,33 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r & 0xFFFFE000u);
 }
 
+// ---- thread-block clusters: rank, barrier, distributed shared memory reads ----------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local` (a shared-memory location of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void *local, uint32_t rank) {
+  uint32_t ra;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ float ld_dsmem(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_dsmem4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---- global-memory flags between CTAs of one (co-resident) grid ------------------------------------
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
   unsigned int v;
