@@ -240,9 +240,16 @@ int fused_phase_launch(const FusedPhase &p, cudaStream_t stream) {
     if (ks < 1) ks = 1;
     d.ks = ks;
   }
-  // the step's weights are re-read by every decode step: keep them in L2 ahead of the streamed context blocks
-  d.pol_w = L2_EVICT_LAST;
-  d.pol_x = L2_EVICT_NORMAL;
+  // L2 priorities: the context blocks the attention kernel re-reads every step own the evict_last set (they do not
+  // all fit anyway); the step's weights are streamed evict_first like the separate GEMMs do, the small activation
+  // rows every CTA re-reads are kept.  STAT_FUSED_L2=last keeps the weights instead (measurement knob).
+  static int wl = -1;
+  if (wl < 0) {
+    const char *e = getenv("STAT_FUSED_L2");
+    wl = (e && !strcmp(e, "last")) ? 1 : 0;
+  }
+  d.pol_w = wl ? L2_EVICT_LAST : L2_EVICT_FIRST;
+  d.pol_x = L2_EVICT_LAST;
   d.e = p.e;
   d.e.rows = p.rows;
   d.trace = gemm_get_trace();
