@@ -98,6 +98,17 @@ const char *stat_last_error(void);
  * GEMM (device-side cross-checks used by the GPU tests; never a CPU path). */
 int stat_set_gemm_impl(int impl);
 
+/* Implementation of the decode step behind stat_forward_teacher / stat_decode_greedy (same results to fp32
+ * summation order; both are device paths):
+ *   0 = separate kernels (default): attention -> ctx.[Wc|Wctx] -> gates -> h.[Wd*|U|W_sel|Wl] as k-split tensor-core
+ *       products + elementwise kernels, readout activation -> logits -> vocabulary reduction beside the next attention
+ *   1 = fused step kernels (step_fused.cu): attention -> ctx.Wc with the gates (S10-S13) in the epilogue ->
+ *       h.[Wd*|W_sel|U|Wl] with the readout activation in the epilogue; logits with the per-tile vocabulary reduction
+ *       in the epilogue -> combine.  K split over thread-block clusters, partial tiles summed through distributed
+ *       shared memory.  Three dependent launches per step instead of four; measured slower end to end in round 2
+ *       (DESIGN.md section 8), kept selectable.  Also: environment STAT_FUSED=1. */
+int stat_set_step_impl(int impl);
+
 /* ---- L2 residency of the context blocks (no reference counterpart) -----------
  * The attention kernel re-reads the projected context blocks of the batch on
  * every decode step and copies them with the L2 evict_last priority; those

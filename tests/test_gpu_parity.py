@@ -330,6 +330,60 @@ def test_alpha_tolerance_margin_over_100_clips(torch_cuda):
     assert worst_lp <= TOL_LP and worst_a <= TOL_A_WIDE
 
 
+# ---------------------------------------------------------------------------
+# the fused step kernels (stat_set_step_impl(1)): same contract as the default path
+# ---------------------------------------------------------------------------
+@pytest.fixture
+def fused_step():
+    from video_description_with_spatial_temporal_attention_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.stat_set_step_impl(1))
+    yield
+    _lib.check(lib.stat_set_step_impl(0))
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_fused_step_golden(torch_cuda, fused_step, name):
+    """Reference-generated fixtures through the fused step kernels: f_log_probs, alphas, batched greedy."""
+    g = Golden(name)
+    _, _, f_log_probs, f_alphas, _, _ = _build(g.options, g.params)
+    np.testing.assert_allclose(f_log_probs(*g.batch), g.out('f_log_probs'), atol=TOL_LP, rtol=0)
+    al, ag, am, alt = f_alphas(*g.batch)
+    np.testing.assert_allclose(al, g.out('alphals'), atol=TOL_A)
+    np.testing.assert_allclose(alt, g.out('alphalts'), atol=TOL_A)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = g.batch
+    model, tp, _, _, _, _ = _build(g.options, g.params)
+    for use_graph in (False, True):
+        toks, lens, scores = model.greedy_batch(tp, g.options, ctxg, mg, ctxl, ctxm, maxlen=g.maxlen, use_graph=use_graph)
+        for b in range(ctxg.shape[0]):
+            want, want_sc = g.hyps(1, b)
+            assert [int(t) for t in toks[b, :lens[b]]] == want[0]
+            np.testing.assert_allclose(scores[b], want_sc[0], atol=TOL_LP)
+
+
+def test_fused_step_full_width(torch_cuda, fused_step):
+    """BASELINE widths, B=64: teacher-forced log-probs and greedy captions of the fused path vs the fp64 oracle, with
+    ragged captions (masks) and explicit dropout factors (the training forward)."""
+    o, params, batch = _case('baseline', B=64, L=20, seed=51)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+    model, tp, f_log_probs, _, _, _ = _build(o, params)
+    lp = f_log_probs(*batch)
+    want = so.forward_teacher(params, o, *batch, dtype=np.float64)
+    np.testing.assert_allclose(lp, want, atol=TOL_LP, rtol=0)
+    toks, lens, scores = model.greedy_batch(tp, o, ctxg, mg, ctxl, ctxm, maxlen=20, use_graph=True)
+    wt, wl, ws, margins = so.greedy_decode_batch(params, o, ctxg, mg, ctxl, ctxm, 20, dtype=np.float64, return_all=True)
+    n_full = 0
+    for b in range(64):
+        n = int(wl[b])
+        tight = np.where(margins[b, :n] < 1e-4)[0]
+        upto = int(tight[0]) if len(tight) else n
+        assert [int(t) for t in toks[b, :upto]] == [int(t) for t in wt[b, :upto]], b
+        if upto == n:
+            n_full += 1
+            np.testing.assert_allclose(scores[b], ws[b], atol=TOL_LP, rtol=4e-6)
+    assert n_full >= 62
+
+
 def test_beam_k1_equals_greedy_and_limits(torch_cuda):
     o, params, batch = _case('baseline', B=4, seed=17)
     x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch

@@ -690,6 +690,14 @@ bool att_group_plan(int rows, int T, int R, int H, int *cluster, int *groups, in
   if ((H & 3) != 0 || H > 1024 || R > RMAX || R < 1 || rows < 1 || T < 1) return false;
   int cs = 1;
   while (cs < 8 && 2 * cs <= T && static_cast<long long>(rows) * 2 * cs <= sm_count()) cs *= 2;
+  {   // measurement knob: STAT_ATT_CS caps the CTAs per decode row (1 leaves SMs free for the readout chain)
+    static int cap = -1;
+    if (cap < 0) {
+      const char *e = getenv("STAT_ATT_CS");
+      cap = e ? atoi(e) : 0;
+    }
+    while (cap > 0 && cs > cap) cs /= 2;
+  }
   // rank 0 of a cluster also holds one landing pad per partner
   while (cs > 1 && SMEM_EXTRA + (cs - 1) * pad_bytes(H) + frame_bytes(R, H) > SMEM_MAX) cs /= 2;
   if (SMEM_EXTRA + (cs - 1) * pad_bytes(H) + frame_bytes(R, H) > SMEM_MAX) return false;

@@ -306,7 +306,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_split + 8 * s, NSPLIT);
+      mbar_init(bar_split + 8 * s, TS ? 4 : NSPLIT);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tmem, 1);
@@ -395,7 +395,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     int s = 0;
     uint32_t ph = 0;
     for (int kb = 0; kb < nk; ++kb) {
-      mbar_wait(bar_full + 8 * s, ph);
+      if (!TS || (kb & 1) == ((warp - 2) >> 2)) mbar_wait(bar_full + 8 * s, ph);
       if (trace && t == 0 && kb < 16) trace[2 + kb] = clock64();
       uint8_t *stage = smem + s * C::STAGE_BYTES;
       float4 *Ph = reinterpret_cast<float4 *>(stage);
@@ -404,41 +404,57 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       float4 *Ql = reinterpret_cast<float4 *>(stage + 2 * C::P_BYTES + C::Q_BYTES);
       constexpr int NQ4 = (C::Q_BYTES / 16 + NSPLIT - 1) / NSPLIT;  // 1 / 2 / 4
       if constexpr (TS) {
-        // P: this thread owns tile row prow (= its TMEM lane) and 16 of the 32 k-columns.  The TMA
-        // tile is SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7).
-        const int prow = (warp & 3) * 32 + lane;
-        const int ch = (warp - 2) >> 2;
-        const uint8_t *rowp = stage + prow * 128;
-        float4 xp[4], xq[NQ4];
+        // The two groups of four splitter warps (one warp per TMEM lane quadrant each) take alternate k-slices, so
+        // that the latencies of one slice's split (shared-memory loads, tensor-memory stores and their wait, the
+        // proxy fence) overlap the other group's; one arrival per warp.  A thread owns tile row prow (= its TMEM
+        // lane) and all 32 k-columns, in two halves of 16.  The TMA tile is SWIZZLE_128B: 16-byte chunk c of row r
+        // sits at chunk c ^ (r & 7).
+        if ((kb & 1) == ((warp - 2) >> 2)) {
+          const int prow = (warp & 3) * 32 + lane;
+          const int tg = ((warp - 2) & 3) * 32 + lane;
+          const uint8_t *rowp = stage + prow * 128;
+          const uint32_t ta = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + C::TS_A_BASE + 64 * s;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          xp[i] = *reinterpret_cast<const float4 *>(rowp + (((4 * ch + i) ^ (prow & 7)) << 4));
+          for (int half = 0; half < 2; ++half) {
+            float4 xp[4];
 #pragma unroll
-        for (int i = 0; i < NQ4; ++i) {
-          const int idx = t + i * NSPLIT;
-          xq[i] = (idx < C::Q_BYTES / 16) ? Qh[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        uint32_t hi[16], lo[16];
+            for (int i = 0; i < 4; ++i)
+              xp[i] = *reinterpret_cast<const float4 *>(rowp + (((4 * half + i) ^ (prow & 7)) << 4));
+            uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float xs[4] = {xp[i].x, xp[i].y, xp[i].z, xp[i].w};
+            for (int i = 0; i < 4; ++i) {
+              const float xs[4] = {xp[i].x, xp[i].y, xp[i].z, xp[i].w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float h = rna_tf32(xs[e]);
-            hi[4 * i + e] = __float_as_uint(h);
-            lo[4 * i + e] = __float_as_uint(xs[e] - h);
+              for (int e = 0; e < 4; ++e) {
+                const float h = rna_tf32(xs[e]);
+                hi[4 * i + e] = __float_as_uint(h);
+                lo[4 * i + e] = __float_as_uint(xs[e] - h);
+              }
+            }
+            tc_st16(ta + 16 * half, hi);
+            tc_st16(ta + 32 + 16 * half, lo);
           }
-        }
-        const uint32_t ta = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + C::TS_A_BASE + 64 * s + 16 * ch;
-        tc_st16(ta, hi);
-        tc_st16(ta + 32, lo);
+          constexpr int NQG = (C::Q_BYTES / 16 + 127) / 128;     // 16-byte chunks of Q per thread of the group
+          float4 xq[NQG];
 #pragma unroll
-        for (int i = 0; i < NQ4; ++i) {
-          const int idx = t + i * NSPLIT;
-          if (idx < C::Q_BYTES / 16) split_store(xq[i], Qh + idx, Ql + idx);
+          for (int i = 0; i < NQG; ++i) {
+            const int idx = tg + i * 128;
+            xq[i] = (idx < C::Q_BYTES / 16) ? Qh[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < NQG; ++i) {
+            const int idx = tg + i * 128;
+            if (idx < C::Q_BYTES / 16) split_store(xq[i], Qh + idx, Ql + idx);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_split + 8 * s);
+          if (trace && tg == 0 && kb < 16) trace[20 + kb] = clock64();
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        continue;
       } else {
         // all 16-byte loads of this thread first, then the arithmetic, then the stores
         constexpr int NP4 = C::P_BYTES / 16 / NSPLIT;                 // 4

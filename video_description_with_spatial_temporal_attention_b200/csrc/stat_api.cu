@@ -536,13 +536,15 @@ int step_out(const StatDims &d, const Prep &p, const float *P, const Ws &w, floa
 // h: next queries, selector logit, h.U of the next cell, readout activation) on the caller's stream, logits (partial
 // vocabulary reduction fused) -> combine beside the next attention.
 // ---------------------------------------------------------------------------
+// step implementation: 0 = separate kernels (k-split products + gates / readout / vocabulary kernels; the default:
+// measured faster inside the captured decode), 1 = the fused step kernels.  stat_set_step_impl / STAT_FUSED=1.
+int g_step_impl = -1;
 bool fused_enabled(const StatDims &d, int rows) {
-  static int on = -1;
-  if (on < 0) {
+  if (g_step_impl < 0) {
     const char *e = getenv("STAT_FUSED");
-    on = (e && e[0] == '0') ? 0 : 1;
+    g_step_impl = (e && e[0] == '1') ? 1 : 0;
   }
-  return on && fused_supported(d.H, d.E) && rows <= 128;
+  return g_step_impl == 1 && fused_supported(d.H, d.E) && rows <= 128;
 }
 
 AttArgs att_args_fused(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, int rows,
@@ -798,6 +800,12 @@ int stat_adadelta_step(float *params, const float *grads, float *rg2, float *ru2
   STAT_REQUIRE(params && grads && rg2 && ru2 && n > 0 && (phase == 0 || phase == 1), STAT_EINVAL,
                "adadelta_step: bad argument");
   return adadelta_launch(params, grads, rg2, ru2, n, phase, static_cast<cudaStream_t>(stream));
+}
+
+int stat_set_step_impl(int impl) {
+  STAT_REQUIRE(impl == 0 || impl == 1, STAT_EINVAL, "step impl must be 0 (separate kernels) or 1 (fused step kernels)");
+  g_step_impl = impl;
+  return STAT_OK;
 }
 
 int stat_set_gemm_impl(int impl) {
