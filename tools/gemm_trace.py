@@ -10,8 +10,8 @@ from video_description_with_spatial_temporal_attention_b200.engine import Engine
 eng = Engine(stat.default_options())
 lib = eng.lib
 lib.stat_debug_gemm_trace.argtypes = [C.c_void_p]
-buf = torch.zeros(128, dtype=torch.int64, device='cuda')
-for (M, N, K) in [(64, 512, 128)]:
+buf = torch.zeros(256, dtype=torch.int64, device='cuda')
+for (M, N, K) in [(64, 12594, 512), (64, 4609, 512), (64, 2560, 512)]:
     A = torch.randn(M, K, device='cuda')
     Bt = torch.randn(N, K, device='cuda')
     for it in range(3):
