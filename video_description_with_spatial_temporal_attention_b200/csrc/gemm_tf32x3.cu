@@ -105,6 +105,7 @@ struct DevArgs {
   int nseg;
   int ksplit;               // gridDim.z: k-slices, slice z accumulates into plane z of the output
   int stages;               // depth of the shared-memory ring
+  int mc;                   // CTAs of a cluster along the P tiles that share (multicast) the Q tile; 1 = off
   long long plane;          // floats between output planes
   long long *trace;         // debug: per-phase clock64 stamps of CTA (0,0,0), or null
   unsigned long long pol_p, pol_q;   // L2 eviction-priority policies of the two operand streams
@@ -152,6 +153,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+// the Q slice of this CTA goes to the same shared-memory offset of every CTA in `mask` and signals each one's barrier
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar,
+                                               uint16_t mask, unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5, %6;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "h"(mask), "l"(policy)
+      : "memory");
+}
+// the stage is free in every CTA of `mask` once the MMAs that read it have completed here
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
@@ -307,7 +324,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_split + 8 * s, TS ? 4 : NSPLIT);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, static_cast<uint32_t>(args.mc));
     }
     mbar_init(bar_tmem, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -321,8 +338,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (args.mc > 1) tcx::cluster_sync_all();     // every CTA's barriers exist before a partner signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t crank = args.mc > 1 ? tcx::cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << args.mc) - 1u);
   if (trace && threadIdx.x == 0) trace[1] = clock64();
   // barrier set-up and the tensor-memory allocation above overlap the previous kernel's tail; its
   // results (an operand, an addend) are read from here on.  The successor may be scheduled now:
@@ -340,7 +360,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         const uint32_t stage = smem_u32(smem + s * C::STAGE_BYTES);
         mbar_expect_tx(bar_full + 8 * s, C::P_BYTES + C::Q_BYTES);
         tma_load_2d(stage, &tmP, (kb0 + kb) * BK, p0, bar_full + 8 * s, args.pol_p);
-        tma_load_2d(stage + 2 * C::P_BYTES, &tmQ, (kb0 + kb) * BK, q0, bar_full + 8 * s, args.pol_q);
+        if (args.mc > 1) {
+          // K0 is bound by L2 -> SM traffic (every CTA pulls 32 KB per k-slice: 294 us for ff_local = the L2's
+          // ~6 TB/s): the CTAs of a cluster work on different row tiles against the SAME weight tile, so each one
+          // fetches 1/mc of it and multicasts it to all
+          const uint32_t slice = static_cast<uint32_t>(C::Q_BYTES / args.mc);
+          tma_load_2d_mc(stage + 2 * C::P_BYTES + crank * slice, &tmQ, (kb0 + kb) * BK,
+                         q0 + static_cast<int>(crank) * (BQ / args.mc), bar_full + 8 * s, cmask, args.pol_q);
+        } else {
+          tma_load_2d(stage + 2 * C::P_BYTES, &tmQ, (kb0 + kb) * BK, q0, bar_full + 8 * s, args.pol_q);
+        }
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -383,7 +412,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             tc_mma_tf32(tmem_u, dPh + adv, dQh + adv, idesc, 1u);
           }
         }
-        tc_commit(bar_empty + 8 * s);
+        if (args.mc > 1) tc_commit_mc(bar_empty + 8 * s, cmask);
+        else tc_commit(bar_empty + 8 * s);
         if (kb == nk - 1) tc_commit(bar_tmem);
       }
       __syncwarp();
@@ -581,6 +611,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   }
 
   __syncthreads();
+  if (args.mc > 1) tcx::cluster_sync_all();     // nobody leaves while a partner may still signal its barriers
   if (trace && threadIdx.x == 0) trace[62] = clock64();
   if (warp == 1) {
     tc_fence_after();
@@ -679,11 +710,27 @@ namespace {
 template <int BQ, bool TS>
 int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   CUtensorMap tmP, tmQ;
+  // wide problems (K0): clusters of mc row tiles share the weight tile by TMA multicast
+  int mc = 1;
+  {
+    static int mc_max = -1;
+    if (mc_max < 0) {
+      const char *e = getenv("STAT_GEMM_MULTICAST");       // 1 = off, 2 / 4 = cluster size limit (default 4)
+      mc_max = e ? atoi(e) : 4;
+      if (mc_max != 1 && mc_max != 2 && mc_max != 4) mc_max = 4;
+    }
+    const int ptiles = (a.NP + BP - 1) / BP;
+    if (TS && BQ == 128 && !a.feat_on_p && da.ksplit == 1 && ptiles >= 8) {
+      for (int c = mc_max; c > 1; c >>= 1)
+        if (ptiles % c == 0) { mc = c; break; }
+    }
+  }
   STAT_TRY(make_tensor_map(&tmP, a.P, a.NP, a.K, a.ldp, BP));
-  STAT_TRY(make_tensor_map(&tmQ, a.Q, a.NQ, a.K, a.ldq, BQ));
+  STAT_TRY(make_tensor_map(&tmQ, a.Q, a.NQ, a.K, a.ldq, BQ / mc));
   static size_t smem_set[STAT_MAX_DEV] = {};
   STAT_TRY(ensure_dyn_smem(gemm_tf32x3_kernel<BQ, TS>, Cfg<BQ>::smem_bytes(Cfg<BQ>::MAX_STAGES), smem_set));
   DevArgs db = da;
+  db.mc = mc;
   const int nk_slice = ((a.K + BK - 1) / BK + da.ksplit - 1) / da.ksplit;
   db.stages = nk_slice < Cfg<BQ>::MAX_STAGES ? nk_slice : Cfg<BQ>::MAX_STAGES;
   dim3 grid((a.NQ + BQ - 1) / BQ, (a.NP + BP - 1) / BP, da.ksplit);
@@ -692,9 +739,18 @@ int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = Cfg<BQ>::smem_bytes(db.stages);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_attr(attr);
+  int na = 0;
+  if (mc > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = mc;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  na += pdl_attr(attr + na);
+  cfg.numAttrs = na;
   STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BQ, TS>, tmP, tmQ, db));
   note_launch();
   return STAT_OK;
@@ -714,6 +770,7 @@ int gemm_launch(const GemmArgs &a, cudaStream_t stream) {
   const int nk_all = (a.K + BK - 1) / BK;
   da.ksplit = a.ksplit < 1 ? 1 : (a.ksplit > nk_all ? nk_all : a.ksplit);
   da.stages = 1;
+  da.mc = 1;
   da.plane = static_cast<long long>(a.plane);
   da.trace = g_trace;
   // Skinny activations ("swap": the weights ride the 128-lane axis): each weight tile is read by one CTA
