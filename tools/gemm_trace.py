@@ -11,7 +11,7 @@ eng = Engine(stat.default_options())
 lib = eng.lib
 lib.stat_debug_gemm_trace.argtypes = [C.c_void_p]
 buf = torch.zeros(256, dtype=torch.int64, device='cuda')
-for (M, N, K) in [(64, 12594, 512), (64, 4609, 512), (64, 2560, 512)]:
+for (M, N, K, SW) in [(64, 12594, 512, True), (13312, 512, 4096, False)]:
     A = torch.randn(M, K, device='cuda')
     Bt = torch.randn(N, K, device='cuda')
     for it in range(3):
@@ -20,7 +20,7 @@ for (M, N, K) in [(64, 12594, 512), (64, 4609, 512), (64, 2560, 512)]:
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.gemm(A, Bt, swap=True)
+        eng.gemm(A, Bt, swap=SW)
         e1.record()
         torch.cuda.synchronize()
         lib.stat_debug_gemm_trace(C.c_void_p(0))

@@ -715,9 +715,9 @@ int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   {
     static int mc_max = -1;
     if (mc_max < 0) {
-      const char *e = getenv("STAT_GEMM_MULTICAST");       // 1 = off, 2 / 4 = cluster size limit (default 4)
-      mc_max = e ? atoi(e) : 4;
-      if (mc_max != 1 && mc_max != 2 && mc_max != 4) mc_max = 4;
+      const char *e = getenv("STAT_GEMM_MULTICAST");       // 1 = off (default), 2 / 4 = cluster size limit
+      mc_max = e ? atoi(e) : 1;       // measured on the B200: no gain at 2, slower at 4 -> off
+      if (mc_max != 1 && mc_max != 2 && mc_max != 4) mc_max = 1;
     }
     const int ptiles = (a.NP + BP - 1) / BP;
     if (TS && BQ == 128 && !a.feat_on_p && da.ksplit == 1 && ptiles >= 8) {
