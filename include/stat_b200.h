@@ -98,15 +98,17 @@ const char *stat_last_error(void);
  * GEMM (device-side cross-checks used by the GPU tests; never a CPU path). */
 int stat_set_gemm_impl(int impl);
 
-/* Implementation of the decode step behind stat_forward_teacher / stat_decode_greedy (same results to fp32
- * summation order; both are device paths):
- *   0 = separate kernels (default): attention -> ctx.[Wc|Wctx] -> gates -> h.[Wd*|U|W_sel|Wl] as k-split tensor-core
- *       products + elementwise kernels, readout activation -> logits -> vocabulary reduction beside the next attention
- *   1 = fused step kernels (step_fused.cu): attention -> ctx.Wc with the gates (S10-S13) in the epilogue ->
- *       h.[Wd*|W_sel|U|Wl] with the readout activation in the epilogue; logits with the per-tile vocabulary reduction
- *       in the epilogue -> combine.  K split over thread-block clusters, partial tiles summed through distributed
- *       shared memory.  Three dependent launches per step instead of four; measured slower end to end in round 2
- *       (DESIGN.md section 8), kept selectable.  Also: environment STAT_FUSED=1. */
+/* Implementation of the decode step behind stat_forward_teacher / stat_decode_greedy / stat_decode_beam (same
+ * results to fp32 summation order; all are device paths):
+ *   2 = cell step (cell_step.cu; the default where the shape allows it: H % 32 == 0, 160 <= H <= 512, no explicit
+ *       dropout mask on h): attention -> ONE kernel for ctx.Wc + gates (S10-S13) | grid barrier | every product of
+ *       the new hidden state + readout activation.  Two dependent launches per step; logits -> vocabulary reduction
+ *       beside the next attention.
+ *   0 = separate kernels: attention -> ctx.[Wc|Wctx] -> gates -> h.[Wd*|U|W_sel|Wl] as k-split tensor-core products +
+ *       elementwise kernels, readout activation -> logits -> vocabulary reduction beside the next attention
+ *   1 = fused tile kernels (step_fused.cu): gates / readout activation / vocabulary reduction in tcgen05 tile
+ *       epilogues; measured slower end to end in round 2, kept selectable.
+ *  -1 = back to the default (environment STAT_STEP=0|1|2, else 2). */
 int stat_set_step_impl(int impl);
 
 /* ---- L2 residency of the context blocks (no reference counterpart) -----------

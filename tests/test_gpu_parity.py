@@ -331,15 +331,16 @@ def test_alpha_tolerance_margin_over_100_clips(torch_cuda):
 
 
 # ---------------------------------------------------------------------------
-# the fused step kernels (stat_set_step_impl(1)): same contract as the default path
+# the other step implementations (stat_set_step_impl): 0 = separate kernels, 1 = fused tile kernels; the default (2,
+# the cell step where the shape allows it) is what every other test runs.  Same contract for all.
 # ---------------------------------------------------------------------------
-@pytest.fixture
-def fused_step():
+@pytest.fixture(params=[0, 1], ids=['separate', 'fused_tiles'])
+def fused_step(request):
     from video_description_with_spatial_temporal_attention_b200 import _lib
     lib = _lib.load()
-    _lib.check(lib.stat_set_step_impl(1))
+    _lib.check(lib.stat_set_step_impl(request.param))
     yield
-    _lib.check(lib.stat_set_step_impl(0))
+    _lib.check(lib.stat_set_step_impl(-1))
 
 
 @pytest.mark.parametrize('name', NAMES)

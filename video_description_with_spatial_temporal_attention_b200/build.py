@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libstat_b200.so')
 OBJ = os.path.join(HERE, 'build')
-SOURCES = ('gemm_tf32x3.cu', 'att_step.cu', 'att_group.cu', 'recurrent.cu', 'optim.cu', 'backward.cu', 'step_fused.cu', 'stat_api.cu')
+SOURCES = ('gemm_tf32x3.cu', 'att_step.cu', 'att_group.cu', 'recurrent.cu', 'optim.cu', 'backward.cu', 'step_fused.cu', 'cell_step.cu', 'stat_api.cu')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC']
 

@@ -92,23 +92,35 @@ __device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * 1.442
 // d_i = 1 + 2^(arg_i).  The exponent arguments are clamped to 30 (tanh is 1 to fp32 precision far
 // below that), so the product of the four denominators stays below 2^121.  5 MUFU per 4 tanh.
 __device__ __forceinline__ float tanh_acc4(const float4 x, const float4 sc, const float4 m2u, float acc) {
+  // packed fp32 (FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of work -- the kernel is issue-bound when the
+  // blocks hit L2): a = (d0, d1), b = (d2, d3);  sum_i m_i / d_i = N.x / D.x + N.y / D.y  with
+  // D = a * b,  N = (m0, m1) * b + (m2, m3) * a
   constexpr float C2 = 2.885390081777927f;
-  const float d0 = ex2_approx(fminf(fmaf(x.x, C2, sc.x), 30.0f)) + 1.0f;
-  const float d1 = ex2_approx(fminf(fmaf(x.y, C2, sc.y), 30.0f)) + 1.0f;
-  const float d2 = ex2_approx(fminf(fmaf(x.z, C2, sc.z), 30.0f)) + 1.0f;
-  const float d3 = ex2_approx(fminf(fmaf(x.w, C2, sc.w), 30.0f)) + 1.0f;
-  const float d01 = d0 * d1, d23 = d2 * d3;
-  const float n01 = fmaf(m2u.y, d0, m2u.x * d1), n23 = fmaf(m2u.w, d2, m2u.z * d3);
-  const float num = fmaf(n23, d01, n01 * d23);
-  return fmaf(num, rcp_approx(d01 * d23), acc);
+  const float2 c2 = make_float2(C2, C2), one = make_float2(1.0f, 1.0f);
+  float2 a = __ffma2_rn(make_float2(x.x, x.y), c2, make_float2(sc.x, sc.y));
+  float2 b = __ffma2_rn(make_float2(x.z, x.w), c2, make_float2(sc.z, sc.w));
+  a.x = ex2_approx(fminf(a.x, 30.0f)); a.y = ex2_approx(fminf(a.y, 30.0f));
+  b.x = ex2_approx(fminf(b.x, 30.0f)); b.y = ex2_approx(fminf(b.y, 30.0f));
+  a = __fadd2_rn(a, one);
+  b = __fadd2_rn(b, one);
+  const float2 D = __fmul2_rn(a, b);
+  float2 N = __fmul2_rn(make_float2(m2u.x, m2u.y), b);
+  N = __ffma2_rn(make_float2(m2u.z, m2u.w), a, N);
+  const float num = fmaf(N.y, D.x, N.x * D.y);
+  return fmaf(num, rcp_approx(D.x * D.y), acc);
 }
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ float sum4(const float4 v) { return (v.x + v.y) + (v.z + v.w); }
 __device__ __forceinline__ void fma4(float4 &acc, float s, const float4 v) {
-  acc.x = fmaf(s, v.x, acc.x);
-  acc.y = fmaf(s, v.y, acc.y);
-  acc.z = fmaf(s, v.z, acc.z);
-  acc.w = fmaf(s, v.w, acc.w);
+  const float2 ss = make_float2(s, s);
+  const float2 lo = __ffma2_rn(ss, make_float2(v.x, v.y), make_float2(acc.x, acc.y));
+  const float2 hi = __ffma2_rn(ss, make_float2(v.z, v.w), make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void scale4(float4 &v, float s) {
+  const float2 ss = make_float2(s, s);
+  const float2 lo = __fmul2_rn(make_float2(v.x, v.y), ss), hi = __fmul2_rn(make_float2(v.z, v.w), ss);
+  v = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // Butterfly reduction of N (power of two, <= 16) per-lane values over the warp: halving steps over
@@ -239,8 +251,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   if (cs > 1) cluster_arrive();     // matched by cluster_wait() before the first remote write (end of kernel)
 
   const uint32_t bytes_rh = static_cast<uint32_t>(RH) * 4u, bytes_h = static_cast<uint32_t>(H) * 4u;
+  // odd decode steps walk the slice backwards: what the previous step read last is read first (L2 reuse)
+  const int rev = a.reverse;
+  auto frame_of = [&](int j) { return t0 + (rev ? nframes - 1 - j : j); };
   auto issue_p = [&](int j) {
-    const size_t frame = static_cast<size_t>(clip) * T + t0 + j;
+    const size_t frame = static_cast<size_t>(clip) * T + frame_of(j);
     const uint32_t dst = smem_u32(slot_p);
     mbar_expect_tx(bar_p, static_cast<uint32_t>(p_floats) * 4u);
     bulk_g2s(dst, a.pctxl + frame * RH, bytes_rh, bar_p, policy);
@@ -248,7 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     bulk_g2s(dst + bytes_rh + bytes_h, a.pctxm + frame * H, bytes_h, bar_p, policy);
   };
   auto issue_v = [&](int j) {
-    const size_t frame = static_cast<size_t>(clip) * T + t0 + j;
+    const size_t frame = static_cast<size_t>(clip) * T + frame_of(j);
     const uint32_t dst = smem_u32(slot_v);
     mbar_expect_tx(bar_v, static_cast<uint32_t>(v_floats) * 4u);
     bulk_g2s(dst, a.ctxl0 + frame * RH, bytes_rh, bar_v, policy);
@@ -358,7 +373,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     uint32_t ph = 0;
     int fi = 0;
     for (int j = g; j < nframes; j += G, ph ^= 1, ++fi) {
-      const int t = t0 + j;
+      const int t = frame_of(j);
       const float *pL = slot_p, *pG = slot_p + RH, *pM = pG + H;
       const float *cL0 = slot_v, *qL = slot_v + RH;
       // the g / m values of the frame (2 x H floats) come straight from global memory: requested at the
@@ -454,8 +469,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 fma4(p0, al[r], ld4(qL + r * H + c));
               }
             }
-            c0.x *= inv; c0.y *= inv; c0.z *= inv; c0.w *= inv;
-            p0.x *= inv; p0.y *= inv; p0.z *= inv; p0.w *= inv;
+            scale4(c0, inv);
+            scale4(p0, inv);
             plt = tanh_acc4(p0, slt[jj], ult[jj], plt);
           }
           cLv[jj] = c0;
@@ -483,9 +498,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           rm[q] = sc3[q];
           rs[q] *= keep;
 #pragma unroll
-          for (int jj = 0; jj < NV; ++jj) {
-            acc[q][jj].x *= keep; acc[q][jj].y *= keep; acc[q][jj].z *= keep; acc[q][jj].w *= keep;
-          }
+          for (int jj = 0; jj < NV; ++jj) scale4(acc[q][jj], keep);
         } else {
           e = exp_fast(sc3[q] - rm[q]);
         }
@@ -540,7 +553,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) {
       const int col = tid + 512 * k;
-      if (col < H) ctx[col] = beta * (ov[0][k] / os[0] + ov[1][k] / os[1] + ov[2][k] / os[2]);
+      if (col < H) {
+        const float v = beta * (ov[0][k] / os[0] + ov[1][k] / os[1] + ov[2][k] / os[2]);
+        ctx[col] = v;
+        if (a.ctx_t) a.ctx_t[(static_cast<size_t>(row >> 6) * H + col) * 64 + (row & 63)] = v;
+      }
     }
     return;
   }
@@ -594,7 +611,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) {
       const int col = tid + 512 * k;
-      if (col < H) ctx[col] = beta * o[k];
+      if (col < H) {
+        ctx[col] = beta * o[k];
+        if (a.ctx_t) a.ctx_t[(static_cast<size_t>(row >> 6) * H + col) * 64 + (row & 63)] = beta * o[k];
+      }
     }
   }
   if (tr) tr[15] = clock64();

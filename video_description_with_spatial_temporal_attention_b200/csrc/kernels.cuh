@@ -29,6 +29,8 @@ struct AttArgs {
   float *att_scores;                             // (3,rows,T) raw temporal scores or null
   float *alpha_l;                                // (rows,T,R) spatial weights or null
   long long *trace;                              // debug: clock stamps per CTA and group (att_group), or null
+  int reverse;                                   // att_group: walk the frames of a slice backwards (odd decode steps)
+  float *ctx_t;                                  // [row / 64][H][64] transposed copy of ctx (cell_kernel operand) or null
 };
 int att_step_launch(const AttArgs &a, cudaStream_t stream);
 // att_group.cu: four independent four-warp groups per CTA, each streaming whole frames (H % 4 == 0,
@@ -183,6 +185,41 @@ bool fused_supported(int H, int E);
 int fused_phase_launch(const FusedPhase &p, cudaStream_t stream);
 // combine of the FE_PICK partials of one step + greedy / teacher-forcing bookkeeping (PickArgs as pick_launch)
 int pick_combine_launch(const PickArgs &a, const float *part, int npart, const float *tgt, cudaStream_t stream);
+
+// ---- cell_step.cu: everything of a decode step between two attentions in one launch --------------------------
+struct CellPlan {
+  int grid;                  // CTAs = SMs (all co-resident: the kernel has a grid-wide barrier)
+  int upc, epc, cpc;         // hidden units / readout columns (phase 1), output columns (phase 2) per CTA
+  int NQ1, NQ;               // 8H+4 (queries | sel | pad | h.U), 8H+4+E (+ readout)
+  size_t w1_floats, w2_floats;   // sizes of the packed weight slabs
+};
+bool cell_plan(int H, int E, CellPlan *out);
+// slabs from the K-major gate-interleaved packs: WcI (4H+E, H), WqT (8H+4+E, H)
+int cell_pack_launch(const float *WcI, const float *WqT, float *W1, float *W2, int H, int E, int ctx2out,
+                     cudaStream_t stream);
+struct CellLaunch {
+  int rows, H, E, V;
+  int do1, do2;              // phase 1: ctx.Wc -> gates -> h, c, zadd;  phase 2: products of the (new) hidden state
+  int want_q, want_z;        // phase 2 outputs: queries / sel / h.U rows (hq), readout activation (z)
+  int prev2out;
+  const float *W1, *W2;      // packed slabs (cell_pack_launch)
+  const float *ctxT;         // [chunk][H][64] fused context, transposed (written by the attention kernel)
+  float *hT;                 // [chunk][H][64] hidden state, transposed: written by phase 1, read by phase 2
+  float *hq;                 // (rows, ldq) [queries 4H | sel | 3 pad | h.U 4H gate-interleaved]: phase 1 reads the
+  int ldq;                   //   h.U block of the previous launch, phase 2 writes the row (to hq_out when not null)
+  float *hq_out;
+  const float *EW, *Wemb, *bz, *bq;
+  const int64_t *tok_prev;   // (rows) or null = no previous word
+  const float *mask;         // (rows) or null
+  const float *dp_gates;     // (rows, 3H) or null = 0.5
+  const float *dp_z;         // (rows, E) or null = 0.5
+  const float *h_in, *c_in;
+  float *h_out, *c_out;      // may alias the inputs
+  float *h_all;              // (rows, H) or null
+  float *zadd, *z;           // (rows, E)
+  unsigned int *bar;         // 2 words, zero before the first launch
+};
+int cell_launch(const CellLaunch &c, cudaStream_t stream);
 
 // ---- optim.cu: gradient clipping and the reference's optimizers over one flat parameter buffer ----
 size_t clip_scratch_bytes();

@@ -103,6 +103,8 @@ struct Prep {
                  //              ff_logit_lstm_W                                             -- multiplies h
   size_t bq;     // (8H+4)    : 0 | 0 | 0 | blt | b_sel | 0 ...
   size_t bdi;    // (4H)      : decoder_b, gate-interleaved
+  // cell step (cell_step.cu): per-CTA [k][column] slabs cut from WcI / WqT
+  size_t W1s, W2s;
   size_t total;  // floats
   int NH, NC;
 };
@@ -149,6 +151,12 @@ Prep prep_layout(const StatDims &d) {
   p.WqT = take((8 * H + 4 + E) * H);
   p.bq = take(8 * H + 4);
   p.bdi = take(4 * H);
+  {
+    CellPlan cp;
+    const bool ok = cell_plan(d.H, d.E, &cp);
+    p.W1s = take(ok ? cp.w1_floats : 0);
+    p.W2s = take(ok ? cp.w2_floats : 0);
+  }
   p.total = o;
   return p;
 }
@@ -168,6 +176,7 @@ struct Ws {
   size_t lpc;                        // Kahan compensation of the teacher-forced log-prob accumulation
   size_t hq, part, tgt;              // fused step: [queries | selector logit | h.U] rows, vocabulary partials
   int ldq2, npart;
+  size_t ctxT, hT, hq2, cell_bar;    // cell step: transposed ctx / h ([chunk][H][64]), second hq (beam), barrier words
   size_t total;                      // floats
   int ldhp, ldpc, ldl, S, Tc;
   int att_impl;      // 2 = att_group_kernel (bulk-copy streaming), 0 = the generic att_step_kernel
@@ -274,6 +283,13 @@ Ws ws_layout(const StatDims &d, int rows) {
   w.part = take(n * w.npart * 4);
   w.tgt = take(n);
   w.lpc = take(n);
+  {
+    const size_t chunks = (n + 63) / 64;
+    w.ctxT = take(chunks * H * 64);
+    w.hT = take(chunks * H * 64);
+    w.hq2 = take(n * w.ldq2);
+    w.cell_bar = take(64);
+  }
   w.total = o;
   return w;
 }
@@ -345,7 +361,14 @@ int side_set(SideSet **out) {
       STAT_CUDA_CHECK(cudaStreamCreateWithFlags(&t.k0[i], cudaStreamNonBlocking));
       STAT_CUDA_CHECK(cudaEventCreateWithFlags(&t.join[i], cudaEventDisableTiming));
     }
-    STAT_CUDA_CHECK(cudaStreamCreateWithFlags(&t.readout, cudaStreamNonBlocking));
+    {
+      // STAT_SIDE_PRIO=1: the readout chain gets the highest stream priority (its blocks are placed before
+      // those of the next attention when both are ready)
+      const char *e = getenv("STAT_SIDE_PRIO");
+      int lo = 0, hi = 0;
+      STAT_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      STAT_CUDA_CHECK(cudaStreamCreateWithPriority(&t.readout, cudaStreamNonBlocking, (e && e[0] == '1') ? hi : 0));
+    }
     STAT_CUDA_CHECK(cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming));
     STAT_CUDA_CHECK(cudaEventCreateWithFlags(&t.state, cudaEventDisableTiming));
     STAT_CUDA_CHECK(cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
@@ -432,6 +455,7 @@ struct StepIO {
   float *h_all;
   float *alpha_l;     // (rows,T,R) or null
   float *att_scores;  // (3,rows,T) or null
+  int reverse;        // attention walks the frames backwards (odd decode steps: L2 reuse across steps)
 };
 
 // what multiplies a hidden state: which = 1 the attention queries / h.U / selector logit of the NEXT
@@ -463,6 +487,7 @@ int step_att(const StatDims &d, const Prep &p, const float *P, const Ws &w, floa
              cudaStream_t st) {
   const int H = d.H, rows = io.rows;
   AttArgs a = att_args(d, p, P, w, W, rows, io.row_clip, io.att_scores, io.alpha_l);
+  a.reverse = io.reverse;
   {
     ProfScope ps(PH_ATT, st);
     STAT_TRY(att_launch(w, a, st));
@@ -536,15 +561,20 @@ int step_out(const StatDims &d, const Prep &p, const float *P, const Ws &w, floa
 // h: next queries, selector logit, h.U of the next cell, readout activation) on the caller's stream, logits (partial
 // vocabulary reduction fused) -> combine beside the next attention.
 // ---------------------------------------------------------------------------
-// step implementation: 0 = separate kernels (k-split products + gates / readout / vocabulary kernels; the default:
-// measured faster inside the captured decode), 1 = the fused step kernels.  stat_set_step_impl / STAT_FUSED=1.
+// step implementation: 0 = separate kernels (k-split products + gates / readout / vocabulary kernels), 1 = the fused
+// tile kernels, 2 = the cell step (cell_step.cu, default).  stat_set_step_impl / STAT_STEP.
 int g_step_impl = -1;
-bool fused_enabled(const StatDims &d, int rows) {
+int step_impl() {
   if (g_step_impl < 0) {
-    const char *e = getenv("STAT_FUSED");
-    g_step_impl = (e && e[0] == '1') ? 1 : 0;
+    const char *e = getenv("STAT_STEP");
+    const char *f = getenv("STAT_FUSED");
+    g_step_impl = e ? atoi(e) : ((f && f[0] == '1') ? 1 : 0);
+    if (g_step_impl < 0 || g_step_impl > 2) g_step_impl = 0;
   }
-  return g_step_impl == 1 && fused_supported(d.H, d.E) && rows <= 128;
+  return g_step_impl;
+}
+bool fused_enabled(const StatDims &d, int rows) {
+  return step_impl() == 1 && fused_supported(d.H, d.E) && rows <= 128;
 }
 
 AttArgs att_args_fused(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, int rows,
@@ -644,6 +674,48 @@ int fused_begin(const StatDims &d, const Prep &p, const float *P, const Ws &w, f
   return fstep_hidden(d, p, P, w, W, io, true, false, st);
 }
 
+// ---------------------------------------------------------------------------
+// cell step (cell_step.cu): attention -> cell on the caller's stream (2 dependent launches per step), logits -> pick
+// beside the next attention.  Default whenever the shape allows it (H % 32 == 0, 160 <= H <= 512, streaming
+// attention kernel, no explicit dropout mask on h); STAT_STEP=0 forces the separate kernels.
+// ---------------------------------------------------------------------------
+bool cell_enabled(const StatDims &d, const Ws &w, bool dp_h) {
+  return step_impl() == 2 && !dp_h && w.att_impl == 2 && cell_plan(d.H, d.E, nullptr);
+}
+
+CellLaunch cell_args(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io) {
+  CellLaunch c;
+  memset(&c, 0, sizeof(c));
+  c.rows = io.rows; c.H = d.H; c.E = d.E; c.V = d.V;
+  c.prev2out = (d.flags & STAT_PREV2OUT) ? 1 : 0;
+  c.W1 = P + p.W1s; c.W2 = P + p.W2s;
+  c.ctxT = W + w.ctxT; c.hT = W + w.hT;
+  c.hq = W + w.hq; c.ldq = w.ldq2;
+  c.EW = P + p.EW; c.Wemb = P + p.Wemb; c.bz = P + p.bz; c.bq = P + p.bq;
+  c.tok_prev = io.tok_prev; c.mask = io.mask; c.dp_gates = io.dp_gates; c.dp_z = io.dp_z;
+  c.h_in = io.h_in; c.c_in = io.c_in; c.h_out = io.h_out; c.c_out = io.c_out; c.h_all = io.h_all;
+  c.zadd = W + w.zadd; c.z = W + w.z;
+  c.bar = reinterpret_cast<unsigned int *>(W + w.cell_bar);
+  return c;
+}
+
+// h (rows, H) -> hT, then the queries / selector logit / h.U of the first cell (phase 2 alone)
+int cell_begin(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const float *h, int rows,
+               cudaStream_t st) {
+  const int H = d.H;
+  STAT_CUDA_CHECK(cudaMemsetAsync(W + w.cell_bar, 0, 64 * sizeof(float), st));
+  for (int r0 = 0; r0 < rows; r0 += 64)
+    STAT_TRY(transpose_launch(h + static_cast<size_t>(r0) * H, rows - r0 < 64 ? rows - r0 : 64, H,
+                              W + w.hT + static_cast<size_t>(r0 / 64) * H * 64, 64, 0, st));
+  StepIO io;
+  memset(&io, 0, sizeof(io));
+  io.rows = rows;
+  CellLaunch c = cell_args(d, p, P, w, W, io);
+  c.do1 = 0; c.do2 = 1; c.want_q = 1; c.want_z = 0;
+  ProfScope ps(PH_HPROJ, st);
+  return cell_launch(c, st);
+}
+
 // The readout chain of step t (step_out + the vocabulary reduction) on a side stream, next to the
 // attention of step t+1 on the caller's stream; the two meet again at the gates of step t+1, which
 // need the token picked in step t.  Event based, so it also works under stream capture.
@@ -683,6 +755,42 @@ struct Overlap {
     return STAT_OK;
   }
 };
+
+// Serpentine frame order: the attention of odd steps walks each slice backwards, so that what step t read last
+// (still in L2) is what step t+1 reads first.   STAT_ATT_SERP=0 turns it off.
+int serpentine(int t) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STAT_ATT_SERP");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on ? (t & 1) : 0;
+}
+
+// attention (writes ctx transposed) -> cell; `ov` = wait for the side stream before the cell (it needs the word
+// picked by the previous step's readout chain)
+int cell_step(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io, bool want_q,
+              float *hq_out, Overlap *ov, cudaStream_t st) {
+  AttArgs a = att_args_fused(d, p, P, w, W, io.rows, io.row_clip, io.att_scores, io.alpha_l);
+  a.reverse = io.reverse;
+  a.ctx_t = W + w.ctxT;
+  {
+    ProfScope ps(PH_ATT, st);
+    STAT_TRY(att_launch(w, a, st));
+  }
+  if (ov) STAT_TRY(ov->join());
+  CellLaunch c = cell_args(d, p, P, w, W, io);
+  c.do1 = 1; c.do2 = 1; c.want_q = want_q ? 1 : 0; c.want_z = 1;
+  c.hq_out = hq_out;
+  ProfScope ps(PH_FUSED_B, st);
+  return cell_launch(c, st);
+}
+
+// logits of the readout activation z (written by the cell kernel)
+int cell_logits(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, int rows, cudaStream_t st) {
+  ProfScope pl(PH_LOGITS, st);
+  return dense(W + w.z, d.E, rows, P + p.WvT, d.E, d.V, P + p.bv, W + w.logits, w.ldl, 0, 1.f, 1.f, nullptr, 0, st);
+}
 
 bool overlap_enabled() {
   static int on = -1;
@@ -803,7 +911,8 @@ int stat_adadelta_step(float *params, const float *grads, float *rg2, float *ru2
 }
 
 int stat_set_step_impl(int impl) {
-  STAT_REQUIRE(impl == 0 || impl == 1, STAT_EINVAL, "step impl must be 0 (separate kernels) or 1 (fused step kernels)");
+  STAT_REQUIRE(impl >= -1 && impl <= 2, STAT_EINVAL,
+               "step impl must be 0 (separate kernels), 1 (fused tile kernels), 2 (cell step) or -1 (default)");
   g_step_impl = impl;
   return STAT_OK;
 }
@@ -917,6 +1026,7 @@ int stat_prepare_params(const StatDims *d, const StatParams *sp, void *prepared,
   STAT_TRY(transpose_launch(sp->ff_logit_lstm_W, H, E, P + p.WqT, H, 8 * H + 4, st));
   STAT_CUDA_CHECK(cp(p.bq + 3 * H, sp->decoder_blt_att, H));
   if (sel) STAT_CUDA_CHECK(cp(p.bq + 4 * H, sp->decoder_b_sel, 1));
+  STAT_TRY(cell_pack_launch(P + p.WcI, P + p.WqT, P + p.W1s, P + p.W2s, H, E, c2o ? 1 : 0, st));
   return STAT_OK;
 }
 
@@ -1050,6 +1160,49 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
   STAT_CUDA_CHECK(cudaMemsetAsync(W + w.lpc, 0, sizeof(float) * B, st));
   STAT_CUDA_CHECK(cudaMemsetAsync(W + w.counters, 0, sizeof(float) * B, st));
   Overlap ov;
+  if (cell_enabled(*d, w, dp_h != nullptr)) {
+    STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.h, sizeof(float) * H, W + w.h0c0, sizeof(float) * 2 * H,
+                                      sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+    STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
+                                      sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+    STAT_TRY(cell_begin(*d, p, P, w, W, W + w.h, B, st));
+    STAT_TRY(ov.open(st, overlap_enabled()));
+    for (int t = 0; t < L; ++t) {
+      StepIO io;
+      memset(&io, 0, sizeof(io));
+      io.rows = B;
+      io.tok_prev = t > 0 ? x + static_cast<size_t>(t - 1) * B : nullptr;   // emb shifted by one step (:613-617)
+      io.mask = mask + static_cast<size_t>(t) * B;
+      io.dp_gates = dp_gates ? dp_gates + static_cast<size_t>(t) * B * 3 * H : nullptr;
+      io.dp_z = dp_z ? dp_z + static_cast<size_t>(t) * B * E : nullptr;
+      io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.h; io.c_out = W + w.c;
+      io.h_all = out_h ? out_h + static_cast<size_t>(t) * B * H : nullptr;
+      io.alpha_l = out_alpha_l ? out_alpha_l + static_cast<size_t>(t) * B * T * R : nullptr;
+      io.att_scores = want_t ? W + w.att_scores : nullptr;
+      io.reverse = serpentine(t);
+      STAT_TRY(cell_step(*d, p, P, w, W, io, t + 1 < L, nullptr, &ov, st));
+      if (want_t) {
+        const size_t n = static_cast<size_t>(B) * T;
+        if (out_alpha_g) STAT_TRY(softmax_rows_launch(W + w.att_scores, out_alpha_g + t * n, B, T, st));
+        if (out_alpha_m) STAT_TRY(softmax_rows_launch(W + w.att_scores + n, out_alpha_m + t * n, B, T, st));
+        if (out_alpha_lt) STAT_TRY(softmax_rows_launch(W + w.att_scores + 2 * n, out_alpha_lt + t * n, B, T, st));
+      }
+      STAT_TRY(ov.state_ready());
+      STAT_TRY(cell_logits(*d, p, P, w, W, B, ov.side()));
+      PickArgs k;
+      memset(&k, 0, sizeof(k));
+      k.rows = B; k.V = d->V; k.ldl = w.ldl; k.logits = W + w.logits;
+      k.x_t = x + static_cast<size_t>(t) * B;
+      k.mask_t = mask + static_cast<size_t>(t) * B;
+      k.logprob = out_logprob; k.logprob_comp = W + w.lpc;
+      {
+        ProfScope ps(PH_PICK, ov.side());
+        STAT_TRY(pick_launch(k, ov.side()));
+      }
+      STAT_TRY(ov.side_enqueued());
+    }
+    return ov.join();
+  }
   if (fused_enabled(*d, B)) {
     STAT_TRY(fused_begin(*d, p, P, w, W, B, st));
     STAT_TRY(ov.open(st, overlap_enabled()));
@@ -1107,6 +1260,7 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
     io.dp_h = dp_h ? dp_h + static_cast<size_t>(t) * B * H : nullptr;
     io.dp_z = dp_z ? dp_z + static_cast<size_t>(t) * B * E : nullptr;
     io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.h; io.c_out = W + w.c;
+    io.reverse = serpentine(t);
     io.h_all = out_h ? out_h + static_cast<size_t>(t) * B * H : nullptr;
     io.alpha_l = out_alpha_l ? out_alpha_l + static_cast<size_t>(t) * B * T * R : nullptr;
     io.att_scores = want_t ? W + w.att_scores : nullptr;
@@ -1153,6 +1307,36 @@ int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws, int ma
   STAT_CUDA_CHECK(cudaMemsetAsync(W + w.counters, 0, sizeof(float) * B, st));
   STAT_TRY(init_rows_launch(B, tok_prev, alive, out_lengths, out_scores, out_tokens, maxlen, st));
   Overlap ov;
+  if (cell_enabled(*d, w, false)) {
+    STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.h, sizeof(float) * H, W + w.h0c0, sizeof(float) * 2 * H,
+                                      sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+    STAT_CUDA_CHECK(cudaMemcpy2DAsync(W + w.c, sizeof(float) * H, W + w.h0c0 + H, sizeof(float) * 2 * H,
+                                      sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+    STAT_TRY(cell_begin(*d, p, P, w, W, W + w.h, B, st));
+    STAT_TRY(ov.open(st, overlap_enabled()));
+    for (int t = 0; t < maxlen; ++t) {
+      StepIO io;
+      memset(&io, 0, sizeof(io));
+      io.rows = B;
+      io.tok_prev = tok_prev;   // -1 on the first step: no previous word (:893, :803-804)
+      io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.h; io.c_out = W + w.c;
+      io.reverse = serpentine(t);
+      STAT_TRY(cell_step(*d, p, P, w, W, io, t + 1 < maxlen, nullptr, &ov, st));
+      STAT_TRY(ov.state_ready());
+      STAT_TRY(cell_logits(*d, p, P, w, W, B, ov.side()));
+      PickArgs k;
+      memset(&k, 0, sizeof(k));
+      k.rows = B; k.V = d->V; k.ldl = w.ldl; k.logits = W + w.logits;
+      k.tokens = out_tokens; k.maxlen = maxlen; k.t = t;
+      k.lengths = out_lengths; k.scores = out_scores; k.alive = alive; k.tok_prev = tok_prev;
+      {
+        ProfScope ps(PH_PICK, ov.side());
+        STAT_TRY(pick_launch(k, ov.side()));
+      }
+      STAT_TRY(ov.side_enqueued());
+    }
+    return ov.join();
+  }
   if (fused_enabled(*d, B)) {
     STAT_TRY(fused_begin(*d, p, P, w, W, B, st));
     STAT_TRY(ov.open(st, overlap_enabled()));
@@ -1192,6 +1376,7 @@ int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws, int ma
     io.rows = B;
     io.tok_prev = tok_prev;   // -1 on the first step: no previous word (:893, :803-804)
     io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.h; io.c_out = W + w.c;
+    io.reverse = serpentine(t);
     STAT_TRY(step_att(*d, p, P, w, W, io, st));
     STAT_TRY(ov.join());
     STAT_TRY(step_gates(*d, p, P, w, W, io, t + 1 < maxlen, st));
@@ -1252,6 +1437,7 @@ int stat_decode_beam(const StatDims *d, const void *prepared, void *ws, int k, i
     io.row_clip = row_clip;
     io.tok_prev = b.tok_prev;
     io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.hb; io.c_out = W + w.cb;
+    io.reverse = serpentine(t);
     STAT_TRY(step_att(*d, p, P, w, W, io, st));
     STAT_TRY(step_gates(*d, p, P, w, W, io, false, st));
     STAT_TRY(step_out(*d, p, P, w, W, io, st));
