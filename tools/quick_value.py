@@ -36,6 +36,19 @@ for L in (2, 20):
     res[L] = a.elapsed_time(b) / n
     if L == 20:
         chk = int(out[0].clamp(min=0).sum().item())
+ws, d = eng.precompute(*devf)
+def eager():
+    eng.decode_greedy(ws, d, 20)
+eager()
+torch.cuda.synchronize()
+def parked():
+    torch.cuda._sleep(12000000)
+    eager()
+acc = {}
+for _ in range(3):
+    for k, (m, c) in eng.profile(parked).items():
+        acc[k] = acc.get(k, 0.0) + m / 3
+phases = ' '.join('%s=%.1f' % (k.replace('step_', ''), v / 20 * 1e3) for k, v in acc.items() if k.startswith('step_'))
 env = ' '.join('%s=%s' % (k, os.environ[k]) for k in sorted(os.environ) if k.startswith('STAT_'))
-print('L20 %.4f ms  L2 %.4f ms  per-step %.2f us  captions/s %.0f  tokens_checksum %d  [%s]' % (
-    res[20], res[2], (res[20] - res[2]) / 18 * 1e3, bench.B / res[20] * 1e3, chk, env))
+print('L20 %.4f ms  L2 %.4f ms  per-step %.2f us  captions/s %.0f  tokens_checksum %d  [%s]\n    eager us/step: %s' % (
+    res[20], res[2], (res[20] - res[2]) / 18 * 1e3, bench.B / res[20] * 1e3, chk, env, phases))

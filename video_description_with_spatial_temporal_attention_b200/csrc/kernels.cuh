@@ -137,6 +137,9 @@ int beam_init_launch(const BeamArgs &a, const float *h0c0, float *h, float *c, i
 int gather_state_launch(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h, float *dst_c,
                         int rows, int H, cudaStream_t stream);
 
+// dst[r][:] = src[src_row[r]][:]   (rows, width), width % 4 == 0
+int gather_rows_launch(const float *src, const int32_t *src_row, float *dst, int rows, int width, cudaStream_t stream);
+
 // ---- step_fused.cu: the fused products of a decode step (fused_tile.cuh) ----------------------------------
 enum { FE_STORE = 0, FE_GATES = 1, FE_ZC = 2, FE_Z = 3, FE_PICK = 4 };
 // epilogue parameters (the union of all kinds; a launch reads what its kinds need)

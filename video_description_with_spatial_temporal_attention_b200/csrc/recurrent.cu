@@ -518,6 +518,16 @@ __global__ void gather_state_kernel(const float *src_h, const float *src_c, cons
   }
 }
 
+// dst[r][:] = src[src_row[r]][:], rows of `width` floats (a multiple of 4, 16-byte aligned)
+__global__ void gather_rows_kernel(const float *src, const int32_t *src_row, float *dst, int width) {
+  pdl_wait();
+  pdl_trigger();
+  const int row = blockIdx.x;
+  const float4 *s = reinterpret_cast<const float4 *>(src + static_cast<size_t>(src_row[row]) * width);
+  float4 *d = reinterpret_cast<float4 *>(dst + static_cast<size_t>(row) * width);
+  for (int i = threadIdx.x; i < width / 4; i += blockDim.x) d[i] = s[i];
+}
+
 // ---------------------------------------------------------------------------
 // prologue helpers
 // ---------------------------------------------------------------------------
@@ -645,6 +655,10 @@ int beam_init_launch(const BeamArgs &a, const float *h0c0, float *h, float *c, i
 int gather_state_launch(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h, float *dst_c,
                         int rows, int H, cudaStream_t stream) {
   return launch_pdl(gather_state_kernel, dim3(rows), dim3(128), 0, stream, src_h, src_c, src_row, dst_h, dst_c, H);
+}
+
+int gather_rows_launch(const float *src, const int32_t *src_row, float *dst, int rows, int width, cudaStream_t stream) {
+  return launch_pdl(gather_rows_kernel, dim3(rows), dim3(256), 0, stream, src, src_row, dst, width);
 }
 
 int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, int T, int D,

@@ -564,6 +564,7 @@ int step_out(const StatDims &d, const Prep &p, const float *P, const Ws &w, floa
 // step implementation: 0 = separate kernels (k-split products + gates / readout / vocabulary kernels), 1 = the fused
 // tile kernels, 2 = the cell step (cell_step.cu, default).  stat_set_step_impl / STAT_STEP.
 int g_step_impl = -1;
+bool g_step_impl_set = false;      // stat_set_step_impl was called with an explicit implementation
 int step_impl() {
   if (g_step_impl < 0) {
     const char *e = getenv("STAT_STEP");
@@ -681,6 +682,18 @@ int fused_begin(const StatDims &d, const Prep &p, const float *P, const Ws &w, f
 // ---------------------------------------------------------------------------
 bool cell_enabled(const StatDims &d, const Ws &w, bool dp_h) {
   return step_impl() == 2 && !dp_h && w.att_impl == 2 && cell_plan(d.H, d.E, nullptr);
+}
+
+// Beam search (rows = B*k): beyond 128 rows the tensor-core products lose their skinny k-split form (two row tiles,
+// full-K loops) and the cell step is the faster chain (measured): default there unless
+// STAT_STEP / stat_set_step_impl says otherwise.
+bool cell_enabled_rows(const StatDims &d, const Ws &w, int rows) {
+  static int forced = -2;
+  if (forced == -2) forced = getenv("STAT_STEP") ? 1 : 0;
+  const bool ok = w.att_impl == 2 && cell_plan(d.H, d.E, nullptr);
+  if (!ok) return false;
+  if (step_impl() == 2) return true;
+  return !forced && !g_step_impl_set && rows > 128;
 }
 
 CellLaunch cell_args(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io) {
@@ -914,6 +927,7 @@ int stat_set_step_impl(int impl) {
   STAT_REQUIRE(impl >= -1 && impl <= 2, STAT_EINVAL,
                "step impl must be 0 (separate kernels), 1 (fused tile kernels), 2 (cell step) or -1 (default)");
   g_step_impl = impl;
+  g_step_impl_set = impl >= 0;
   return STAT_OK;
 }
 
@@ -1427,6 +1441,39 @@ int stat_decode_beam(const StatDims *d, const void *prepared, void *ws, int k, i
   b.out_tokens = out_tokens; b.out_lengths = out_lengths; b.out_scores = out_scores; b.out_count = out_count;
   STAT_CUDA_CHECK(cudaMemsetAsync(W + w.counters, 0, sizeof(float) * rows, st));
   STAT_TRY(beam_init_launch(b, W + w.h0c0, W + w.h, W + w.c, d->H, row_clip, st));
+  if (cell_enabled_rows(*d, w, rows)) {
+    // attention -> cell (gates | barrier | every product of the new state, for the rows as they are) -> logits ->
+    // pick -> select; the rows of the next step are gathered by src_row: h, c and the h-products (no second pass
+    // over the weights for the re-ordered rows)
+    STAT_TRY(cell_begin(*d, p, P, w, W, W + w.h, rows, st));
+    for (int t = 0; t < maxlen; ++t) {
+      StepIO io;
+      memset(&io, 0, sizeof(io));
+      io.rows = rows;
+      io.row_clip = row_clip;
+      io.tok_prev = b.tok_prev;
+      io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.hb; io.c_out = W + w.cb;
+      io.reverse = serpentine(t);
+      STAT_TRY(cell_step(*d, p, P, w, W, io, t + 1 < maxlen, W + w.hq2, nullptr, st));
+      STAT_TRY(cell_logits(*d, p, P, w, W, rows, st));
+      PickArgs pk;
+      memset(&pk, 0, sizeof(pk));
+      pk.rows = rows; pk.V = d->V; pk.ldl = w.ldl; pk.logits = W + w.logits;
+      pk.beam_k = k; pk.row_alive = b.alive; pk.row_score = b.score;
+      pk.cand_cost = W + w.cand_cost; pk.cand_word = reinterpret_cast<int32_t *>(W + w.cand_word);
+      {
+        ProfScope ps(PH_PICK, st);
+        STAT_TRY(pick_launch(pk, st));
+        b.t = t;
+        STAT_TRY(beam_select_launch(b, st));
+      }
+      if (t + 1 < maxlen) {
+        STAT_TRY(gather_state_launch(W + w.hb, W + w.cb, b.src_row, W + w.h, W + w.c, rows, d->H, st));
+        STAT_TRY(gather_rows_launch(W + w.hq2, b.src_row, W + w.hq, rows, w.ldq2, st));
+      }
+    }
+    return STAT_OK;
+  }
   STAT_TRY(h_proj(*d, p, P, w, W, W + w.h, rows, 1, st));
   for (int t = 0; t < maxlen; ++t) {
     // the k row slots of a clip share its context blocks; slot order changes every step, so the new
