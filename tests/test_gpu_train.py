@@ -27,10 +27,20 @@ def torch_cuda():
     return torch
 
 
-def _compare(got, want, rtol=RTOL, atol=5e-6):
+# The four score biases c of e = U.tanh(..) + c are shift invariant: their data gradient is sum_r d e_r over a soft-max
+# backward, analytically 0, numerically s * (1 - sum_r alpha_r) per (step, clip, frame) with fp32-normalised weights
+# (|1 - sum alpha| ~ 6e-8).  Over the 66 560 (step, clip, frame) triples of config 3 that is a random walk of a few 1e-6:
+# the noise floor of any fp32 implementation (the reference's included), not an error of the backward pass.
+SHIFT_INVARIANT = ('decoder_cl_att', 'decoder_cg_att', 'decoder_cm_att', 'decoder_clt_att')
+
+
+def _compare(got, want, rtol=RTOL, atol=5e-6, atol_shift=None):
     assert list(got.keys()) == list(want.keys())
     worst = ('', 0.0)
     for k, w in want.items():
+        if atol_shift is not None and k in SHIFT_INVARIANT:
+            assert float(np.abs(got[k].astype('float64') - w).max()) <= atol_shift, k
+            continue
         g = got[k].astype('float64')
         assert g.shape == w.shape, k
         assert np.isfinite(g).all(), k
@@ -124,7 +134,7 @@ def test_grad_shared_config3_width_vs_oracle(torch_cuda):
     cost = tr.f_grad_shared(*batch)[0]
     want_cost, want, _ = go.cost_and_grads(params, o, batch, **kw)
     assert abs(cost - want_cost) < 1e-4 * max(1.0, abs(want_cost))
-    worst = _compare(tr.grads(), want, rtol=5e-4)
+    worst = _compare(tr.grads(), want, rtol=5e-4, atol_shift=3e-5)
     print('config 3 (B=%d): worst relative gradient error' % B, worst)
 
 
@@ -152,7 +162,8 @@ def test_grad_shared_config3_b128_properties(torch_cuda):
         s_ = halves[0][k] + halves[1][k]
         scale = max(float(np.abs(s_).max()), 1e-6)
         # different summation orders (row counts change the k-split of the tall products): fp32 reassociation only
-        assert float(np.abs(g[k] - s_).max()) <= 3e-4 * scale + 1e-7, k
+        tol = 3e-5 if k in SHIFT_INVARIANT else 3e-4 * scale + 1e-7
+        assert float(np.abs(g[k] - s_).max()) <= tol, k
 
 
 @pytest.mark.parametrize('optimizer', ['adam', 'adadelta'])

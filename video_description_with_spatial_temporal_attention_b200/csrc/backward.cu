@@ -99,6 +99,14 @@ inline void bw_mark(int phase, cudaStream_t st) {
 // device helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+// tanh of the attention-score backward (11 per column and step in k_att_main, L*R per element in k_att_accum: the
+// accurate tanhf made those kernels instruction-bound).  Same 2-MUFU form as the forward attention kernel, absolute
+// error ~1.5e-7; the CPU emulation keeps tanhf.
+#ifdef STAT_EMU
+__device__ __forceinline__ float tanh_bw(float x) { return tanhf(x); }
+#else
+__device__ __forceinline__ float tanh_bw(float x) { return tanh_fast(x); }
+#endif
 
 // Sum over the block, result in every thread (same summation order everywhere).  All threads
 // of the block must call; blockDim.x is a multiple of 32; sh holds 32 floats.
@@ -111,6 +119,32 @@ __device__ __forceinline__ float block_sum(float v, float *sh) {
   float r = 0.f;
   for (int i = 0; i < nw; ++i) r += sh[i];
   return r;
+}
+
+// N sums over the block at once (one barrier pair for all of them; same summation order as block_sum):
+// v[i] <- block total of v[i], in every thread.  sh holds 32 * N floats.
+template <int N>
+__device__ __forceinline__ void block_sum_n(float (&v)[N], int n, float *sh) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (i < n)
+      for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (i < n) sh[w * N + i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if (i < n) {
+      float r = 0.f;
+      for (int k = 0; k < nw; ++k) r += sh[k * N + i];
+      v[i] = r;
+    }
+  }
 }
 
 __device__ __forceinline__ float block_max(float v, float *sh) {
@@ -384,20 +418,34 @@ __global__ void k_selector_bw(int t, const float *DCTX, const float *DCR, const 
 }
 
 // per (clip, frame): cL = sum_r alpha_l * Lc, and the three d alpha = dC . value   (:383,:399,:412,:426)
+// (RT = compile-time R, 0 = runtime: with the region loops unrolled the loads of a column go out together instead of
+// one DRAM round trip per region)
+template <int RT>
 __global__ void k_att_dots(int t_step, const float *al, const float *Lc, const float *G, const float *M,
-                           const float *DC, float *CL, float *DA3, int B, int T, int R, int H) {
+                           const float *DC, float *CL, float *DA3, int B, int T, int R_, int H) {
   __shared__ float sh[32];
+  const int R = RT ? RT : R_;
+  constexpr int RU = RT ? RT : RMAX;
   const int bt = blockIdx.x, b = bt / T;
   const size_t n = static_cast<size_t>(t_step) * B + b;
   const size_t nt = n * T + (bt % T);
+  float alr[RU];
+#pragma unroll
+  for (int r = 0; r < RU; ++r) alr[r] = (RT || r < R) ? al[nt * R + r] : 0.f;
   float pg = 0.f, pm = 0.f, pl = 0.f;
   for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float cl = 0.f;
-    for (int r = 0; r < R; ++r) cl = fmaf(al[nt * R + r], Lc[(static_cast<size_t>(bt) * R + r) * H + h], cl);
-    CL[static_cast<size_t>(bt) * H + h] = cl;
+    float lc[RU];
+#pragma unroll
+    for (int r = 0; r < RU; ++r) lc[r] = (RT || r < R) ? Lc[(static_cast<size_t>(bt) * R + r) * H + h] : 0.f;
     const float d = DC[static_cast<size_t>(b) * H + h];
-    pg = fmaf(d, G[static_cast<size_t>(bt) * H + h], pg);
-    pm = fmaf(d, M[static_cast<size_t>(bt) * H + h], pm);
+    const float gv = G[static_cast<size_t>(bt) * H + h], mv = M[static_cast<size_t>(bt) * H + h];
+    float cl = 0.f;
+#pragma unroll
+    for (int r = 0; r < RU; ++r)
+      if (RT || r < R) cl = fmaf(alr[r], lc[r], cl);
+    CL[static_cast<size_t>(bt) * H + h] = cl;
+    pg = fmaf(d, gv, pg);
+    pm = fmaf(d, mv, pm);
     pl = fmaf(d, cl, pl);
   }
   pg = block_sum(pg, sh);
@@ -453,18 +501,21 @@ struct AttBw {
   float *DPLT;                            // (L,B,T,H) dpLT of every step
 };
 
+template <int RT>
 __global__ void k_att_main(const AttBw a) {
-  __shared__ float sh[32];
-  const int H = a.H, R = a.R, T = a.T;
+  __shared__ float sh[32 * RMAX];
+  constexpr int RU = RT ? RT : RMAX;
+  const int H = a.H, R = RT ? RT : a.R, T = a.T;
   const int bt = blockIdx.x, b = bt / T;
   const size_t n = static_cast<size_t>(a.t_step) * a.B + b;
   const size_t nt = n * T + (bt % T);
   const size_t BT = static_cast<size_t>(a.B) * T;
   const float daG = a.DS3[bt], daM = a.DS3[BT + bt], daLT = a.DS3[2 * BT + bt];
   const float aG = a.ag[nt], aM = a.am[nt], aLT = a.alt[nt];
-  float alr[RMAX], part[RMAX];
-  for (int r = 0; r < R; ++r) {
-    alr[r] = a.al[nt * R + r];
+  float alr[RU], part[RU];
+#pragma unroll
+  for (int r = 0; r < RU; ++r) {
+    alr[r] = (RT || r < R) ? a.al[nt * R + r] : 0.f;
     part[r] = 0.f;
   }
   const float *hq = a.HQ + n * a.ldq;
@@ -472,63 +523,89 @@ __global__ void k_att_main(const AttBw a) {
   int k = 0;
   for (int h = threadIdx.x; h < H; h += blockDim.x, ++k) {
     const size_t o = static_cast<size_t>(bt) * H + h, o4 = static_cast<size_t>(bt) * 4 * H + h;
+    // the loads of this column first (independent addresses: one memory round trip), then the arithmetic
+    float q[RU], lc[RU];
+#pragma unroll
+    for (int r = 0; r < RU; ++r) {
+      const size_t ol = (static_cast<size_t>(bt) * R + r) * H + h;
+      q[r] = (RT || r < R) ? a.Q[ol] : 0.f;
+      lc[r] = (RT || r < R) ? a.Lc[ol] : 0.f;
+    }
     const float dc = a.DC[static_cast<size_t>(b) * H + h];
+    const float pg = a.pG[o], pm = a.pM[o], sg = hq[H + h], sm = hq[2 * H + h], slt = hq[3 * H + h];
+    const float ug = a.Ug[h], um = a.Um[h], ult = a.Ult[h];
     // global / motion attention (:389-412)
-    const float tg = tanhf(a.pG[o] + hq[H + h]);
-    const float dqg = daG * a.Ug[h] * (1.0f - tg * tg);
+    const float tg = tanh_bw(pg + sg);
+    const float dqg = daG * ug * (1.0f - tg * tg);
     a.DPG[o] += dqg;
     a.DSQP[o4 + H] = dqg;
     a.DUACC[o4 + H] += daG * tg;
     if (a.global_proj) a.DG[o] += aG * dc;
-    const float tm = tanhf(a.pM[o] + hq[2 * H + h]);
-    const float dqm = daM * a.Um[h] * (1.0f - tm * tm);
+    const float tm = tanh_bw(pm + sm);
+    const float dqm = daM * um * (1.0f - tm * tm);
     a.DPM[o] += dqm;
     a.DSQP[o4 + 2 * H] = dqm;
     a.DUACC[o4 + 2 * H] += daM * tm;
     a.DM[o] += aM * dc;
     // local-temporal attention (:415-426), pLT = sum_r alpha_l Q_r + blt + slt
-    float plt = hq[3 * H + h];
-    for (int r = 0; r < R; ++r) plt = fmaf(alr[r], a.Q[(static_cast<size_t>(bt) * R + r) * H + h], plt);
-    const float tl = tanhf(plt);
-    const float dp = daLT * a.Ult[h] * (1.0f - tl * tl);
+    float plt = slt;
+#pragma unroll
+    for (int r = 0; r < RU; ++r)
+      if (RT || r < R) plt = fmaf(alr[r], q[r], plt);
+    const float tl = tanh_bw(plt);
+    const float dp = daLT * ult * (1.0f - tl * tl);
     a.DSQP[o4 + 3 * H] = dp;
     a.DUACC[o4 + 3 * H] += daLT * tl;
     const float dcL = aLT * dc;
     dcl[k] = dcL;
     dpl[k] = dp;
     if (a.DPLT) a.DPLT[nt * H + h] = dp;
-    for (int r = 0; r < R; ++r) {
-      const size_t ol = (static_cast<size_t>(bt) * R + r) * H + h;
-      part[r] = fmaf(dcL, a.Lc[ol], fmaf(dp, a.Q[ol], part[r]));
-    }
+#pragma unroll
+    for (int r = 0; r < RU; ++r)
+      if (RT || r < R) part[r] = fmaf(dcL, lc[r], fmaf(dp, q[r], part[r]));
   }
   // spatial soft-max backward (:380-383)
+  block_sum_n<RU>(part, R, sh);
   float s = 0.f;
-  for (int r = 0; r < R; ++r) {
-    part[r] = block_sum(part[r], sh) + a.COVL[static_cast<size_t>(bt) * R + r];
-    s = fmaf(alr[r], part[r], s);
+#pragma unroll
+  for (int r = 0; r < RU; ++r) {
+    if (RT || r < R) {
+      part[r] += a.COVL[static_cast<size_t>(bt) * R + r];
+      s = fmaf(alr[r], part[r], s);
+    }
   }
-  float dal[RMAX], dsum = 0.f;
-  for (int r = 0; r < R; ++r) {
-    dal[r] = alr[r] * (part[r] - s);
+  float dal[RU], dsum = 0.f;
+#pragma unroll
+  for (int r = 0; r < RU; ++r) {
+    dal[r] = (RT || r < R) ? alr[r] * (part[r] - s) : 0.f;
     dsum += dal[r];
   }
   if (threadIdx.x == 0) a.DCACC[static_cast<size_t>(bt) * 4] += dsum;
-  if (a.DAL && threadIdx.x < R) a.DAL[nt * R + threadIdx.x] = dal[threadIdx.x];
+  if (a.DAL) {
+#pragma unroll
+    for (int r = 0; r < RU; ++r)
+      if ((RT || r < R) && threadIdx.x == r) a.DAL[nt * R + r] = dal[r];
+  }
   k = 0;
   for (int h = threadIdx.x; h < H; h += blockDim.x, ++k) {
     const float sl = hq[h], ul = a.Ul[h];
+    float pl[RU];
+#pragma unroll
+    for (int r = 0; r < RU; ++r) pl[r] = (RT || r < R) ? a.pL[(static_cast<size_t>(bt) * R + r) * H + h] : 0.f;
     float dsl = 0.f, dul = 0.f;
-    for (int r = 0; r < R; ++r) {
-      const size_t ol = (static_cast<size_t>(bt) * R + r) * H + h;
-      const float tl = tanhf(a.pL[ol] + sl);
-      const float dq = dal[r] * ul * (1.0f - tl * tl);
-      dsl += dq;
-      dul = fmaf(dal[r], tl, dul);
-      if (!a.DAL) {
-        a.DPL[ol] += dq;
-        a.DLC[ol] = fmaf(alr[r], dcl[k], a.DLC[ol]);
-        a.DQ[ol] = fmaf(alr[r], dpl[k], a.DQ[ol]);
+#pragma unroll
+    for (int r = 0; r < RU; ++r) {
+      if (RT || r < R) {
+        const size_t ol = (static_cast<size_t>(bt) * R + r) * H + h;
+        const float tl = tanh_bw(pl[r] + sl);
+        const float dq = dal[r] * ul * (1.0f - tl * tl);
+        dsl += dq;
+        dul = fmaf(dal[r], tl, dul);
+        if (!a.DAL) {
+          a.DPL[ol] += dq;
+          a.DLC[ol] = fmaf(alr[r], dcl[k], a.DLC[ol]);
+          a.DQ[ol] = fmaf(alr[r], dpl[k], a.DQ[ol]);
+        }
       }
     }
     const size_t o4 = static_cast<size_t>(bt) * 4 * H + h;
@@ -550,10 +627,11 @@ __global__ void k_att_accum(int L, int B, int T, int R, int H, int ldq, const fl
       const size_t ol = (static_cast<size_t>(bt) * R + r) * H + h;
       const float pl = pL[ol];
       float apl = 0.f, alc = 0.f, aq = 0.f;
+#pragma unroll 4
       for (int s = L - 1; s >= 0; --s) {
         const size_t n = static_cast<size_t>(s) * B + b, nt = n * T + t;
         const float ar = al[nt * R + r];
-        const float tl = tanhf(pl + HQ[n * ldq + h]);
+        const float tl = tanh_bw(pl + HQ[n * ldq + h]);
         apl = fmaf(DAL[nt * R + r] * ul, 1.0f - tl * tl, apl);
         alc = fmaf(ar, alt[nt] * DCS[n * H + h], alc);
         aq = fmaf(ar, DPLT[nt * H + h], aq);
@@ -1007,7 +1085,7 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     STAT_TRY(BW_LAUNCH(k_selector_bw, dim3(B), dim3(NT), st, t, W + w.DCTX, W + w.DCR, W + w.csum, W + w.beta,
                        W + w.DHQ, ldq, 8 * H, DCt, B, H, sel ? 1 : 0));
     bw_mark(BP_ATT_DOTS, st);
-    STAT_TRY(BW_LAUNCH(k_att_dots, dim3(BT), dim3(NT), st, t, alpha_l, f->ctxl0, f->ctxg0, f->ctxm0, DCt,
+    STAT_TRY(BW_LAUNCH((R == 8 ? k_att_dots<8> : k_att_dots<0>), dim3(BT), dim3(NT), st, t, alpha_l, f->ctxl0, f->ctxg0, f->ctxm0, DCt,
                        W + w.CL, W + w.DA3, B, T, R, H));
     bw_mark(BP_ATT_SOFT, st);
     STAT_TRY(BW_LAUNCH(k_att_soft, g1(3 * B, 128), dim3(128), st, t, alpha_g, alpha_m, alpha_lt, W + w.DA3,
@@ -1025,7 +1103,7 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     a.DPG = W + w.DPG; a.DPM = W + w.DPM; a.DG = W + w.DG; a.DM = W + w.DM;
     a.DUACC = W + w.DUACC; a.DCACC = W + w.DCACC; a.DSQP = W + w.DSQP;
     if (fast) { a.DAL = W + w.DAL; a.DPLT = W + w.DPLT; }
-    STAT_TRY(BW_LAUNCH(k_att_main, dim3(BT), dim3(NT), st, a));
+    STAT_TRY(BW_LAUNCH((R == 8 ? k_att_main<8> : k_att_main<0>), dim3(BT), dim3(NT), st, a));
     bw_mark(BP_REDUCE_T, st);
     STAT_TRY(BW_LAUNCH(k_reduce_t, g1(static_cast<size_t>(B) * 4 * H), dim3(256), st, t, W + w.DSQP, W + w.DHQ, ldq,
                        B, T, 4 * H));
