@@ -331,10 +331,12 @@ def test_alpha_tolerance_margin_over_100_clips(torch_cuda):
 
 
 # ---------------------------------------------------------------------------
-# the other step implementations (stat_set_step_impl): 0 = separate kernels, 1 = fused tile kernels; the default (2,
-# the cell step where the shape allows it) is what every other test runs.  Same contract for all.
+# the other step implementations (stat_set_step_impl): 1 = fused tile kernels, 2 = cell step (one cooperative kernel
+# between two attentions; where the shape does not allow it -- the toy fixtures -- the call falls back to the separate
+# kernels).  The default (0, separate kernels; the cell step for beam searches over more than 128 rows) is what every
+# other test runs.  Same contract for all.
 # ---------------------------------------------------------------------------
-@pytest.fixture(params=[0, 1], ids=['separate', 'fused_tiles'])
+@pytest.fixture(params=[1, 2], ids=['fused_tiles', 'cell'])
 def fused_step(request):
     from video_description_with_spatial_temporal_attention_b200 import _lib
     lib = _lib.load()
@@ -383,6 +385,36 @@ def test_fused_step_full_width(torch_cuda, fused_step):
             n_full += 1
             np.testing.assert_allclose(scores[b], ws[b], atol=TOL_LP, rtol=4e-6)
     assert n_full >= 62
+
+
+@pytest.mark.parametrize('H,E,B,opts', [(256, 192, 70, {}), (384, 512, 9, dict(ctx2out=False, prev2out=False)),
+                                        (512, 300, 130, dict(selector=False))])
+def test_cell_step_shapes(torch_cuda, H, E, B, opts):
+    """The cell step (stat_set_step_impl(2)) away from the BASELINE shape: other widths (units / columns per CTA, K
+    slices), more than one 64-row chunk, ragged last chunk, options off -- teacher-forced log-probs with masks and
+    greedy captions against the fp64 oracle."""
+    from video_description_with_spatial_temporal_attention_b200 import _lib
+    lib = _lib.load()
+    o, params, batch = _case('faithful', B=B, T=7, R=4, L=6, seed=3, dim=H, ctxg_dim=H, dim_word=E, ctxl_dim=64, ctxm_dim=48,
+                             n_words=301, **opts)
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+    _lib.check(lib.stat_set_step_impl(2))
+    try:
+        model, tp, f_log_probs, _, _, _ = _build(o, params)
+        lp = f_log_probs(*batch)
+        toks, lens, scores = model.greedy_batch(tp, o, ctxg, mg, ctxl, ctxm, maxlen=6)
+    finally:
+        _lib.check(lib.stat_set_step_impl(-1))
+    want = so.forward_teacher(params, o, *batch, dtype=np.float64)
+    np.testing.assert_allclose(lp, want, atol=TOL_LP, rtol=0)
+    wt, wl, ws, margins = so.greedy_decode_batch(params, o, ctxg, mg, ctxl, ctxm, 6, dtype=np.float64, return_all=True)
+    for b in range(B):
+        n = int(wl[b])
+        tight = np.where(margins[b, :n] < 1e-4)[0]
+        upto = int(tight[0]) if len(tight) else n
+        assert [int(t) for t in toks[b, :upto]] == [int(t) for t in wt[b, :upto]], b
+        if upto == n:
+            np.testing.assert_allclose(scores[b], ws[b], atol=TOL_LP, rtol=4e-6)
 
 
 def test_beam_k1_equals_greedy_and_limits(torch_cuda):
