@@ -42,6 +42,11 @@
 namespace stat {
 namespace {
 
+// L2 eviction priorities of the four bulk-copy streams of a frame
+struct AttPolicies {
+  uint64_t pl, gm, cl, q;      // pctxl | pctxg, pctxm | ctxl0 | qctxl
+};
+
 constexpr int GMAX = 4;                   // groups per CTA
 constexpr int GT = 128;                   // threads per group
 constexpr int NTHREADS = GMAX * GT;       // 512
@@ -198,8 +203,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 // RT = compile-time R (8) or 0 for a runtime R <= 16;  HT = compile-time H (512) or 0.
 template <int NV, int RT, int HT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-    att_group_kernel(const AttArgs a, const int G, const int cs, const uint64_t policy, const uint64_t policy_q,
-                     const int stagger) {
+    att_group_kernel(const AttArgs a, const int G, const int cs, const AttPolicies pol, const int stagger) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int RU = RT ? RT : RMAX;              // unroll bound of the region loops
   const int H = HT ? HT : a.H, T = a.T;
@@ -258,16 +262,16 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const size_t frame = static_cast<size_t>(clip) * T + frame_of(j);
     const uint32_t dst = smem_u32(slot_p);
     mbar_expect_tx(bar_p, static_cast<uint32_t>(p_floats) * 4u);
-    bulk_g2s(dst, a.pctxl + frame * RH, bytes_rh, bar_p, policy);
-    bulk_g2s(dst + bytes_rh, a.pctxg + frame * H, bytes_h, bar_p, policy);
-    bulk_g2s(dst + bytes_rh + bytes_h, a.pctxm + frame * H, bytes_h, bar_p, policy);
+    bulk_g2s(dst, a.pctxl + frame * RH, bytes_rh, bar_p, pol.pl);
+    bulk_g2s(dst + bytes_rh, a.pctxg + frame * H, bytes_h, bar_p, pol.gm);
+    bulk_g2s(dst + bytes_rh + bytes_h, a.pctxm + frame * H, bytes_h, bar_p, pol.gm);
   };
   auto issue_v = [&](int j) {
     const size_t frame = static_cast<size_t>(clip) * T + frame_of(j);
     const uint32_t dst = smem_u32(slot_v);
     mbar_expect_tx(bar_v, static_cast<uint32_t>(v_floats) * 4u);
-    bulk_g2s(dst, a.ctxl0 + frame * RH, bytes_rh, bar_v, policy);
-    bulk_g2s(dst + bytes_rh, a.qctxl + frame * RH, bytes_rh, bar_v, policy_q);
+    bulk_g2s(dst, a.ctxl0 + frame * RH, bytes_rh, bar_v, pol.cl);
+    bulk_g2s(dst + bytes_rh, a.qctxl + frame * RH, bytes_rh, bar_v, pol.q);
   };
   // The context blocks were written by the prologue of the batch, long before the kernel this launch
   // programmatically depends on: their first copies start before that kernel has finished.
@@ -636,35 +640,32 @@ size_t pad_bytes(int H) { return (static_cast<size_t>(H <= 512 ? 1 : 2) * 512 * 
 constexpr size_t SMEM_EXTRA = (GMAX * (RMAX + 2) * 4 + GMAX * 4 + GMAX * 8) * 4 + (2 * GMAX + 2) * 8 + 128;
 constexpr size_t SMEM_MAX = 227 * 1024;
 
-// L2 eviction priority of the context-block copies: the blocks are re-read on every decode step,
-// the weights and activations between two attention launches are streamed once.  evict_last
-// lines survive only inside the persisting-L2 carve-out (stat_set_l2_persist).
-//   STAT_ATT_L2 = last (default) | normal | first
-uint64_t l2_policy() {
-  static uint64_t pol = 0;
-  if (pol == 0) {
+// L2 eviction priorities of the context-block copies.  The blocks are re-read on every decode step while the weights
+// and activations between two attention launches are streamed once; evict_last lines survive inside the
+// persisting-L2 carve-out (stat_set_l2_persist, 79 MB on the B200).  Marking everything evict_last does not work:
+// the working set then exceeds what the carve-out holds, all lines have the same priority, the access is cyclic and
+// nearly everything misses (measured: 19 % hits with 68 MB marked).  STAT_ATT_KEEP is the set of streams that are
+// kept (bit 0 pctxl, bit 1 pctxg / pctxm, bit 2 ctxl0, bit 3 qctxl); the others are streamed evict_first.
+//   STAT_ATT_L2 = last (default) | normal | first : the priority of the kept streams
+AttPolicies l2_policies() {
+  static AttPolicies pol = {0, 0, 0, 0};
+  if (pol.pl == 0) {
     const char *e = getenv("STAT_ATT_L2");
-    pol = 0x14F0000000000000ull;                               // evict_last
-    if (e && !strcmp(e, "normal")) pol = 0x1000000000000000ull;
-    if (e && !strcmp(e, "first")) pol = 0x12F0000000000000ull;
+    uint64_t keep = 0x14F0000000000000ull;                               // evict_last
+    if (e && !strcmp(e, "normal")) keep = 0x1000000000000000ull;
+    if (e && !strcmp(e, "first")) keep = 0x12F0000000000000ull;
+    const uint64_t stream = 0x12F0000000000000ull;                      // evict_first
+    const char *k = getenv("STAT_ATT_KEEP");
+    const int mask = k ? atoi(k) : 7;
+    pol.pl = (mask & 1) ? keep : stream;
+    pol.gm = (mask & 2) ? keep : stream;
+    pol.cl = (mask & 4) ? keep : stream;
+    pol.q = (mask & 8) ? keep : stream;
   }
   return pol;
 }
 
 long long *g_group_trace = nullptr;
-
-// The seven blocks of a B=64 batch (95 MB) are more than the L2 keeps across a step (about 90 MB, less
-// the weights and activations streamed in between): cyclically re-reading all of them with one
-// priority would miss everywhere.  One block, qctxl, is therefore streamed (evict_first) every step and
-// leaves the L2 to the other six (68 MB).   STAT_ATT_Q_L2 = first (default) | same
-uint64_t l2_policy_q() {
-  static uint64_t pol = 0;
-  if (pol == 0) {
-    const char *e = getenv("STAT_ATT_Q_L2");
-    pol = (e && !strcmp(e, "same")) ? l2_policy() : 0x12F0000000000000ull;
-  }
-  return pol;
-}
 
 template <int NV, int RT, int HT>
 int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
@@ -697,7 +698,7 @@ int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
     const char *e = getenv("STAT_ATT_STAGGER");
     stagger = (e && e[0] == '0') ? 0 : 1;
   }
-  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_group_kernel<NV, RT, HT>, a, G, cs, l2_policy(), l2_policy_q(), stagger));
+  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_group_kernel<NV, RT, HT>, a, G, cs, l2_policies(), stagger));
   note_launch();
   return STAT_OK;
 }
