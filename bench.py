@@ -430,6 +430,7 @@ def run_ours(args, rank, world, local_rank):
         dur = att['ms_per_step'] / att['launch_groups_per_step'] * 1e-3
         ach = ctx_step_bytes / dur / 1e9
         traffic = None
+        traffic_src = None
         tp = os.path.join(ROOT, 'profiles', 'att_step_traffic.json')
         if os.path.isfile(tp):
             with open(tp) as fh:
@@ -438,9 +439,13 @@ def run_ours(args, rank, world, local_rank):
                 # in situ (one ncu pass per launch, caches untouched) when captured, else the cold capture
                 traffic = (ins['dram_read_bytes_per_launch'] + ins['dram_write_bytes_per_launch']) if ins else \
                     tj.get('dram_bytes_per_launch')
+                # NOT measured in this run: the committed ncu capture of this kernel (dram__bytes_read + write per
+                # launch); it is re-captured whenever the kernel changes and carries the commit it was taken at
+                traffic_src = 'committed ncu capture %s, kernel source at commit %s' % (
+                    (ins or tj).get('source', 'profiles/att_step_traffic.json'), tj.get('captured_at_commit', '?'))
         roof = {'bound': 'hbm', 'kernel': 'att_group_kernel (4 soft-attentions of one decode step, all rows)',
                 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic,
-                'peak_source': peak_src, 'algorithmic_bytes_per_launch': ctx_step_bytes,
+                'traffic_source': traffic_src, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': ctx_step_bytes,
                 'avg_launch_us': dur * 1e6, 'timing': 'CUDA events around each launch inside the 20-step decode '
                                                       '(eager launches, host enqueued ahead of the GPU)',
                 'isolated_cold_l2_us': att_cold_us, 'isolated_cold_l2_GBps': ctx_step_bytes / att_cold_us / 1e3,

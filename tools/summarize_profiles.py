@@ -249,6 +249,14 @@ def main():
                          'B=64 T=26 R=8 H=512)' % tag}
         if insitu:
             rec['in_situ'] = insitu
+        # the commit whose att_group.cu the capture was taken from (bench.py prints it next to roofline.traffic)
+        try:
+            rec['captured_at_commit'] = subprocess.run(
+                ['git', 'log', '-1', '--format=%h', '--',
+                 'video_description_with_spatial_temporal_attention_b200/csrc/att_group.cu'],
+                capture_output=True, text=True, cwd=ROOT).stdout.strip()
+        except Exception:
+            rec['captured_at_commit'] = '?'
         with open(os.path.join(OUT, 'att_step_traffic.json'), 'w') as f:
             json.dump(rec, f, indent=1)
     print('\n'.join(md[:60]))
