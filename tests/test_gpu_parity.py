@@ -417,6 +417,33 @@ def test_cell_step_shapes(torch_cuda, H, E, B, opts):
             np.testing.assert_allclose(scores[b], ws[b], atol=TOL_LP, rtol=4e-6)
 
 
+def test_caption_stream_equals_batchwise_greedy(torch_cuda):
+    """The host streaming API (pinned host features -> captions, H2D of batch i+1 beside the decode of batch i, one
+    captured graph per pipeline slot): five different batches, results in order and bit-identical to decoding each
+    batch on its own."""
+    torch = torch_cuda
+    from video_description_with_spatial_temporal_attention_b200.engine import Engine
+    o, params, _ = _case('baseline', B=2, seed=3)
+    eng = Engine(o)
+    eng.set_params(params)
+    batches = []
+    for i in range(5):
+        _, _, ctxg, mg, ctxl, _, ctxm, _ = synthetic.make_batch(o, B=8, T=26, R=8, L=4, seed=100 + i, zero_tail=(i % 2 == 0))
+        batches.append([torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (ctxg, mg, ctxl, ctxm)])
+    got = list(eng.caption_stream(iter(batches), 12))
+    assert len(got) == 5
+    for hb, (toks, lens, scores) in zip(batches, got):
+        t2, l2, s2 = eng.greedy_captions(*[h.cuda() for h in hb], maxlen=12, use_graph=False)
+        np.testing.assert_array_equal(toks, t2.cpu().numpy())
+        np.testing.assert_array_equal(lens, l2.cpu().numpy())
+        np.testing.assert_array_equal(scores, s2.cpu().numpy())
+    # a second stream on the same engine reuses the captured slots
+    again = list(eng.caption_stream(iter(batches[:3]), 12, depth=3))
+    for a, b in zip(again, got[:3]):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+
+
 def test_beam_k1_equals_greedy_and_limits(torch_cuda):
     o, params, batch = _case('baseline', B=4, seed=17)
     x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch

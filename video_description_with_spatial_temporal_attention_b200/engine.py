@@ -36,6 +36,7 @@ def _release_graphs():
     except Exception:
         pass
     for e in list(_ENGINES):
+        e.__dict__.get('_stream_slots', {}).clear()
         e._graphs.clear()
 
 
@@ -164,6 +165,7 @@ class Engine(object):
             self.prepared = torch.empty((n + 3) // 4, dtype=torch.float32, device=self.device)
         check(self.lib.stat_prepare_params(C.byref(d), C.byref(sp), _ptr(self.prepared), _stream()))
         self._dev_params = dev      # keep alive until the packing kernels have run
+        self.__dict__.get('_stream_slots', {}).clear()      # (they hold references to the captured graphs)
         self._graphs.clear()
 
     def _need_params(self):
@@ -333,17 +335,19 @@ class Engine(object):
 
     # ---- whole-batch greedy captioning, optionally replayed from a CUDA graph ------
     @_on_device
-    def greedy_captions(self, ctxg, mask_ctxg, ctxl, ctxm, maxlen, use_graph=True):
+    def greedy_captions(self, ctxg, mask_ctxg, ctxl, ctxm, maxlen, use_graph=True, slot=0):
         """Features already on the device -> (tokens (B,maxlen) i64, lengths (B,) i32,
         scores (B,) f32), all device tensors.  Runs K0 + the maxlen-step decode; with
-        use_graph the launch sequence is captured once per shape and replayed."""
+        use_graph the launch sequence is captured once per shape (and `slot`: independent copies of the
+        graph with their own static input / output tensors, for pipelines that fill one set of inputs while
+        another is being decoded) and replayed."""
         self._need_params()
         B, T = ctxg.shape[0], ctxg.shape[1]
         R = ctxl.shape[2]
         if not use_graph:
             ws, d = self.precompute(ctxg, mask_ctxg, ctxl, ctxm)
             return self.decode_greedy(ws, d, maxlen)
-        key = ('greedy', B, T, R, maxlen)
+        key = ('greedy', B, T, R, maxlen) if slot == 0 else ('greedy', B, T, R, maxlen, slot)
         g = self._graphs.get(key)
         if g is None:
             st = dict(ctxg=torch.empty_like(ctxg), mask=torch.empty_like(mask_ctxg), ctxl=torch.empty_like(ctxl),
@@ -379,8 +383,11 @@ class Engine(object):
 
     def caption_stream(self, host_batches, maxlen, depth=2):
         """Greedy captions for a stream of host-resident batches, pipelined: the H2D copy of
-        batch i+1 (copy stream, pinned host memory -> staging buffer) overlaps the decode of
-        batch i (compute stream: staging -> graph inputs, graph replay, D2H of the captions).
+        batch i+1 (copy stream, pinned host memory -> the static inputs of graph copy (i+1) % depth)
+        overlaps the decode of batch i (compute stream: replay of graph copy i % depth, D2H of the
+        captions).  One captured graph per pipeline slot, each with its own input / output tensors:
+        the copies land where the graph reads them, nothing is staged on the device (a device-to-device
+        staging copy on the compute stream cost 8 % of the H2D rate: tools/e2e_probe.py).
 
         host_batches: iterable of (ctxg, mask_ctxg, ctxl, ctxm) float32 torch tensors on the
         host (pinned memory for a truly asynchronous copy), all of one shape.  Yields
@@ -401,43 +408,49 @@ class Engine(object):
         for i, hb in enumerate(host_batches):
             ctxg, mask, ctxl, ctxm = hb
             if slots is None:
+                # the pipeline slots (captured graphs, pinned result buffers, events) are built on the first
+                # call for a shape and kept on the engine: later streams start copying at once
                 B, T, R = ctxg.shape[0], ctxg.shape[1], ctxl.shape[2]
-                dev0 = [t.to(self.device) for t in hb]
-                self.greedy_captions(*dev0, maxlen=maxlen, use_graph=True)      # capture once
-                st = self.graph_inputs(B, T, R, maxlen)
-                static = [st['ctxg'], st['mask'], st['ctxl'], st['ctxm']]
-                gout = self._graphs[('greedy', B, T, R, maxlen)][2]
-                slots = [dict(stage=[torch.empty_like(s) for s in static],
-                              out=[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in gout],
-                              ready=torch.cuda.Event(), consumed=torch.cuda.Event(), done=torch.cuda.Event())
-                         for _ in range(depth)]
+                skey = ('stream', B, T, R, maxlen, depth)
+                cache = self.__dict__.setdefault('_stream_slots', {})
+                slots = cache.get(skey)
+                if slots is None:
+                    dev0 = [t.to(self.device) for t in hb]
+                    slots = []
+                    for k in range(depth):
+                        self.greedy_captions(*dev0, maxlen=maxlen, use_graph=True, slot=k)      # capture once per slot
+                        graph, st, gout = self._graphs[('greedy', B, T, R, maxlen) if k == 0 else
+                                                       ('greedy', B, T, R, maxlen, k)]
+                        slots.append(dict(graph=graph, inputs=[st['ctxg'], st['mask'], st['ctxl'], st['ctxm']],
+                                          gout=gout,
+                                          out=[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in gout],
+                                          ready=torch.cuda.Event(), done=torch.cuda.Event()))
+                    del dev0
+                    cache[skey] = slots
                 for sl in slots:
-                    sl['consumed'].record(compute)
+                    sl['done'].record(compute)
             slot = i % depth
             sl = slots[slot]
             if len(pending) >= depth:                       # the slot's previous results must be read first
                 yield collect(*pending.pop(0))
             with torch.cuda.stream(copy):
-                copy.wait_event(sl['consumed'])
-                for dst, src in zip(sl['stage'], hb):
+                copy.wait_event(sl['done'])                 # the slot's previous decode has read its inputs
+                for dst, src in zip(sl['inputs'], hb):
                     dst.copy_(src, non_blocking=True)
                 sl['ready'].record(copy)
             compute.wait_event(sl['ready'])
-            for dst, src in zip(static, sl['stage']):
-                dst.copy_(src, non_blocking=True)
-            sl['consumed'].record(compute)
-            out = self.greedy_captions(*static, maxlen=maxlen, use_graph=True)
-            for dst, src in zip(sl['out'], out):
+            sl['graph'].replay()
+            for dst, src in zip(sl['out'], sl['gout']):
                 dst.copy_(src, non_blocking=True)
             sl['done'].record(compute)
             pending.append((slot, sl['done']))
         while pending:
             yield collect(*pending.pop(0))
 
-    def graph_inputs(self, B, T, R, maxlen):
+    def graph_inputs(self, B, T, R, maxlen, slot=0):
         """The static input tensors of the captured greedy graph (fill these in place to
         avoid the device-to-device staging copy)."""
-        g = self._graphs.get(('greedy', B, T, R, maxlen))
+        g = self._graphs.get(('greedy', B, T, R, maxlen) if slot == 0 else ('greedy', B, T, R, maxlen, slot))
         return None if g is None else g[1]
 
     # ---- the attention fragment alone (timing) ------------------------------------
