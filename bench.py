@@ -510,8 +510,8 @@ def run_ours(args, rank, world, local_rank):
                 return out
             except Exception as e:
                 return {'error': str(e)[:200]}
-        # (one retry: about 1 run in 25 of this subprocess has ended in a device fault that neither compute-sanitizer
-        # nor 40 repeats reproduce -- DESIGN.md section 9; the attempt count is part of the record)
+        # (one retry, kept from the hunt for the GEMM splitter race that made about 1 run in 25 of this subprocess end
+        # in a device fault -- fixed; the attempt count is part of the record)
         train = train_line({})
         if 'error' in train:
             first = train['error']

@@ -111,6 +111,11 @@ int stat_set_gemm_impl(int impl);
  *  -1 = back to the default (environment STAT_STEP=0|1|2, else 2). */
 int stat_set_step_impl(int impl);
 
+/* Fault hunting: arms the spin-wait give-up sites of the attention and GEMM kernels to record where they trap
+ * (4 ints: site = file tag + source line, blockIdx.x, threadIdx.x, blockIdx.y << 16 | blockIdx.z) in host-mapped
+ * memory, which survives the device fault.  Returns the host pointer (NULL on failure). */
+int *stat_debug_trap_log(void);
+
 /* ---- L2 residency of the context blocks (no reference counterpart) -----------
  * The attention kernel re-reads the projected context blocks of the batch on
  * every decode step and copies them with the L2 evict_last priority; those

@@ -61,11 +61,24 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// fault hunting (stat_debug_trap_log): a host-mapped word that survives the fault receives the site of the trap
+__device__ volatile int *g_trap_log = nullptr;
+__device__ __forceinline__ void trap_at(int site) {
+  if (g_trap_log) {
+    g_trap_log[0] = site;
+    g_trap_log[1] = static_cast<int>(blockIdx.x);
+    g_trap_log[2] = static_cast<int>(threadIdx.x);
+    g_trap_log[3] = static_cast<int>(blockIdx.y) * 65536 + static_cast<int>(blockIdx.z);
+    __threadfence_system();
+  }
+  __trap();
+}
+#define mbar_wait(bar, parity) mbar_wait_((bar), (parity), 2000000 + __LINE__)
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity, int site) {
   uint32_t ok;
   uint32_t spins = 0;
   do {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 26)) trap_at(site);
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -186,7 +199,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   uint32_t ok;
   uint32_t spins = 0;
   do {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 26)) trap_at(2999999);
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -698,6 +711,7 @@ int launch(const AttArgs &a, int cs, int G, cudaStream_t stream) {
     const char *e = getenv("STAT_ATT_STAGGER");
     stagger = (e && e[0] == '0') ? 0 : 1;
   }
+  set_launch_label("att_group");
   STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_group_kernel<NV, RT, HT>, a, G, cs, l2_policies(), stagger));
   note_launch();
   return STAT_OK;
@@ -732,6 +746,10 @@ bool att_group_plan(int rows, int T, int R, int H, int *cluster, int *groups, in
 
 // debug: device buffer of >= ctas * 64 int64 (clock stamps per CTA and group), or null
 void att_group_set_trace(long long *p) { g_group_trace = p; }
+int att_group_set_trap_log(int *dev_ptr) {
+  STAT_CUDA_CHECK(cudaMemcpyToSymbol(g_trap_log, &dev_ptr, sizeof(dev_ptr)));
+  return STAT_OK;
+}
 
 int att_group_launch(const AttArgs &a_in, cudaStream_t stream) {
   AttArgs a = a_in;

@@ -535,18 +535,23 @@ __global__ void k_att_main(const AttBw a) {
     const float pg = a.pG[o], pm = a.pM[o], sg = hq[H + h], sm = hq[2 * H + h], slt = hq[3 * H + h];
     const float ug = a.Ug[h], um = a.Um[h], ult = a.Ult[h];
     // global / motion attention (:389-412)
+    // (deferred mode, a.DAL != null: the per-(clip, frame) accumulators DPG / DPM / DG / DM / DUACC are not touched
+    // here -- k_att_accum / k_att_accum2 sum all steps after the loop)
+    const bool rmw = a.DAL == nullptr;
     const float tg = tanh_bw(pg + sg);
     const float dqg = daG * ug * (1.0f - tg * tg);
-    a.DPG[o] += dqg;
     a.DSQP[o4 + H] = dqg;
-    a.DUACC[o4 + H] += daG * tg;
-    if (a.global_proj) a.DG[o] += aG * dc;
     const float tm = tanh_bw(pm + sm);
     const float dqm = daM * um * (1.0f - tm * tm);
-    a.DPM[o] += dqm;
     a.DSQP[o4 + 2 * H] = dqm;
-    a.DUACC[o4 + 2 * H] += daM * tm;
-    a.DM[o] += aM * dc;
+    if (rmw) {
+      a.DPG[o] += dqg;
+      a.DUACC[o4 + H] += daG * tg;
+      if (a.global_proj) a.DG[o] += aG * dc;
+      a.DPM[o] += dqm;
+      a.DUACC[o4 + 2 * H] += daM * tm;
+      a.DM[o] += aM * dc;
+    }
     // local-temporal attention (:415-426), pLT = sum_r alpha_l Q_r + blt + slt
     float plt = slt;
 #pragma unroll
@@ -555,7 +560,7 @@ __global__ void k_att_main(const AttBw a) {
     const float tl = tanh_bw(plt);
     const float dp = daLT * ult * (1.0f - tl * tl);
     a.DSQP[o4 + 3 * H] = dp;
-    a.DUACC[o4 + 3 * H] += daLT * tl;
+    if (rmw) a.DUACC[o4 + 3 * H] += daLT * tl;
     const float dcL = aLT * dc;
     dcl[k] = dcL;
     dpl[k] = dp;
@@ -610,7 +615,7 @@ __global__ void k_att_main(const AttBw a) {
     }
     const size_t o4 = static_cast<size_t>(bt) * 4 * H + h;
     a.DSQP[o4] = dsl;
-    a.DUACC[o4] += dul;
+    if (!a.DAL) a.DUACC[o4] += dul;
   }
 }
 
@@ -619,10 +624,11 @@ __global__ void k_att_main(const AttBw a) {
 //   DPL = sum_s dal_r(s) Ul (1 - tanh^2(pL + sl_s)),  DLC = sum_s alpha_l,r(s) alpha_lt(s) dC_s,  DQ = sum_s alpha_l,r(s) dpLT_s
 __global__ void k_att_accum(int L, int B, int T, int R, int H, int ldq, const float *al, const float *alt,
                             const float *DAL, const float *DPLT, const float *DCS, const float *HQ, const float *pL,
-                            const float *Ul, float *DPL, float *DLC, float *DQ) {
+                            const float *Ul, float *DPL, float *DLC, float *DQ, float *DUACC) {
   const int bt = blockIdx.x, b = bt / T, t = bt % T;
   for (int h = threadIdx.x; h < H; h += blockDim.x) {
     const float ul = Ul[h];
+    float dul = 0.f;                 // sum over steps and regions of dal * tanh(pL + sl): the Ul-gradient share
     for (int r = 0; r < R; ++r) {
       const size_t ol = (static_cast<size_t>(bt) * R + r) * H + h;
       const float pl = pL[ol];
@@ -631,8 +637,10 @@ __global__ void k_att_accum(int L, int B, int T, int R, int H, int ldq, const fl
       for (int s = L - 1; s >= 0; --s) {
         const size_t n = static_cast<size_t>(s) * B + b, nt = n * T + t;
         const float ar = al[nt * R + r];
+        const float da = DAL[nt * R + r];
         const float tl = tanh_bw(pl + HQ[n * ldq + h]);
-        apl = fmaf(DAL[nt * R + r] * ul, 1.0f - tl * tl, apl);
+        apl = fmaf(da * ul, 1.0f - tl * tl, apl);
+        dul = fmaf(da, tl, dul);
         alc = fmaf(ar, alt[nt] * DCS[n * H + h], alc);
         aq = fmaf(ar, DPLT[nt * H + h], aq);
       }
@@ -640,6 +648,58 @@ __global__ void k_att_accum(int L, int B, int T, int R, int H, int ldq, const fl
       DLC[ol] = alc;
       DQ[ol] = aq;
     }
+    DUACC[static_cast<size_t>(bt) * 4 * H + h] = dul;
+  }
+}
+
+// Deferred mode, the global / motion / local-temporal shares: per (clip, frame, column) the sum over all steps of what
+// k_att_main otherwise read-modify-writes every step (218 MB per step at B = 128):
+//   DPG = sum_s daG_s Ug (1 - tanh^2(pG + sg_s)),  DUACC_g = sum_s daG_s tanh(pG + sg_s),  DG = sum_s alpha_g(s) dC_s
+//   (same for m),  DUACC_lt = sum_s daLT_s tanh(sum_r alpha_l,r(s) Q_r + slt_s)
+template <int RT>
+__global__ void k_att_accum2(int L, int B, int T, int R_, int H, int ldq, int global_proj, const float *al,
+                             const float *ag, const float *am, const float *DS3S, const float *DCS, const float *HQ,
+                             const float *pG, const float *pM, const float *Q, const float *Ug, const float *Um,
+                             float *DPG, float *DPM, float *DG, float *DM, float *DUACC) {
+  const int R = RT ? RT : R_;
+  constexpr int RU = RT ? RT : RMAX;
+  const int bt = blockIdx.x, b = bt / T, t = bt % T;
+  const size_t BT = static_cast<size_t>(B) * T;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const size_t o = static_cast<size_t>(bt) * H + h, o4 = static_cast<size_t>(bt) * 4 * H + h;
+    const float pg = pG[o], pm = pM[o], ug = Ug[h], um = Um[h];
+    float q[RU];
+#pragma unroll
+    for (int r = 0; r < RU; ++r) q[r] = (RT || r < R) ? Q[(static_cast<size_t>(bt) * R + r) * H + h] : 0.f;
+    float dpg = 0.f, dpm = 0.f, dg = 0.f, dm = 0.f, dug = 0.f, dum = 0.f, dult = 0.f;
+#pragma unroll 2
+    for (int s = L - 1; s >= 0; --s) {
+      const size_t n = static_cast<size_t>(s) * B + b, nt = n * T + t;
+      const float *ds = DS3S + static_cast<size_t>(s) * 3 * BT;
+      const float daG = ds[bt], daM = ds[BT + bt], daLT = ds[2 * BT + bt];
+      const float *hq = HQ + n * ldq;
+      const float dc = DCS[n * H + h];
+      const float tg = tanh_bw(pg + hq[H + h]);
+      dpg = fmaf(daG * ug, 1.0f - tg * tg, dpg);
+      dug = fmaf(daG, tg, dug);
+      dg = fmaf(ag[nt], dc, dg);
+      const float tm = tanh_bw(pm + hq[2 * H + h]);
+      dpm = fmaf(daM * um, 1.0f - tm * tm, dpm);
+      dum = fmaf(daM, tm, dum);
+      dm = fmaf(am[nt], dc, dm);
+      float plt = hq[3 * H + h];
+#pragma unroll
+      for (int r = 0; r < RU; ++r)
+        if (RT || r < R) plt = fmaf(al[nt * R + r], q[r], plt);
+      dult = fmaf(daLT, tanh_bw(plt), dult);
+    }
+    DPG[o] = dpg;
+    DPM[o] = dpm;
+    if (global_proj) DG[o] = dg;
+    DM[o] = dm;
+    DUACC[o4 + H] = dug;
+    DUACC[o4 + 2 * H] = dum;
+    DUACC[o4 + 3 * H] = dult;
   }
 }
 
@@ -802,7 +862,7 @@ struct GW {   // float offsets into the gradient workspace
   size_t Hprev, EMB, HQ, csum, beta, ctx, XW, CW, ZC, GATES, Call, HD, ZT, Z, LOG, DLT;
   size_t DZ, DZP, DHR, DCR, DHQ, DHc, DCc, DHm, DCTX, DC, TMPH, CL, DA3, DS3, COV3, COVL, DSQP;
   size_t DPG, DPM, DG, DM, DPL, DLC, DQ, DUACC, DCACC;
-  size_t T1, T2, T3, DEMB, DWH, GBAR, DP0, SMALL, CS, PLANES, ALN, DAL, DPLT, DCS;
+  size_t T1, T2, T3, DEMB, DWH, GBAR, DP0, SMALL, CS, PLANES, ALN, DAL, DPLT, DCS, DS3S;
   size_t total;
   int ldq, Vp;
 };
@@ -850,6 +910,7 @@ GW gw_layout(const StatDims &d, int L) {
   w.DAL = take(N * T * R);
   w.DPLT = take(N * T * H);
   w.DCS = take(N * H);
+  w.DS3S = take(static_cast<size_t>(L) * 3 * BT);
   w.total = o;
   return w;
 }
@@ -1088,8 +1149,10 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     STAT_TRY(BW_LAUNCH((R == 8 ? k_att_dots<8> : k_att_dots<0>), dim3(BT), dim3(NT), st, t, alpha_l, f->ctxl0, f->ctxg0, f->ctxm0, DCt,
                        W + w.CL, W + w.DA3, B, T, R, H));
     bw_mark(BP_ATT_SOFT, st);
+    // deferred mode keeps the score gradients of every step (k_att_accum2 reads them after the loop)
+    float *DS3t = fast ? W + w.DS3S + static_cast<size_t>(t) * 3 * BT : W + w.DS3;
     STAT_TRY(BW_LAUNCH(k_att_soft, g1(3 * B, 128), dim3(128), st, t, alpha_g, alpha_m, alpha_lt, W + w.DA3,
-                       W + w.COV3, W + w.DS3, W + w.DCACC, B, T));
+                       W + w.COV3, DS3t, W + w.DCACC, B, T));
     bw_mark(BP_ATT_MAIN, st);
     AttBw a;
     memset(&a, 0, sizeof(a));
@@ -1098,7 +1161,7 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     a.HQ = W + w.HQ;
     a.pL = f->pctxl; a.Lc = f->ctxl0; a.Q = f->qctxl; a.pG = f->pctxg; a.pM = f->pctxm;
     a.Ul = p->decoder_Ul_att; a.Ug = p->decoder_Ug_att; a.Um = p->decoder_Um_att; a.Ult = p->decoder_Ult_att;
-    a.DC = DCt; a.DS3 = W + w.DS3; a.COVL = W + w.COVL;
+    a.DC = DCt; a.DS3 = DS3t; a.COVL = W + w.COVL;
     a.DPL = W + w.DPL; a.DLC = W + w.DLC; a.DQ = W + w.DQ;
     a.DPG = W + w.DPG; a.DPM = W + w.DPM; a.DG = W + w.DG; a.DM = W + w.DM;
     a.DUACC = W + w.DUACC; a.DCACC = W + w.DCACC; a.DSQP = W + w.DSQP;
@@ -1117,7 +1180,11 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
   if (fast) {
     bw_mark(BP_ATT_MAIN, st);
     STAT_TRY(BW_LAUNCH(k_att_accum, dim3(BT), dim3(NT), st, L, B, T, R, H, ldq, alpha_l, alpha_lt, W + w.DAL, W + w.DPLT,
-                       W + w.DCS, W + w.HQ, f->pctxl, p->decoder_Ul_att, W + w.DPL, W + w.DLC, W + w.DQ));
+                       W + w.DCS, W + w.HQ, f->pctxl, p->decoder_Ul_att, W + w.DPL, W + w.DLC, W + w.DQ, W + w.DUACC));
+    STAT_TRY(BW_LAUNCH((R == 8 ? k_att_accum2<8> : k_att_accum2<0>), dim3(BT), dim3(NT), st, L, B, T, R, H, ldq,
+                       gp ? 1 : 0, alpha_l, alpha_g, alpha_m, W + w.DS3S, W + w.DCS, W + w.HQ, f->pctxg, f->pctxm,
+                       f->qctxl, p->decoder_Ug_att, p->decoder_Um_att, W + w.DPG, W + w.DPM, W + w.DG, W + w.DM,
+                       W + w.DUACC));
   }
   bw_mark(BP_WGRAD_STEPS, st);
   // ---- D: weight gradients over the stacked steps ----------------------------------------------------

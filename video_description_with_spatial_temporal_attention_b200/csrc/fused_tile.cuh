@@ -188,8 +188,10 @@ __device__ __forceinline__ void split(const Cta &c, Ring &r, int nk, int mp, int
   const int prow = (warp & 3) * 32 + lane;
   const int nq4 = bq * (BK / 4);                     // 16-byte chunks of the Q tile
   for (int kb = 0; kb < nk; ++kb, ++kc) {
+    // both groups observe every phase of a stage's barrier (a parity wait is only valid one phase behind; with an
+    // odd ring depth a group would otherwise skip the other group's phase of a stage -- see gemm_tf32x3.cu)
+    mbar_wait(c.bar_full + 8 * r.s, r.ph());
     if ((kc & 1u) == static_cast<uint32_t>(grp)) {
-      mbar_wait(c.bar_full + 8 * r.s, r.ph());
       if (trace && tg == 0 && kb < 32) trace[2 + kb] = clock64();
       uint8_t *stage = c.ring + r.s * g.stage_bytes;
       const uint8_t *rowp = stage + prow * 128;

@@ -46,7 +46,27 @@ void set_error(const char *fmt, ...) {
 const char *get_error() { return g_err; }
 
 static unsigned long long g_launches = 0;
-void note_launch() { ++g_launches; }
+// STAT_SYNC_DEBUG=1 (fault hunting): every launch is followed by a device synchronisation; the first launch that
+// leaves an error behind is reported with its index and the label of its launch site.
+static const char *g_launch_label = "";
+void set_launch_label(const char *label) { g_launch_label = label; }
+void note_launch() {
+  ++g_launches;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char *e = getenv("STAT_SYNC_DEBUG");
+    dbg = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (dbg) {
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+      fprintf(stderr, "[stat] launch #%llu (%s) failed: %s\n", g_launches, g_launch_label, cudaGetErrorString(err));
+      fflush(stderr);
+      dbg = 0;
+    }
+  }
+  g_launch_label = "";
+}
 
 int pdl_attr(cudaLaunchAttribute *attr) {
   static int on = -1;
@@ -131,11 +151,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// fault hunting (stat_debug_trap_log): a host-mapped word that survives the fault receives the site of the trap
+__device__ volatile int *g_trap_log = nullptr;
+__device__ __forceinline__ void trap_at(int site) {
+  if (g_trap_log) {
+    g_trap_log[0] = site;
+    g_trap_log[1] = static_cast<int>(blockIdx.x);
+    g_trap_log[2] = static_cast<int>(threadIdx.x);
+    g_trap_log[3] = static_cast<int>(blockIdx.y) * 65536 + static_cast<int>(blockIdx.z);
+    __threadfence_system();
+  }
+  __trap();
+}
+#define mbar_wait(bar, parity) mbar_wait_((bar), (parity), 1000000 + __LINE__)
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity, int site) {
   uint32_t ok;
   uint32_t spins = 0;
   do {
-    if (++spins > (1u << 26)) __trap();   // a lost TMA / commit becomes an error, never a hang
+    if (++spins > (1u << 26)) trap_at(site);   // a lost TMA / commit becomes an error, never a hang
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -425,7 +458,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     int s = 0;
     uint32_t ph = 0;
     for (int kb = 0; kb < nk; ++kb) {
-      if (!TS || (kb & 1) == ((warp - 2) >> 2)) mbar_wait(bar_full + 8 * s, ph);
+      // EVERY splitter warp observes EVERY phase of a stage's barrier, also the k-slices its group does not split
+      // (TS: the two groups alternate).  A parity wait is only valid for a waiter at most one phase behind: with an
+      // odd ring depth a group that skipped the other group's phase of a stage could find that phase still pending
+      // when it came back, see the parity of the phase before it and read the stage early -- rare (it needs the
+      // loads of two consecutive slices to land out of order), fatal (double arrivals on the split barrier:
+      // `unspecified launch failure`; found with cuda-gdb under STAT_PDL=0).
+      mbar_wait(bar_full + 8 * s, ph);
       if (trace && t == 0 && kb < 16) trace[2 + kb] = clock64();
       uint8_t *stage = smem + s * C::STAGE_BYTES;
       float4 *Ph = reinterpret_cast<float4 *>(stage);
@@ -751,12 +790,18 @@ int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   }
   na += pdl_attr(attr + na);
   cfg.numAttrs = na;
+  set_launch_label("gemm_tf32x3");
   STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BQ, TS>, tmP, tmQ, db));
   note_launch();
   return STAT_OK;
 }
 
 }  // namespace
+
+int gemm_set_trap_log(int *dev_ptr) {
+  STAT_CUDA_CHECK(cudaMemcpyToSymbol(g_trap_log, &dev_ptr, sizeof(dev_ptr)));
+  return STAT_OK;
+}
 
 int gemm_launch(const GemmArgs &a, cudaStream_t stream) {
   STAT_REQUIRE(a.NP > 0 && a.NQ > 0 && a.K > 0, STAT_EINVAL, "gemm: empty problem %d x %d x %d", a.NP, a.NQ, a.K);

@@ -626,21 +626,26 @@ int gates_launch(const GateArgs &a, cudaStream_t stream) {
                     a.hp_parts <= 4 && a.pc_parts <= 4 && (a.hp_plane % 2 == 0) && (a.pc_plane % 2 == 0);
   if (vec2) {
     dim3 grid((w / 2 + 127) / 128 + ((w % 2) ? 1 : 0), a.rows);
-    return launch_pdl(gates2_kernel, grid, dim3(128), 0, stream, a);
+    set_launch_label("gates2_kernel");
+  return launch_pdl(gates2_kernel, grid, dim3(128), 0, stream, a);
   }
   dim3 grid((w + 127) / 128, a.rows);
+  set_launch_label("gates_kernel");
   return launch_pdl(gates_kernel, grid, dim3(128), 0, stream, a);
 }
 
 int zact_launch(const ZactArgs &a, cudaStream_t stream) {
+  set_launch_label("zact_kernel");
   return launch_pdl(zact_kernel, dim3((a.rows * a.E + 255) / 256), dim3(256), 0, stream, a);
 }
 
 int pick_launch(const PickArgs &a, cudaStream_t stream) {
+  set_launch_label("pick_kernel");
   return launch_pdl(pick_kernel, dim3(a.rows), dim3(256), 0, stream, a);
 }
 
 int beam_select_launch(const BeamArgs &a, cudaStream_t stream) {
+  set_launch_label("beam_select_kernel");
   return launch_pdl(beam_select_kernel, dim3(a.B), dim3(32), 0, stream, a);
 }
 
@@ -654,10 +659,12 @@ int beam_init_launch(const BeamArgs &a, const float *h0c0, float *h, float *c, i
 
 int gather_state_launch(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h, float *dst_c,
                         int rows, int H, cudaStream_t stream) {
+  set_launch_label("gather_state_kernel");
   return launch_pdl(gather_state_kernel, dim3(rows), dim3(128), 0, stream, src_h, src_c, src_row, dst_h, dst_c, H);
 }
 
 int gather_rows_launch(const float *src, const int32_t *src_row, float *dst, int rows, int width, cudaStream_t stream) {
+  set_launch_label("gather_rows_kernel");
   return launch_pdl(gather_rows_kernel, dim3(rows), dim3(256), 0, stream, src, src_row, dst, width);
 }
 

@@ -14,6 +14,8 @@
 namespace stat {
 const char *get_error();
 unsigned long long launch_count();
+int gemm_set_trap_log(int *dev_ptr);
+int att_group_set_trap_log(int *dev_ptr);
 
 namespace {
 
@@ -868,6 +870,20 @@ int stat_profile_collect(float *ms_by_phase, int *count_by_phase, int nphase) {
   }
   g_prof.clear();
   return STAT_OK;
+}
+
+// fault hunting: 4 ints in host-mapped memory [site, blockIdx.x, threadIdx.x, blockIdx.y<<16|z], written by the
+// spin-wait that gives up (its __trap() kills the context; the host word survives).  Returns the HOST pointer.
+int *stat_debug_trap_log(void) {
+  static int *host = nullptr;
+  if (!host) {
+    int *dev = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void **>(&host), 64, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(host, 0, 64);
+    if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&dev), host, 0) != cudaSuccess) return nullptr;
+    if (stat::gemm_set_trap_log(dev) != STAT_OK || stat::att_group_set_trap_log(dev) != STAT_OK) return nullptr;
+  }
+  return host;
 }
 
 int stat_debug_gemm_trace(void *dev_buffer_64_int64) {

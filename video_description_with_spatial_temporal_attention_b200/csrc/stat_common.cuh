@@ -15,6 +15,7 @@ namespace stat {
 void set_error(const char *fmt, ...);
 // every kernel launch of the library passes through here (stat_launch_count)
 void note_launch();
+void set_launch_label(const char *label);      // STAT_SYNC_DEBUG: names the next launch in the fault report
 
 // Programmatic dependent launch (STAT_PDL=0 switches it off): fills attr[0] and returns the number
 // of launch attributes (0 or 1).  Kernels launched this way call pdl_wait() before the first read of
