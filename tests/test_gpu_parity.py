@@ -417,6 +417,21 @@ def test_cell_step_shapes(torch_cuda, H, E, B, opts):
             np.testing.assert_allclose(scores[b], ws[b], atol=TOL_LP, rtol=4e-6)
 
 
+def test_b128_forward_repeatable_without_programmatic_launch(torch_cuda):
+    """Regression test of the GEMM splitter race of round 2: with STAT_PDL=0 the teacher-forced
+    forward at B=128 (BQ=128 tiles: 3-stage ring, alternating splitter groups) used to die with `unspecified launch
+    failure` within two calls.  Twelve forward + alpha passes in a fresh process must finish and be bit-identical."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, STAT_PDL='0')
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'fwd_repro.py'), '12'], capture_output=True, text=True,
+                       timeout=300, env=env, cwd=root)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-1500:])
+    assert 'B=128: 0 of 11 runs differ from run 0' in r.stdout, r.stdout[-500:]
+
+
 def test_caption_stream_equals_batchwise_greedy(torch_cuda):
     """The host streaming API (pinned host features -> captions, H2D of batch i+1 beside the decode of batch i, one
     captured graph per pipeline slot): five different batches, results in order and bit-identical to decoding each
