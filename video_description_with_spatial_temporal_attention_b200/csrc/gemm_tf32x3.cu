@@ -97,15 +97,23 @@ constexpr int UMMA_K = 8;    // tf32 MMA K
 constexpr int NSPLIT = 256;               // splitter / epilogue threads (8 warps: 2 per scheduler)
 constexpr int NTHREADS = 64 + NSPLIT;     // + TMA producer warp + MMA issuer warp
 
-template <int BQ>
+template <int BQ, bool TS>
 struct Cfg {
   static constexpr int P_BYTES = BP * BK * 4;
   static constexpr int Q_BYTES = BQ * BK * 4;
-  static constexpr int STAGE_BYTES = 2 * P_BYTES + 2 * Q_BYTES;
-  static constexpr int MAX_STAGES = (BQ >= 128) ? 3 : 4;
-  // TS variant: accumulator in columns [0, BQ), A-operand stage s (hi 32 cols | lo 32 cols) at 256 + 64 s
-  static constexpr int TS_A_BASE = 256;
+  // stage = raw P (-> hi in place) | [lo of P: SS variant only; TS keeps hi / lo of P in tensor memory] | Q hi | Q lo
+  static constexpr int Q_OFF = TS ? P_BYTES : 2 * P_BYTES;
+  static constexpr int STAGE_BYTES = Q_OFF + 2 * Q_BYTES;
+  // TS variant: accumulator in columns [0, BQ), A-operand stage s (hi 32 cols | lo 32 cols) at TS_A_BASE + 64 s
+  static constexpr int TS_A_BASE = BQ <= 64 ? 128 : 256;
   static constexpr int TS_TMEM_COLS = 512;
+  // Ring depth: what fits in shared memory (TS: and in the tensor-memory columns behind the accumulator).  The skinny
+  // per-step products are bound by the latency of a stage's refill (TMA round trip + split + MMAs) divided by the
+  // number of stages in flight: 6 stages of 32 KB instead of 4 of 48 KB for BQ = 64.
+  static constexpr int SMEM_RING = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 1024 /*static*/;
+  static constexpr int BY_SMEM = SMEM_RING / STAGE_BYTES;
+  static constexpr int BY_TMEM = (TS_TMEM_COLS - TS_A_BASE) / 64;
+  static constexpr int MAX_STAGES = TS ? (BY_SMEM < BY_TMEM ? BY_SMEM : BY_TMEM) : ((BQ >= 128) ? 3 : 4);
   static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
   static constexpr int TMEM_COLS = BQ < 32 ? 32 : BQ;
 };
@@ -327,7 +335,7 @@ template <int BQ, bool TS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
                    const DevArgs args) {
-  using C = Cfg<BQ>;
+  using C = Cfg<BQ, TS>;
   const int STAGES = args.stages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B needs the ring 1024-byte aligned; keep the pointer in the shared state space
@@ -398,10 +406,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
           // ~6 TB/s): the CTAs of a cluster work on different row tiles against the SAME weight tile, so each one
           // fetches 1/mc of it and multicasts it to all
           const uint32_t slice = static_cast<uint32_t>(C::Q_BYTES / args.mc);
-          tma_load_2d_mc(stage + 2 * C::P_BYTES + crank * slice, &tmQ, (kb0 + kb) * BK,
+          tma_load_2d_mc(stage + C::Q_OFF + crank * slice, &tmQ, (kb0 + kb) * BK,
                          q0 + static_cast<int>(crank) * (BQ / args.mc), bar_full + 8 * s, cmask, args.pol_q);
         } else {
-          tma_load_2d(stage + 2 * C::P_BYTES, &tmQ, (kb0 + kb) * BK, q0, bar_full + 8 * s, args.pol_q);
+          tma_load_2d(stage + C::Q_OFF, &tmQ, (kb0 + kb) * BK, q0, bar_full + 8 * s, args.pol_q);
         }
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -430,8 +438,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       const uint32_t stage = ring_u + static_cast<uint32_t>(s) * C::STAGE_BYTES;
       const uint64_t dPh = make_desc(stage);
       const uint64_t dPl = make_desc(stage + C::P_BYTES);
-      const uint64_t dQh = make_desc(stage + 2 * C::P_BYTES);
-      const uint64_t dQl = make_desc(stage + 2 * C::P_BYTES + C::Q_BYTES);
+      const uint64_t dQh = make_desc(stage + C::Q_OFF);
+      const uint64_t dQl = make_desc(stage + C::Q_OFF + C::Q_BYTES);
       const uint32_t a_hi = tmem_u + C::TS_A_BASE + 64 * s;
       if (leader) {
         if constexpr (TS) {
@@ -469,8 +477,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       uint8_t *stage = smem + s * C::STAGE_BYTES;
       float4 *Ph = reinterpret_cast<float4 *>(stage);
       float4 *Pl = reinterpret_cast<float4 *>(stage + C::P_BYTES);
-      float4 *Qh = reinterpret_cast<float4 *>(stage + 2 * C::P_BYTES);
-      float4 *Ql = reinterpret_cast<float4 *>(stage + 2 * C::P_BYTES + C::Q_BYTES);
+      float4 *Qh = reinterpret_cast<float4 *>(stage + C::Q_OFF);
+      float4 *Ql = reinterpret_cast<float4 *>(stage + C::Q_OFF + C::Q_BYTES);
       constexpr int NQ4 = (C::Q_BYTES / 16 + NSPLIT - 1) / NSPLIT;  // 1 / 2 / 4
       if constexpr (TS) {
         // The two groups of four splitter warps (one warp per TMEM lane quadrant each) take alternate k-slices, so
@@ -767,16 +775,16 @@ int launch_tc(const GemmArgs &a, const DevArgs &da, cudaStream_t stream) {
   STAT_TRY(make_tensor_map(&tmP, a.P, a.NP, a.K, a.ldp, BP));
   STAT_TRY(make_tensor_map(&tmQ, a.Q, a.NQ, a.K, a.ldq, BQ / mc));
   static size_t smem_set[STAT_MAX_DEV] = {};
-  STAT_TRY(ensure_dyn_smem(gemm_tf32x3_kernel<BQ, TS>, Cfg<BQ>::smem_bytes(Cfg<BQ>::MAX_STAGES), smem_set));
+  STAT_TRY(ensure_dyn_smem(gemm_tf32x3_kernel<BQ, TS>, Cfg<BQ, TS>::smem_bytes(Cfg<BQ, TS>::MAX_STAGES), smem_set));
   DevArgs db = da;
   db.mc = mc;
   const int nk_slice = ((a.K + BK - 1) / BK + da.ksplit - 1) / da.ksplit;
-  db.stages = nk_slice < Cfg<BQ>::MAX_STAGES ? nk_slice : Cfg<BQ>::MAX_STAGES;
+  db.stages = nk_slice < Cfg<BQ, TS>::MAX_STAGES ? nk_slice : Cfg<BQ, TS>::MAX_STAGES;
   dim3 grid((a.NQ + BQ - 1) / BQ, (a.NP + BP - 1) / BP, da.ksplit);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(NTHREADS);
-  cfg.dynamicSmemBytes = Cfg<BQ>::smem_bytes(db.stages);
+  cfg.dynamicSmemBytes = Cfg<BQ, TS>::smem_bytes(db.stages);
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
