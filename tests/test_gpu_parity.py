@@ -49,7 +49,8 @@ def _build(options, params):
 @pytest.mark.parametrize('impl', [0, 1, 2])
 @pytest.mark.parametrize('M,N,K,swap', [(64, 4097, 512, True), (300, 512, 4096, False), (1, 50, 24, True),
                                         (128, 128, 32, False), (13, 100, 40, True), (257, 96, 36, False),
-                                        (64, 12594, 512, True), (1664, 512, 512, False)])
+                                        (64, 12594, 512, True), (1664, 512, 512, False),
+                                        (13312, 1024, 512, False)])      # the last one takes the 128 x 256 tiles
 def test_gemm_matches_fp64(torch_cuda, impl, M, N, K, swap):
     torch = torch_cuda
     from video_description_with_spatial_temporal_attention_b200 import _lib

@@ -864,6 +864,21 @@ int gemm_launch(const GemmArgs &a, cudaStream_t stream) {
     if (a.NQ > 32) return launch_tc<64, false>(a, da, stream);
     return launch_tc<32, false>(a, da, stream);
   }
+  {
+    // 128 x 256 tiles where they still fill the SMs more than twice over (the context projections of K0: 13 312 rows
+    // x 1 024 features): an MMA instruction costs ~46 + 0.36 N cycles, so N = 256 runs the tensor pipe at ~0.9 of
+    // its peak where N = 128 reaches 0.75, the P tile is split once for twice the columns, and half as many CTAs
+    // pay a prologue and an epilogue.   STAT_GEMM_BQ256=0 switches it off.
+    static int wide = -1;
+    if (wide < 0) {
+      const char *e = getenv("STAT_GEMM_BQ256");
+      wide = (e && e[0] == '0') ? 0 : 1;
+    }
+    const long long tiles256 = static_cast<long long>((a.NQ + 255) / 256) * ((a.NP + BP - 1) / BP);
+    if (wide && !a.feat_on_p && da.ksplit == 1 && a.NQ % 256 == 0 && tiles256 >= 2 * 148 &&
+        (a.nseg == 1 || a.seg[1].f0 % 256 == 0))
+      return launch_tc<256, true>(a, da, stream);
+  }
   if (a.NQ > 64) return launch_tc<128, true>(a, da, stream);
   if (a.NQ > 32) return launch_tc<64, true>(a, da, stream);
   return launch_tc<32, true>(a, da, stream);
