@@ -118,12 +118,14 @@ int *stat_debug_trap_log(void);
 
 /* ---- L2 residency of the context blocks (no reference counterpart) -----------
  * The attention kernel re-reads the projected context blocks of the batch on
- * every decode step and copies them with the L2 evict_last priority; those
- * lines outlive the weights streamed between two steps only inside the
- * persisting-L2 carve-out of the device.  Sets that carve-out
- * (cudaLimitPersistingL2CacheSize, a per-device setting of the calling
- * process): bytes < 0 = the device maximum (79 MB of the 126 MB on B200),
- * 0 = none.  Returns the size now in effect, or a negative STAT_E* code. */
+ * every decode step and copies them with the L2 evict_last priority (everything
+ * streamed between two steps is evict_first).  This call sets the persisting-L2
+ * carve-out of the device (cudaLimitPersistingL2CacheSize, a per-device setting
+ * of the calling process): bytes < 0 = the device maximum (79 MB of the 126 MB on
+ * B200), 0 = none.  Measured in round 2: bulk copies with an evict_last hint do
+ * not use the set-aside, so a carve-out only shrinks the L2 they compete for --
+ * the host mirror sets none.  Returns the size now in effect, or a negative
+ * STAT_E* code. */
 long long stat_set_l2_persist(long long bytes);
 
 /* ---- parameter preparation (once per parameter set) ----------------------
