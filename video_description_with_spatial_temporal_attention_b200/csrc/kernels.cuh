@@ -129,16 +129,18 @@ struct BeamArgs {
   int32_t *out_lengths;      // (B,k)
   float *out_scores;         // (B,k)
   int32_t *out_count;        // (B) finished hypotheses so far
+  // state gather of the next step, done by the same launch (dst_h null: none): slot j of a clip continues row
+  // src_row[j]; src_q / dst_q (ldq floats per row, a multiple of 4; null: none) are the h-products of the cell step
+  const float *src_h, *src_c;
+  float *dst_h, *dst_c;
+  int H;
+  const float *src_q;
+  float *dst_q;
+  int ldq;
 };
 int beam_select_launch(const BeamArgs &a, cudaStream_t stream);
 int beam_init_launch(const BeamArgs &a, const float *h0c0, float *h, float *c, int H, int32_t *row_clip,
                      cudaStream_t stream);
-// dst_h[r] = src_h[src_row[r]], same for c   (rows,H)
-int gather_state_launch(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h, float *dst_c,
-                        int rows, int H, cudaStream_t stream);
-
-// dst[r][:] = src[src_row[r]][:]   (rows, width), width % 4 == 0
-int gather_rows_launch(const float *src, const int32_t *src_row, float *dst, int rows, int width, cudaStream_t stream);
 
 // ---- step_fused.cu: the fused products of a decode step (fused_tile.cuh) ----------------------------------
 enum { FE_STORE = 0, FE_GATES = 1, FE_ZC = 2, FE_Z = 3, FE_PICK = 4 };

@@ -371,10 +371,194 @@ __global__ void __launch_bounds__(256) pick_kernel(const PickArgs a) {
   }
 }
 
+// The same reduction with the row held in registers: NT threads, NJ float4 of the row per thread (float4
+// k = tid + NT j: coalesced), every load issued before the first value is used -- one memory round trip
+// instead of two rolled passes -- and every later step (maximum, sum of exponentials, probabilities, the
+// beam_k arg-max rounds of the beam search) works on registers.  Needs V <= 4 NT NJ and 16-byte aligned
+// rows; other shapes take pick_kernel.  Ties: the lowest index wins (a thread walks its words in ascending
+// order, merges compare (value, index)).
+struct PickTriple {
+  float m, s;
+  int i;
+};
+__device__ __forceinline__ PickTriple pick_merge_warp(PickTriple t) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, t.m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, t.i, o);
+    const float os = __shfl_xor_sync(0xffffffffu, t.s, o);
+    const float mn = fmaxf(t.m, om);
+    // empty partners carry (-inf, 0): -inf - -inf would be NaN, so their weight is forced to 0
+    const float w1 = (t.m == -INFINITY) ? 0.f : expf(t.m - mn);
+    const float w2 = (om == -INFINITY) ? 0.f : expf(om - mn);
+    t.s = t.s * w1 + os * w2;
+    if (om > t.m || (om == t.m && oi < t.i)) t.i = oi;
+    t.m = mn;
+  }
+  return t;
+}
+__device__ __forceinline__ void argmax_merge_warp(float &m, int &i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (om > m || (om == m && oi < i)) { m = om; i = oi; }
+  }
+}
+
+template <int NT, int NJ>
+__global__ void __launch_bounds__(NT) pick_regs_kernel(const PickArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int NW = NT / 32;
+  __shared__ float s_val[2][NW];
+  __shared__ int s_idx[2][NW];
+  __shared__ float s_sum[NW];
+  __shared__ float s_bm, s_bs;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const float *l = a.logits + static_cast<size_t>(row) * a.ldl;
+  const int nf4 = (a.V + 3) >> 2;       // ldl is a multiple of 4 and >= V: the last (partial) float4 is inside the row
+  float x[NJ][4];
+  {
+    const float4 *l4 = reinterpret_cast<const float4 *>(l);
+    float4 v[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int k = tid + NT * j;
+      v[j] = k < nf4 ? l4[k] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int w0 = 4 * (tid + NT * j);
+      x[j][0] = v[j].x;                                   // w0 < V whenever the float4 was loaded
+      x[j][1] = w0 + 1 < a.V ? v[j].y : -INFINITY;
+      x[j][2] = w0 + 2 < a.V ? v[j].z : -INFINITY;
+      x[j][3] = w0 + 3 < a.V ? v[j].w : -INFINITY;
+    }
+  }
+  PickTriple t;
+  t.m = -INFINITY; t.s = 0.f; t.i = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (x[j][e] > t.m) { t.m = x[j][e]; t.i = 4 * (tid + NT * j) + e; }
+  if (t.m > -INFINITY) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+      t.s += (__expf(x[j][0] - t.m) + __expf(x[j][1] - t.m)) + (__expf(x[j][2] - t.m) + __expf(x[j][3] - t.m));
+  }
+  const float own_m = t.m;
+  const int own_i = t.i;
+  t = pick_merge_warp(t);
+  if (lane == 0) { s_val[0][warp] = t.m; s_idx[0][warp] = t.i; s_sum[warp] = t.s; }
+  __syncthreads();
+  if (warp == 0) {
+    t.m = lane < NW ? s_val[0][lane] : -INFINITY;
+    t.i = lane < NW ? s_idx[0][lane] : 0x7fffffff;
+    t.s = lane < NW ? s_sum[lane] : 0.f;
+    t = pick_merge_warp(t);
+    if (lane == 0) {
+      const float b = t.m, tot = t.s;
+      const int tok = t.i;
+      s_bm = b;
+      s_bs = tot;
+      if (a.tokens) {
+        const bool live = a.alive[row] != 0;
+        a.tokens[static_cast<size_t>(row) * a.maxlen + a.t] = live ? tok : -1;
+        if (live) {
+          a.scores[row] += logf(tot);              // -log p(argmax) = log sum exp(l - max)
+          a.lengths[row] = a.t + 1;
+          a.alive[row] = tok != 0;
+          a.tok_prev[row] = tok;
+        }
+      }
+      if (a.x_t) {
+        const float p = expf(l[a.x_t[row]] - b) / tot;
+        // compensated accumulation: the sum of L terms of magnitude ~10 would otherwise lose ~L/2 ulp of the sum
+        const float term = a.mask_t[row] * logf(p + 1e-8f);      // model_attention.py:712-715
+        if (a.logprob_comp) {
+          const float y = term - a.logprob_comp[row];
+          const float sum = a.logprob[row];
+          const float tt = sum + y;
+          a.logprob_comp[row] = (tt - sum) - y;
+          a.logprob[row] = tt;
+        } else {
+          a.logprob[row] += term;
+        }
+      }
+    }
+  }
+  if (!a.probs && a.beam_k <= 0) return;
+  __syncthreads();
+  const float mm = s_bm, inv = 1.0f / s_bs;
+  if (a.probs) {
+    float *p = a.probs + static_cast<size_t>(row) * a.V;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int v = 4 * (tid + NT * j) + e;
+        if (v < a.V) p[v] = expf(x[j][e] - mm) * inv;
+      }
+  }
+  if (a.beam_k > 0) {
+    // The cost score - log p[v] falls as the logit rises: the beam_k cheapest continuations of the row are its
+    // beam_k largest logits (lower index first among equals), found by beam_k arg-max rounds.  Every thread offers
+    // the best of its not-yet-taken words; after a round only the owner of the winner looks at its words again.
+    // One barrier per round: the per-warp winners alternate between two shared-memory buffers, every warp
+    // reduces them for itself.
+    float *cc = a.cand_cost + static_cast<size_t>(row) * BEAM_KMAX;
+    int32_t *cw = a.cand_word + static_cast<size_t>(row) * BEAM_KMAX;
+    if (!a.row_alive[row]) {
+      if (tid < BEAM_KMAX) { cc[tid] = INFINITY; cw[tid] = 0; }
+      return;
+    }
+    const float sc = a.row_score[row];
+    float bm = own_m;
+    int bv = own_i;
+    for (int r = 0; r < a.beam_k; ++r) {
+      const int par = (r + 1) & 1;          // buffer 0 was last read before the barrier above
+      float wm = bm;
+      int wv = bv;
+      argmax_merge_warp(wm, wv);
+      if (lane == 0) { s_val[par][warp] = wm; s_idx[par][warp] = wv; }
+      __syncthreads();
+      float b = lane < NW ? s_val[par][lane] : -INFINITY;
+      int i = lane < NW ? s_idx[par][lane] : 0x7fffffff;
+      argmax_merge_warp(b, i);
+      const bool ok = i < a.V;               // V < beam_k: no candidate left
+      if (tid == 0) {
+        cc[r] = ok ? sc - logf(expf(b - mm) * inv) : INFINITY;   // as the reference: -log of the fp32 probability
+        cw[r] = ok ? i : 0;
+      }
+      if (ok && ((i >> 2) & (NT - 1)) == tid) {
+        // my best word was taken: next best of my words
+        bm = -INFINITY;
+        bv = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int v = 4 * (tid + NT * j) + e;
+            if (v == i) x[j][e] = -INFINITY;
+            if (x[j][e] > bm) { bm = x[j][e]; bv = v; }
+          }
+      }
+    }
+    if (tid >= a.beam_k && tid < BEAM_KMAX) { cc[tid] = INFINITY; cw[tid] = 0; }
+  }
+}
+
 // ---------------------------------------------------------------------------
-// beam search bookkeeping (model_attention.py:852-994), one warp per clip
+// beam search bookkeeping (model_attention.py:852-994), one CTA per clip
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) beam_select_kernel(const BeamArgs a) {
+// One CTA per clip: warp 0 does the bookkeeping (every global read it needs is issued up front: one memory
+// round trip), then the whole CTA gathers the LSTM state (and, for the cell step, the h-products) of the clip's new
+// row slots from the rows they continue -- the k slots of a clip only ever continue rows of the same clip.
+constexpr int BEAM_SELECT_NT = 1024;
+__global__ void __launch_bounds__(BEAM_SELECT_NT) beam_select_kernel(const BeamArgs a) {
   pdl_wait();
   pdl_trigger();
   __shared__ int s_hist[BEAM_KMAX][BEAM_LMAX];
@@ -382,105 +566,161 @@ __global__ void __launch_bounds__(32) beam_select_kernel(const BeamArgs a) {
   __shared__ int s_src[BEAM_KMAX], s_word[BEAM_KMAX];
   __shared__ float s_cost[BEAM_KMAX];
   __shared__ int s_nsel;
-  const int b = blockIdx.x, lane = threadIdx.x, k = a.k;
-  const int r0 = b * k;
-  if (a.done[b]) {
-    for (int j = lane; j < k; j += 32) { a.src_row[r0 + j] = r0 + j; a.tok_prev[r0 + j] = 0; }
-    return;
-  }
-  // old histories of the clip's slots
-  for (int j = 0; j < k; ++j) {
-    const int n = a.hist_len[r0 + j];
-    for (int i = lane; i < n; i += 32) s_hist[j][i] = a.hist[static_cast<size_t>(r0 + j) * BEAM_LMAX + i];
-    if (lane == 0) s_len[j] = n;
-  }
-  // candidates and flags of the clip into shared memory with all lanes (the selection below walks them
-  // serially: from global memory every probe would be a dependent L2 round trip)
   __shared__ float s_cc[BEAM_KMAX][BEAM_KMAX];
   __shared__ int s_cw[BEAM_KMAX][BEAM_KMAX];
   __shared__ int s_alive[BEAM_KMAX];
-  for (int e = lane; e < k * k; e += 32) {
-    const int j = e / k, c = e - j * k;
-    s_cc[j][c] = a.cand_cost[static_cast<size_t>(r0 + j) * BEAM_KMAX + c];
-    s_cw[j][c] = a.cand_word[static_cast<size_t>(r0 + j) * BEAM_KMAX + c];
-  }
-  for (int j = lane; j < k; j += 32) s_alive[j] = a.alive[r0 + j];
-  const int dead0 = a.dead_k[b], nout0 = a.out_count[b];
-  __syncwarp();
-  if (lane == 0) {
-    // the k - dead cheapest of the live slots' candidates: ascending cost, lower flat index (slot*V + word) first
-    const int want = k - dead0;
-    int head[BEAM_KMAX];                      // every slot's candidates are already in ascending order
-    for (int j = 0; j < k; ++j) head[j] = 0;
-    int n = 0;
-    for (; n < want; ++n) {
-      float bc = INFINITY;
-      int bj = -1;
-      long long bf = 0;
-      for (int j = 0; j < k; ++j) {
-        if (!s_alive[j] || head[j] >= k) continue;
-        const float c = s_cc[j][head[j]];
-        const long long f = static_cast<long long>(j) * a.V + s_cw[j][head[j]];
-        if (c < bc || (c == bc && bj >= 0 && f < bf)) { bc = c; bj = j; bf = f; }
-      }
-      if (bj < 0 || bc == INFINITY) break;
-      s_src[n] = bj;
-      s_word[n] = s_cw[bj][head[bj]];
-      s_cost[n] = bc;
-      ++head[bj];
-    }
-    s_nsel = n;
-  }
-  __syncwarp();
-  const int nsel = s_nsel;
-  // new hypotheses in rank order: token 0 retires one, the others become the live slots 0, 1, ...
-  int n_live = 0, n_out = nout0, dead = dead0;
-  for (int n = 0; n < nsel; ++n) {
-    const int src = s_src[n], word = s_word[n], len = s_len[src];
-    if (word == 0) {
-      int64_t *ot = a.out_tokens + (static_cast<size_t>(b) * k + n_out) * a.maxlen;
-      for (int i = lane; i < a.maxlen; i += 32) ot[i] = i < len ? s_hist[src][i] : (i == len ? 0 : -1);
-      if (lane == 0) { a.out_lengths[b * k + n_out] = len + 1; a.out_scores[b * k + n_out] = s_cost[n]; }
-      ++n_out;
-      ++dead;
+  __shared__ int s_from[BEAM_KMAX];           // row whose state slot j continues, -1: nothing to gather
+  const int b = blockIdx.x, tid = threadIdx.x, k = a.k;
+  const int r0 = b * k;
+  const int was_done = a.done[b];
+  if (tid < 32) {
+    const int lane = tid;
+    if (was_done) {
+      for (int j = lane; j < k; j += 32) { a.src_row[r0 + j] = r0 + j; a.tok_prev[r0 + j] = 0; s_from[j] = -1; }
     } else {
-      const int row = r0 + n_live;
-      int32_t *h = a.hist + static_cast<size_t>(row) * BEAM_LMAX;
-      for (int i = lane; i < len; i += 32) h[i] = s_hist[src][i];
-      if (lane == 0) {
-        h[len] = word;
-        a.hist_len[row] = len + 1;
-        a.score[row] = s_cost[n];
-        a.src_row[row] = r0 + src;
-        a.tok_prev[row] = word;
-        a.alive[row] = 1;
+      // old histories (a hypothesis has at most t words before step t), candidates and flags of the clip's slots into
+      // shared memory with all lanes: the selection below walks them serially, from global memory every probe
+      // would be a dependent L2 round trip
+      const int tmax = min(a.t, BEAM_LMAX);
+      for (int e = lane; e < k * tmax; e += 32) {
+        const int j = e / tmax, i = e - j * tmax;
+        s_hist[j][i] = a.hist[static_cast<size_t>(r0 + j) * BEAM_LMAX + i];
       }
-      ++n_live;
+      for (int e = lane; e < k * k; e += 32) {
+        const int j = e / k, c = e - j * k;
+        s_cc[j][c] = a.cand_cost[static_cast<size_t>(r0 + j) * BEAM_KMAX + c];
+        s_cw[j][c] = a.cand_word[static_cast<size_t>(r0 + j) * BEAM_KMAX + c];
+      }
+      for (int j = lane; j < k; j += 32) {
+        s_alive[j] = a.alive[r0 + j];
+        s_len[j] = a.hist_len[r0 + j];
+      }
+      const int dead0 = a.dead_k[b], nout0 = a.out_count[b];
+      __syncwarp();
+      if (lane == 0) {
+        // the k - dead cheapest of the live slots' candidates: ascending cost, lower flat index (slot*V + word) first
+        const int want = k - dead0;
+        int head[BEAM_KMAX];                      // every slot's candidates are already in ascending order
+        for (int j = 0; j < k; ++j) head[j] = 0;
+        int n = 0;
+        for (; n < want; ++n) {
+          float bc = INFINITY;
+          int bj = -1;
+          long long bf = 0;
+          for (int j = 0; j < k; ++j) {
+            if (!s_alive[j] || head[j] >= k) continue;
+            const float c = s_cc[j][head[j]];
+            const long long f = static_cast<long long>(j) * a.V + s_cw[j][head[j]];
+            if (c < bc || (c == bc && bj >= 0 && f < bf)) { bc = c; bj = j; bf = f; }
+          }
+          if (bj < 0 || bc == INFINITY) break;
+          s_src[n] = bj;
+          s_word[n] = s_cw[bj][head[bj]];
+          s_cost[n] = bc;
+          ++head[bj];
+        }
+        s_nsel = n;
+      }
+      __syncwarp();
+      const int nsel = s_nsel;
+      // new hypotheses in rank order: token 0 retires one, the others become the live slots 0, 1, ...
+      int n_live = 0, n_out = nout0, dead = dead0;
+      for (int n = 0; n < nsel; ++n) {
+        const int src = s_src[n], word = s_word[n], len = s_len[src];
+        if (word == 0) {
+          int64_t *ot = a.out_tokens + (static_cast<size_t>(b) * k + n_out) * a.maxlen;
+          for (int i = lane; i < a.maxlen; i += 32) ot[i] = i < len ? s_hist[src][i] : (i == len ? 0 : -1);
+          if (lane == 0) { a.out_lengths[b * k + n_out] = len + 1; a.out_scores[b * k + n_out] = s_cost[n]; }
+          ++n_out;
+          ++dead;
+        } else {
+          const int row = r0 + n_live;
+          int32_t *h = a.hist + static_cast<size_t>(row) * BEAM_LMAX;
+          for (int i = lane; i < len; i += 32) h[i] = s_hist[src][i];
+          if (lane == 0) {
+            h[len] = word;
+            a.hist_len[row] = len + 1;
+            a.score[row] = s_cost[n];
+            a.src_row[row] = r0 + src;
+            a.tok_prev[row] = word;
+            a.alive[row] = 1;
+            s_from[n_live] = r0 + src;
+          }
+          ++n_live;
+        }
+      }
+      __syncwarp();
+      const bool finished = n_live < 1 || dead >= k || a.t + 1 >= a.maxlen;   // :969-972 and the end of the loop
+      if (finished) {
+        // the survivors follow the retired hypotheses (:975-979)
+        for (int j = 0; j < n_live; ++j) {
+          const int row = r0 + j;
+          const int len = a.hist_len[row];
+          int64_t *ot = a.out_tokens + (static_cast<size_t>(b) * k + n_out) * a.maxlen;
+          for (int i = lane; i < a.maxlen; i += 32) ot[i] = i < len ? a.hist[static_cast<size_t>(row) * BEAM_LMAX + i] : -1;
+          if (lane == 0) { a.out_lengths[b * k + n_out] = len; a.out_scores[b * k + n_out] = a.score[row]; }
+          ++n_out;
+        }
+        n_live = 0;
+      }
+      for (int j = n_live + lane; j < k; j += 32) {
+        a.alive[r0 + j] = 0;
+        a.src_row[r0 + j] = r0 + j;
+        a.tok_prev[r0 + j] = 0;
+        s_from[j] = -1;
+      }
+      if (finished) for (int j = lane; j < k; j += 32) s_from[j] = -1;
+      if (lane == 0) {
+        a.out_count[b] = n_out;
+        a.dead_k[b] = dead;
+        a.done[b] = finished ? 1 : 0;
+      }
     }
   }
-  __syncwarp();
-  const bool finished = n_live < 1 || dead >= k || a.t + 1 >= a.maxlen;   // :969-972 and the end of the loop
-  if (finished) {
-    // the survivors follow the retired hypotheses (:975-979)
-    for (int j = 0; j < n_live; ++j) {
-      const int row = r0 + j;
-      const int len = a.hist_len[row];
-      int64_t *ot = a.out_tokens + (static_cast<size_t>(b) * k + n_out) * a.maxlen;
-      for (int i = lane; i < a.maxlen; i += 32) ot[i] = i < len ? a.hist[static_cast<size_t>(row) * BEAM_LMAX + i] : -1;
-      if (lane == 0) { a.out_lengths[b * k + n_out] = len; a.out_scores[b * k + n_out] = a.score[row]; }
-      ++n_out;
+  if (!a.dst_h) return;
+  __syncthreads();
+  // state (and h-products) of the live slots in their new order; the dead slots of a clip are never read again.
+  // Four independent 16-byte loads per thread go out before the first store: the rows of a clip (k x 20 KB at H = 512)
+  // move in two or three memory round trips.
+  if ((a.H & 3) == 0) {
+    const int H4 = a.H >> 2, Q4 = a.dst_q ? (a.ldq >> 2) : 0;
+    const int per_row = 2 * H4 + Q4, total = k * per_row;
+    for (int base = 0; base < total; base += 4 * BEAM_SELECT_NT) {
+      float4 v[4];
+      float4 *dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = base + u * BEAM_SELECT_NT + tid;
+        dst[u] = nullptr;
+        if (e >= total) continue;
+        const int j = e / per_row, i = e - j * per_row;
+        const int from = s_from[j];
+        if (from < 0) continue;
+        const size_t so = static_cast<size_t>(from), dd = static_cast<size_t>(r0 + j);
+        const float *sp;
+        float *dp;
+        if (i < H4) { sp = a.src_h + so * a.H + 4 * i; dp = a.dst_h + dd * a.H + 4 * i; }
+        else if (i < 2 * H4) { sp = a.src_c + so * a.H + 4 * (i - H4); dp = a.dst_c + dd * a.H + 4 * (i - H4); }
+        else { sp = a.src_q + so * a.ldq + 4 * (i - 2 * H4); dp = a.dst_q + dd * a.ldq + 4 * (i - 2 * H4); }
+        v[u] = *reinterpret_cast<const float4 *>(sp);
+        dst[u] = reinterpret_cast<float4 *>(dp);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (dst[u]) *dst[u] = v[u];
     }
-    n_live = 0;
-  }
-  for (int j = n_live + lane; j < k; j += 32) {
-    a.alive[r0 + j] = 0;
-    a.src_row[r0 + j] = r0 + j;
-    a.tok_prev[r0 + j] = 0;
-  }
-  if (lane == 0) {
-    a.out_count[b] = n_out;
-    a.dead_k[b] = dead;
-    a.done[b] = finished ? 1 : 0;
+  } else {
+    for (int j = 0; j < k; ++j) {
+      const int from = s_from[j];
+      if (from < 0) continue;
+      const size_t so = static_cast<size_t>(from), dd = static_cast<size_t>(r0 + j);
+      for (int i = tid; i < a.H; i += BEAM_SELECT_NT) {
+        a.dst_h[dd * a.H + i] = a.src_h[so * a.H + i];
+        a.dst_c[dd * a.H + i] = a.src_c[so * a.H + i];
+      }
+      if (a.dst_q)
+        for (int i = tid; i < a.ldq; i += BEAM_SELECT_NT) a.dst_q[dd * a.ldq + i] = a.src_q[so * a.ldq + i];
+    }
   }
 }
 
@@ -504,28 +744,6 @@ __global__ void beam_init_kernel(const BeamArgs a, const float *h0c0, float *h, 
     a.out_scores[row] = 0.f;
     if (j == 0) { a.dead_k[b] = 0; a.done[b] = 0; a.out_count[b] = 0; }
   }
-}
-
-__global__ void gather_state_kernel(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h,
-                                    float *dst_c, int H) {
-  pdl_wait();
-  pdl_trigger();
-  const int row = blockIdx.x;
-  const size_t s = static_cast<size_t>(src_row[row]) * H, d = static_cast<size_t>(row) * H;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    dst_h[d + i] = src_h[s + i];
-    dst_c[d + i] = src_c[s + i];
-  }
-}
-
-// dst[r][:] = src[src_row[r]][:], rows of `width` floats (a multiple of 4, 16-byte aligned)
-__global__ void gather_rows_kernel(const float *src, const int32_t *src_row, float *dst, int width) {
-  pdl_wait();
-  pdl_trigger();
-  const int row = blockIdx.x;
-  const float4 *s = reinterpret_cast<const float4 *>(src + static_cast<size_t>(src_row[row]) * width);
-  float4 *d = reinterpret_cast<float4 *>(dst + static_cast<size_t>(row) * width);
-  for (int i = threadIdx.x; i < width / 4; i += blockDim.x) d[i] = s[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -639,14 +857,30 @@ int zact_launch(const ZactArgs &a, cudaStream_t stream) {
   return launch_pdl(zact_kernel, dim3((a.rows * a.E + 255) / 256), dim3(256), 0, stream, a);
 }
 
+// STAT_PICK_NT = 256 | 512 | 1024: threads per row of the register-resident reduction (0: the two-pass kernel).
+// Default: 1024 up to 128 rows (B = 64 greedy decode in the captured graph: 43.5 us per step against 44.6 at 512 and
+// 45.4 with the two-pass kernel), 512 beyond (beam search over 160 rows: more than one CTA per SM).
 int pick_launch(const PickArgs &a, cudaStream_t stream) {
+  static int nt_env = -1;
+  if (nt_env < 0) {
+    const char *e = getenv("STAT_PICK_NT");
+    nt_env = e ? atoi(e) : -2;
+  }
+  const int nt = nt_env >= 0 ? nt_env : (a.rows <= 128 ? 1024 : 512);
+  const bool aligned = (a.ldl & 3) == 0 && (reinterpret_cast<uintptr_t>(a.logits) & 15) == 0;
   set_launch_label("pick_kernel");
+  if (aligned && nt == 1024 && a.V <= 4 * 1024 * 4)
+    return launch_pdl(pick_regs_kernel<1024, 4>, dim3(a.rows), dim3(1024), 0, stream, a);
+  if (aligned && nt == 512 && a.V <= 4 * 512 * 7)
+    return launch_pdl(pick_regs_kernel<512, 7>, dim3(a.rows), dim3(512), 0, stream, a);
+  if (aligned && nt == 256 && a.V <= 4 * 256 * 13)
+    return launch_pdl(pick_regs_kernel<256, 13>, dim3(a.rows), dim3(256), 0, stream, a);
   return launch_pdl(pick_kernel, dim3(a.rows), dim3(256), 0, stream, a);
 }
 
 int beam_select_launch(const BeamArgs &a, cudaStream_t stream) {
   set_launch_label("beam_select_kernel");
-  return launch_pdl(beam_select_kernel, dim3(a.B), dim3(32), 0, stream, a);
+  return launch_pdl(beam_select_kernel, dim3(a.B), dim3(BEAM_SELECT_NT), 0, stream, a);
 }
 
 int beam_init_launch(const BeamArgs &a, const float *h0c0, float *h, float *c, int H, int32_t *row_clip,
@@ -655,17 +889,6 @@ int beam_init_launch(const BeamArgs &a, const float *h0c0, float *h, float *c, i
   note_launch();
   STAT_CUDA_CHECK(cudaGetLastError());
   return STAT_OK;
-}
-
-int gather_state_launch(const float *src_h, const float *src_c, const int32_t *src_row, float *dst_h, float *dst_c,
-                        int rows, int H, cudaStream_t stream) {
-  set_launch_label("gather_state_kernel");
-  return launch_pdl(gather_state_kernel, dim3(rows), dim3(128), 0, stream, src_h, src_c, src_row, dst_h, dst_c, H);
-}
-
-int gather_rows_launch(const float *src, const int32_t *src_row, float *dst, int rows, int width, cudaStream_t stream) {
-  set_launch_label("gather_rows_kernel");
-  return launch_pdl(gather_rows_kernel, dim3(rows), dim3(256), 0, stream, src, src_row, dst, width);
 }
 
 int meanpool_launch(const float *ctxg, const float *mask, float *gbar, int B, int T, int D,

@@ -1481,11 +1481,12 @@ int stat_decode_beam(const StatDims *d, const void *prepared, void *ws, int k, i
         ProfScope ps(PH_PICK, st);
         STAT_TRY(pick_launch(pk, st));
         b.t = t;
+        // the selection also gathers the state and the h-products of the rows the new slots continue
+        const bool more = t + 1 < maxlen;
+        b.src_h = W + w.hb; b.src_c = W + w.cb; b.H = d->H;
+        b.dst_h = more ? W + w.h : nullptr; b.dst_c = more ? W + w.c : nullptr;
+        b.src_q = W + w.hq2; b.dst_q = more ? W + w.hq : nullptr; b.ldq = w.ldq2;
         STAT_TRY(beam_select_launch(b, st));
-      }
-      if (t + 1 < maxlen) {
-        STAT_TRY(gather_state_launch(W + w.hb, W + w.cb, b.src_row, W + w.h, W + w.c, rows, d->H, st));
-        STAT_TRY(gather_rows_launch(W + w.hq2, b.src_row, W + w.hq, rows, w.ldq2, st));
       }
     }
     return STAT_OK;
@@ -1513,10 +1514,12 @@ int stat_decode_beam(const StatDims *d, const void *prepared, void *ws, int k, i
       ProfScope ps(PH_PICK, st);
       STAT_TRY(pick_launch(pk, st));
       b.t = t;
+      const bool more = t + 1 < maxlen;
+      b.src_h = W + w.hb; b.src_c = W + w.cb; b.H = d->H;
+      b.dst_h = more ? W + w.h : nullptr; b.dst_c = more ? W + w.c : nullptr;
       STAT_TRY(beam_select_launch(b, st));
     }
     if (t + 1 < maxlen) {
-      STAT_TRY(gather_state_launch(W + w.hb, W + w.cb, b.src_row, W + w.h, W + w.c, rows, d->H, st));
       STAT_TRY(h_proj(*d, p, P, w, W, W + w.h, rows, 1, st));
     }
   }
