@@ -111,6 +111,12 @@ int stat_set_gemm_impl(int impl);
  *  -1 = back to the default (environment STAT_STEP=0|1|2, else 2). */
 int stat_set_step_impl(int impl);
 
+/* Beam search attention (stat_decode_beam): 1 = the k row slots of a clip share ONE pass over the clip's context
+ * blocks (att_clip_kernel: a frame is brought on chip once for all k hypotheses, as the reference broadcasts one
+ * clip's context to its k live rows, model_attention.py:786-788), 0 = one cluster per row (k passes over the same
+ * blocks), -1 = back to the default (environment STAT_ATT_SHARE=0|1, else 1).  Same results to fp32 summation order. */
+int stat_set_beam_share(int on);
+
 /* Fault hunting: arms the spin-wait give-up sites of the attention and GEMM kernels to record where they trap
  * (4 ints: site = file tag + source line, blockIdx.x, threadIdx.x, blockIdx.y << 16 | blockIdx.z) in host-mapped
  * memory, which survives the device fault.  Returns the host pointer (NULL on failure). */

@@ -483,6 +483,39 @@ def test_beam_k1_equals_greedy_and_limits(torch_cuda):
         model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=2, maxlen=65)
 
 
+@pytest.mark.parametrize('B,k,T,R,kw', [(32, 5, 26, 8, {}),              # config 5's share: 128 CTAs, 5 row slots each
+                                         (3, 3, 26, 8, {}),               # clusters of 8 CTAs
+                                         (2, 7, 5, 8, {}),                # two passes per clip (4 + 3 slots), T < 8
+                                         (2, 16, 9, 8, {}),               # four passes of 4 slots
+                                         (4, 4, 7, 3, {'dim': 96, 'dim_word': 64, 'ctxg_dim': 96, 'ctxglm_dim': 96, 'ctxl_dim': 128, 'ctxm_dim': 64, 'n_words': 301}),   # generic R / H
+                                         (150, 2, 3, 2, {'dim': 32, 'dim_word': 32, 'ctxg_dim': 32, 'ctxglm_dim': 32, 'ctxl_dim': 64, 'ctxm_dim': 64, 'n_words': 200})])  # more clips than SMs
+def test_beam_shared_frames_equal_one_cluster_per_row(torch_cuda, B, k, T, R, kw):
+    """stat_set_beam_share: the k row slots of a clip attending over ONE pass of the clip's frames (att_clip_kernel)
+    give the hypotheses and scores of the search with one attention cluster per row (fp32 summation order aside)."""
+    from video_description_with_spatial_temporal_attention_b200 import _lib
+    lib = _lib.load()
+    o, params, batch = _case('baseline', B=B, T=T, R=R, seed=23 + k, **kw)
+    params['ff_logit_b'] = params['ff_logit_b'].copy()
+    params['ff_logit_b'][0] += 1.0          # hypotheses retire at different steps: dead slots, shrinking beams
+    x, m, ctxg, mg, ctxl, ml, ctxm, mm = batch
+    model, tp, _, _, _, _ = _build(o, params)
+    res = {}
+    try:
+        for share in (0, 1):
+            _lib.check(lib.stat_set_beam_share(share))
+            res[share] = model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=k, maxlen=10)
+    finally:
+        _lib.check(lib.stat_set_beam_share(-1))
+    n_same = 0
+    for b in range(B):
+        if res[0][b][0] == res[1][b][0]:
+            n_same += 1
+            np.testing.assert_allclose(np.asarray(res[1][b][1]), np.asarray(res[0][b][1]), atol=2e-5, rtol=4e-6)
+        else:      # an fp32 near-tie between two candidates may swap them
+            assert abs(float(res[0][b][1][0]) - float(res[1][b][1][0])) < 1e-3, b
+    assert n_same >= B - max(1, B // 16)
+
+
 # ---------------------------------------------------------------------------
 # size-independent properties at BASELINE size (B=64)
 # ---------------------------------------------------------------------------

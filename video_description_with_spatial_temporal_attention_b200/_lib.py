@@ -97,6 +97,8 @@ def _declare(lib):
     lib.stat_profile_phase_name.argtypes = [i32]
     lib.stat_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int), i32]
     lib.stat_set_step_impl.argtypes = [i32]
+    lib.stat_set_beam_share.argtypes = [i32]
+    lib.stat_set_beam_share.restype = i32
     for n in ('stat_set_step_impl', 'stat_attention', 'stat_profile_enable', 'stat_profile_collect', 'stat_set_gemm_impl', 'stat_prepare_params', 'stat_init_state', 'stat_workspace_region', 'stat_precompute',
               'stat_forward_teacher', 'stat_decode_greedy', 'stat_decode_beam', 'stat_step', 'stat_gemm', 'stat_grad_clip',
               'stat_adam_step', 'stat_adadelta_step', 'stat_alpha_coverage', 'stat_grad_shared', 'stat_grad_profile_enable', 'stat_grad_profile_collect'):

@@ -61,6 +61,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // fault hunting (stat_debug_trap_log): a host-mapped word that survives the fault receives the site of the trap
 __device__ volatile int *g_trap_log = nullptr;
 __device__ __forceinline__ void trap_at(int site) {
@@ -637,6 +640,323 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   if (tr) tr[15] = clock64();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// att_clip_kernel: the same four soft-attentions for the beam search, where the k row slots of a clip attend
+// over the SAME context blocks (model_attention.py:786-788, 328-332: the reference broadcasts one clip's
+// context to its k live hypotheses).  One cluster per (clip, pass of <= KSH slots); the CTAs of the cluster
+// take contiguous slices of the clip's T frames as above, but a frame is brought to shared memory ONCE and
+// every group of four warps computes a different ROW against it: group g <-> row slot g of the clip.  The
+// frames travel through a ring of NS whole-frame slots filled by a producer warp (bulk copies, one "P" and
+// one "V" barrier per slot as above); a group arrives on the slot's `empty` barrier after its last read, the
+// producer refills the slot when all groups have.  k-fold fewer bytes than one cluster per row, and
+// clips x cs CTAs fill the SMs once where k x clips rows needed a second, nearly empty wave (32 clips, k = 5:
+// 160 one-CTA rows on 148 SMs).
+// A group keeps the running soft-max states of its row in registers for the whole slice, so there is no
+// merge inside the CTA; across the cluster the other ranks push their states into landing pads of rank 0 as
+// above -- the pads reuse the drained ring (a cluster barrier separates the two uses).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KSH = 5;                         // row slots (groups) per CTA
+constexpr int CLIP_THREADS = KSH * GT + 32;    // + the producer warp
+
+template <int RT, int HT>
+__global__ void __launch_bounds__(CLIP_THREADS, 1)
+    att_clip_kernel(const AttArgs a, const int K, const int npass, const int cs, const int NS, const AttPolicies pol) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int RU = RT ? RT : RMAX;
+  const int H = HT ? HT : a.H, T = a.T;
+  const int R = RT ? RT : a.R;
+  const int RH = R * H;
+  const int p_floats = RH + 2 * H, v_floats = 2 * RH;
+  const int slot_floats = p_floats + v_floats;
+  float *ring = reinterpret_cast<float *>(smem_raw);                 // [NS][slot_floats]; later the landing pads
+  float *s_red = ring + static_cast<size_t>(NS) * slot_floats;       // [KSH][RMAX + 2][4] per-warp score partials
+  float *s_lt = s_red + KSH * (RMAX + 2) * 4;                        // [KSH][4]
+  float *s_u = s_lt + KSH * 4;                                       // -2 Ug | -2 Um | -2 Ult  (3 x H)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_u + 3 * H);        // fullP[NS] fullV[NS] empty[NS] merge
+  constexpr int NSMAX = 4;
+  const int PAD_FLOATS = H * 4 + 8;          // per (rank, slot): [H][4] weighted sums of a column (g, m, lt, -) | (max, sum) x 3
+
+  const int rpc = a.rows_per_clip;
+  const int cl_id = static_cast<int>(blockIdx.x) / cs;
+  const int clip = cl_id / npass, slot0 = (cl_id - clip * npass) * K;
+  const int nrows = min(K, rpc - slot0);                              // row slots of this cluster
+  const int rank = cs > 1 ? static_cast<int>(cluster_rank()) : 0;
+  const int t0 = (rank * T) / cs;
+  const int nframes = ((rank + 1) * T) / cs - t0;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = tid >> 7, gt = tid & (GT - 1), gw = gt >> 5;
+  const bool producer = tid >= K * GT;
+  const bool active = !producer && g < nrows;
+  const int row = clip * rpc + slot0 + (active ? g : 0);
+  const int c = 4 * gt;
+  const bool okc = HT || c < H;
+
+  if (tid < 2 * NS) mbar_init(smem_u32(bars + (tid < NS ? tid : NSMAX + tid - NS)), 1);
+  if (tid >= 2 * NS && tid < 3 * NS) mbar_init(smem_u32(bars + 2 * NSMAX + tid - 2 * NS), static_cast<uint32_t>(nrows));
+  if (tid == 0) {
+    if (cs > 1 && rank == 0) {
+      mbar_init(smem_u32(bars + 3 * NSMAX), 1);
+      mbar_expect_tx(smem_u32(bars + 3 * NSMAX),
+                     static_cast<uint32_t>(cs - 1) * static_cast<uint32_t>(nrows) * (static_cast<uint32_t>(H) * 16u + 32u));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // score vectors (parameters: not written by the previous kernel).  Ul stays in registers, the other three are
+  // shared by all groups from shared memory, already folded (u -> -2u, see tanh_acc4)
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ul = z4;
+  float su_l = 0.f, su_g = 0.f, su_m = 0.f, su_lt = 0.f;
+  if (!producer && okc) {
+    ul = ld4(a.Ul + c);
+    const float4 ug = ld4(a.Ug + c), um = ld4(a.Um + c), ult = ld4(a.Ult + c);
+    su_l = sum4(ul); su_g = sum4(ug); su_m = sum4(um); su_lt = sum4(ult);
+    ul.x *= -2.0f; ul.y *= -2.0f; ul.z *= -2.0f; ul.w *= -2.0f;
+    if (g == 0) {
+      *reinterpret_cast<float4 *>(s_u + c) = make_float4(-2.0f * ug.x, -2.0f * ug.y, -2.0f * ug.z, -2.0f * ug.w);
+      *reinterpret_cast<float4 *>(s_u + H + c) = make_float4(-2.0f * um.x, -2.0f * um.y, -2.0f * um.z, -2.0f * um.w);
+      *reinterpret_cast<float4 *>(s_u + 2 * H + c) = make_float4(-2.0f * ult.x, -2.0f * ult.y, -2.0f * ult.z, -2.0f * ult.w);
+    }
+  }
+  const float cl = __ldg(a.cl), cg = __ldg(a.cg), cm = __ldg(a.cm), clt = __ldg(a.clt);
+  __syncthreads();
+
+  const int rev = a.reverse;
+  auto frame_of = [&](int j) { return t0 + (rev ? nframes - 1 - j : j); };
+
+  // ================================ producer warp ================================
+  if (producer) {
+    if (lane == 0) {
+      // the context blocks were written by the prologue of the batch, long before the kernel this launch depends on
+      const uint32_t bytes_rh = static_cast<uint32_t>(RH) * 4u, bytes_h = static_cast<uint32_t>(H) * 4u;
+      for (int j = 0; j < nframes; ++j) {
+        const int s = j % NS, use = j / NS;
+        if (use > 0) mbar_wait(smem_u32(bars + 2 * NSMAX + s), static_cast<uint32_t>((use - 1) & 1));
+        const size_t frame = static_cast<size_t>(clip) * T + frame_of(j);
+        const uint32_t dst = smem_u32(ring + static_cast<size_t>(s) * slot_floats);
+        const uint32_t bp = smem_u32(bars + s), bv = smem_u32(bars + NSMAX + s);
+        mbar_expect_tx(bp, static_cast<uint32_t>(p_floats) * 4u);
+        bulk_g2s(dst, a.pctxl + frame * RH, bytes_rh, bp, pol.pl);
+        bulk_g2s(dst + bytes_rh, a.pctxg + frame * H, bytes_h, bp, pol.gm);
+        bulk_g2s(dst + bytes_rh + bytes_h, a.pctxm + frame * H, bytes_h, bp, pol.gm);
+        mbar_expect_tx(bv, static_cast<uint32_t>(v_floats) * 4u);
+        bulk_g2s(dst + static_cast<uint32_t>(p_floats) * 4u, a.ctxl0 + frame * RH, bytes_rh, bv, pol.cl);
+        bulk_g2s(dst + static_cast<uint32_t>(p_floats) * 4u + bytes_rh, a.qctxl + frame * RH, bytes_rh, bv, pol.q);
+      }
+    }
+  }
+
+  // ================================ one row per group ================================
+  float4 acc[3] = {z4, z4, z4};
+  float rm[3] = {-INFINITY, -INFINITY, -INFINITY}, rs[3] = {0.f, 0.f, 0.f};
+  float beta = 1.0f;
+  // everything below reads what the previous kernel wrote (the h-projections)
+  pdl_wait();
+  pdl_trigger();
+  if (active) {
+    constexpr float C2 = 2.885390081777927f;
+    float4 sl = z4, sg = z4, sm = z4, slt = z4;
+    {
+      // the h-projections arrive as k-slice planes, summed in plane order
+      const float *hp = a.hp + static_cast<size_t>(row) * a.ldhp;
+      float bsel = 0.f;
+      auto add4 = [](float4 &d, const float4 v) { d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w; };
+      for (int q = 0; q < a.hp_parts; ++q) {
+        const float *hq = hp + static_cast<size_t>(q) * a.hp_plane;
+        if (okc) {
+          add4(sl, ld4(hq + a.off_sl + c));
+          add4(sg, ld4(hq + a.off_sg + c));
+          add4(sm, ld4(hq + a.off_sm + c));
+          add4(slt, ld4(hq + a.off_slt + c));
+        }
+        if (a.selector) bsel += hq[a.off_sel];
+      }
+      beta = a.selector ? sigmoid_acc(bsel) : 1.0f;
+      auto fold = [&](float4 &v) { v.x *= C2; v.y *= C2; v.z *= C2; v.w *= C2; };
+      fold(sl); fold(sg); fold(sm); fold(slt);
+    }
+    float *red = s_red + g * (RMAX + 2) * 4;
+    for (int j = 0; j < nframes; ++j) {
+      const int s = j % NS;
+      const uint32_t ph = static_cast<uint32_t>((j / NS) & 1);
+      const int t = frame_of(j);
+      const float *slot_p = ring + static_cast<size_t>(s) * slot_floats, *slot_v = slot_p + p_floats;
+      const float *pL = slot_p, *pG = slot_p + RH, *pM = pG + H;
+      const float *cL0 = slot_v, *qL = slot_v + RH;
+      const float *G0 = a.ctxg0 + (static_cast<size_t>(clip) * T + t) * H;
+      const float *M0 = a.ctxm0 + (static_cast<size_t>(clip) * T + t) * H;
+
+      // ---- A: region scores and the g / m scores of the frame
+      mbar_wait(smem_u32(bars + s), ph);
+      {
+        float part[RU];
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+          part[r] = (RT || r < R) ? su_l : 0.f;
+          if ((RT || r < R) && okc) part[r] = tanh_acc4(ld4(pL + r * H + c), sl, ul, part[r]);
+        }
+        float gm[2] = {su_g, su_m};
+        if (okc) {
+          gm[0] = tanh_acc4(ld4(pG + c), sg, ld4(s_u + c), gm[0]);
+          gm[1] = tanh_acc4(ld4(pM + c), sm, ld4(s_u + H + c), gm[1]);
+        }
+        warp_multi_reduce<RU>(part, lane);
+        warp_multi_reduce<2>(gm, lane);
+        constexpr int STEP = 32 / RU;
+        if ((lane & (STEP - 1)) == 0) red[multi_reduce_index<RU>(lane) * 4 + gw] = part[0];
+        if ((lane & 15) == 0) red[(RMAX + (lane >> 4)) * 4 + gw] = gm[0];
+      }
+      group_sync(g);                            // scores complete
+
+      // ---- soft-max over the regions
+      float al[RU];
+      float inv;
+      {
+        float sc[RU];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+          sc[r] = (RT || r < R) ? sum4(ld4(red + r * 4)) + cl : -INFINITY;
+          mx = fmaxf(mx, sc[r]);
+        }
+        float mine = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < RU; ++r) mine = (lane == r) ? sc[r] : mine;
+        const float e_mine = (lane < R) ? exp_fast(mine - mx) : 0.f;
+        float den = 0.f;
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+          al[r] = __shfl_sync(0xffffffffu, e_mine, r);
+          den += al[r];
+        }
+        inv = rcp_approx(den);
+        if (a.alpha_l && gt < R) a.alpha_l[(static_cast<size_t>(row) * T + t) * R + gt] = e_mine * inv;
+      }
+      float sc3[3];
+      sc3[0] = sum4(ld4(red + RMAX * 4)) + cg;
+      sc3[1] = sum4(ld4(red + (RMAX + 1) * 4)) + cm;
+
+      // ---- C: attended local context, its projection, the lt score
+      mbar_wait(smem_u32(bars + NSMAX + s), ph);
+      const float4 g0 = okc ? __ldg(reinterpret_cast<const float4 *>(G0 + c)) : z4;
+      const float4 m0 = okc ? __ldg(reinterpret_cast<const float4 *>(M0 + c)) : z4;
+      float4 cLv = z4;
+      {
+        float plt = su_lt;
+        if (okc) {
+          float4 p0 = z4;
+#pragma unroll
+          for (int r = 0; r < RU; ++r) {
+            if (RT || r < R) {
+              fma4(cLv, al[r], ld4(cL0 + r * H + c));
+              fma4(p0, al[r], ld4(qL + r * H + c));
+            }
+          }
+          scale4(cLv, inv);
+          scale4(p0, inv);
+          plt = tanh_acc4(p0, slt, ld4(s_u + 2 * H + c), plt);
+        }
+        plt = warp_sum(plt);
+        if (lane == 0) s_lt[g * 4 + gw] = plt;
+      }
+      group_sync(g);                            // lt score complete; the group is done with the slot
+      if (gt == 0) mbar_arrive_local(smem_u32(bars + 2 * NSMAX + s));
+      sc3[2] = sum4(ld4(s_lt + g * 4)) + clt;
+      if (a.att_scores && gt == 0) {
+        const size_t plane = static_cast<size_t>(a.rows) * T, at = static_cast<size_t>(row) * T + t;
+        a.att_scores[at] = sc3[0];
+        a.att_scores[plane + at] = sc3[1];
+        a.att_scores[2 * plane + at] = sc3[2];
+      }
+
+      // ---- D: fold the frame into the three running soft-max states
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        float e = 1.0f;
+        if (sc3[q] > rm[q]) {
+          const float keep = exp_fast(rm[q] - sc3[q]);      // 0 on the first frame (rm = -inf)
+          rm[q] = sc3[q];
+          rs[q] *= keep;
+          scale4(acc[q], keep);
+        } else {
+          e = exp_fast(sc3[q] - rm[q]);
+        }
+        rs[q] += e;
+        fma4(acc[q], e, q == 0 ? g0 : (q == 1 ? m0 : cLv));
+      }
+    }
+  }
+
+  float *ctx = a.ctx + static_cast<size_t>(row) * (a.ldctx ? a.ldctx : H);
+  auto write_ctx = [&](const float4 v) {
+    if (!okc) return;
+    *reinterpret_cast<float4 *>(ctx + c) = v;
+    if (a.ctx_t) {
+      float *ct = a.ctx_t + (static_cast<size_t>(row >> 6) * H + c) * 64 + (row & 63);
+      ct[0] = v.x; ct[64] = v.y; ct[128] = v.z; ct[192] = v.w;
+    }
+  };
+  if (cs == 1) {
+    if (active) {
+      const float i0 = 1.0f / rs[0], i1 = 1.0f / rs[1], i2 = 1.0f / rs[2];
+      write_ctx(make_float4(beta * (acc[0].x * i0 + acc[1].x * i1 + acc[2].x * i2),
+                            beta * (acc[0].y * i0 + acc[1].y * i1 + acc[2].y * i2),
+                            beta * (acc[0].z * i0 + acc[1].z * i1 + acc[2].z * i2),
+                            beta * (acc[0].w * i0 + acc[1].w * i1 + acc[2].w * i2)));
+    }
+    return;
+  }
+  // every CTA of the cluster is done with its ring (and has initialised its barriers): rank 0's ring becomes the pads
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+  if (rank != 0) {
+    if (active) {
+      float *pad = ring + (static_cast<size_t>(rank - 1) * K + g) * PAD_FLOATS;
+      const uint32_t rbar = dsmem_addr(bars + 3 * NSMAX, 0);
+      if (okc) {
+        st_async_v4(dsmem_addr(pad + 4 * c, 0), acc[0].x, acc[1].x, acc[2].x, 0.f, rbar);
+        st_async_v4(dsmem_addr(pad + 4 * c + 4, 0), acc[0].y, acc[1].y, acc[2].y, 0.f, rbar);
+        st_async_v4(dsmem_addr(pad + 4 * c + 8, 0), acc[0].z, acc[1].z, acc[2].z, 0.f, rbar);
+        st_async_v4(dsmem_addr(pad + 4 * c + 12, 0), acc[0].w, acc[1].w, acc[2].w, 0.f, rbar);
+      }
+      if (gt == 0) {
+        st_async_v4(dsmem_addr(pad + 4 * H, 0), rm[0], rs[0], rm[1], rs[1], rbar);
+        st_async_v4(dsmem_addr(pad + 4 * H + 4, 0), rm[2], rs[2], 0.f, 0.f, rbar);
+      }
+    }
+    return;
+  }
+  if (!active) return;
+  mbar_wait_cluster(smem_u32(bars + 3 * NSMAX), 0);
+  {
+    // fixed order: this CTA first, then the pads by rank
+    float4 o = z4;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      float mx = rm[q];
+      for (int p = 0; p + 1 < cs; ++p) mx = fmaxf(mx, ring[(static_cast<size_t>(p) * K + g) * PAD_FLOATS + 4 * H + 2 * q]);
+      const float w0 = expf(rm[q] - mx);
+      float den = w0 * rs[q];
+      float4 num = acc[q];
+      num.x *= w0; num.y *= w0; num.z *= w0; num.w *= w0;
+      for (int p = 0; p + 1 < cs; ++p) {
+        const float *pad = ring + (static_cast<size_t>(p) * K + g) * PAD_FLOATS;
+        const float w = expf(pad[4 * H + 2 * q] - mx);
+        den = fmaf(w, pad[4 * H + 2 * q + 1], den);
+        if (okc) {
+          num.x = fmaf(w, pad[4 * c + q], num.x);
+          num.y = fmaf(w, pad[4 * c + 4 + q], num.y);
+          num.z = fmaf(w, pad[4 * c + 8 + q], num.z);
+          num.w = fmaf(w, pad[4 * c + 12 + q], num.w);
+        }
+      }
+      const float inv = 1.0f / den;
+      o.x = fmaf(num.x, inv, o.x); o.y = fmaf(num.y, inv, o.y); o.z = fmaf(num.z, inv, o.z); o.w = fmaf(num.w, inv, o.w);
+    }
+    write_ctx(make_float4(beta * o.x, beta * o.y, beta * o.z, beta * o.w));
+  }
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -751,9 +1071,71 @@ int att_group_set_trap_log(int *dev_ptr) {
   return STAT_OK;
 }
 
+// att_clip_kernel: plan (row slots per cluster, passes per clip, cluster size, ring depth) and launch
+namespace {
+size_t clip_extra_bytes(int H) {
+  return (static_cast<size_t>(KSH) * (RMAX + 2) * 4 + KSH * 4 + 3 * static_cast<size_t>(H)) * 4 + (3 * 4 + 1) * 8 + 128;
+}
+bool att_clip_plan(int clips, int rpc, int T, int R, int H, int *K, int *npass, int *cs, int *NS) {
+  if ((H & 3) != 0 || H > 512 || R > RMAX || R < 1 || clips < 1 || rpc < 2 || T < 1) return false;
+  const size_t extra = clip_extra_bytes(H);
+  if (extra + 2 * frame_bytes(R, H) > SMEM_MAX) return false;
+  int ns = static_cast<int>((SMEM_MAX - extra) / frame_bytes(R, H));
+  if (ns > 4) ns = 4;
+  const int np = (rpc + KSH - 1) / KSH, k = (rpc + np - 1) / np;
+  int c = 1;
+  while (c < 8 && 2 * c <= T && static_cast<long long>(clips) * np * 2 * c <= sm_count()) c *= 2;
+  // the landing pads of rank 0 reuse the ring
+  while (c > 1 && static_cast<size_t>(c - 1) * k * (static_cast<size_t>(H) * 4 + 8) * 4 > ns * frame_bytes(R, H)) c /= 2;
+  *K = k; *npass = np; *cs = c; *NS = ns;
+  return true;
+}
+
+template <int RT, int HT>
+int launch_clip(const AttArgs &a, int clips, int K, int npass, int cs, int NS, cudaStream_t stream) {
+  const size_t smem = NS * frame_bytes(a.R, a.H) + clip_extra_bytes(a.H);
+  static size_t smem_set[STAT_MAX_DEV] = {};
+  STAT_TRY(ensure_dyn_smem(att_clip_kernel<RT, HT>, smem, smem_set));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(clips) * npass * cs);
+  cfg.blockDim = dim3(K * GT + 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  set_launch_label("att_clip");
+  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_clip_kernel<RT, HT>, a, K, npass, cs, NS, l2_policies()));
+  note_launch();
+  return STAT_OK;
+}
+}  // namespace
+
+static int g_share = -1;
+void att_group_set_share(int on) { g_share = on; }
+
 int att_group_launch(const AttArgs &a_in, cudaStream_t stream) {
   AttArgs a = a_in;
   a.trace = g_group_trace;
+  if (a.rows_per_clip >= 2 && a.rows % a.rows_per_clip == 0) {
+    // beam search: the row slots of a clip share one pass over its frames (STAT_ATT_SHARE=0: one cluster per row)
+    if (g_share < 0) {
+      const char *e = getenv("STAT_ATT_SHARE");
+      g_share = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int share = g_share;
+    int K, np, c, ns;
+    if (share && att_clip_plan(a.rows / a.rows_per_clip, a.rows_per_clip, a.T, a.R, a.H, &K, &np, &c, &ns)) {
+      const int clips = a.rows / a.rows_per_clip;
+      if (a.H == 512 && a.R == 8) return launch_clip<8, 512>(a, clips, K, np, c, ns, stream);
+      return launch_clip<0, 0>(a, clips, K, np, c, ns, stream);
+    }
+  }
   int cs, G, S;
   STAT_REQUIRE(att_group_plan(a.rows, a.T, a.R, a.H, &cs, &G, &S), STAT_EINVAL,
                "att_group: unsupported shape R=%d H=%d", a.R, a.H);

@@ -31,6 +31,8 @@ struct AttArgs {
   long long *trace;                              // debug: clock stamps per CTA and group (att_group), or null
   int reverse;                                   // att_group: walk the frames of a slice backwards (odd decode steps)
   float *ctx_t;                                  // [row / 64][H][64] transposed copy of ctx (cell_kernel operand) or null
+  int rows_per_clip;                             // beam search: row = clip * rows_per_clip + slot, the slots of a clip share
+                                                 // its context blocks (att_clip_kernel); 0 = no such layout (row_clip decides)
 };
 int att_step_launch(const AttArgs &a, cudaStream_t stream);
 // att_group.cu: four independent four-warp groups per CTA, each streaming whole frames (H % 4 == 0,
@@ -38,6 +40,7 @@ int att_step_launch(const AttArgs &a, cudaStream_t stream);
 bool att_group_plan(int rows, int T, int R, int H, int *nctas, int *groups, int *max_parts);
 int att_group_launch(const AttArgs &a, cudaStream_t stream);
 void att_group_set_trace(long long *p);
+void att_group_set_share(int on);   // att_clip_kernel for rows_per_clip >= 2: 1 on, 0 off, -1 default (STAT_ATT_SHARE, else on)
 
 // ---- recurrent.cu --------------------------------------------------------------
 // LSTM gates + state update (model_attention.py:437-457) and the emb / bias part of

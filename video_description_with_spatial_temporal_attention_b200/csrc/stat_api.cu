@@ -458,6 +458,7 @@ struct StepIO {
   float *alpha_l;     // (rows,T,R) or null
   float *att_scores;  // (3,rows,T) or null
   int reverse;        // attention walks the frames backwards (odd decode steps: L2 reuse across steps)
+  int rows_per_clip;  // beam search: row = clip * rows_per_clip + slot (0: row_clip / identity)
 };
 
 // what multiplies a hidden state: which = 1 the attention queries / h.U / selector logit of the NEXT
@@ -490,6 +491,7 @@ int step_att(const StatDims &d, const Prep &p, const float *P, const Ws &w, floa
   const int H = d.H, rows = io.rows;
   AttArgs a = att_args(d, p, P, w, W, rows, io.row_clip, io.att_scores, io.alpha_l);
   a.reverse = io.reverse;
+  a.rows_per_clip = io.rows_per_clip;
   {
     ProfScope ps(PH_ATT, st);
     STAT_TRY(att_launch(w, a, st));
@@ -788,6 +790,7 @@ int cell_step(const StatDims &d, const Prep &p, const float *P, const Ws &w, flo
               float *hq_out, Overlap *ov, cudaStream_t st) {
   AttArgs a = att_args_fused(d, p, P, w, W, io.rows, io.row_clip, io.att_scores, io.alpha_l);
   a.reverse = io.reverse;
+  a.rows_per_clip = io.rows_per_clip;
   a.ctx_t = W + w.ctxT;
   {
     ProfScope ps(PH_ATT, st);
@@ -944,6 +947,12 @@ int stat_set_step_impl(int impl) {
                "step impl must be 0 (separate kernels), 1 (fused tile kernels), 2 (cell step) or -1 (default)");
   g_step_impl = impl;
   g_step_impl_set = impl >= 0;
+  return STAT_OK;
+}
+
+int stat_set_beam_share(int on) {
+  STAT_REQUIRE(on >= -1 && on <= 1, STAT_EINVAL, "beam share must be 0, 1 or -1 (default)");
+  att_group_set_share(on);
   return STAT_OK;
 }
 
@@ -1467,6 +1476,7 @@ int stat_decode_beam(const StatDims *d, const void *prepared, void *ws, int k, i
       memset(&io, 0, sizeof(io));
       io.rows = rows;
       io.row_clip = row_clip;
+      io.rows_per_clip = k;
       io.tok_prev = b.tok_prev;
       io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.hb; io.c_out = W + w.cb;
       io.reverse = serpentine(t);
@@ -1499,6 +1509,7 @@ int stat_decode_beam(const StatDims *d, const void *prepared, void *ws, int k, i
     memset(&io, 0, sizeof(io));
     io.rows = rows;
     io.row_clip = row_clip;
+    io.rows_per_clip = k;
     io.tok_prev = b.tok_prev;
     io.h_in = W + w.h; io.c_in = W + w.c; io.h_out = W + w.hb; io.c_out = W + w.cb;
     io.reverse = serpentine(t);
