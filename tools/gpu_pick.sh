@@ -1,8 +1,6 @@
 #!/bin/bash
-# round-2 session 3: attention g/m prefetch experiment
+# full parity suite + bench line (round-2 session 3)
 mkdir -p gpurun_out
-for v in - STAT_ATT_PF=1 - STAT_ATT_PF=1 STAT_ATT_CS=1 STAT_ATT_CS=1,STAT_ATT_PF=1; do
-  if [ "$v" = "-" ]; then v="X_=0"; fi
-  env ${v//,/ } timeout 300 python tools/quick_value.py 2>&1 | tail -2
-  env ${v//,/ } timeout 300 python tools/att_time.py 2>&1 | tail -2
-done | tee gpurun_out/sweep_pf.txt
+timeout 1500 python -m pytest tests -m gpu -q --timeout 400 -p no:cacheprovider 2>&1 | tail -15 | tee gpurun_out/t_all_s3.log
+timeout 900 python bench.py --steps 50 --warmup 5 2>gpurun_out/bench_r2_t.err | tail -1 > gpurun_out/bench_r2_t.json
+tail -3 gpurun_out/bench_r2_t.err

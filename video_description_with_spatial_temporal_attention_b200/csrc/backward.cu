@@ -1283,9 +1283,16 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
   // weight decay (:1130-1136): every parameter, biases included
   if (decay_c > 0.f) {
     const float c2 = 2.0f * decay_c;
+    // Tensors that lie back to back in both the gradient and the parameter buffer (the optimizer's flat buffers:
+    // all of them, in init_params order) are decayed by one launch: 43 launches -> 1 for the Trainer.
+    struct Run { float *g; const float *p; size_t n; };
+    Run runs[64];
+    int nruns = 0;
     auto dec = [&](const float *g, const float *pp, size_t n) -> int {
-      if (!g || !pp) return STAT_OK;
-      return BW_LAUNCH(k_decay, g1(n), dim3(256), st, const_cast<float *>(g), pp, n, c2);
+      if (!g || !pp || n == 0) return STAT_OK;
+      STAT_REQUIRE(nruns < 64, STAT_EINVAL, "grad_shared: too many decayed tensors");
+      runs[nruns++] = Run{const_cast<float *>(g), pp, n};
+      return STAT_OK;
     };
     const size_t h = H, e = E, v = V;
 #define DEC(name, n) STAT_TRY(dec(grads->name, p->name, (n)))
@@ -1305,6 +1312,13 @@ int stat_grad_shared(const StatDims *d, const StatParams *p, const StatFwdBlocks
     if (c2o) { DEC(ff_logit_ctxglm_W, h * e); DEC(ff_logit_ctxglm_b, e); }
     DEC(ff_logit_W, e * v); DEC(ff_logit_b, v);
 #undef DEC
+    for (int i = 1; i < nruns; ++i)            // by gradient address (insertion sort: <= 43 entries)
+      for (int j = i; j > 0 && runs[j].g < runs[j - 1].g; --j) { const Run t = runs[j]; runs[j] = runs[j - 1]; runs[j - 1] = t; }
+    for (int i = 0; i < nruns;) {
+      Run r = runs[i++];
+      while (i < nruns && runs[i].g == r.g + r.n && runs[i].p == r.p + r.n) r.n += runs[i++].n;
+      STAT_TRY(BW_LAUNCH(k_decay, g1(r.n), dim3(256), st, r.g, r.p, r.n, c2));
+    }
   }
 #undef GRAD
   bw_mark(BP_COUNT, st);
