@@ -243,7 +243,9 @@ int transpose_launch(const float *src, int K, int N, float *dst, int ld_dst, int
 // gate-interleaving variants (rows 4*unit + gate): weights (K, 4H) -> K-major rows at column offset c0; vectors (4H)
 int transpose_il_launch(const float *src, int K, int H, float *dst, int ld_dst, int c0, cudaStream_t stream);
 int interleave4_launch(const float *src, float *dst, int H, cudaStream_t stream);
-int softmax_rows_launch(const float *scores, float *out, int nrows, int n, cudaStream_t stream);
+// out_q = row-wise softmax of plane q of scores (3, nrows, n) for the non-null outputs, one launch
+int softmax_rows3_launch(const float *scores, float *out0, float *out1, float *out2, int nrows, int n,
+                         cudaStream_t stream);
 int scale_launch(float *x, const float *f, size_t n, cudaStream_t stream);
 int init_rows_launch(int rows, int64_t *tok_prev, int32_t *alive, int32_t *lengths, float *scores,
                      int64_t *tokens, int maxlen, cudaStream_t stream);

@@ -800,11 +800,16 @@ __global__ void interleave4_kernel(const float *__restrict__ src, float *__restr
   if (i < 4 * H) dst[4 * (i % H) + i / H] = src[i];
 }
 
-__global__ void softmax_rows_kernel(const float *__restrict__ sc, float *__restrict__ out, int nrows, int n) {
+// out_q[row][:] = softmax(sc[q][row][:]) for the planes q = blockIdx.y whose output pointer is not null
+struct SoftmaxOuts {
+  float *out[3];
+};
+__global__ void softmax_rows_kernel(const float *__restrict__ sc, SoftmaxOuts o, int nrows, int n) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= nrows) return;
-  const float *p = sc + static_cast<size_t>(row) * n;
+  float *out = o.out[blockIdx.y];
+  if (row >= nrows || !out) return;
+  const float *p = sc + (static_cast<size_t>(blockIdx.y) * nrows + row) * n;
   float m = -INFINITY;
   for (int i = lane; i < n; i += 32) m = fmaxf(m, p[i]);
   m = warp_max(m);
@@ -923,8 +928,12 @@ int interleave4_launch(const float *src, float *dst, int H, cudaStream_t stream)
   return STAT_OK;
 }
 
-int softmax_rows_launch(const float *scores, float *out, int nrows, int n, cudaStream_t stream) {
-  softmax_rows_kernel<<<(nrows + 3) / 4, 128, 0, stream>>>(scores, out, nrows, n);
+int softmax_rows3_launch(const float *scores, float *out0, float *out1, float *out2, int nrows, int n,
+                         cudaStream_t stream) {
+  if (!out0 && !out1 && !out2) return STAT_OK;
+  SoftmaxOuts o;
+  o.out[0] = out0; o.out[1] = out1; o.out[2] = out2;
+  softmax_rows_kernel<<<dim3((nrows + 3) / 4, 3), 128, 0, stream>>>(scores, o, nrows, n);
   note_launch();
   STAT_CUDA_CHECK(cudaGetLastError());
   return STAT_OK;

@@ -1222,9 +1222,9 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
       STAT_TRY(cell_step(*d, p, P, w, W, io, t + 1 < L, nullptr, &ov, st));
       if (want_t) {
         const size_t n = static_cast<size_t>(B) * T;
-        if (out_alpha_g) STAT_TRY(softmax_rows_launch(W + w.att_scores, out_alpha_g + t * n, B, T, st));
-        if (out_alpha_m) STAT_TRY(softmax_rows_launch(W + w.att_scores + n, out_alpha_m + t * n, B, T, st));
-        if (out_alpha_lt) STAT_TRY(softmax_rows_launch(W + w.att_scores + 2 * n, out_alpha_lt + t * n, B, T, st));
+        STAT_TRY(softmax_rows3_launch(W + w.att_scores, out_alpha_g ? out_alpha_g + t * n : nullptr,
+                                      out_alpha_m ? out_alpha_m + t * n : nullptr,
+                                      out_alpha_lt ? out_alpha_lt + t * n : nullptr, B, T, st));
       }
       STAT_TRY(ov.state_ready());
       STAT_TRY(cell_logits(*d, p, P, w, W, B, ov.side()));
@@ -1264,9 +1264,9 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
       }
       if (want_t) {
         const size_t n = static_cast<size_t>(B) * T;
-        if (out_alpha_g) STAT_TRY(softmax_rows_launch(W + w.att_scores, out_alpha_g + t * n, B, T, st));
-        if (out_alpha_m) STAT_TRY(softmax_rows_launch(W + w.att_scores + n, out_alpha_m + t * n, B, T, st));
-        if (out_alpha_lt) STAT_TRY(softmax_rows_launch(W + w.att_scores + 2 * n, out_alpha_lt + t * n, B, T, st));
+        STAT_TRY(softmax_rows3_launch(W + w.att_scores, out_alpha_g ? out_alpha_g + t * n : nullptr,
+                                      out_alpha_m ? out_alpha_m + t * n : nullptr,
+                                      out_alpha_lt ? out_alpha_lt + t * n : nullptr, B, T, st));
       }
       STAT_TRY(ov.join());                  // zadd / z / partial buffers of the previous step's readout are free
       STAT_TRY(fstep_gates(*d, p, P, w, W, io, st));
@@ -1310,9 +1310,9 @@ int stat_forward_teacher(const StatDims *d, const void *prepared, void *ws, int 
     STAT_TRY(step_out(*d, p, P, w, W, io, ov.side()));
     if (want_t) {
       const size_t n = static_cast<size_t>(B) * T;
-      if (out_alpha_g) STAT_TRY(softmax_rows_launch(W + w.att_scores, out_alpha_g + t * n, B, T, st));
-      if (out_alpha_m) STAT_TRY(softmax_rows_launch(W + w.att_scores + n, out_alpha_m + t * n, B, T, st));
-      if (out_alpha_lt) STAT_TRY(softmax_rows_launch(W + w.att_scores + 2 * n, out_alpha_lt + t * n, B, T, st));
+      STAT_TRY(softmax_rows3_launch(W + w.att_scores, out_alpha_g ? out_alpha_g + t * n : nullptr,
+                                    out_alpha_m ? out_alpha_m + t * n : nullptr,
+                                    out_alpha_lt ? out_alpha_lt + t * n : nullptr, B, T, st));
     }
     PickArgs k;
     memset(&k, 0, sizeof(k));

@@ -73,9 +73,9 @@ class Trainer(object):
             return None, None, None
         H, E = self.options['dim'], self.options['dim_word']
         dev = self.engine.device
-        # one draw for the three masks (contiguous chunks of one buffer): 2 launches instead of 6
+        # one Bernoulli draw straight into the float buffer of the three masks (contiguous chunks): 1 launch, one write
         n = L * B
-        u = (torch.rand(n * (4 * H + E), device=dev, generator=self.gen) < 0.5).float()
+        u = torch.empty(n * (4 * H + E), dtype=torch.float32, device=dev).bernoulli_(0.5, generator=self.gen)
         return (u[:n * 3 * H].view(L, B, 3 * H), u[n * 3 * H:n * 4 * H].view(L, B, H),
                 u[n * 4 * H:].view(L, B, E))
 
