@@ -324,6 +324,16 @@ int check_device() {
 int dense(const float *x, int ldx, int rows, const float *Wt, int K, int nfeat, const float *bias, float *out,
           int ldc, int act, float alpha, float post, const float *addend, int ld_add, cudaStream_t st,
           int ksplit = 1, size_t plane = 0) {
+  if (rows > 128 && rows <= 192 && ksplit == 1 && nfeat >= 1024) {
+    // A few rows more than one 128-row tile (beam search: 32 clips x k = 5 = 160 rows): with the rows on the 128-lane
+    // axis the second row tile would be mostly padding and the tile count (2 x 99 for the vocabulary) a second,
+    // one-third-full wave.  Two skinny launches instead: 128 rows, then the rest with a narrow tile (N = 32 / 64 per
+    // MMA instruction: about half the cost), which run side by side (programmatic dependent launch).
+    STAT_TRY(dense(x, ldx, 128, Wt, K, nfeat, bias, out, ldc, act, alpha, post, addend, ld_add, st));
+    return dense(x + static_cast<size_t>(128) * ldx, ldx, rows - 128, Wt, K, nfeat, bias,
+                 out + static_cast<size_t>(128) * ldc, ldc, act, alpha, post,
+                 addend ? addend + static_cast<size_t>(128) * ld_add : nullptr, ld_add, st);
+  }
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.K = K;
