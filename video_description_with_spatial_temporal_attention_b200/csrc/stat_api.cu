@@ -184,9 +184,13 @@ struct Ws {
   int att_impl;      // 2 = att_group_kernel (bulk-copy streaming), 0 = the generic att_step_kernel
 };
 
-// k-slices for a skinny (rows <= 128) projection: enough CTAs to cover the SMs once
+// most rows of a product that dense() issues as a 128-row and a narrow skinny launch (beam search: 32 clips x 5 slots)
+constexpr int SPLIT_ROWS_MAX = 192;
+
+// k-slices for a skinny (rows <= 128, or 128 + a few: see dense()) projection: enough CTAs to cover the SMs once
 int pick_ksplit(int nfeat, int rows, int K) {
-  if (rows > 128) return 1;
+  if (rows > SPLIT_ROWS_MAX) return 1;
+  if (rows > 128) rows = 128;
   const int bq = rows > 64 ? 128 : (rows > 32 ? 64 : 32);
   const int tiles = ((nfeat + 127) / 128) * ((rows + bq - 1) / bq);
   const int nk = (K + 31) / 32;
@@ -324,15 +328,16 @@ int check_device() {
 int dense(const float *x, int ldx, int rows, const float *Wt, int K, int nfeat, const float *bias, float *out,
           int ldc, int act, float alpha, float post, const float *addend, int ld_add, cudaStream_t st,
           int ksplit = 1, size_t plane = 0) {
-  if (rows > 128 && rows <= 192 && ksplit == 1 && nfeat >= 1024) {
+  if (rows > 128 && rows <= SPLIT_ROWS_MAX) {
     // A few rows more than one 128-row tile (beam search: 32 clips x k = 5 = 160 rows): with the rows on the 128-lane
     // axis the second row tile would be mostly padding and the tile count (2 x 99 for the vocabulary) a second,
     // one-third-full wave.  Two skinny launches instead: 128 rows, then the rest with a narrow tile (N = 32 / 64 per
-    // MMA instruction: about half the cost), which run side by side (programmatic dependent launch).
-    STAT_TRY(dense(x, ldx, 128, Wt, K, nfeat, bias, out, ldc, act, alpha, post, addend, ld_add, st));
+    // MMA instruction: about half the cost), which run side by side (programmatic dependent launch).  Both keep the
+    // k-split of the skinny form (same planes, `plane` floats apart).
+    STAT_TRY(dense(x, ldx, 128, Wt, K, nfeat, bias, out, ldc, act, alpha, post, addend, ld_add, st, ksplit, plane));
     return dense(x + static_cast<size_t>(128) * ldx, ldx, rows - 128, Wt, K, nfeat, bias,
                  out + static_cast<size_t>(128) * ldc, ldc, act, alpha, post,
-                 addend ? addend + static_cast<size_t>(128) * ld_add : nullptr, ld_add, st);
+                 addend ? addend + static_cast<size_t>(128) * ld_add : nullptr, ld_add, st, ksplit, plane);
   }
   GemmArgs g;
   memset(&g, 0, sizeof(g));
@@ -701,13 +706,23 @@ bool cell_enabled(const StatDims &d, const Ws &w, bool dp_h) {
 // Beam search (rows = B*k): beyond 128 rows the tensor-core products lose their skinny k-split form (two row tiles,
 // full-K loops) and the cell step is the faster chain (measured): default there unless
 // STAT_STEP / stat_set_step_impl says otherwise.
+// STAT_SPLIT_CHAIN=0: beam searches over 129..192 rows take the cell step (the default before the products of such a
+// step were issued as two skinny k-split launches)
+bool split_chain() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STAT_SPLIT_CHAIN");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 bool cell_enabled_rows(const StatDims &d, const Ws &w, int rows) {
   static int forced = -2;
   if (forced == -2) forced = getenv("STAT_STEP") ? 1 : 0;
   const bool ok = w.att_impl == 2 && cell_plan(d.H, d.E, nullptr);
   if (!ok) return false;
   if (step_impl() == 2) return true;
-  return !forced && !g_step_impl_set && rows > 128;
+  return !forced && !g_step_impl_set && rows > (split_chain() ? SPLIT_ROWS_MAX : 128);
 }
 
 CellLaunch cell_args(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io) {
