@@ -100,15 +100,16 @@ int stat_set_gemm_impl(int impl);
 
 /* Implementation of the decode step behind stat_forward_teacher / stat_decode_greedy / stat_decode_beam (same
  * results to fp32 summation order; all are device paths):
- *   2 = cell step (cell_step.cu; the default where the shape allows it: H % 32 == 0, 160 <= H <= 512, no explicit
- *       dropout mask on h): attention -> ONE kernel for ctx.Wc + gates (S10-S13) | grid barrier | every product of
- *       the new hidden state + readout activation.  Two dependent launches per step; logits -> vocabulary reduction
- *       beside the next attention.
- *   0 = separate kernels: attention -> ctx.[Wc|Wctx] -> gates -> h.[Wd*|U|W_sel|Wl] as k-split tensor-core products +
- *       elementwise kernels, readout activation -> logits -> vocabulary reduction beside the next attention
+ *   0 = separate kernels (the default): attention -> ctx.[Wc|Wctx] -> gates -> h.[Wd*|U|W_sel|Wl] as k-split
+ *       tensor-core products + elementwise kernels, readout activation -> logits -> vocabulary reduction beside the
+ *       next attention.  Products over 129..192 rows (beam search) go out as a 128-row and a narrow skinny launch.
+ *   2 = cell step (cell_step.cu; where the shape allows it: H % 32 == 0, 160 <= H <= 512, no explicit dropout mask
+ *       on h): attention -> ONE kernel for ctx.Wc + gates (S10-S13) | grid barrier | every product of the new hidden
+ *       state + readout activation.  Two dependent launches per step; measured slower than 0 for greedy decoding,
+ *       the default of beam searches over more than 192 rows.
  *   1 = fused tile kernels (step_fused.cu): gates / readout activation / vocabulary reduction in tcgen05 tile
  *       epilogues; measured slower end to end in round 2, kept selectable.
- *  -1 = back to the default (environment STAT_STEP=0|1|2, else 2). */
+ *  -1 = back to the default (environment STAT_STEP=0|1|2, else as above). */
 int stat_set_step_impl(int impl);
 
 /* Beam search attention (stat_decode_beam): 1 = the k row slots of a clip share ONE pass over the clip's context
