@@ -483,10 +483,10 @@ def test_beam_k1_equals_greedy_and_limits(torch_cuda):
         model.beam_batch(tp, o, ctxg, mg, ctxl, ctxm, k=2, maxlen=65)
 
 
-@pytest.mark.parametrize('B,k,T,R,kw', [(32, 5, 26, 8, {}),              # config 5's share: 128 CTAs, 5 row slots each
+@pytest.mark.parametrize('B,k,T,R,kw', [(32, 5, 26, 8, {}),              # config 5's share: 128 CTAs, 3 + 2 row slots
                                          (3, 3, 26, 8, {}),               # clusters of 8 CTAs
-                                         (2, 7, 5, 8, {}),                # two passes per clip (4 + 3 slots), T < 8
-                                         (2, 16, 9, 8, {}),               # four passes of 4 slots
+                                         (2, 7, 5, 8, {}),                # three passes per clip (3 + 3 + 1 slots), T < 8
+                                         (2, 16, 9, 8, {}),               # six passes of 3, 3, 3, 3, 3, 1 slots
                                          (4, 4, 7, 3, {'dim': 96, 'dim_word': 64, 'ctxg_dim': 96, 'ctxglm_dim': 96, 'ctxl_dim': 128, 'ctxm_dim': 64, 'n_words': 301}),   # generic R / H
                                          (150, 2, 3, 2, {'dim': 32, 'dim_word': 32, 'ctxg_dim': 32, 'ctxglm_dim': 32, 'ctxl_dim': 64, 'ctxm_dim': 64, 'n_words': 200})])  # more clips than SMs
 def test_beam_shared_frames_equal_one_cluster_per_row(torch_cuda, B, k, T, R, kw):

@@ -655,11 +655,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 // merge inside the CTA; across the cluster the other ranks push their states into landing pads of rank 0 as
 // above -- the pads reuse the drained ring (a cluster barrier separates the two uses).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int KSH = 5;                         // row slots (groups) per CTA
-constexpr int CLIP_THREADS = KSH * GT + 32;    // + the producer warp
+constexpr int KSH = 5;                         // most row slots (groups) per CTA; shared memory is laid out for KSH
 
-template <int RT, int HT>
-__global__ void __launch_bounds__(CLIP_THREADS, 1)
+// KT = most groups of a launch (3 or KSH): the register budget of a thread follows from it -- 65 536 / (KT x 128 + 32):
+// 80 registers at five groups, 128 at three, where the ten tanh chains of a frame are all in flight.
+template <int RT, int HT, int KT>
+__global__ void __launch_bounds__(KT * GT + 32, 1)
     att_clip_kernel(const AttArgs a, const int K, const int npass, const int cs, const int NS, const AttPolicies pol) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int RU = RT ? RT : RMAX;
@@ -1076,13 +1077,13 @@ namespace {
 size_t clip_extra_bytes(int H) {
   return (static_cast<size_t>(KSH) * (RMAX + 2) * 4 + KSH * 4 + 3 * static_cast<size_t>(H)) * 4 + (3 * 4 + 1) * 8 + 128;
 }
-bool att_clip_plan(int clips, int rpc, int T, int R, int H, int *K, int *npass, int *cs, int *NS) {
+bool att_clip_plan(int clips, int rpc, int kmax, int T, int R, int H, int *K, int *npass, int *cs, int *NS) {
   if ((H & 3) != 0 || H > 512 || R > RMAX || R < 1 || clips < 1 || rpc < 2 || T < 1) return false;
   const size_t extra = clip_extra_bytes(H);
   if (extra + 2 * frame_bytes(R, H) > SMEM_MAX) return false;
   int ns = static_cast<int>((SMEM_MAX - extra) / frame_bytes(R, H));
   if (ns > 4) ns = 4;
-  const int np = (rpc + KSH - 1) / KSH, k = (rpc + np - 1) / np;
+  const int np = (rpc + kmax - 1) / kmax, k = (rpc + np - 1) / np;
   int c = 1;
   while (c < 8 && 2 * c <= T && static_cast<long long>(clips) * np * 2 * c <= sm_count()) c *= 2;
   // the landing pads of rank 0 reuse the ring
@@ -1091,11 +1092,11 @@ bool att_clip_plan(int clips, int rpc, int T, int R, int H, int *K, int *npass, 
   return true;
 }
 
-template <int RT, int HT>
+template <int RT, int HT, int KT>
 int launch_clip(const AttArgs &a, int clips, int K, int npass, int cs, int NS, cudaStream_t stream) {
   const size_t smem = NS * frame_bytes(a.R, a.H) + clip_extra_bytes(a.H);
   static size_t smem_set[STAT_MAX_DEV] = {};
-  STAT_TRY(ensure_dyn_smem(att_clip_kernel<RT, HT>, smem, smem_set));
+  STAT_TRY(ensure_dyn_smem(att_clip_kernel<RT, HT, KT>, smem, smem_set));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(clips) * npass * cs);
@@ -1110,7 +1111,7 @@ int launch_clip(const AttArgs &a, int clips, int K, int npass, int cs, int NS, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   set_launch_label("att_clip");
-  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_clip_kernel<RT, HT>, a, K, npass, cs, NS, l2_policies()));
+  STAT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, att_clip_kernel<RT, HT, KT>, a, K, npass, cs, NS, l2_policies()));
   note_launch();
   return STAT_OK;
 }
@@ -1129,11 +1130,22 @@ int att_group_launch(const AttArgs &a_in, cudaStream_t stream) {
       g_share = (e && e[0] == '0') ? 0 : 1;
     }
     const int share = g_share;
+    // STAT_ATT_KSH = 3 (default) | 5: most row slots per CTA.  Three slots = 128 registers per thread and, at k = 5, two
+    // passes per clip (3 + 2 slots, 64 clusters of 2 CTAs); five slots = one pass at 80 registers.  Measured at 32 clips
+    // x k = 5: 39.6 against 45.7 us per launch (one cluster per row: 47.8), 4.22 against 4.41 ms per beam batch.
+    static int kmax = -1;
+    if (kmax < 0) {
+      const char *e = getenv("STAT_ATT_KSH");
+      kmax = (e && atoi(e) == KSH) ? KSH : 3;
+    }
     int K, np, c, ns;
-    if (share && att_clip_plan(a.rows / a.rows_per_clip, a.rows_per_clip, a.T, a.R, a.H, &K, &np, &c, &ns)) {
+    if (share && att_clip_plan(a.rows / a.rows_per_clip, a.rows_per_clip, kmax, a.T, a.R, a.H, &K, &np, &c, &ns)) {
       const int clips = a.rows / a.rows_per_clip;
-      if (a.H == 512 && a.R == 8) return launch_clip<8, 512>(a, clips, K, np, c, ns, stream);
-      return launch_clip<0, 0>(a, clips, K, np, c, ns, stream);
+      const bool base = a.H == 512 && a.R == 8;
+      if (K <= 3) return base ? launch_clip<8, 512, 3>(a, clips, K, np, c, ns, stream)
+                              : launch_clip<0, 0, 3>(a, clips, K, np, c, ns, stream);
+      return base ? launch_clip<8, 512, KSH>(a, clips, K, np, c, ns, stream)
+                  : launch_clip<0, 0, KSH>(a, clips, K, np, c, ns, stream);
     }
   }
   int cs, G, S;
