@@ -56,6 +56,17 @@ def test_sizes_and_argument_errors_without_gpu():
     bad = _lib.StatDims(B=1, T=2, R=2, Dg=16, Dm=8, Dr=8, H=8, E=8, V=11, flags=0)
     assert lib.stat_prepared_bytes(ctypes.byref(bad)) == 0
     assert b'ctxg_dim == dim' in lib.stat_last_error()
+    # a beam search over 160 rows (32 clips x k = 5) keeps the k-split planes of the skinny products: its workspace
+    # holds 160 rows of them (the products are issued as a 128-row and a 32-row launch), 200 rows fall back to one plane
+    w128 = lib.stat_workspace_bytes(ctypes.byref(d), 128)
+    w160 = lib.stat_workspace_bytes(ctypes.byref(d), 160)
+    w200 = lib.stat_workspace_bytes(ctypes.byref(d), 200)
+    assert w128 < w160 and (w160 - w128) / 32 > (w200 - w160) / 40
+    # process-wide switches validate their argument (no GPU needed)
+    assert lib.stat_set_beam_share(2) != 0 and b'beam share' in lib.stat_last_error()
+    assert lib.stat_set_beam_share(0) == 0 and lib.stat_set_beam_share(-1) == 0
+    assert lib.stat_set_step_impl(3) != 0
+    assert lib.stat_set_step_impl(-1) == 0
 
 
 def test_training_entry_points_without_gpu():
