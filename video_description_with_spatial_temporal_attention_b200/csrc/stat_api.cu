@@ -518,7 +518,7 @@ int step_att(const StatDims &d, const Prep &p, const float *P, const Ws &w, floa
 }
 
 int step_gates(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, const StepIO &io,
-               bool next_hproj, cudaStream_t st) {
+               bool next_hproj, cudaStream_t st, bool gates_only = false) {
   const int H = d.H, E = d.E, V = d.V, rows = io.rows;
   const bool ctx2out = (d.flags & STAT_CTX2OUT) != 0;
   GateArgs g;
@@ -540,6 +540,7 @@ int step_gates(const StatDims &d, const Prep &p, const float *P, const Ws &w, fl
     ProfScope ps(PH_GATES, st);
     STAT_TRY(gates_launch(g, st));
   }
+  if (gates_only) return STAT_OK;
   if (io.dp_h) {
     // explicit dropout mask on h (use_noise=1): the readout multiplies h*mask, the next cell h itself
     {
@@ -833,6 +834,19 @@ int cell_step(const StatDims &d, const Prep &p, const float *P, const Ws &w, flo
 int cell_logits(const StatDims &d, const Prep &p, const float *P, const Ws &w, float *W, int rows, cudaStream_t st) {
   ProfScope pl(PH_LOGITS, st);
   return dense(W + w.z, d.E, rows, P + p.WvT, d.E, d.V, P + p.bv, W + w.logits, w.ldl, 0, 1.f, 1.f, nullptr, 0, st);
+}
+
+// Greedy decoding forks the readout chain right after the gates: h.Wl (4 feature tiles x k-split) goes out on the side
+// stream while the products the next attention needs run on the caller's stream, so the readout activation does not
+// wait for the larger product.  Measured at B = 64 in the captured graph: 43.50 -> 42.93 us per step (two alternating
+// runs each).  STAT_SPLIT_HPROJ=0: one product for both (h.[Wl | Wd* | U | W_sel]) on the caller's stream.
+bool split_hproj() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STAT_SPLIT_HPROJ");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 bool overlap_enabled() {
@@ -1443,8 +1457,17 @@ int stat_decode_greedy(const StatDims *d, const void *prepared, void *ws, int ma
     io.reverse = serpentine(t);
     STAT_TRY(step_att(*d, p, P, w, W, io, st));
     STAT_TRY(ov.join());
-    STAT_TRY(step_gates(*d, p, P, w, W, io, t + 1 < maxlen, st));
-    STAT_TRY(ov.state_ready());
+    if (split_hproj() && ov.on_) {
+      // the readout chain forks right after the gates: h.Wl (4 feature tiles) on the side stream, the products the
+      // next attention needs on the caller's stream -- the readout activation does not wait for the larger product
+      STAT_TRY(step_gates(*d, p, P, w, W, io, false, st, true));
+      STAT_TRY(ov.state_ready());
+      if (t + 1 < maxlen) STAT_TRY(h_proj(*d, p, P, w, W, io.h_out, B, 1, st));
+      STAT_TRY(h_proj(*d, p, P, w, W, io.h_out, B, 2, ov.side()));
+    } else {
+      STAT_TRY(step_gates(*d, p, P, w, W, io, t + 1 < maxlen, st));
+      STAT_TRY(ov.state_ready());
+    }
     STAT_TRY(step_out(*d, p, P, w, W, io, ov.side()));
     PickArgs k;
     memset(&k, 0, sizeof(k));
